@@ -1,0 +1,179 @@
+/*
+ * lash_gpu.h -- C ABI of the B200 (sm_100a) implementation of lash's two hot paths.
+ *
+ * This is the drop-in boundary a host (the Rust `lash` binary through a bindgen/cc FFI crate,
+ * or the C++/Python hosts in this repo) binds.  The reference has no FFI layer of its own; the
+ * seams it replaces are Rust generics (file:line under the reference tree):
+ *
+ *   sketch side  src/utils.rs:377-386  trait KmerSketch { new, add_kmer, save }
+ *                src/utils.rs:457-503  the per-file record loop (filter -> 2-bit -> k-mers ->
+ *                                      canonical -> mask -> add_kmer).  A per-k-mer call is far too
+ *                                      fine for a device boundary, so the ABI lifts the seam to
+ *                                      "packed bases of whole records in, registers out".
+ *   dist side    src/utils.rs:150-180 (hmh_distance), :248-285 (ull_distance), :342-370
+ *                (hll_distance) par_iter bodies + src/main.rs:415-423 compute_distance.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (lash_gpu_last_error() gives the
+ *     thread-local message); no exceptions cross the boundary; nothing falls back to the CPU.
+ *   - the caller owns every host buffer; the library owns device memory behind opaque handles.
+ *   - a handle is not thread-safe; distinct handles are (one sketcher per host worker, like
+ *     "one sketch object per rayon task", utils.rs:454).
+ *   - register layout == what `S::save` serialises (utils.rs:400-433): HMH u16[16384] (host
+ *     endianness, LE on every supported host), HLL/ULL u8[2^p].
+ */
+#ifndef LASH_GPU_H
+#define LASH_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LASH_GPU_ABI_VERSION 1
+
+/* algorithm ids (main.rs:210-246: "hmh" | "hll" | "ull") */
+#define LASH_ALGO_HMH 0
+#define LASH_ALGO_HLL 1
+#define LASH_ALGO_ULL 2
+/* ULL estimator (main.rs:144-149, utils.rs:214-218) */
+#define LASH_EST_FGRA 0
+#define LASH_EST_ML 1
+/* Mash distance model (main.rs:415-423): 0 binomial, 1 poisson */
+#define LASH_MODEL_BINOMIAL 0
+#define LASH_MODEL_POISSON 1
+
+/* error codes */
+#define LASH_OK 0
+#define LASH_E_INVALID -1     /* bad argument (k outside 1..32: utils.rs:500-502; p out of range; ...) */
+#define LASH_E_CUDA -2        /* CUDA runtime failure, message has the cudaError string */
+#define LASH_E_NOMEM -3       /* device or pinned-host allocation failed */
+#define LASH_E_STATE -4       /* call sequence error (e.g. fetch before sync) */
+/* lash_dist* warning (positive): some pair hit the HLL++ bias-table regime (estimate <= 5m outside
+ * linear counting).  Google's empirical bias tables are not reproducible offline; those cells are
+ * computed with union = NaN (=> s = max(NaN,0) = 0, distance 1) and counted here. */
+#define LASH_W_HLL_BIAS_REGIME 1
+
+typedef struct lash_ctx lash_ctx;
+typedef struct lash_sketcher lash_sketcher;
+
+const char* lash_gpu_last_error(void);
+int lash_gpu_abi_version(void);
+int lash_gpu_device_count(void);
+
+/* One context per GPU (one host process/thread per GPU is the intended deployment). */
+int lash_ctx_create(int device, lash_ctx** out);
+int lash_ctx_destroy(lash_ctx* ctx);
+int lash_ctx_device(const lash_ctx* ctx);
+
+/* Pinned host memory for the packer (so lash_sketch_push copies are truly asynchronous). */
+int lash_host_alloc(size_t bytes, void** out);
+int lash_host_free(void* p);
+
+/* register bytes of one sketch: HMH 32768, HLL/ULL 2^p */
+size_t lash_sketch_reg_bytes(int algo, int p);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sketching.  Replaces utils.rs:454-507 for a whole batch of files.
+ *
+ * Packed base format (what kmerutils `Sequence::new(&seq, 2)` holds, utils.rs:464): A=0 C=1 G=2 T=3,
+ * four bases per byte, FIRST base in the MOST significant two bits of the byte.  Only bases that
+ * survive filter_out_n (utils.rs:33-41: uppercase A/C/G/T) are packed; records shorter than k may be
+ * passed or dropped by the host (the kernel produces no k-mer for them, utils.rs:460-462).
+ *
+ * A push carries one contiguous buffer holding any number of *spans*.  A span is a run of records
+ * of ONE genome (input file), packed densely back to back (a record may start in the middle of a
+ * byte); each span starts at a 16-byte aligned offset of the buffer and the buffer must be readable
+ * up to a multiple of 16 bytes past the last span (lash_sketch_padded_bytes()).  k-mers never cross
+ * record boundaries (utils.rs:457-464).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lash_span {
+    uint64_t genome;     /* accumulator slot in [0, n_genomes) */
+    uint64_t byte_off;   /* offset of the span's first base in the push buffer, multiple of 16 */
+    uint64_t n_bases;    /* bases in the span (all records together) */
+    uint64_t rec_first;  /* index of the span's first entry in rec_start[] (ignored when n_rec <= 1) */
+    uint32_t n_rec;      /* records in the span; 0 or 1: the whole span is one record */
+    uint32_t reserved;
+} lash_span;
+
+/* bytes a span of n_bases occupies in a push buffer, including alignment padding */
+uint64_t lash_sketch_padded_bytes(uint64_t n_bases);
+
+/* algo: LASH_ALGO_*; p: precision for HLL (4..18) / ULL (3..26), ignored for HMH (fixed 14);
+ * k in [1,32]; seed: xxh3 seed (main.rs:88-94, default 42); n_genomes accumulators, zeroed. */
+int lash_sketch_open(lash_ctx* ctx, int algo, int p, int k, uint64_t seed, uint64_t n_genomes, lash_sketcher** out);
+
+/* Enqueue H2D copy + kernels for one buffer.  rec_start: for spans with n_rec > 1, the n_rec+1
+ * ascending base offsets (relative to the span's first base; first = 0, last = n_bases) stored at
+ * rec_start[rec_first .. rec_first+n_rec].  n_rec_entries = length of rec_start (may be 0 / NULL).
+ * Returns immediately when `packed` is pinned; *ticket (optional) identifies the push. */
+int lash_sketch_push(lash_sketcher* s, const uint8_t* packed, uint64_t n_bytes, const lash_span* spans,
+                     uint32_t n_spans, const uint64_t* rec_start, uint64_t n_rec_entries, uint64_t* ticket);
+/* Same, but `packed` already lives in device memory of the context's GPU (no copy). */
+int lash_sketch_push_dev(lash_sketcher* s, const void* packed_dev, uint64_t n_bytes, const lash_span* spans,
+                         uint32_t n_spans, const uint64_t* rec_start, uint64_t n_rec_entries, uint64_t* ticket);
+/* Block until the H2D copy of push `ticket` has completed (its host buffer may be reused). */
+int lash_sketch_wait_copied(lash_sketcher* s, uint64_t ticket);
+/* Block until every enqueued push has been folded into the accumulators. */
+int lash_sketch_sync(lash_sketcher* s);
+/* Copy registers of genomes [first, first+n) to host: n * lash_sketch_reg_bytes bytes. Implies sync. */
+int lash_sketch_fetch(lash_sketcher* s, uint64_t first, uint64_t n, void* regs_out);
+/* Device pointer to the accumulator array [n_genomes][reg_bytes] (valid until close; after sync). */
+int lash_sketch_regs_dev(lash_sketcher* s, void** regs_dev);
+/* Zero all accumulators (reuse the sketcher for another batch). */
+int lash_sketch_reset(lash_sketcher* s);
+/* GPU time (ms, CUDA events on the sketcher's streams) spent in sketch kernels since open/reset,
+ * and kernel launches issued; for bench.py's roofline accounting. */
+int lash_sketch_stats(lash_sketcher* s, double* kernel_ms, uint64_t* launches);
+int lash_sketch_close(lash_sketcher* s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Distance.  Replaces the par_iter bodies of utils.rs:150-180 / 248-285 / 342-370 and
+ * compute_distance (main.rs:415-423): for every (reference i, query j) pair
+ *     union -> estimator -> s = max(0,(a+b-U)/U)   [HMH: similarity()]  -> frac = 2s/(1+s)
+ *     -> cast to T (f32 when fp32) -> model 1: min(1, -ln(frac)/k) | model 0: 1 - frac^(1/k)
+ * out[i * n_qry + j] (row-major, f64 or f32).  triangular != 0 (the reference's same_files rule,
+ * utils.rs:158-160,256-258,350-352, with idx = array position): requires the same set on both
+ * sides; only j <= i is computed and `out` is the PACKED lower triangle, row i at i*(i+1)/2.
+ * The name-equality => 0 rule (main.rs:452-453) stays with the host, which owns the names.
+ * estimator is used for ULL only.  Returns LASH_OK, an error, or LASH_W_HLL_BIAS_REGIME.
+ * ---------------------------------------------------------------------------------------------- */
+int lash_dist(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_regs,
+              uint64_t n_ref, const void* qry_regs, uint64_t n_qry, int triangular, void* out);
+
+/* Device-resident variant: register arrays and `out_dev` are device pointers on the context's GPU;
+ * work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = the context's stream) and
+ * NOT synchronised.  Computes reference rows [row_begin, row_end) only (output tiling across GPUs:
+ * each rank takes a row range); out_dev is indexed like `out` above (full-matrix indexing).
+ * card_ref_dev / card_qry_dev: per-sketch cardinalities from lash_cardinality_dev (ignored for HMH).
+ * flags_dev: optional uint32 counter incremented for each pair in the HLL bias regime. */
+int lash_dist_dev(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_dev,
+                  uint64_t n_ref, const void* qry_dev, uint64_t n_qry, const double* card_ref_dev,
+                  const double* card_qry_dev, int triangular, uint64_t row_begin, uint64_t row_end, void* out_dev,
+                  uint32_t* flags_dev, void* stream);
+
+/* Per-sketch cardinality (utils.rs:213-219 ULL, :314-316 HLL, hyperminhash cardinality()):
+ * card_dev[i] for n sketches in device memory; enqueued on `stream`, not synchronised. */
+int lash_cardinality_dev(lash_ctx* ctx, int algo, int p, int estimator, const void* regs_dev, uint64_t n,
+                         double* card_dev, void* stream);
+/* Host-buffer convenience: cardinalities of n sketches. */
+int lash_cardinality(lash_ctx* ctx, int algo, int p, int estimator, const void* regs, uint64_t n, double* card_out);
+
+/* Streaming all-vs-all for matrices larger than host memory (config "100k x 100k --dm"):
+ * computes row blocks of `rows_per_block` references, copies each to a pinned buffer and calls
+ * cb(user, row_begin, n_rows, block) from the calling thread while the next block computes.
+ * block is dense [n_rows][n_qry] (triangular: cells j > i are unspecified). */
+typedef int (*lash_dist_block_cb)(void* user, uint64_t row_begin, uint64_t n_rows, const void* block);
+int lash_dist_stream(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_regs,
+                     uint64_t n_ref, const void* qry_regs, uint64_t n_qry, int triangular, uint64_t rows_per_block,
+                     lash_dist_block_cb cb, void* user);
+
+/* Kernel time (ms) and launches of the last lash_dist / lash_dist_stream call on this ctx. */
+int lash_dist_stats(lash_ctx* ctx, double* kernel_ms, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LASH_GPU_H */

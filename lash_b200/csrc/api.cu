@@ -1,0 +1,690 @@
+// C ABI of the B200 lash hot paths (see include/lash_gpu.h for the contract and the reference
+// seams each entry point replaces).  Host-side orchestration only: staging, tile planning,
+// stream double-buffering, launches.  No CPU fallback anywhere: every entry point either runs the
+// CUDA kernels or returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lash_gpu.h"
+#include "kernels.h"
+
+using namespace lash;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) {                                                                          \
+            return fail(e__ == cudaErrorMemoryAllocation ? LASH_E_NOMEM : LASH_E_CUDA,                     \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                              \
+        }                                                                                                  \
+    } while (0)
+
+extern "C" const char* lash_gpu_last_error(void) { return g_err.c_str(); }
+extern "C" int lash_gpu_abi_version(void) { return LASH_GPU_ABI_VERSION; }
+extern "C" int lash_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+struct lash_ctx {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    double dist_ms = 0.0;
+    uint64_t dist_launches = 0;
+};
+
+extern "C" int lash_ctx_create(int device, lash_ctx** out) {
+    if (!out) return fail(LASH_E_INVALID, "lash_ctx_create: out is NULL");
+    int n = lash_gpu_device_count();
+    if (n <= 0) return fail(LASH_E_CUDA, "lash_ctx_create: no CUDA device visible (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(LASH_E_INVALID, "lash_ctx_create: device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(LASH_E_CUDA, std::string("lash_ctx_create: device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                     ", this build carries sm_100a code only");
+    lash_ctx* c = new (std::nothrow) lash_ctx();
+    if (!c) return fail(LASH_E_NOMEM, "lash_ctx_create: out of host memory");
+    c->device = device;
+    c->n_sm = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(ensure_tables());
+    *out = c;
+    return LASH_OK;
+}
+extern "C" int lash_ctx_destroy(lash_ctx* c) {
+    if (!c) return LASH_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return LASH_OK;
+}
+extern "C" int lash_ctx_device(const lash_ctx* c) { return c ? c->device : -1; }
+
+extern "C" int lash_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(LASH_E_INVALID, "lash_host_alloc: out is NULL");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return LASH_OK;
+}
+extern "C" int lash_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return LASH_OK;
+}
+
+static bool valid_algo_p(int algo, int p) {
+    if (algo == LASH_ALGO_HMH) return true;
+    if (algo == LASH_ALGO_HLL) return p >= 4 && p <= 18;   // streaming_algorithms threshold table range
+    if (algo == LASH_ALGO_ULL) return p >= 3 && p <= 26;   // ultraloglog::new range
+    return false;
+}
+extern "C" size_t lash_sketch_reg_bytes(int algo, int p) {
+    if (algo == LASH_ALGO_HMH) return 32768;
+    if (!valid_algo_p(algo, p)) return 0;
+    return (size_t)1 << p;
+}
+extern "C" uint64_t lash_sketch_padded_bytes(uint64_t n_bases) {
+    uint64_t b = (n_bases + 3) / 4;
+    return ((b + 15) / 16) * 16 + 16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// growable device / pinned buffers
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(n, (size_t)1 << 16);
+        want += want / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(n, (size_t)1 << 16);
+        want += want / 4;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// sketcher
+// ------------------------------------------------------------------------------------------------
+static constexpr int kSlots = 2;  // double-buffered staging: copy of push n+1 overlaps kernels of push n
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t copied = nullptr;   // H2D of packed + metadata done
+    cudaEvent_t k_start = nullptr, k_stop = nullptr;
+    bool timing_pending = false;
+    DevBuf packed, meta, mask;
+    PinBuf meta_host;
+    uint64_t ticket = 0;
+    bool used = false;
+};
+
+struct lash_sketcher {
+    lash_ctx* ctx = nullptr;
+    SketchParams sp;
+    uint64_t n_genomes = 0;
+    size_t reg_bytes = 0;
+    uint32_t* acc = nullptr;  // [n_genomes][cell_words]
+    Slot slot[kSlots];
+    uint64_t next_ticket = 1;
+    double kernel_ms = 0.0;
+    uint64_t launches = 0;
+    uint64_t min_chunk = 0;
+};
+
+static int harvest_timing(lash_sketcher* s, Slot& sl) {
+    if (sl.timing_pending) {
+        CU(cudaEventSynchronize(sl.k_stop));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, sl.k_start, sl.k_stop));
+        s->kernel_ms += ms;
+        sl.timing_pending = false;
+    }
+    return LASH_OK;
+}
+
+extern "C" int lash_sketch_open(lash_ctx* ctx, int algo, int p, int k, uint64_t seed, uint64_t n_genomes,
+                                lash_sketcher** out) {
+    if (!ctx || !out) return fail(LASH_E_INVALID, "lash_sketch_open: NULL argument");
+    if (k < 1 || k > 32) return fail(LASH_E_INVALID, "k-mer length must be 1-32");  // utils.rs:500-502
+    if (!valid_algo_p(algo, p)) return fail(LASH_E_INVALID, "lash_sketch_open: bad algorithm / precision");
+    if (n_genomes == 0 || n_genomes > 0xffffffffull) return fail(LASH_E_INVALID, "lash_sketch_open: n_genomes out of range");
+    CU(cudaSetDevice(ctx->device));
+    lash_sketcher* s = new (std::nothrow) lash_sketcher();
+    if (!s) return fail(LASH_E_NOMEM, "lash_sketch_open: out of host memory");
+    s->ctx = ctx;
+    s->n_genomes = n_genomes;
+    s->reg_bytes = lash_sketch_reg_bytes(algo, p);
+    s->sp.algo = algo;
+    s->sp.p = algo == LASH_ALGO_HMH ? 14 : p;
+    s->sp.k = k;
+    s->sp.hc = make_hash_consts(seed);
+    s->sp.cell_words = (uint32_t)std::max<size_t>(s->reg_bytes / 4, 1);
+    s->sp.global_acc = s->reg_bytes > kMaxSmemAccBytes;
+    // a CTA should see enough k-mers to warm its private accumulator (>= ~64 per cell)
+    s->min_chunk = std::max<uint64_t>((uint64_t)kStartsPerIter, 64ull * (s->reg_bytes / (algo == LASH_ALGO_HMH ? 2 : 1)));
+    size_t acc_bytes = std::max<size_t>(s->reg_bytes, 4) * n_genomes;
+    cudaError_t e = cudaMalloc((void**)&s->acc, acc_bytes);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(LASH_E_NOMEM, std::string("lash_sketch_open: accumulator allocation failed: ") + cudaGetErrorString(e));
+    }
+    CU(cudaMemsetAsync(s->acc, 0, acc_bytes, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < kSlots; ++i) {
+        CU(cudaStreamCreateWithFlags(&s->slot[i].stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->slot[i].copied, cudaEventDisableTiming));
+        CU(cudaEventCreate(&s->slot[i].k_start));
+        CU(cudaEventCreate(&s->slot[i].k_stop));
+    }
+    *out = s;
+    return LASH_OK;
+}
+
+static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device, uint64_t n_bytes, const lash_span* spans,
+                     uint32_t n_spans, const uint64_t* rec_start, uint64_t n_rec_entries, uint64_t* ticket_out) {
+    if (!s) return fail(LASH_E_INVALID, "lash_sketch_push: NULL sketcher");
+    if (n_spans && (!spans || !packed)) return fail(LASH_E_INVALID, "lash_sketch_push: NULL buffer");
+    CU(cudaSetDevice(s->ctx->device));
+    const int k = s->sp.k;
+
+    // ---- validate + plan tiles (host) --------------------------------------------------------
+    uint64_t total_starts = 0;
+    uint64_t mask_words = 0;
+    uint32_t n_multi = 0;
+    for (uint32_t i = 0; i < n_spans; ++i) {
+        const lash_span& sp = spans[i];
+        if (sp.genome >= s->n_genomes) return fail(LASH_E_INVALID, "lash_sketch_push: span.genome out of range");
+        if (sp.byte_off % 16) return fail(LASH_E_INVALID, "lash_sketch_push: span.byte_off must be a multiple of 16");
+        if (sp.byte_off + (sp.n_bases + 3) / 4 > n_bytes) return fail(LASH_E_INVALID, "lash_sketch_push: span exceeds buffer");
+        if (sp.n_rec > 1) {
+            if (!rec_start || sp.rec_first + sp.n_rec + 1 > n_rec_entries)
+                return fail(LASH_E_INVALID, "lash_sketch_push: rec_start table too short");
+            const uint64_t* rs = rec_start + sp.rec_first;
+            if (rs[0] != 0 || rs[sp.n_rec] != sp.n_bases)
+                return fail(LASH_E_INVALID, "lash_sketch_push: rec_start must run from 0 to n_bases");
+            for (uint32_t r = 0; r < sp.n_rec; ++r)
+                if (rs[r] > rs[r + 1]) return fail(LASH_E_INVALID, "lash_sketch_push: rec_start not ascending");
+            ++n_multi;
+            mask_words += ((sp.n_bases + 63) / 64) * 2 + 2;
+        }
+        if (sp.n_bases >= (uint64_t)k) total_starts += sp.n_bases - k + 1;
+    }
+    // chunk size: aim for ~8 CTAs per SM over the push, but keep chunks long enough to warm the
+    // private accumulator; always a multiple of the per-iteration CTA footprint.
+    const uint64_t target_tiles = (uint64_t)s->ctx->n_sm * 8;
+    uint64_t chunk = (total_starts + target_tiles - 1) / target_tiles;
+    chunk = std::max(chunk, s->min_chunk);
+    chunk = ((chunk + kStartsPerIter - 1) / kStartsPerIter) * kStartsPerIter;
+
+    std::vector<SketchTile> tiles;
+    std::vector<SpanRecs> mspans;
+    tiles.reserve(n_spans * 2);
+    mspans.reserve(n_multi);
+    uint64_t mask_off = 0;
+    for (uint32_t i = 0; i < n_spans; ++i) {
+        const lash_span& sp = spans[i];
+        uint64_t this_mask = ~0ull;
+        if (sp.n_rec > 1) {
+            SpanRecs sr;
+            sr.mask_word_off = mask_off;
+            sr.rec_first = sp.rec_first;
+            sr.n_rec = sp.n_rec;
+            sr.pad = 0;
+            mspans.push_back(sr);
+            this_mask = mask_off;
+            mask_off += ((sp.n_bases + 63) / 64) * 2 + 2;
+        }
+        if (sp.n_bases < (uint64_t)k) continue;  // utils.rs:460-462
+        const uint64_t starts = sp.n_bases - k + 1;
+        const uint64_t n_t = (starts + chunk - 1) / chunk;
+        // equalise the chunks of one span (multiples of the CTA iteration)
+        uint64_t per = (starts + n_t - 1) / n_t;
+        per = ((per + kStartsPerIter - 1) / kStartsPerIter) * kStartsPerIter;
+        for (uint64_t b = 0; b < starts; b += per) {
+            SketchTile t;
+            t.word_off = sp.byte_off / 4;
+            t.mask_word_off = this_mask;
+            t.begin = b;
+            t.end = std::min(starts, b + per);
+            t.genome = (uint32_t)sp.genome;
+            t.pad = 0;
+            tiles.push_back(t);
+        }
+    }
+    if (tiles.size() > 0x7fffffffull) return fail(LASH_E_INVALID, "lash_sketch_push: too many tiles in one push");
+
+    // ---- stage ---------------------------------------------------------------------------------
+    const uint64_t ticket = s->next_ticket++;
+    Slot& sl = s->slot[ticket % kSlots];
+    if (sl.used) {
+        // host-side reuse of this slot's pinned metadata and timing events
+        CU(cudaEventSynchronize(sl.copied));
+        int rc = harvest_timing(s, sl);
+        if (rc) return rc;
+    }
+    const size_t tiles_bytes = tiles.size() * sizeof(SketchTile);
+    const size_t mspans_bytes = mspans.size() * sizeof(SpanRecs);
+    const size_t recs_bytes = n_multi ? n_rec_entries * sizeof(uint64_t) : 0;
+    const size_t off_mspans = (tiles_bytes + 15) / 16 * 16;
+    const size_t off_recs = off_mspans + (mspans_bytes + 15) / 16 * 16;
+    const size_t meta_bytes = off_recs + recs_bytes;
+    if (meta_bytes) {
+        CU(sl.meta_host.reserve(meta_bytes));
+        CU(sl.meta.reserve(meta_bytes));
+        char* mh = (char*)sl.meta_host.p;
+        if (tiles_bytes) memcpy(mh, tiles.data(), tiles_bytes);
+        if (mspans_bytes) memcpy(mh + off_mspans, mspans.data(), mspans_bytes);
+        if (recs_bytes) memcpy(mh + off_recs, rec_start, recs_bytes);
+        CU(cudaMemcpyAsync(sl.meta.p, mh, meta_bytes, cudaMemcpyHostToDevice, sl.stream));
+    }
+    const uint32_t* packed_dev = nullptr;
+    if (packed_on_device) {
+        packed_dev = (const uint32_t*)packed;
+    } else if (n_bytes) {
+        CU(sl.packed.reserve(n_bytes + 64));
+        CU(cudaMemcpyAsync(sl.packed.p, packed, n_bytes, cudaMemcpyHostToDevice, sl.stream));
+        packed_dev = (const uint32_t*)sl.packed.p;
+    }
+    CU(cudaEventRecord(sl.copied, sl.stream));
+    uint32_t* mask_dev = nullptr;
+    if (n_multi) {
+        CU(sl.mask.reserve(mask_off * 4));
+        mask_dev = (uint32_t*)sl.mask.p;
+        CU(cudaMemsetAsync(mask_dev, 0, mask_off * 4, sl.stream));
+    }
+    CU(cudaEventRecord(sl.k_start, sl.stream));
+    if (n_multi) {
+        CU(launch_build_invalid_mask((const SpanRecs*)((char*)sl.meta.p + off_mspans), n_multi,
+                                     (const uint64_t*)((char*)sl.meta.p + off_recs), mask_dev, k, sl.stream));
+        s->launches += 1;
+    }
+    if (!tiles.empty()) {
+        CU(launch_sketch(s->sp, packed_dev, mask_dev, (const SketchTile*)sl.meta.p, (uint32_t)tiles.size(), s->acc, sl.stream));
+        s->launches += 1;
+    }
+    CU(cudaEventRecord(sl.k_stop, sl.stream));
+    sl.timing_pending = true;
+    sl.used = true;
+    sl.ticket = ticket;
+    if (ticket_out) *ticket_out = ticket;
+    return LASH_OK;
+}
+
+extern "C" int lash_sketch_push(lash_sketcher* s, const uint8_t* packed, uint64_t n_bytes, const lash_span* spans,
+                                uint32_t n_spans, const uint64_t* rec_start, uint64_t n_rec_entries, uint64_t* ticket) {
+    return push_impl(s, packed, false, n_bytes, spans, n_spans, rec_start, n_rec_entries, ticket);
+}
+extern "C" int lash_sketch_push_dev(lash_sketcher* s, const void* packed_dev, uint64_t n_bytes, const lash_span* spans,
+                                    uint32_t n_spans, const uint64_t* rec_start, uint64_t n_rec_entries, uint64_t* ticket) {
+    if (((uintptr_t)packed_dev) % 16) return fail(LASH_E_INVALID, "lash_sketch_push_dev: device buffer must be 16-byte aligned");
+    return push_impl(s, packed_dev, true, n_bytes, spans, n_spans, rec_start, n_rec_entries, ticket);
+}
+extern "C" int lash_sketch_wait_copied(lash_sketcher* s, uint64_t ticket) {
+    if (!s) return fail(LASH_E_INVALID, "lash_sketch_wait_copied: NULL sketcher");
+    if (ticket == 0 || ticket >= s->next_ticket) return fail(LASH_E_INVALID, "lash_sketch_wait_copied: unknown ticket");
+    Slot& sl = s->slot[ticket % kSlots];
+    // a newer push on the same slot implies the older copy completed (stream order)
+    if (sl.used && sl.ticket >= ticket) CU(cudaEventSynchronize(sl.copied));
+    return LASH_OK;
+}
+extern "C" int lash_sketch_sync(lash_sketcher* s) {
+    if (!s) return fail(LASH_E_INVALID, "lash_sketch_sync: NULL sketcher");
+    CU(cudaSetDevice(s->ctx->device));
+    for (int i = 0; i < kSlots; ++i) {
+        CU(cudaStreamSynchronize(s->slot[i].stream));
+        int rc = harvest_timing(s, s->slot[i]);
+        if (rc) return rc;
+    }
+    return LASH_OK;
+}
+extern "C" int lash_sketch_fetch(lash_sketcher* s, uint64_t first, uint64_t n, void* regs_out) {
+    if (!s || (!regs_out && n)) return fail(LASH_E_INVALID, "lash_sketch_fetch: NULL argument");
+    if (first + n > s->n_genomes) return fail(LASH_E_INVALID, "lash_sketch_fetch: genome range out of bounds");
+    int rc = lash_sketch_sync(s);
+    if (rc) return rc;
+    if (n) CU(cudaMemcpy(regs_out, (const char*)s->acc + first * s->reg_bytes, n * s->reg_bytes, cudaMemcpyDeviceToHost));
+    return LASH_OK;
+}
+extern "C" int lash_sketch_regs_dev(lash_sketcher* s, void** regs_dev) {
+    if (!s || !regs_dev) return fail(LASH_E_INVALID, "lash_sketch_regs_dev: NULL argument");
+    *regs_dev = s->acc;
+    return LASH_OK;
+}
+extern "C" int lash_sketch_reset(lash_sketcher* s) {
+    if (!s) return fail(LASH_E_INVALID, "lash_sketch_reset: NULL sketcher");
+    int rc = lash_sketch_sync(s);
+    if (rc) return rc;
+    CU(cudaMemset(s->acc, 0, std::max<size_t>(s->reg_bytes, 4) * s->n_genomes));
+    s->kernel_ms = 0.0;
+    s->launches = 0;
+    return LASH_OK;
+}
+extern "C" int lash_sketch_stats(lash_sketcher* s, double* kernel_ms, uint64_t* launches) {
+    if (!s) return fail(LASH_E_INVALID, "lash_sketch_stats: NULL sketcher");
+    int rc = lash_sketch_sync(s);
+    if (rc) return rc;
+    if (kernel_ms) *kernel_ms = s->kernel_ms;
+    if (launches) *launches = s->launches;
+    return LASH_OK;
+}
+extern "C" int lash_sketch_close(lash_sketcher* s) {
+    if (!s) return LASH_OK;
+    cudaSetDevice(s->ctx->device);
+    for (int i = 0; i < kSlots; ++i) {
+        Slot& sl = s->slot[i];
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        sl.packed.release();
+        sl.meta.release();
+        sl.mask.release();
+        sl.meta_host.release();
+        if (sl.copied) cudaEventDestroy(sl.copied);
+        if (sl.k_start) cudaEventDestroy(sl.k_start);
+        if (sl.k_stop) cudaEventDestroy(sl.k_stop);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+    if (s->acc) cudaFree(s->acc);
+    delete s;
+    return LASH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// distance
+// ------------------------------------------------------------------------------------------------
+static int check_dist_args(int algo, int p, int k, int estimator, int model, uint64_t n_ref, uint64_t n_qry, int triangular) {
+    if (!valid_algo_p(algo, p)) return fail(LASH_E_INVALID, "lash_dist: bad algorithm / precision");
+    if (k < 1 || k > 32) return fail(LASH_E_INVALID, "k-mer length must be 1-32");
+    if (model != 0 && model != 1) return fail(LASH_E_INVALID, "model needs to be 0 or 1");  // main.rs:421
+    if (algo == LASH_ALGO_ULL && estimator != 0 && estimator != 1)
+        return fail(LASH_E_INVALID, "estimator needs to be either fgra or ml");  // utils.rs:217
+    if (triangular && n_ref != n_qry) return fail(LASH_E_INVALID, "lash_dist: triangular needs the same set on both sides");
+    return LASH_OK;
+}
+
+extern "C" int lash_cardinality_dev(lash_ctx* ctx, int algo, int p, int estimator, const void* regs_dev, uint64_t n,
+                                    double* card_dev, void* stream) {
+    if (!ctx) return fail(LASH_E_INVALID, "lash_cardinality_dev: NULL ctx");
+    if (!valid_algo_p(algo, p)) return fail(LASH_E_INVALID, "lash_cardinality_dev: bad algorithm / precision");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    CU(launch_cardinality(algo, algo == LASH_ALGO_HMH ? 14 : p, estimator, regs_dev, n, card_dev, nullptr, st));
+    return LASH_OK;
+}
+
+extern "C" int lash_cardinality(lash_ctx* ctx, int algo, int p, int estimator, const void* regs, uint64_t n, double* card_out) {
+    if (!ctx || (n && (!regs || !card_out))) return fail(LASH_E_INVALID, "lash_cardinality: NULL argument");
+    if (!valid_algo_p(algo, p)) return fail(LASH_E_INVALID, "lash_cardinality: bad algorithm / precision");
+    if (n == 0) return LASH_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t rb = lash_sketch_reg_bytes(algo, p);
+    DevBuf d, c;
+    CU(d.reserve(rb * n));
+    CU(c.reserve(8 * n));
+    CU(cudaMemcpyAsync(d.p, regs, rb * n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = lash_cardinality_dev(ctx, algo, p, estimator, d.p, n, (double*)c.p, ctx->stream);
+    if (rc == LASH_OK) {
+        cudaError_t e = cudaMemcpyAsync(card_out, c.p, 8 * n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(LASH_E_CUDA, cudaGetErrorString(e));
+    }
+    d.release();
+    c.release();
+    return rc;
+}
+
+extern "C" int lash_dist_dev(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_dev,
+                             uint64_t n_ref, const void* qry_dev, uint64_t n_qry, const double* card_ref_dev,
+                             const double* card_qry_dev, int triangular, uint64_t row_begin, uint64_t row_end, void* out_dev,
+                             uint32_t* flags_dev, void* stream) {
+    if (!ctx) return fail(LASH_E_INVALID, "lash_dist_dev: NULL ctx");
+    int rc = check_dist_args(algo, p, k, estimator, model, n_ref, n_qry, triangular);
+    if (rc) return rc;
+    if (row_end > n_ref || row_begin > row_end) return fail(LASH_E_INVALID, "lash_dist_dev: bad row range");
+    if (row_begin == row_end || n_qry == 0) return LASH_OK;
+    if (!ref_dev || !qry_dev || !out_dev || !card_ref_dev || !card_qry_dev)
+        return fail(LASH_E_INVALID, "lash_dist_dev: NULL device pointer");
+    CU(cudaSetDevice(ctx->device));
+    DistParams dp;
+    dp.algo = algo;
+    dp.p = algo == LASH_ALGO_HMH ? 14 : p;
+    dp.k = k;
+    dp.estimator = estimator;
+    dp.model = model;
+    dp.fp32 = fp32 ? 1 : 0;
+    dp.triangular = triangular ? 1 : 0;
+    dp.ref = ref_dev;
+    dp.qry = qry_dev;
+    dp.n_ref = n_ref;
+    dp.n_qry = n_qry;
+    dp.card_ref = card_ref_dev;
+    dp.card_qry = card_qry_dev;
+    dp.row_begin = row_begin;
+    dp.row_end = row_end;
+    dp.out = out_dev;
+    dp.packed_tri = triangular ? 1 : 0;
+    dp.out_row0 = 0;
+    dp.flags = flags_dev;
+    uint32_t nl = 0;
+    CU(launch_dist(dp, stream ? (cudaStream_t)stream : ctx->stream, &nl));
+    ctx->dist_launches += nl;
+    return LASH_OK;
+}
+
+// shared body of lash_dist / lash_dist_stream: upload, cardinalities, row blocks
+static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_regs,
+                     uint64_t n_ref, const void* qry_regs, uint64_t n_qry, int triangular, void* out, uint64_t rows_per_block,
+                     lash_dist_block_cb cb, void* user) {
+    if (!ctx) return fail(LASH_E_INVALID, "lash_dist: NULL ctx");
+    int rc = check_dist_args(algo, p, k, estimator, model, n_ref, n_qry, triangular);
+    if (rc) return rc;
+    ctx->dist_ms = 0.0;
+    ctx->dist_launches = 0;
+    if (n_ref == 0 || n_qry == 0) return LASH_OK;
+    if (!ref_regs || !qry_regs) return fail(LASH_E_INVALID, "lash_dist: NULL register array");
+    if (!out && !cb) return fail(LASH_E_INVALID, "lash_dist: no output");
+    CU(cudaSetDevice(ctx->device));
+    const int pp = algo == LASH_ALGO_HMH ? 14 : p;
+    const size_t rb = lash_sketch_reg_bytes(algo, p);
+    const size_t esz = fp32 ? 4 : 8;
+    const bool same = (ref_regs == qry_regs && n_ref == n_qry);
+    cudaStream_t st = ctx->stream;
+    DevBuf d_ref, d_qry, d_card, d_out[2], d_flags;
+    PinBuf h_out[2];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+        d_ref.release(); d_qry.release(); d_card.release(); d_out[0].release(); d_out[1].release(); d_flags.release();
+        h_out[0].release(); h_out[1].release();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        for (int i = 0; i < 2; ++i) if (done[i]) cudaEventDestroy(done[i]);
+    };
+#define CUC(call)                                                                     \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            cleanup();                                                                \
+            return fail(e__ == cudaErrorMemoryAllocation ? LASH_E_NOMEM : LASH_E_CUDA, \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));         \
+        }                                                                             \
+    } while (0)
+    CUC(d_ref.reserve(rb * n_ref));
+    if (!same) CUC(d_qry.reserve(rb * n_qry));
+    CUC(d_card.reserve(8 * (n_ref + n_qry)));
+    CUC(d_flags.reserve(4));
+    CUC(cudaEventCreate(&ev0));
+    CUC(cudaEventCreate(&ev1));
+    CUC(cudaMemcpyAsync(d_ref.p, ref_regs, rb * n_ref, cudaMemcpyHostToDevice, st));
+    if (!same) CUC(cudaMemcpyAsync(d_qry.p, qry_regs, rb * n_qry, cudaMemcpyHostToDevice, st));
+    CUC(cudaMemsetAsync(d_flags.p, 0, 4, st));
+    const void* qdev = same ? d_ref.p : d_qry.p;
+    double* card_r = (double*)d_card.p;
+    double* card_q = same ? card_r : card_r + n_ref;
+    float ms_total = 0.f;
+    CUC(cudaEventRecord(ev0, st));
+    CUC(launch_cardinality(algo, pp, estimator, d_ref.p, n_ref, card_r, (uint32_t*)d_flags.p, st));
+    ctx->dist_launches += 1;
+    if (!same) {
+        CUC(launch_cardinality(algo, pp, estimator, d_qry.p, n_qry, card_q, (uint32_t*)d_flags.p, st));
+        ctx->dist_launches += 1;
+    }
+    CUC(cudaEventRecord(ev1, st));
+
+    DistParams dp;
+    dp.algo = algo; dp.p = pp; dp.k = k; dp.estimator = estimator; dp.model = model; dp.fp32 = fp32 ? 1 : 0;
+    dp.triangular = triangular ? 1 : 0;
+    dp.ref = d_ref.p; dp.qry = qdev; dp.n_ref = n_ref; dp.n_qry = n_qry;
+    dp.card_ref = card_r; dp.card_qry = card_q; dp.flags = (uint32_t*)d_flags.p;
+
+    if (!cb) {
+        // whole result on device, one D2H
+        const uint64_t cells = triangular ? n_ref * (n_ref + 1) / 2 : n_ref * n_qry;
+        CUC(d_out[0].reserve(cells * esz));
+        dp.row_begin = 0; dp.row_end = n_ref; dp.out = d_out[0].p; dp.packed_tri = triangular ? 1 : 0; dp.out_row0 = 0;
+        cudaEvent_t k0, k1;
+        CUC(cudaEventCreate(&k0));
+        done[0] = k0;
+        CUC(cudaEventCreate(&k1));
+        done[1] = k1;
+        CUC(cudaEventRecord(k0, st));
+        uint32_t nl = 0;
+        CUC(launch_dist(dp, st, &nl));
+        ctx->dist_launches += nl;
+        CUC(cudaEventRecord(k1, st));
+        CUC(cudaMemcpyAsync(out, d_out[0].p, cells * esz, cudaMemcpyDeviceToHost, st));
+        CUC(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CUC(cudaEventElapsedTime(&ms, k0, k1));
+        ms_total += ms;
+    } else {
+        if (rows_per_block == 0) rows_per_block = std::max<uint64_t>(1, ((uint64_t)256 << 20) / (n_qry * esz));
+        rows_per_block = std::min(rows_per_block, n_ref);
+        const size_t blk_bytes = rows_per_block * n_qry * esz;
+        cudaStream_t st2;
+        CUC(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+        cudaEvent_t kdone[2], copied[2];
+        for (int i = 0; i < 2; ++i) {
+            CUC(d_out[i].reserve(blk_bytes));
+            CUC(h_out[i].reserve(blk_bytes));
+            CUC(cudaEventCreate(&kdone[i]));
+            CUC(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        }
+        // kernels on st, copies on st2; callback for block b-1 runs on the host while block b computes
+        struct Pending { uint64_t row0, nrows; int buf; bool valid; } pend = {0, 0, 0, false};
+        cudaEvent_t kstart;
+        CUC(cudaEventCreate(&kstart));
+        int buf = 0;
+        int cb_rc = 0;
+        uint64_t nblocks = 0;
+        for (uint64_t r0 = 0; r0 < n_ref && cb_rc == 0; r0 += rows_per_block, buf ^= 1, ++nblocks) {
+            const uint64_t r1 = std::min(n_ref, r0 + rows_per_block);
+            if (nblocks >= 2) CUC(cudaEventSynchronize(copied[buf]));  // device buffer free again (its D2H finished)
+            dp.row_begin = r0; dp.row_end = r1; dp.out = d_out[buf].p; dp.packed_tri = 0; dp.out_row0 = r0;
+            CUC(cudaEventRecord(kstart, st));
+            uint32_t nl = 0;
+            CUC(launch_dist(dp, st, &nl));
+            ctx->dist_launches += nl;
+            CUC(cudaEventRecord(kdone[buf], st));
+            // deliver the previous block while this one computes
+            if (pend.valid) {
+                CUC(cudaEventSynchronize(copied[pend.buf]));
+                cb_rc = cb(user, pend.row0, pend.nrows, h_out[pend.buf].p);
+                pend.valid = false;
+            }
+            CUC(cudaStreamWaitEvent(st2, kdone[buf], 0));
+            CUC(cudaMemcpyAsync(h_out[buf].p, d_out[buf].p, (r1 - r0) * n_qry * esz, cudaMemcpyDeviceToHost, st2));
+            CUC(cudaEventRecord(copied[buf], st2));
+            CUC(cudaEventSynchronize(kdone[buf]));
+            float ms = 0.f;
+            CUC(cudaEventElapsedTime(&ms, kstart, kdone[buf]));
+            ms_total += ms;
+            pend = {r0, r1 - r0, buf, true};
+        }
+        if (pend.valid && cb_rc == 0) {
+            CUC(cudaEventSynchronize(copied[pend.buf]));
+            cb_rc = cb(user, pend.row0, pend.nrows, h_out[pend.buf].p);
+        }
+        cudaStreamSynchronize(st2);
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st2);
+        cudaEventDestroy(kstart);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(kdone[i]); cudaEventDestroy(copied[i]); }
+        if (cb_rc != 0) {
+            cleanup();
+            return fail(LASH_E_STATE, "lash_dist_stream: callback returned non-zero");
+        }
+    }
+    float ms_card = 0.f;
+    CUC(cudaEventElapsedTime(&ms_card, ev0, ev1));
+    ctx->dist_ms = ms_total + ms_card;
+    uint32_t flags = 0;
+    CUC(cudaMemcpy(&flags, d_flags.p, 4, cudaMemcpyDeviceToHost));
+    cleanup();
+#undef CUC
+    return flags ? LASH_W_HLL_BIAS_REGIME : LASH_OK;
+}
+
+extern "C" int lash_dist(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_regs,
+                         uint64_t n_ref, const void* qry_regs, uint64_t n_qry, int triangular, void* out) {
+    if (!out && n_ref && n_qry) return fail(LASH_E_INVALID, "lash_dist: out is NULL");
+    return dist_host(ctx, algo, p, k, estimator, model, fp32, ref_regs, n_ref, qry_regs, n_qry, triangular, out, 0, nullptr, nullptr);
+}
+extern "C" int lash_dist_stream(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_regs,
+                                uint64_t n_ref, const void* qry_regs, uint64_t n_qry, int triangular, uint64_t rows_per_block,
+                                lash_dist_block_cb cb, void* user) {
+    if (!cb) return fail(LASH_E_INVALID, "lash_dist_stream: callback is NULL");
+    return dist_host(ctx, algo, p, k, estimator, model, fp32, ref_regs, n_ref, qry_regs, n_qry, triangular, nullptr, rows_per_block, cb, user);
+}
+extern "C" int lash_dist_stats(lash_ctx* ctx, double* kernel_ms, uint64_t* launches) {
+    if (!ctx) return fail(LASH_E_INVALID, "lash_dist_stats: NULL ctx");
+    if (kernel_ms) *kernel_ms = ctx->dist_ms;
+    if (launches) *launches = ctx->dist_launches;
+    return LASH_OK;
+}

@@ -1,0 +1,87 @@
+// XXH3 short-input paths on the integer pipe (sm_100a).
+//
+// What the reference hashes (file:line under the reference tree):
+//   HLL/ULL  utils.rs:412,428  xxh3_64_with_seed(&masked.to_le_bytes(), seed)     -> 8-byte input
+//   HMH      utils.rs:397      add_bytes_with_seed(&(masked as u32).to_le_bytes()) -> 4-byte input,
+//                              128-bit XXH3 inside hyperminhash
+// Both are XXH3 "len 4..8" short paths with the default secret (XXH3 v0.8 spec); the seed-dependent
+// constants (bitflip words) are folded on the host once per sketcher (HashConsts).
+#pragma once
+#include <cstdint>
+
+namespace lash {
+
+struct HashConsts {
+    // 64-bit path: bitflip = (secret[8..16] ^ secret[16..24]) - seed'
+    uint32_t bf64_lo, bf64_hi;
+    // 128-bit path: bitflip = (secret[16..24] ^ secret[24..32]) + seed'
+    uint32_t bf128_lo, bf128_hi;
+};
+
+constexpr uint64_t kSecretX_8_16 = 0xc73ab174c5ecd5a2ULL;   // readLE64(kSecret+8) ^ readLE64(kSecret+16)
+constexpr uint64_t kSecretX_16_24 = 0xc4f023344dc994acULL;  // readLE64(kSecret+16) ^ readLE64(kSecret+24)
+constexpr uint64_t kPrimeMX1 = 0x165667919E3779F9ULL;
+constexpr uint64_t kPrimeMX2 = 0x9FB21C651E98DF25ULL;
+constexpr uint64_t kPrime64_1 = 0x9E3779B185EBCA87ULL;
+
+inline HashConsts make_hash_consts(uint64_t seed) {
+    uint32_t s32 = (uint32_t)seed;
+    uint32_t sw = (s32 >> 24) | ((s32 >> 8) & 0xff00u) | ((s32 << 8) & 0xff0000u) | (s32 << 24);
+    uint64_t sp = seed ^ ((uint64_t)sw << 32);
+    uint64_t b64 = kSecretX_8_16 - sp;
+    uint64_t b128 = kSecretX_16_24 + sp;
+    HashConsts c;
+    c.bf64_lo = (uint32_t)b64;
+    c.bf64_hi = (uint32_t)(b64 >> 32);
+    c.bf128_lo = (uint32_t)b128;
+    c.bf128_hi = (uint32_t)(b128 >> 32);
+    return c;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// XXH3_rrmxmx(h, len = 8)
+__device__ __forceinline__ uint64_t xxh3_rrmxmx8(uint64_t h) {
+    uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+    // rotl64(h,49) = rotr64(h,15); rotl64(h,24)
+    uint32_t r49_lo = __funnelshift_r(lo, hi, 15), r49_hi = __funnelshift_r(hi, lo, 15);
+    uint32_t r24_lo = __funnelshift_l(hi, lo, 24), r24_hi = __funnelshift_l(lo, hi, 24);
+    lo ^= r49_lo ^ r24_lo;
+    hi ^= r49_hi ^ r24_hi;
+    h = mk64(lo, hi) * kPrimeMX2;
+    h ^= (h >> 35) + 8;
+    h *= kPrimeMX2;
+    return h ^ (h >> 28);
+}
+
+// xxh3_64_with_seed(le64(v), seed); v given as two 32-bit halves.
+// input64 = in2 + (in1 << 32) with in1 = low half, in2 = high half  => (lo,hi) swapped.
+__device__ __forceinline__ uint64_t xxh3_64_le64(uint32_t v_lo, uint32_t v_hi, const HashConsts& c) {
+    return xxh3_rrmxmx8(mk64(v_hi ^ c.bf64_lo, v_lo ^ c.bf64_hi));
+}
+
+// xxh3_128_with_seed(le32(w), seed) -> (lo64, hi64)
+__device__ __forceinline__ void xxh3_128_le32(uint32_t w, const HashConsts& c, uint64_t& out_lo, uint64_t& out_hi) {
+    uint64_t keyed = mk64(w ^ c.bf128_lo, w ^ c.bf128_hi);
+    constexpr uint64_t mult = kPrime64_1 + (4u << 2);
+    uint64_t lo = keyed * mult;
+    uint64_t hi = __umul64hi(keyed, mult);
+    hi += lo << 1;
+    lo ^= hi >> 3;
+    lo ^= lo >> 35;
+    lo *= kPrimeMX2;
+    lo ^= lo >> 28;
+    hi ^= hi >> 37;
+    hi *= kPrimeMX1;
+    hi ^= hi >> 32;
+    out_lo = lo;
+    out_hi = hi;
+}
+
+__device__ __forceinline__ int clz64_parts(uint32_t lo, uint32_t hi) {
+    return hi ? __clz(hi) : 32 + __clz(lo);  // __clz(0) == 32
+}
+#endif
+
+}  // namespace lash

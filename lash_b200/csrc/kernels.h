@@ -1,0 +1,68 @@
+// Internal launcher interface between the C ABI (api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "hash.cuh"
+
+namespace lash {
+
+// One CTA's share of a span: k-mer start positions [begin, end) of the span whose first base sits
+// at 32-bit word `word_off` of the staged buffer.  begin is a multiple of 64.
+struct SketchTile {
+    uint64_t word_off;      // span start, in 32-bit words (multiple of 4)
+    uint64_t mask_word_off; // offset (32-bit words) of the span's invalid-start bitmask, or ~0ull
+    uint64_t begin, end;    // k-mer start range inside the span
+    uint32_t genome;
+    uint32_t pad;
+};
+
+// A multi-record span, for the boundary-mask builder.
+struct SpanRecs {
+    uint64_t mask_word_off;  // into the mask buffer
+    uint64_t rec_first;      // into rec_start[]
+    uint32_t n_rec;
+    uint32_t pad;
+};
+
+constexpr int kSketchThreads = 256;
+constexpr int kStartsPerThread = 64;
+constexpr int kStartsPerIter = kSketchThreads * kStartsPerThread;  // 16384 k-mer starts per CTA iteration
+
+struct SketchParams {
+    int algo, p, k;
+    HashConsts hc;
+    uint32_t cell_words;  // 32-bit words per sketch accumulator
+    bool global_acc;      // accumulator too large for shared memory: update global memory directly
+};
+
+// max dynamic shared memory we are willing to use for a private accumulator
+constexpr uint32_t kMaxSmemAccBytes = 160 * 1024;
+
+cudaError_t launch_build_invalid_mask(const SpanRecs* spans_dev, uint32_t n_spans, const uint64_t* rec_start_dev,
+                                      uint32_t* mask_dev, int k, cudaStream_t st);
+cudaError_t launch_sketch(const SketchParams& sp, const uint32_t* packed_dev, const uint32_t* mask_dev,
+                          const SketchTile* tiles_dev, uint32_t n_tiles, uint32_t* acc_dev, cudaStream_t st);
+
+struct DistParams {
+    int algo, p, k, estimator, model, fp32, triangular;
+    const void* ref;
+    const void* qry;
+    uint64_t n_ref, n_qry;
+    const double* card_ref;
+    const double* card_qry;
+    uint64_t row_begin, row_end;
+    void* out;
+    // output addressing: packed_tri ? out[i*(i+1)/2 + j] : out[(i - out_row0) * n_qry + j]
+    int packed_tri;
+    uint64_t out_row0;
+    uint32_t* flags;  // optional bias-regime counter
+};
+cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launches);
+cudaError_t launch_cardinality(int algo, int p, int estimator, const void* regs, uint64_t n, double* card,
+                               uint32_t* flags, cudaStream_t st);
+// host-side one-time upload of estimator tables into constant memory (idempotent, per device)
+cudaError_t ensure_tables();
+
+}  // namespace lash

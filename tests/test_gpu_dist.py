@@ -1,0 +1,227 @@
+"""GPU all-vs-all distance vs the CPU oracle, through the C ABI.
+
+Mirrors what a test of hmh_distance / ull_distance / hll_distance (src/utils.rs:84-373) +
+compute_distance (src/main.rs:415-423) would check.
+
+Tolerance (north_star: 1e-12 relative in f64, 1e-6 with --fp32), written out:
+  * per-sketch cardinalities: <= 8 ulp (only pow/log differ between CUDA and glibc; every sum runs
+    in register order on both sides and is bit-identical);
+  * distances: |d_gpu - d_cpu| <= 1e-12*|d_cpu| + C(s), where C(s) = 64*eps/(s*k) is the
+    first-order effect on d of a 4-ulp change of the union estimate U through
+    s = (a+b-U)/U  (d = -ln(2s/(1+s))/k  =>  |dd/dU * U| ~ 1/(s*k)): the Jaccard subtraction
+    cancels catastrophically for unrelated genomes, so a pure relative 1e-12 on d is not a
+    property of the formula itself (any two libm's differ there).  C(s) is < 1e-12 whenever
+    s > 1e-3/k; the test also asserts that almost all cells meet the plain 1e-12 bound.
+"""
+import numpy as np
+import pytest
+
+from lash_b200 import ALGO_HLL, ALGO_HMH, ALGO_ULL, EST_FGRA, EST_ML, MODEL_BINOMIAL, MODEL_POISSON, LashError
+from lash_b200 import ops
+from lash_b200.capi import W_HLL_BIAS_REGIME
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(np.float64).eps
+
+
+def _sketches(oracle, algo, p, k, n, length, seed=42):
+    """CPU-oracle sketches as inputs, so this file tests the dist path in isolation."""
+    return oracle.sketch_genomes(algo, p, k, seed, synth.genomes(n, length, seed=seed), threads=8)
+
+
+def _assert_close_f64(got, exp, frac, k, what):
+    assert got.shape == exp.shape
+    both_nan = np.isnan(got) & np.isnan(exp)
+    s = frac / (2.0 - frac)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cond = 64 * EPS / (np.maximum(s, 1e-300) * k)
+    tol = 1e-12 * np.abs(exp) + np.minimum(cond, 1.0)
+    err = np.abs(got - exp)
+    bad = ~((err <= tol) | both_nan)
+    assert not bad.any(), f"{what}: {bad.sum()} cells off, worst {np.nanmax(err[bad])} at {np.argwhere(bad)[0]}"
+    strict = (err <= 1e-12 * np.abs(exp)) | both_nan
+    assert strict.mean() > 0.98, f"{what}: only {strict.mean():.4f} of cells within plain 1e-12 relative"
+
+
+CASES = [
+    # algo, p, k, estimator, n, genome length
+    (ALGO_ULL, 10, 16, EST_FGRA, 40, 200_000),
+    (ALGO_ULL, 10, 16, EST_ML, 40, 200_000),
+    (ALGO_ULL, 14, 21, EST_FGRA, 12, 300_000),
+    (ALGO_ULL, 14, 21, EST_ML, 12, 300_000),
+    (ALGO_HLL, 14, 21, 0, 12, 2_000_000),
+    (ALGO_HLL, 10, 16, 0, 40, 200_000),
+    (ALGO_HMH, 14, 16, 0, 10, 1_500_000),
+]
+
+
+@pytest.mark.parametrize("algo,p,k,est,n,length", CASES)
+@pytest.mark.parametrize("model", [MODEL_POISSON, MODEL_BINOMIAL])
+def test_dist_matches_oracle_f64(oracle, gpu_ctx, algo, p, k, est, n, length, model):
+    regs = _sketches(oracle, algo, p, k, n, length)
+    ref, qry = regs[: n // 2 + 3], regs[n // 3:]
+    exp = oracle.dist(algo, p, k, est, model, False, ref, qry, threads=8)
+    frac = oracle.dist(algo, p, k, est, 2, False, ref, qry, threads=8)
+    got, w = ops.dist(gpu_ctx, algo, p, k, est, model, False, ref, qry)
+    assert w == 0
+    _assert_close_f64(got, exp, frac, k, f"algo={algo} p={p} est={est} model={model}")
+    assert np.isfinite(got).all() and (got >= 0).all() and (got <= 1).all()
+    assert (got < 0.5).any(), "related genomes should be close"
+
+
+@pytest.mark.parametrize("algo,p,k,est,n,length", CASES[:2] + CASES[4:5] + CASES[6:])
+def test_dist_fp32(oracle, gpu_ctx, algo, p, k, est, n, length):
+    """--fp32: frac is cast to f32 and ln/powf run in f32 (utils.rs:176,277,364; main.rs:415-423)."""
+    regs = _sketches(oracle, algo, p, k, n, length)
+    for model in (MODEL_POISSON, MODEL_BINOMIAL):
+        exp = oracle.dist(algo, p, k, est, model, True, regs, regs, threads=8)
+        got, _ = ops.dist(gpu_ctx, algo, p, k, est, model, True, regs, regs)
+        assert got.dtype == np.float32
+        np.testing.assert_allclose(got, exp, rtol=1e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize("algo,p,k,est", [(ALGO_ULL, 10, 16, EST_FGRA), (ALGO_ULL, 10, 16, EST_ML), (ALGO_HLL, 12, 21, 0),
+                                          (ALGO_HMH, 14, 16, 0)])
+def test_cardinalities(oracle, gpu_ctx, algo, p, k, est):
+    regs = _sketches(oracle, algo, p, k, 9, 700_000)
+    got = ops.cardinality(gpu_ctx, algo, p, est, regs)
+    exp = np.array([oracle.cardinality(algo, p, est, r) for r in regs])
+    assert np.all(np.abs(got - exp) <= 8 * EPS * np.abs(exp)), (got, exp)
+    if algo == ALGO_HLL:  # raw HLL estimate is +,*,/ only: bit-exact
+        assert np.array_equal(got, exp)
+
+
+def test_triangular_packed_equals_dense_lower(oracle, gpu_ctx):
+    """same_files rule (utils.rs:158-160,256-258,350-352): only j <= i, diagonal included."""
+    regs = _sketches(oracle, ALGO_ULL, 10, 16, 45, 100_000)
+    dense, _ = ops.dist(gpu_ctx, ALGO_ULL, 10, 16, EST_FGRA, MODEL_POISSON, False, regs, regs)
+    tri, _ = ops.dist(gpu_ctx, ALGO_ULL, 10, 16, EST_FGRA, MODEL_POISSON, False, regs, regs, triangular=True)
+    n = len(regs)
+    assert tri.shape == (n * (n + 1) // 2,)
+    for i in range(n):
+        assert np.array_equal(tri[i * (i + 1) // 2: i * (i + 1) // 2 + i + 1], dense[i, : i + 1])
+    # symmetry of the union: d(i,j) == d(j,i) bit for bit for ULL/HLL (same merged registers, same order)
+    assert np.array_equal(dense, dense.T)
+    # a sketch against itself: union == itself, s = 1, frac = 1, d = 0 exactly (no name rule needed)
+    assert np.all(np.diag(dense) == 0.0)
+
+
+def test_stream_blocks_equal_dense(oracle, gpu_ctx):
+    regs = _sketches(oracle, ALGO_HLL, 10, 21, 70, 60_000)
+    dense, _ = ops.dist(gpu_ctx, ALGO_HLL, 10, 21, 0, MODEL_POISSON, False, regs[:50], regs)
+    got = np.full_like(dense, np.nan)
+    seen = []
+
+    def on_block(row0, block):
+        got[row0: row0 + block.shape[0]] = block
+        seen.append((row0, block.shape[0]))
+
+    ops.dist_stream(gpu_ctx, ALGO_HLL, 10, 21, 0, MODEL_POISSON, False, regs[:50], regs, False, 16, on_block)
+    assert seen == [(0, 16), (16, 16), (32, 16), (48, 2)]
+    assert np.array_equal(got, dense)
+
+
+def test_small_sketches_hit_small_range_paths(oracle, gpu_ctx):
+    """Tiny inputs: most registers empty -> ULL FGRA small-range correction (c0..c10, sigma),
+    ULL ML with b[0], b[1] contributions, HLL linear counting, HMH with few collisions."""
+    rng = np.random.default_rng(1)
+    gs = [[synth.to_ascii(rng.integers(0, 4, size=int(n), dtype=np.uint8))] for n in (16, 40, 100, 300, 1000, 3000, 10_000)]
+    gs.append([b""])  # completely empty sketch
+    for algo, p, est in ((ALGO_ULL, 10, EST_FGRA), (ALGO_ULL, 10, EST_ML), (ALGO_ULL, 4, EST_FGRA), (ALGO_ULL, 4, EST_ML),
+                         (ALGO_HLL, 10, 0)):
+        regs = oracle.sketch_genomes(algo, p, 16, 42, gs)
+        exp, flags = oracle.dist(algo, p, 16, est, MODEL_POISSON, False, regs, regs, return_flags=True)
+        frac = oracle.dist(algo, p, 16, est, 2, False, regs, regs)
+        got, w = ops.dist(gpu_ctx, algo, p, 16, est, MODEL_POISSON, False, regs, regs)
+        assert (w == W_HLL_BIAS_REGIME) == bool(flags.any())
+        ok = flags == 0
+        both_nan = np.isnan(got) & np.isnan(exp)
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+        _assert_close_f64(np.where(both_nan, 0, got)[ok], np.where(both_nan, 0, exp)[ok], np.nan_to_num(frac)[ok], 16,
+                          f"small algo={algo} p={p} est={est}")
+        card_g = ops.cardinality(gpu_ctx, algo, p, est, regs)
+        card_c = np.array([oracle.cardinality(algo, p, est, r) for r in regs])
+        fin = np.isfinite(card_c)
+        assert np.array_equal(np.isfinite(card_g), fin)
+        assert np.all(np.abs(card_g[fin] - card_c[fin]) <= 8 * EPS * np.abs(card_c[fin]))
+
+
+def test_hll_bias_regime_is_flagged_not_silently_different(oracle, gpu_ctx):
+    """HLL++ estimates in (threshold, 5m] need Google's empirical bias tables (not reproducible
+    offline): both sides must flag those cells instead of inventing a number."""
+    regs = oracle.sketch_genomes(ALGO_HLL, 10, 16, 42, synth.genomes(3, 3000, seed=3))
+    exp, flags = oracle.dist(ALGO_HLL, 10, 16, 0, MODEL_POISSON, False, regs, regs, return_flags=True)
+    assert flags.any()
+    got, w = ops.dist(gpu_ctx, ALGO_HLL, 10, 16, 0, MODEL_POISSON, False, regs, regs)
+    assert w == W_HLL_BIAS_REGIME
+    np.testing.assert_array_equal(got, exp)
+
+
+def test_saturated_ull_registers_large_range_path(oracle, gpu_ctx):
+    """Registers >= 252 (unreachable for genomes, part of the estimator): FGRA large-range term."""
+    rng = np.random.default_rng(4)
+    regs = rng.integers(200, 256, size=(6, 256), dtype=np.uint8)
+    regs[0, :] = 255
+    for est in (EST_FGRA, EST_ML):
+        exp = oracle.dist(ALGO_ULL, 8, 16, est, MODEL_BINOMIAL, False, regs, regs)
+        got, _ = ops.dist(gpu_ctx, ALGO_ULL, 8, 16, est, MODEL_BINOMIAL, False, regs, regs)
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+        m = ~np.isnan(exp)
+        np.testing.assert_allclose(got[m], exp[m], rtol=1e-9, atol=1e-12)
+
+
+def test_ull_merge_in_packed_domain_is_exhaustively_correct(oracle, gpu_ctx):
+    """ULL union is pack(unpack(a)|unpack(b)), not max(a,b).  Every ordered pair of valid register
+    bytes for p=8 goes through the kernel's SIMD merge; the union's ML statistics are integers, so
+    the resulting estimates must match the oracle to the last few ulps on every row."""
+    p = 8
+    valid = np.array([0, 4 * p - 4, 4 * p, 4 * p + 2] + list(range(4 * p + 4, 256)), dtype=np.uint8)
+    nv = len(valid)
+    m = 1 << p
+    assert nv <= m
+    a = np.zeros((nv, m), dtype=np.uint8)
+    b = np.zeros((nv, m), dtype=np.uint8)
+    for i, v in enumerate(valid):
+        a[i, :nv] = v           # row i: constant register v ...
+        b[i, :nv] = np.roll(valid, i)  # ... against every valid value, rotated
+    for est in (EST_ML, EST_FGRA):
+        exp = oracle.dist(ALGO_ULL, p, 16, est, MODEL_BINOMIAL, False, a, b)
+        got, _ = ops.dist(gpu_ctx, ALGO_ULL, p, 16, est, MODEL_BINOMIAL, False, a, b)
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+        mm = ~np.isnan(exp)
+        np.testing.assert_allclose(got[mm], exp[mm], rtol=1e-9, atol=1e-12)
+
+
+def test_dist_error_behaviour(oracle, gpu_ctx):
+    regs = _sketches(oracle, ALGO_ULL, 10, 16, 4, 20_000)
+    with pytest.raises(LashError):   # main.rs:421 "model needs to be 0 or 1"
+        ops.dist(gpu_ctx, ALGO_ULL, 10, 16, EST_FGRA, 3, False, regs, regs)
+    with pytest.raises(LashError):   # utils.rs:217 "estimator needs to be either fgra or ml"
+        ops.dist(gpu_ctx, ALGO_ULL, 10, 16, 5, MODEL_POISSON, False, regs, regs)
+    with pytest.raises(LashError):
+        ops.dist(gpu_ctx, ALGO_ULL, 10, 16, EST_FGRA, MODEL_POISSON, False, regs, regs[:2], triangular=True)
+    with pytest.raises(ValueError):
+        ops.ull_distance(gpu_ctx, 10, 16, 1, False, ["a"], regs[:1], ["a"], regs[:1], "mle", False, True, lambda r: None)
+
+
+def test_reference_style_emit_interface(oracle, gpu_ctx):
+    """ull_distance(..., emit) as main.rs:557-566 drives it: rows per reference, lower triangle when
+    same_files, d = 0 whenever the two names are equal (main.rs:452-453), header row with --dm."""
+    names = [f"g{i}.fa" for i in range(6)]
+    regs = _sketches(oracle, ALGO_ULL, 10, 16, 6, 80_000)
+    rows = []
+    ops.ull_distance(gpu_ctx, 10, 16, MODEL_POISSON, False, names, regs, names, regs, "fgra", True, True, rows.append)
+    assert rows[0] == [("", q, 1.0) for q in names]
+    body = rows[1:]
+    assert [len(r) for r in body] == [1, 2, 3, 4, 5, 6]
+    exp = oracle.dist(ALGO_ULL, 10, 16, EST_FGRA, MODEL_POISSON, False, regs, regs)
+    for i, r in enumerate(body):
+        for j, (rn, qn, d) in enumerate(r):
+            assert (rn, qn) == (names[i], names[j])
+            assert d == (0.0 if i == j else pytest.approx(exp[i, j], rel=1e-9))
+    # different file sets, duplicate name across them -> forced zero
+    rows = []
+    ops.hll_distance(gpu_ctx, 10, 16, MODEL_POISSON, False, ["x", "y"], oracle.sketch_genomes(ALGO_HLL, 10, 16, 42, synth.genomes(2, 50_000)),
+                     ["y", "z"], oracle.sketch_genomes(ALGO_HLL, 10, 16, 42, synth.genomes(2, 50_000, seed=1)), False, False, rows.append)
+    assert len(rows) == 2 and rows[1][0][:2] == ("y", "y") and rows[1][0][2] == 0.0 and rows[0][0][2] > 0.0

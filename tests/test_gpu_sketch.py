@@ -1,0 +1,140 @@
+"""GPU sketch kernel vs the CPU oracle: registers must be BIT-EXACT (integer work).
+
+Mirrors what a test of the reference's sketch_files (src/utils.rs:439-510) would check: per-file
+registers for each algorithm / k dispatch branch (k<=14 Kmer32bit, 16 Kmer16b32bit, else
+Kmer64bit, utils.rs:466-502), the filter quirks (utils.rs:33-41) and the skip-short rule (:460).
+All calls go through the C ABI (lash_b200.ops -> liblash_gpu.so).
+"""
+import numpy as np
+import pytest
+
+from lash_b200 import ALGO_HLL, ALGO_HMH, ALGO_ULL, LashError
+from lash_b200.ops import Sketcher, sketch_genomes
+from lash_b200.pack import PackedBatch
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+SEED = 42
+
+
+def _check(oracle, gpu_ctx, algo, p, k, genomes, seed=SEED, **kw):
+    got = sketch_genomes(gpu_ctx, algo, p, k, seed, genomes, **kw)
+    exp = oracle.sketch_genomes(algo, p, k, seed, [list(g) for g in genomes], threads=4)
+    assert got.dtype == exp.dtype and got.shape == exp.shape
+    bad = np.argwhere(got != exp)
+    assert bad.size == 0, f"{len(bad)} register mismatches, first at {bad[0]}: gpu={got[tuple(bad[0])]} cpu={exp[tuple(bad[0])]}"
+    return got
+
+
+@pytest.mark.parametrize("algo,p,k", [
+    (ALGO_ULL, 10, 16),   # BASELINE config 2 / reference default k
+    (ALGO_HLL, 14, 21),   # config 3
+    (ALGO_HMH, 14, 16),   # config 1
+    (ALGO_ULL, 14, 31),   # config 4 precision, wide k
+    (ALGO_HLL, 10, 16),
+    (ALGO_HMH, 14, 21),   # HMH hashes only the low 32 bits of a 42-bit k-mer (utils.rs:397)
+])
+def test_registers_bit_exact_configs(oracle, gpu_ctx, algo, p, k):
+    genomes = synth.genomes(5, 300_000, seed=SEED)
+    regs = _check(oracle, gpu_ctx, algo, p, k, genomes)
+    assert (regs != 0).any()
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 7, 13, 14, 15, 16, 17, 20, 24, 31, 32])
+@pytest.mark.parametrize("algo,p", [(ALGO_ULL, 8), (ALGO_HLL, 8), (ALGO_HMH, 14)])
+def test_every_k_dispatch_branch(oracle, gpu_ctx, algo, p, k):
+    genomes = synth.genomes(2, 40_000, seed=k)
+    _check(oracle, gpu_ctx, algo, p, k, genomes)
+
+
+@pytest.mark.parametrize("algo,p", [(ALGO_ULL, 3), (ALGO_ULL, 5), (ALGO_ULL, 12), (ALGO_ULL, 17), (ALGO_HLL, 4),
+                                    (ALGO_HLL, 16), (ALGO_HLL, 17)])
+def test_precision_range_shared_memory_path(oracle, gpu_ctx, algo, p):
+    genomes = synth.genomes(2, 150_000, seed=p)
+    _check(oracle, gpu_ctx, algo, p, 16, genomes)
+
+
+@pytest.mark.parametrize("algo,p", [(ALGO_ULL, 18), (ALGO_ULL, 20), (ALGO_HLL, 18)])
+def test_precision_range_global_accumulator_path(oracle, gpu_ctx, algo, p):
+    """2^p bytes no longer fit a CTA's shared memory: the kernel updates HBM/L2 directly."""
+    genomes = synth.genomes(2, 200_000, seed=p)
+    _check(oracle, gpu_ctx, algo, p, 21, genomes)
+
+
+@pytest.mark.parametrize("algo,p,k", [(ALGO_ULL, 10, 16), (ALGO_HLL, 12, 21), (ALGO_HMH, 14, 16), (ALGO_ULL, 10, 5), (ALGO_ULL, 10, 32)])
+def test_dirty_multi_record_genomes(oracle, gpu_ctx, algo, p, k):
+    """lowercase / N / IUPAC deleted with flanks joined (utils.rs:36), k-mers never span records,
+    records shorter than k skipped (:460), empty records, all-filtered records."""
+    genomes = [synth.dirty_genome(60_000, k, seed=s) for s in range(4)]
+    genomes.append([b""])                # file with one empty record
+    genomes.append([])                   # file with no records at all
+    genomes.append([b"ACGT" * 3, b"NNNN", b"acgt"])
+    _check(oracle, gpu_ctx, algo, p, k, genomes)
+
+
+def test_short_reads_many_records(oracle, gpu_ctx):
+    """config 4 shape in miniature: 150 bp reads, every read its own record."""
+    rng = np.random.default_rng(3)
+    pool = synth.ancestor_codes(200_000, seed=9)
+    reads = []
+    for _ in range(4000):
+        s = int(rng.integers(0, len(pool) - 150))
+        reads.append(synth.to_ascii(pool[s:s + 150]))
+    _check(oracle, gpu_ctx, ALGO_ULL, 14, 21, [reads, reads[:1000]])
+
+
+def test_split_pushes_and_repeats_are_idempotent(oracle, gpu_ctx):
+    """Register updates are commutative, associative and idempotent: the same genome pushed as one
+    span, as many spans over several pushes, or twice, must give identical registers."""
+    g = synth.dirty_genome(120_000, 16, seed=11)
+    exp = oracle.sketch_genomes(ALGO_ULL, 12, 16, SEED, [g])
+    for per_push in (1, 3, 1000):
+        with Sketcher(gpu_ctx, ALGO_ULL, 12, 16, SEED, 1) as sk:
+            for i in range(0, len(g), per_push):
+                b = PackedBatch()
+                b.add_genome(0, g[i:i + per_push])
+                sk.push_batch(b)
+            for i in range(0, len(g), per_push):  # and once more
+                b = PackedBatch()
+                b.add_genome(0, g[i:i + per_push])
+                sk.push_batch(b)
+            got = sk.fetch()
+        assert np.array_equal(got, exp)
+
+
+def test_seed_changes_sketch_and_matches(oracle, gpu_ctx):
+    genomes = synth.genomes(1, 50_000, seed=5)
+    a = _check(oracle, gpu_ctx, ALGO_ULL, 10, 16, genomes, seed=42)
+    b = _check(oracle, gpu_ctx, ALGO_ULL, 10, 16, genomes, seed=(1 << 63) + 12345)
+    assert not np.array_equal(a, b)
+
+
+def test_many_small_genomes_one_push(oracle, gpu_ctx):
+    genomes = synth.genomes(300, 3_000, seed=8)
+    _check(oracle, gpu_ctx, ALGO_ULL, 10, 16, genomes, genomes_per_push=300)
+    _check(oracle, gpu_ctx, ALGO_HMH, 14, 16, genomes[:40], genomes_per_push=7)
+
+
+def test_large_genome_many_tiles(oracle, gpu_ctx):
+    genomes = synth.genomes(2, 6_000_000, seed=21)
+    _check(oracle, gpu_ctx, ALGO_ULL, 10, 16, genomes)
+    _check(oracle, gpu_ctx, ALGO_HLL, 14, 21, genomes)
+
+
+def test_error_behaviour(gpu_ctx):
+    """k outside 1..32 is a hard error in the reference (utils.rs:500-502 panics)."""
+    for k in (0, 33):
+        with pytest.raises(LashError):
+            Sketcher(gpu_ctx, ALGO_ULL, 10, k, SEED, 1)
+    with pytest.raises(LashError):
+        Sketcher(gpu_ctx, ALGO_ULL, 2, 16, SEED, 1)   # UltraLogLog::new rejects p < 3
+    with pytest.raises(LashError):
+        Sketcher(gpu_ctx, ALGO_ULL, 27, 16, SEED, 1)
+    with pytest.raises(LashError):
+        Sketcher(gpu_ctx, 7, 10, 16, SEED, 1)         # main.rs:245 "Algorithm must be either hmh, ull, or hll"
+    with Sketcher(gpu_ctx, ALGO_ULL, 10, 16, SEED, 2) as sk:
+        b = PackedBatch()
+        b.add_genome(5, [b"ACGT" * 10])               # genome slot out of range
+        with pytest.raises(LashError):
+            sk.push_batch(b)

@@ -1,0 +1,150 @@
+"""Host-side logic and the C-ABI surface, without a GPU (-m "not gpu")."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from lash_b200 import capi
+    L = capi.lib()
+    header = open(os.path.join(ROOT, "include", "lash_gpu.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(lash_[a-z0-9_]+)\s*\(", header))
+    declared -= {"lash_dist_block_cb"}
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/lash_gpu.h but not exported"
+    assert declared == set(capi.PROTOTYPES), declared ^ set(capi.PROTOTYPES)
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.lib_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (lash_[a-z0-9_]+)", out))
+    assert declared <= exported
+    assert L.lash_gpu_abi_version() == 1
+
+
+def test_library_carries_sm100a_code_only():
+    from lash_b200 import capi
+    out = subprocess.run(["cuobjdump", "-lelf", capi.lib_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a GPU the product must fail loudly, not compute on the CPU."""
+    from lash_b200 import LashError, capi
+    from lash_b200.ops import Context
+    if capi.lib().lash_gpu_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(LashError, match="no CUDA device"):
+        Context(0)
+
+
+def test_product_never_touches_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "lash_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in src.replace("the oracle's", "").replace("oracle/", "ORACLEDIR") or "import oracle" not in src
+                assert "import oracle" not in src and "liblash_oracle" not in src and "lo_" + "dist" not in src, f
+
+
+def test_static_size_helpers():
+    from lash_b200 import capi
+    from lash_b200.pack import padded_bytes
+    L = capi.lib()
+    assert L.lash_sketch_reg_bytes(capi.ALGO_HMH, 0) == 32768
+    assert L.lash_sketch_reg_bytes(capi.ALGO_ULL, 10) == 1024
+    assert L.lash_sketch_reg_bytes(capi.ALGO_HLL, 14) == 16384
+    assert L.lash_sketch_reg_bytes(capi.ALGO_ULL, 2) == 0 and L.lash_sketch_reg_bytes(capi.ALGO_HLL, 19) == 0
+    for n in (0, 1, 3, 4, 63, 64, 65, 1000, 12345):
+        assert L.lash_sketch_padded_bytes(n) == padded_bytes(n)
+        assert padded_bytes(n) % 16 == 0 and padded_bytes(n) >= (n + 3) // 4 + 8
+
+
+def test_packer_matches_reference_front_end(oracle):
+    from lash_b200.pack import PackedBatch, encode_record, pack_codes
+    seq = b"ACgtNNRYGT\nAC-*TTTGACCA"
+    codes = encode_record(seq)
+    assert bytes(b"ACGT"[c] for c in codes) == oracle.filter_out_n(seq)
+    packed = pack_codes(codes)
+    # first base in the two most significant bits of byte 0
+    assert packed[0] >> 6 == codes[0] and (packed[0] >> 4) & 3 == codes[1] and packed[0] & 3 == codes[3]
+    b = PackedBatch()
+    b.add_genome(0, [b"ACGTACGTAC", b"", b"nnnn", b"GGGTTTAAACCC"])
+    b.add_genome(1, [b"ACGT" * 100])
+    buf = b.buffer()
+    assert b.spans[0][1] == 0 and b.spans[1][1] % 16 == 0 and len(buf) == b.n_bytes
+    assert b.spans[0][2] == 22 and b.spans[0][4] == 4 and b.spans[1][4] == 1
+    assert b.rec_start == [0, 10, 10, 10, 22]
+    # unpack and compare with the concatenated filtered records
+    def unpack(buf, off, n):
+        by = buf[off: off + (n + 3) // 4]
+        c = np.stack([(by >> 6) & 3, (by >> 4) & 3, (by >> 2) & 3, by & 3], axis=1).reshape(-1)[:n]
+        return bytes(b"ACGT"[x] for x in c)
+    assert unpack(buf, 0, 22) == b"ACGTACGTACGGGTTTAAACCC"
+    assert unpack(buf, b.spans[1][1], 400) == b"ACGT" * 100
+
+
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lash_b200 import shard
+    import torch
+    sizes = [5_000_000 + 1000 * (i % 7) for i in range(37)]
+    mine = shard.genome_shard(sizes, rank, world)
+    rows = shard.row_shard(1001, rank, world, triangular=True)
+    t = torch.zeros(37 + 1001, dtype=torch.int64)
+    for g in mine:
+        t[g] += 1
+    t[37 + rows[0]: 37 + rows[1]] += 1
+    dist.all_reduce(t)
+    load = torch.tensor([float(sum(sizes[g] for g in mine)), float(shard.pair_count(rows, 1001, True))], dtype=torch.float64)
+    loads = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(loads, load)
+    # the "broadcast of the reference sketch set" step: rank 0's registers reach everyone
+    regs = torch.arange(64, dtype=torch.uint8) if rank == 0 else torch.zeros(64, dtype=torch.uint8)
+    dist.broadcast(regs, src=0)
+    if rank == 0:
+        q.put((t.tolist(), [l.tolist() for l in loads], regs.tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharding_covers_everything_once_world_size_2():
+    """N>1 host logic on CPU (gloo, world_size 2): genome shards and distance row ranges are a
+    partition, balanced, and the one collective (broadcast of the sketch set) delivers rank 0's data."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    cover, loads, regs = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert cover == [1] * (37 + 1001)
+    g0, g1 = loads[0][0], loads[1][0]
+    assert abs(g0 - g1) / max(g0, g1) < 0.06
+    p0, p1 = loads[0][1], loads[1][1]
+    assert p0 + p1 == 1001 * 1002 // 2 and abs(p0 - p1) / max(p0, p1) < 0.01
+    assert regs == list(range(64))
+
+
+def test_shard_functions_edge_cases():
+    from lash_b200 import shard
+    for world in (1, 2, 3, 4, 8):
+        for n in (0, 1, 5, 8, 1000):
+            got = sorted(g for r in range(world) for g in shard.genome_shard([10] * n, r, world))
+            assert got == list(range(n))
+            for tri in (False, True):
+                rows = [shard.row_shard(n, r, world, tri) for r in range(world)]
+                assert rows[0][0] == 0 and rows[-1][1] == n
+                assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+                assert sum(shard.pair_count(rw, n, tri) for rw in rows) == (n * (n + 1) // 2 if tri else n * n)
