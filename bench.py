@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- lash hot paths on B200: k-mer sketch Gbp/s + all-vs-all dist pairs/s.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on at N=1):
+    ULL p=10 k=16 seed=42 sketch of 1,000 synthetic 5 Mbp genomes + FGRA all-vs-all dist
+A "step" = one pass of the hot path over the batch: sketch every genome of this rank, then
+(N>1: all-gather the sketches over NCCL -- the path's one exchange step) compute this rank's row
+range of the lower-triangular all-vs-all distance matrix (poisson model, f64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU reference arm (oracle port)
+    torchrun ... bench.py --gpus N ...                             # N>1, one rank per GPU
+
+Prints ONE JSON line (rank 0).  value = whole-job Gbp/s with inputs resident in HBM; e2e = the same
+through the host-buffer C ABI (lash_sketch_push / lash_sketch_fetch / lash_dist) with H2D/D2H
+inside the timed region.  All compute goes through liblash_gpu.so; torch only provides device
+memory, the stream, events and torch.distributed.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO, P, K, SEED = "ull", 10, 16, 42
+N_GENOMES, GENOME_LEN = 1000, 5_000_000
+EST, MODEL = "fgra", 1
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        busy = [x for x in sm if x > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic genomes directly in HBM (torch is plumbing: RNG + byte packing, not the measured path)
+# --------------------------------------------------------------------------------------------------
+def make_packed_genomes(torch, device, n_genomes: int, length: int, seed: int, rank: int):
+    """Returns (uint8 device tensor holding all spans, span byte offsets, span stride)."""
+    from lash_b200.pack import padded_bytes
+    from tools import synth
+    stride = padded_bytes(length)
+    buf = torch.zeros(n_genomes * stride + 64, dtype=torch.uint8, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    anc = torch.randint(0, 4, (length,), dtype=torch.uint8, device=device, generator=g)   # shared ancestor
+    pad = (-length) % 4
+    for i in range(n_genomes):
+        gid = rank * n_genomes + i
+        mu = synth.mutation_rate(gid, seed)
+        g.manual_seed(seed * 7919 + gid + 1)
+        hit = torch.rand(length, device=device, generator=g) < mu
+        sub = torch.randint(1, 4, (length,), dtype=torch.uint8, device=device, generator=g)
+        codes = torch.where(hit, (anc + sub) & 3, anc)
+        if pad:
+            codes = torch.cat([codes, torch.zeros(pad, dtype=torch.uint8, device=device)])
+        q = codes.view(-1, 4)
+        packed = (q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]
+        buf[i * stride: i * stride + packed.numel()] = packed
+    return buf, stride
+
+
+def unpack_to_ascii(packed: np.ndarray, n_bases: int) -> bytes:
+    c = np.stack([(packed >> 6) & 3, (packed >> 4) & 3, (packed >> 2) & 3, packed & 3], axis=1).reshape(-1)[:n_bases]
+    return np.frombuffer(b"ACGT", dtype=np.uint8)[c].tobytes()
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of lash's rayon path, on all host cores, bounded sample
+# --------------------------------------------------------------------------------------------------
+def cpu_sample(n_sample: int, threads: int, repeats: int = 1):
+    """Sketch n_sample genomes of GENOME_LEN (one task per genome, like rayon's per-file par_iter,
+    utils.rs:450-452) and the n_sample x n_sample lower-triangular FGRA dist (one task per reference
+    row, utils.rs:248).  Returns (bases, pairs, sketch_s, dist_s)."""
+    import oracle as O
+    from tools import synth
+    gs = synth.genomes(n_sample, GENOME_LEN, seed=SEED)
+    best_s, best_d = 1e30, 1e30
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        regs = O.sketch_genomes(O.ULL, P, K, SEED, gs, threads=threads)
+        t1 = time.perf_counter()
+        O.dist(O.ULL, P, K, O.FGRA, O.POISSON, False, regs, regs, triangular=True, threads=threads)
+        t2 = time.perf_counter()
+        best_s, best_d = min(best_s, t1 - t0), min(best_d, t2 - t1)
+    return n_sample * GENOME_LEN, n_sample * (n_sample + 1) // 2, best_s, best_d
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    n_sample = max(8, 2 * cores)
+    times = []
+    for it in range(args.warmup + args.steps):
+        bases, pairs, ts, td = cpu_sample(n_sample, cores)
+        if it >= args.warmup:
+            times.append((ts, td))
+    step_s = float(np.mean([a + b for a, b in times]))
+    sk_s = float(np.mean([a for a, _ in times]))
+    d_s = float(np.mean([b for _, b in times]))
+    value = bases / step_s / 1e9
+    sample = f"{n_sample} genomes x {GENOME_LEN} bp sketched (one task per genome) + {n_sample}x{n_sample} triangular FGRA dist per step"
+    line = {
+        "impl": "reference", "metric": "kmer_sketch_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64/f64", "data": "synthetic",
+        "config": {"workload": f"ULL p={P} k={K} seed={SEED}: sketch + FGRA all-vs-all dist (poisson), CPU sample of configs[1]",
+                   "genome_len": GENOME_LEN, "sample_genomes": n_sample},
+        "cpu_baseline": {"value": value, "unit": "Gbp/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "CPU restatement of lash (oracle/lash_oracle.c); the Rust reference is not buildable offline",
+                         "sketch_gbp_per_s": bases / sk_s / 1e9, "dist_pairs_per_s": pairs / d_s},
+        "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_graft(args):
+    import torch
+    import torch.distributed as dist
+
+    from lash_b200 import ALGO_ULL, EST_FGRA, capi, ops, shard
+    from lash_b200.capi import Span, check, lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    hbm_peak, peak_src, sm_max = load_peaks()
+    L = lib()
+    ctx = ops.Context(local)
+    stream = torch.cuda.current_stream(device)
+    sptr = stream.cuda_stream
+
+    # ---- inputs, resident in HBM ---------------------------------------------------------------
+    n_g = args.genomes                   # per rank (weak scaling: per-GPU work fixed)
+    n_all = n_g * world
+    buf, stride = make_packed_genomes(torch, device, n_g, GENOME_LEN, SEED, rank)
+    spans = (Span * n_g)()
+    for i in range(n_g):
+        spans[i] = Span(i, i * stride, GENOME_LEN, 0, 1, 0)
+    n_bytes = n_g * stride
+    bases_rank = n_g * GENOME_LEN
+    rb = 1 << P
+    sk = ops.Sketcher(ctx, ALGO_ULL, P, K, SEED, n_g)
+    sk.set_stream(sptr)
+    regs_local = sk.regs_dev()
+    regs_all = torch.empty(n_all * rb, dtype=torch.uint8, device=device)
+    card = torch.empty(n_all, dtype=torch.float64, device=device)
+    rows = shard.row_shard(n_all, rank, world, triangular=True)
+    n_pairs_rank = shard.pair_count(rows, n_all, True)
+    out = torch.empty(n_all * (n_all + 1) // 2, dtype=torch.float64, device=device)  # packed lower triangle (full indexing)
+    flags = torch.zeros(1, dtype=torch.int32, device=device)
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    regs_view = _as_tensor(torch, regs_local, n_g * rb, device)   # the sketcher's accumulators, no copy
+
+    def step(timed_events=None):
+        if timed_events:
+            timed_events[0].record(stream)
+        sk.reset()                                                  # async clear on the stream
+        sk.push_raw(buf.data_ptr(), n_bytes, spans, n_g, None, 0, dev=True)
+        if timed_events:
+            timed_events[1].record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(regs_all, regs_view)        # the path's single exchange step (NCCL)
+            src = regs_all.data_ptr()
+        else:
+            src = regs_local
+        if timed_events:
+            timed_events[2].record(stream)
+        check(L.lash_cardinality_dev(ctx.handle, ALGO_ULL, P, EST_FGRA, C.c_void_p(src), n_all, C.c_void_p(card.data_ptr()),
+                                     C.c_void_p(sptr)))
+        check(L.lash_dist_dev(ctx.handle, ALGO_ULL, P, K, EST_FGRA, MODEL, 0, C.c_void_p(src), n_all, C.c_void_p(src), n_all,
+                              C.c_void_p(card.data_ptr()), C.c_void_p(card.data_ptr()), 1, rows[0], rows[1],
+                              C.c_void_p(out.data_ptr()), C.c_void_p(flags.data_ptr()), C.c_void_p(sptr)))
+        if timed_events:
+            timed_events[3].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_stop = torch.cuda.Event(enable_timing=True)
+    phase = np.zeros(3)
+    barrier()
+    t_start.record(stream)
+    for it in range(args.steps):
+        step(ev)
+        # phase events are read after the loop for the last step only (no sync inside the loop)
+    t_stop.record(stream)
+    barrier()
+    total_ms = t_start.elapsed_time(t_stop)
+    phase[0] = ev[0].elapsed_time(ev[1])   # sketch (last step)
+    phase[1] = ev[1].elapsed_time(ev[2])   # gather
+    phase[2] = ev[2].elapsed_time(ev[3])   # cardinality + dist
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms, _ = sk.stats()              # library-side CUDA events around the sketch kernel launches
+    t = torch.tensor([total_ms, phase[0], phase[1], phase[2]], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, sk_ms, ga_ms, di_ms = [float(x) for x in t.tolist()]
+    ms_per_step = total_ms / args.steps
+    value = (bases_rank * world) / (ms_per_step * 1e-3) / 1e9
+    n_pairs_all = n_all * (n_all + 1) // 2
+
+    # ---- roofline of the dominant kernel (sketch_kernel): algorithmic HBM bytes = 0.25 B/base ----
+    # measured live: the library brackets every sketch launch with CUDA events on the launching stream
+    n_sk_launch = args.steps + max(args.warmup, 3)
+    sk_kernel_ms = kernel_ms / n_sk_launch
+    algo_bytes = bases_rank * 0.25
+    achieved = algo_bytes / (sk_kernel_ms * 1e-3) / 1e9
+    kmers = n_g * (GENOME_LEN - K + 1)
+    sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
+    # ALU-pipe bound (the real limiter): 148 SMs x 64 INT lanes/clk
+    int_peak = 148 * 64 * sm_mhz * 1e6
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "lash::sketch_kernel<ULL,narrow,smem>",
+                "kernel_ms": sk_kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                "note": "0.25 B/base streamed once; the kernel is integer-pipe bound, not HBM bound (see int_pipe)",
+                "int_pipe": {"kmers_per_s": kmers / (sk_kernel_ms * 1e-3), "alu_lane_ops_peak_per_s": int_peak,
+                             "sm_mhz_used": sm_mhz,
+                             "alu_instr_per_kmer_at_peak": int_peak / (kmers / (sk_kernel_ms * 1e-3))}}
+
+    # ---- parity spot check against the oracle (checker only) -------------------------------------
+    parity = None
+    e2e = None
+    cpu_baseline = None
+    if rank == 0:
+        import oracle as O
+        host_regs = regs_view.view(n_g, rb)[:2].cpu().numpy()
+        gen = [[unpack_to_ascii(buf[i * stride: i * stride + (GENOME_LEN + 3) // 4].cpu().numpy(), GENOME_LEN)] for i in range(2)]
+        parity = bool(np.array_equal(O.sketch_genomes(O.ULL, P, K, SEED, gen, threads=2), host_regs))
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------------
+    e2e_ms = None
+    h2d = d2h = 0
+    if not args.no_e2e:
+        sk.set_stream(None)
+        pin = C.c_void_p()
+        check(L.lash_host_alloc(n_bytes + 64, C.byref(pin)))
+        host_in = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_uint8)), shape=(n_bytes + 64,))
+        host_in[:n_bytes] = buf[:n_bytes].cpu().numpy()
+        per_push = 50
+        host_regs_all = np.empty((n_g, rb), dtype=np.uint8)
+        tri_out = np.empty(n_g * (n_g + 1) // 2, dtype=np.float64)
+        pushes = []
+        for g0 in range(0, n_g, per_push):
+            g1 = min(n_g, g0 + per_push)
+            sp = (Span * (g1 - g0))()
+            for i in range(g0, g1):
+                sp[i - g0] = Span(i, (i - g0) * stride, GENOME_LEN, 0, 1, 0)
+            pushes.append((g0 * stride, (g1 - g0) * stride, sp, g1 - g0))
+
+        def e2e_step():
+            check(L.lash_sketch_reset(sk._h))
+            for off, nb, sp, ns in pushes:
+                check(L.lash_sketch_push(sk._h, C.c_void_p(pin.value + off), nb, sp, ns, None, 0, None))
+            check(L.lash_sketch_fetch(sk._h, 0, n_g, host_regs_all.ctypes.data_as(C.c_void_p)))
+            check(L.lash_dist(ctx.handle, ALGO_ULL, P, K, EST_FGRA, MODEL, 0, host_regs_all.ctypes.data_as(C.c_void_p), n_g,
+                              host_regs_all.ctypes.data_as(C.c_void_p), n_g, 1, tri_out.ctypes.data_as(C.c_void_p)))
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize(device)
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te.item()) * 1e3 / args.steps
+        h2d = n_bytes + n_g * rb
+        d2h = n_g * rb + tri_out.nbytes
+        if rank == 0:
+            e2e_parity = bool(np.array_equal(host_regs_all[:2], regs_view.view(n_g, rb)[:2].cpu().numpy()))
+            parity = parity and e2e_parity
+        check(L.lash_host_free(pin))
+        e2e = {"value": (bases_rank * world) / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
+               "note": "per rank: 1000 genomes pushed from pinned host memory in 50-genome slices (double-buffered H2D), registers "
+                       "fetched to host, lash_dist on host registers (per-rank 1000x1000 triangle), result copied back"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_sample = max(8, 2 * cores)
+        bases, pairs, ts, td = cpu_sample(n_sample, cores)
+        cpu_baseline = {"value": bases / (ts + td) / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "port",
+                        "sample": f"{n_sample} genomes x {GENOME_LEN} bp sketched (one task per genome) + {n_sample}x{n_sample} "
+                                  "triangular FGRA dist, oracle/lash_oracle.c on all host cores",
+                        "sketch_gbp_per_s": bases / ts / 1e9, "dist_pairs_per_s": pairs / td}
+
+    if rank == 0:
+        line = {
+            "metric": "kmer_sketch_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64/f64", "data": "synthetic",
+            "config": {"workload": f"configs[1]: ULL p={P} k={K} seed={SEED} sketch of {n_g} synthetic {GENOME_LEN} bp genomes per GPU + "
+                                   f"FGRA all-vs-all dist (poisson, f64, lower triangle) over all {n_all} sketches",
+                       "genomes_per_gpu": n_g, "genome_len": GENOME_LEN, "l2": "inputs (1.25 GB/GPU) larger than L2; no flush needed",
+                       "parallelism": f"genome shards x{world}; dist rows tiled x{world}; one NCCL all-gather of sketches" if world > 1 else "single GPU"},
+            "phases_ms_last_step": {"sketch": sk_ms, "gather": ga_ms, "cardinality+dist": di_ms},
+            "dist": {"metric": "all_vs_all_pairs_per_s", "value": n_pairs_all / (di_ms * 1e-3), "unit": "pairs/s", "pairs": n_pairs_all,
+                     "register_merges_per_s": n_pairs_all * rb / (di_ms * 1e-3)},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(args.steps * 3), "parity_spot_check": parity, "hll_bias_flags": int(flags.item()),
+        }
+        print(json.dumps(line), flush=True)
+    sk.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _as_tensor(torch, ptr: int, nbytes: int, device):
+    """Wrap a raw device pointer owned by liblash_gpu.so as a torch uint8 tensor (no copy)."""
+    class _Iface:
+        pass
+    o = _Iface()
+    o.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+    return torch.as_tensor(o, device=device)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--genomes", type=int, default=N_GENOMES, help="genomes per GPU (default = the BASELINE config; other values are for profiling)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_graft(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -122,8 +122,13 @@ int lash_sketch_sync(lash_sketcher* s);
 int lash_sketch_fetch(lash_sketcher* s, uint64_t first, uint64_t n, void* regs_out);
 /* Device pointer to the accumulator array [n_genomes][reg_bytes] (valid until close; after sync). */
 int lash_sketch_regs_dev(lash_sketcher* s, void** regs_dev);
-/* Zero all accumulators (reuse the sketcher for another batch). */
+/* Zero all accumulators (reuse the sketcher for another batch).  Synchronises first, unless a
+ * caller stream is set (lash_sketch_set_stream), in which case the clear is enqueued on it. */
 int lash_sketch_reset(lash_sketcher* s);
+/* Run all further pushes on the caller's stream (a cudaStream_t passed as void*; NULL restores the
+ * sketcher's own double-buffered streams).  Lets a host that already owns a stream (e.g. the one
+ * its NCCL collectives run on) order sketching against its other work and time it with its events. */
+int lash_sketch_set_stream(lash_sketcher* s, void* stream);
 /* GPU time (ms, CUDA events on the sketcher's streams) spent in sketch kernels since open/reset,
  * and kernel launches issued; for bench.py's roofline accounting. */
 int lash_sketch_stats(lash_sketcher* s, double* kernel_ms, uint64_t* launches);

@@ -48,6 +48,7 @@ PROTOTYPES = {
     "lash_sketch_fetch": (i32, [vp, u64, u64, vp]),
     "lash_sketch_regs_dev": (i32, [vp, C.POINTER(vp)]),
     "lash_sketch_reset": (i32, [vp]),
+    "lash_sketch_set_stream": (i32, [vp, vp]),
     "lash_sketch_stats": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
     "lash_sketch_close": (i32, [vp]),
     "lash_dist": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, u64, vp, u64, i32, vp]),

@@ -178,6 +178,7 @@ struct lash_sketcher {
     double kernel_ms = 0.0;
     uint64_t launches = 0;
     uint64_t min_chunk = 0;
+    cudaStream_t ext_stream = nullptr;  // caller-provided stream (lash_sketch_set_stream)
 };
 
 static int harvest_timing(lash_sketcher* s, Slot& sl) {
@@ -305,6 +306,7 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
     // ---- stage ---------------------------------------------------------------------------------
     const uint64_t ticket = s->next_ticket++;
     Slot& sl = s->slot[ticket % kSlots];
+    const cudaStream_t stream = s->ext_stream ? s->ext_stream : sl.stream;
     if (sl.used) {
         // host-side reuse of this slot's pinned metadata and timing events
         CU(cudaEventSynchronize(sl.copied));
@@ -324,34 +326,34 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
         if (tiles_bytes) memcpy(mh, tiles.data(), tiles_bytes);
         if (mspans_bytes) memcpy(mh + off_mspans, mspans.data(), mspans_bytes);
         if (recs_bytes) memcpy(mh + off_recs, rec_start, recs_bytes);
-        CU(cudaMemcpyAsync(sl.meta.p, mh, meta_bytes, cudaMemcpyHostToDevice, sl.stream));
+        CU(cudaMemcpyAsync(sl.meta.p, mh, meta_bytes, cudaMemcpyHostToDevice, stream));
     }
     const uint32_t* packed_dev = nullptr;
     if (packed_on_device) {
         packed_dev = (const uint32_t*)packed;
     } else if (n_bytes) {
         CU(sl.packed.reserve(n_bytes + 64));
-        CU(cudaMemcpyAsync(sl.packed.p, packed, n_bytes, cudaMemcpyHostToDevice, sl.stream));
+        CU(cudaMemcpyAsync(sl.packed.p, packed, n_bytes, cudaMemcpyHostToDevice, stream));
         packed_dev = (const uint32_t*)sl.packed.p;
     }
-    CU(cudaEventRecord(sl.copied, sl.stream));
+    CU(cudaEventRecord(sl.copied, stream));
     uint32_t* mask_dev = nullptr;
     if (n_multi) {
         CU(sl.mask.reserve(mask_off * 4));
         mask_dev = (uint32_t*)sl.mask.p;
-        CU(cudaMemsetAsync(mask_dev, 0, mask_off * 4, sl.stream));
+        CU(cudaMemsetAsync(mask_dev, 0, mask_off * 4, stream));
     }
-    CU(cudaEventRecord(sl.k_start, sl.stream));
+    CU(cudaEventRecord(sl.k_start, stream));
     if (n_multi) {
         CU(launch_build_invalid_mask((const SpanRecs*)((char*)sl.meta.p + off_mspans), n_multi,
-                                     (const uint64_t*)((char*)sl.meta.p + off_recs), mask_dev, k, sl.stream));
+                                     (const uint64_t*)((char*)sl.meta.p + off_recs), mask_dev, k, stream));
         s->launches += 1;
     }
     if (!tiles.empty()) {
-        CU(launch_sketch(s->sp, packed_dev, mask_dev, (const SketchTile*)sl.meta.p, (uint32_t)tiles.size(), s->acc, sl.stream));
+        CU(launch_sketch(s->sp, packed_dev, mask_dev, (const SketchTile*)sl.meta.p, (uint32_t)tiles.size(), s->acc, stream));
         s->launches += 1;
     }
-    CU(cudaEventRecord(sl.k_stop, sl.stream));
+    CU(cudaEventRecord(sl.k_stop, stream));
     sl.timing_pending = true;
     sl.used = true;
     sl.ticket = ticket;
@@ -379,6 +381,7 @@ extern "C" int lash_sketch_wait_copied(lash_sketcher* s, uint64_t ticket) {
 extern "C" int lash_sketch_sync(lash_sketcher* s) {
     if (!s) return fail(LASH_E_INVALID, "lash_sketch_sync: NULL sketcher");
     CU(cudaSetDevice(s->ctx->device));
+    if (s->ext_stream) CU(cudaStreamSynchronize(s->ext_stream));
     for (int i = 0; i < kSlots; ++i) {
         CU(cudaStreamSynchronize(s->slot[i].stream));
         int rc = harvest_timing(s, s->slot[i]);
@@ -399,8 +402,20 @@ extern "C" int lash_sketch_regs_dev(lash_sketcher* s, void** regs_dev) {
     *regs_dev = s->acc;
     return LASH_OK;
 }
+extern "C" int lash_sketch_set_stream(lash_sketcher* s, void* stream) {
+    if (!s) return fail(LASH_E_INVALID, "lash_sketch_set_stream: NULL sketcher");
+    int rc = lash_sketch_sync(s);
+    if (rc) return rc;
+    s->ext_stream = (cudaStream_t)stream;
+    return LASH_OK;
+}
 extern "C" int lash_sketch_reset(lash_sketcher* s) {
     if (!s) return fail(LASH_E_INVALID, "lash_sketch_reset: NULL sketcher");
+    if (s->ext_stream) {
+        CU(cudaSetDevice(s->ctx->device));
+        CU(cudaMemsetAsync(s->acc, 0, std::max<size_t>(s->reg_bytes, 4) * s->n_genomes, s->ext_stream));
+        return LASH_OK;
+    }
     int rc = lash_sketch_sync(s);
     if (rc) return rc;
     CU(cudaMemset(s->acc, 0, std::max<size_t>(s->reg_bytes, 4) * s->n_genomes));

@@ -108,6 +108,9 @@ class Sketcher:
     def reset(self):
         check(lib().lash_sketch_reset(self._h))
 
+    def set_stream(self, cuda_stream: int | None):
+        check(lib().lash_sketch_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
     def stats(self) -> tuple[float, int]:
         ms, n = C.c_double(), C.c_uint64()
         check(lib().lash_sketch_stats(self._h, C.byref(ms), C.byref(n)))

@@ -83,6 +83,8 @@ def lib() -> C.CDLL:
         L.lo_cardinality.argtypes = [i32, i32, i32, vp, C.POINTER(i32)]
         L.lo_dist.restype = i32
         L.lo_dist.argtypes = [i32, i32, i32, i32, i32, i32, vp, u64, vp, u64, i32, vp, vp, i32]
+        L.lo_selfcheck.restype = i32
+        assert L.lo_selfcheck() == 1, 'oracle secret constants corrupted'
         _lib = L
     return _lib
 

@@ -57,6 +57,9 @@ static const uint8_t kSecret32[32] = {
     0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
 };
 
+/* the two secret words the short paths need, folded (checked against kSecret32 in lo_selfcheck) */
+#define LO_SECRET_X_8_16 0xc73ab174c5ecd5a2ULL
+#define LO_SECRET_X_16_24 0xc4f023344dc994acULL
 static uint64_t rd64(const uint8_t* p) {
     uint64_t v = 0;
     for (int i = 7; i >= 0; --i) v = (v << 8) | p[i];
@@ -67,13 +70,18 @@ static uint32_t bswap32(uint32_t x) {
     return (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24);
 }
 
+int lo_selfcheck(void) {
+    return (rd64(kSecret32 + 8) ^ rd64(kSecret32 + 16)) == LO_SECRET_X_8_16 &&
+           (rd64(kSecret32 + 16) ^ rd64(kSecret32 + 24)) == LO_SECRET_X_16_24;
+}
+
 /* xxh3_64_with_seed(&v.to_le_bytes(), seed): the 4..8-byte short path, len = 8.
  * Call sites: utils.rs:412 (HLL), utils.rs:428 (ULL). */
-uint64_t lo_xxh3_64_le64(uint64_t v, uint64_t seed) {
+__attribute__((hot)) uint64_t lo_xxh3_64_le64(uint64_t v, uint64_t seed) {
     uint64_t s = seed ^ ((uint64_t)bswap32((uint32_t)seed) << 32);
     uint32_t in1 = (uint32_t)v;         /* bytes 0..3 */
     uint32_t in2 = (uint32_t)(v >> 32); /* bytes len-4..len-1 */
-    uint64_t bitflip = (rd64(kSecret32 + 8) ^ rd64(kSecret32 + 16)) - s;
+    uint64_t bitflip = LO_SECRET_X_8_16 - s; /* readLE64(kSecret+8) ^ readLE64(kSecret+16) */
     uint64_t in64 = (uint64_t)in2 + ((uint64_t)in1 << 32);
     uint64_t h = in64 ^ bitflip;
     /* XXH3_rrmxmx(h, len=8) */
@@ -90,7 +98,7 @@ void lo_xxh3_128_le32(uint32_t w, uint64_t seed, uint64_t* out_lo, uint64_t* out
     uint64_t s = seed ^ ((uint64_t)bswap32((uint32_t)seed) << 32);
     uint32_t in_lo = w, in_hi = w; /* len == 4: both reads cover the same 4 bytes */
     uint64_t in64 = (uint64_t)in_lo + ((uint64_t)in_hi << 32);
-    uint64_t bitflip = (rd64(kSecret32 + 16) ^ rd64(kSecret32 + 24)) + s;
+    uint64_t bitflip = LO_SECRET_X_16_24 + s; /* readLE64(kSecret+16) ^ readLE64(kSecret+24) */
     uint64_t keyed = in64 ^ bitflip;
     __uint128_t m = (__uint128_t)keyed * (XXH_PRIME64_1 + (4u << 2));
     uint64_t lo = (uint64_t)m, hi = (uint64_t)(m >> 64);
