@@ -178,6 +178,7 @@ struct lash_sketcher {
     double kernel_ms = 0.0;
     uint64_t launches = 0;
     uint64_t min_chunk = 0;
+    uint64_t per_iter = 0;  // k-mer starts one CTA iteration covers
     cudaStream_t ext_stream = nullptr;  // caller-provided stream (lash_sketch_set_stream)
 };
 
@@ -208,11 +209,11 @@ extern "C" int lash_sketch_open(lash_ctx* ctx, int algo, int p, int k, uint64_t 
     s->sp.p = algo == LASH_ALGO_HMH ? 14 : p;
     s->sp.k = k;
     s->sp.hc = make_hash_consts(seed);
-    s->sp.cell_words = (uint32_t)std::max<size_t>(s->reg_bytes / 4, 1);
-    s->sp.global_acc = s->reg_bytes > kMaxSmemAccBytes;
+    plan_sketch(s->sp);
+    s->per_iter = (uint64_t)s->sp.threads * kStartsPerThread;
     // a CTA should see enough k-mers to warm its private accumulator (>= ~64 per cell)
-    s->min_chunk = std::max<uint64_t>((uint64_t)kStartsPerIter, 64ull * (s->reg_bytes / (algo == LASH_ALGO_HMH ? 2 : 1)));
-    size_t acc_bytes = std::max<size_t>(s->reg_bytes, 4) * n_genomes;
+    s->min_chunk = std::max<uint64_t>(s->per_iter, 64ull * s->sp.n_cells);
+    size_t acc_bytes = (size_t)s->sp.cell_words * 4 * n_genomes;
     cudaError_t e = cudaMalloc((void**)&s->acc, acc_bytes);
     if (e != cudaSuccess) {
         delete s;
@@ -264,6 +265,7 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
     const uint64_t target_tiles = (uint64_t)s->ctx->n_sm * 8;
     uint64_t chunk = (total_starts + target_tiles - 1) / target_tiles;
     chunk = std::max(chunk, s->min_chunk);
+    const uint64_t kStartsPerIter = s->per_iter;
     chunk = ((chunk + kStartsPerIter - 1) / kStartsPerIter) * kStartsPerIter;
 
     std::vector<SketchTile> tiles;
@@ -413,14 +415,12 @@ extern "C" int lash_sketch_reset(lash_sketcher* s) {
     if (!s) return fail(LASH_E_INVALID, "lash_sketch_reset: NULL sketcher");
     if (s->ext_stream) {
         CU(cudaSetDevice(s->ctx->device));
-        CU(cudaMemsetAsync(s->acc, 0, std::max<size_t>(s->reg_bytes, 4) * s->n_genomes, s->ext_stream));
+        CU(cudaMemsetAsync(s->acc, 0, (size_t)s->sp.cell_words * 4 * s->n_genomes, s->ext_stream));
         return LASH_OK;
     }
     int rc = lash_sketch_sync(s);
     if (rc) return rc;
-    CU(cudaMemset(s->acc, 0, std::max<size_t>(s->reg_bytes, 4) * s->n_genomes));
-    s->kernel_ms = 0.0;
-    s->launches = 0;
+    CU(cudaMemset(s->acc, 0, (size_t)s->sp.cell_words * 4 * s->n_genomes));
     return LASH_OK;
 }
 extern "C" int lash_sketch_stats(lash_sketcher* s, double* kernel_ms, uint64_t* launches) {

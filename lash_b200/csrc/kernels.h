@@ -26,19 +26,22 @@ struct SpanRecs {
     uint32_t pad;
 };
 
-constexpr int kSketchThreads = 256;
-constexpr int kStartsPerThread = 64;
-constexpr int kStartsPerIter = kSketchThreads * kStartsPerThread;  // 16384 k-mer starts per CTA iteration
+constexpr int kStartsPerThread = 64;  // one 16-byte load of packed bases per thread per iteration
 
 struct SketchParams {
     int algo, p, k;
     HashConsts hc;
-    uint32_t cell_words;  // 32-bit words per sketch accumulator
+    uint32_t cell_words;  // 32-bit words per sketch in the register domain (global accumulator)
+    uint32_t n_cells;     // registers per sketch
+    uint32_t smem_bytes;  // private accumulator size (ULL 8 B, HLL/HMH 4 B per register)
+    uint32_t threads;     // CTA size: grows with smem_bytes so the SM keeps >= 32 warps resident
     bool global_acc;      // accumulator too large for shared memory: update global memory directly
 };
 
 // max dynamic shared memory we are willing to use for a private accumulator
-constexpr uint32_t kMaxSmemAccBytes = 160 * 1024;
+constexpr uint32_t kMaxSmemAccBytes = 128 * 1024;
+// fills n_cells / smem_bytes / threads / global_acc from algo and p
+void plan_sketch(SketchParams& sp);
 
 cudaError_t launch_build_invalid_mask(const SpanRecs* spans_dev, uint32_t n_spans, const uint64_t* rec_start_dev,
                                       uint32_t* mask_dev, int k, cudaStream_t st);

@@ -69,6 +69,11 @@ struct Cell<HLL> {
         uint32_t wl = __funnelshift_r(lo, hi, p), wh = hi >> p;
         val = (uint32_t)(clz64_parts(wl, wh) - p + 1);
     }
+    // shared-memory accumulator cells hold the same rho
+    __device__ static __forceinline__ void from_kmer_smem(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t& idx,
+                                                          uint32_t& val) {
+        from_kmer(klo, khi, hc, p, idx, val);
+    }
     __device__ static __forceinline__ uint32_t update(uint32_t r, uint32_t v) { return max(r, v); }
     __device__ static __forceinline__ uint32_t merge_word(uint32_t a, uint32_t b) { return __vmaxu4(a, b); }
 };
@@ -85,6 +90,15 @@ struct Cell<ULL> {
         // nlz = clz64(~(~h << p)) = clz64((h << p) | (2^p - 1))
         uint32_t yh = __funnelshift_l(lo, hi, p), yl = (lo << p) | ((1u << p) - 1u);
         val = (uint32_t)(clz64_parts(yl, yh) + p - 1);
+    }
+    // shared-memory accumulator cells are indexed by nlz itself (u = nlz + p - 1 is applied at flush)
+    __device__ static __forceinline__ void from_kmer_smem(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t& idx,
+                                                          uint32_t& nlz) {
+        uint64_t h = xxh3_64_le64(klo, khi, hc);
+        uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+        idx = hi >> (32 - p);
+        uint32_t yh = __funnelshift_l(lo, hi, p), yl = (lo << p) | ((1u << p) - 1u);
+        nlz = (uint32_t)clz64_parts(yl, yh);
     }
     __device__ static __forceinline__ uint32_t update(uint32_t r, uint32_t v) { return ull_update(r, v); }
     __device__ static __forceinline__ uint32_t merge_word(uint32_t a, uint32_t b) { return ull_merge4(a, b); }
@@ -107,6 +121,10 @@ struct Cell<HMH> {
         uint64_t t = (x << 14) | 0x3fffULL;
         uint32_t lz = (uint32_t)__clzll((long long)t) + 1u;
         val = (lz << 10) | ((uint32_t)y & 1023u);
+    }
+    __device__ static __forceinline__ void from_kmer_smem(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t& idx,
+                                                          uint32_t& val) {
+        from_kmer(klo, khi, hc, p, idx, val);
     }
     __device__ static __forceinline__ uint32_t update(uint32_t r, uint32_t v) { return max(r, v); }
     __device__ static __forceinline__ uint32_t merge_word(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }

@@ -4,15 +4,16 @@
 //   for each record: KmerSeqIterator -> min(kmer, reverse_complement) -> mask_bits -> add_kmer
 // Design (not a port of the serial iterator):
 //   * a CTA owns a chunk of ONE genome's k-mer start positions and a PRIVATE shared-memory
-//     accumulator in the final register domain (u8 / u16), so registers never round-trip HBM
-//     per k-mer; at the end the non-zero words are merged into the genome's global accumulator
-//     with word CAS (max for HLL/HMH, packed-domain OR-merge for ULL -- ULL is not a max sketch).
+//     accumulator, so registers never round-trip HBM per k-mer; at the end the cells are converted
+//     to the register domain (u8 / u16) and the non-zero words merged into the genome's global
+//     accumulator with word CAS (max for HLL/HMH, packed-domain OR-merge for ULL -- ULL is not a
+//     max sketch).
 //   * a thread owns 64 consecutive start positions = one coalesced 16-byte load (+8 bytes halo).
 //     k-mers are NOT rolled serially: forward words are funnel-shift windows of the big-endian
 //     base stream, reverse-complement words are funnel-shift windows of the per-word
 //     reverse-complemented stream (brev + pair swap + not), so all 64 hashes are independent (ILP).
-//   * register update = byte/halfword load + "would it change?" filter; the CAS loop runs only
-//     for the (rare, after warm-up) k-mers that actually raise a register.
+//   * register update = one shared-memory load as a "would it change?" filter + one native
+//     32-bit shared atomic (OR of a seen-value bit for ULL, max for HLL/HMH) only when it would.
 //   * record boundaries (k-mers never span records, utils.rs:457-464) come from an
 //     "invalid start" bitmask built on device from rec_start[] by build_invalid_mask().
 #include "kernels.h"
@@ -27,49 +28,109 @@ __device__ __forceinline__ uint32_t rc16(uint32_t f) {
     return ~y;
 }
 
-template <typename CellT, bool GLOBAL>
-__device__ __forceinline__ uint32_t load_cell(const uint32_t* acc, uint32_t idx) {
-    const CellT* a = reinterpret_cast<const CellT*>(acc);
-    if (GLOBAL) {
-        return (uint32_t)(*reinterpret_cast<const volatile CellT*>(a + idx));
-    } else {
-        return (uint32_t)a[idx];
-    }
+// ------------------------------------------------------------------------------------------------
+// Private (shared-memory) accumulators.  They are NOT kept in the byte/halfword register domain:
+// a sub-word read-modify-write needs a CAS loop, and a CAS loop inside the k-mer loop makes lanes
+// diverge for good.  Instead every cell is laid out so that ONE native 32-bit shared-memory atomic
+// (predicated on a plain-load filter) is the whole update:
+//   ULL  cell = 64-bit mask of seen update values u (two 32-bit words)  -> atomicOr;
+//        register = pack(mask) at flush time (exact: sequential add()s == pack(OR of 1<<u))
+//   HLL  cell = u32 rho                                                 -> atomicMax
+//   HMH  cell = u32 (lz<<10 | sig)                                      -> atomicMax
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+// predicated shared-memory reductions: one ATOMS, no branch, no divergence
+__device__ __forceinline__ void red_or_if_nonzero(uint32_t saddr, uint32_t bits) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q red.shared.or.b32 [%0], %1; }" ::"r"(saddr), "r"(bits) : "memory");
+}
+__device__ __forceinline__ void red_max_if_greater(uint32_t saddr, uint32_t cur, uint32_t v) {
+    asm volatile("{ .reg .pred q; setp.lt.u32 q, %1, %2; @q red.shared.max.u32 [%0], %2; }" ::"r"(saddr), "r"(cur), "r"(v) : "memory");
 }
 
-// CAS loop on the containing 32-bit word; only reached when the filter saw a change.
 template <int ALGO>
-__device__ __noinline__ void cell_cas(uint32_t* acc, uint32_t idx, uint32_t val) {
+struct SmemAcc;
+
+// ULL cell: bit j of the 64-bit mask <=> an update with nlz == j was seen (j in [0, 64-p]);
+// the unpacked hash prefix of the register is mask' = bitreverse-free: bit (nlz + p - 1), i.e.
+// prefix = sum over seen nlz of 1 << (nlz + p - 1)  ==  mask << (p - 1).
+template <>
+struct SmemAcc<ULL> {
+    static constexpr uint32_t kWordsPerCell = 2;
+    // val = nlz (see Cell<ULL>::from_kmer_nlz)
+    __device__ static __forceinline__ void update(uint32_t sbase, uint32_t idx, uint32_t nlz, uint32_t ok01) {
+        const uint32_t saddr = sbase + idx * 8u + ((nlz >> 5) << 2);
+        const uint32_t bit = ok01 << (nlz & 31u);
+        red_or_if_nonzero(saddr, ~lds_u32(saddr) & bit);
+    }
+    __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int p) {
+        const uint32_t lo = acc[2u * cell], hi = acc[2u * cell + 1u];
+        if ((lo | hi) == 0u) return 0u;
+        const uint64_t m = mk64(lo, hi) << (p - 1);                 // unpacked hash prefix
+        const uint32_t u = 63u - (uint32_t)__clzll((long long)m);  // u >= p-1 >= 2
+        return (u << 2) | ((uint32_t)(m >> (u - 2u)) & 3u);         // ultraloglog pack()
+    }
+};
+template <>
+struct SmemAcc<HLL> {
+    static constexpr uint32_t kWordsPerCell = 1;
+    __device__ static __forceinline__ void update(uint32_t sbase, uint32_t idx, uint32_t v, uint32_t ok01) {
+        const uint32_t saddr = sbase + idx * 4u;
+        red_max_if_greater(saddr, lds_u32(saddr), ok01 ? v : 0u);
+    }
+    __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int) { return acc[cell]; }
+};
+template <>
+struct SmemAcc<HMH> {
+    static constexpr uint32_t kWordsPerCell = 1;
+    __device__ static __forceinline__ void update(uint32_t sbase, uint32_t idx, uint32_t v, uint32_t ok01) {
+        const uint32_t saddr = sbase + idx * 4u;
+        red_max_if_greater(saddr, lds_u32(saddr), ok01 ? v : 0u);
+    }
+    __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int) { return acc[cell]; }
+};
+
+// Global-accumulator fallback (2^p too large for shared memory): byte / halfword cells of the
+// genome's accumulator in HBM/L2, volatile-load filter + CAS on the containing word.
+template <int ALGO>
+__device__ __forceinline__ void global_update(uint32_t* gacc, uint32_t idx, uint32_t val, bool valid) {
     using C = Cell<ALGO>;
+    if (!valid) return;
+    const uint32_t r = (uint32_t)(*reinterpret_cast<const volatile typename C::T*>(reinterpret_cast<typename C::T*>(gacc) + idx));
+    if (C::update(r, val) == r) return;
     constexpr uint32_t per = 4 / C::kBytes;
     constexpr uint32_t cmask = C::kBytes == 1 ? 0xffu : 0xffffu;
-    uint32_t* wp = acc + idx / per;
-    uint32_t sh = (idx % per) * (8 * C::kBytes);
+    uint32_t* wp = gacc + idx / per;
+    const uint32_t sh = (idx % per) * (8 * C::kBytes);
     uint32_t old = *reinterpret_cast<volatile uint32_t*>(wp);
     for (;;) {
-        uint32_t r = (old >> sh) & cmask;
-        uint32_t nw = C::update(r, val);
-        if (nw == r) break;
-        uint32_t assumed = old;
+        const uint32_t cur = (old >> sh) & cmask;
+        const uint32_t nw = C::update(cur, val);
+        if (nw == cur) break;
+        const uint32_t assumed = old;
         old = atomicCAS(wp, assumed, (assumed & ~(cmask << sh)) | (nw << sh));
         if (old == assumed) break;
     }
 }
 
 template <int ALGO, bool WIDE, bool GLOBAL>
-__global__ void __launch_bounds__(kSketchThreads)
+__global__ void __launch_bounds__(1024)
     sketch_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ inv_mask,
                   const SketchTile* __restrict__ tiles, uint32_t* __restrict__ acc_global, int p, int k, HashConsts hc,
-                  uint32_t cell_words) {
+                  uint32_t cell_words, uint32_t n_cells) {
     using C = Cell<ALGO>;
+    using A = SmemAcc<ALGO>;
     extern __shared__ uint32_t sacc[];
     const SketchTile t = tiles[blockIdx.x];
     uint32_t* gacc = acc_global + (size_t)t.genome * cell_words;
-    uint32_t* acc = GLOBAL ? gacc : sacc;
     if (!GLOBAL) {
-        for (uint32_t i = threadIdx.x; i < cell_words; i += kSketchThreads) sacc[i] = 0u;
+        for (uint32_t i = threadIdx.x; i < n_cells * A::kWordsPerCell; i += blockDim.x) sacc[i] = 0u;
         __syncthreads();
     }
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sacc);
     const uint32_t* base = packed + t.word_off;
     const uint32_t* mbase = (t.mask_word_off != ~0ull) ? inv_mask + t.mask_word_off : nullptr;
 
@@ -79,17 +140,25 @@ __global__ void __launch_bounds__(kSketchThreads)
     const uint32_t wide_shr = WIDE ? (uint32_t)(64 - 2 * k) : 0u;               // in [0,30]
     const uint32_t wide_mask_hi = (k >= 32) ? 0xffffffffu : ((1u << ((2 * k - 32) & 31)) - 1u);
 
-    for (uint64_t s0 = t.begin + (uint64_t)threadIdx.x * kStartsPerThread; s0 < t.end;
-         s0 += (uint64_t)kStartsPerIter) {
-        const uint32_t* wp = base + (s0 >> 4);
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(wp));
-        const uint2 h = __ldg(reinterpret_cast<const uint2*>(wp + 4));
-        // validity of the 64 starts of this thread
-        uint64_t remain = t.end - s0;
-        uint64_t valid = remain >= 64 ? ~0ull : ((1ull << remain) - 1ull);
-        if (mbase) {
-            const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mbase + (s0 >> 5)));
-            valid &= ~(((uint64_t)mv.y << 32) | mv.x);
+    // The trip count is uniform over the CTA (out-of-range threads carry valid == 0), so the warp can
+    // be re-converged explicitly at the end of every iteration.
+    const uint64_t per_iter = (uint64_t)blockDim.x * kStartsPerThread;
+    const uint32_t n_iter = (uint32_t)((t.end - t.begin + per_iter - 1) / per_iter);
+    for (uint32_t it = 0; it < n_iter; ++it) {
+        const uint64_t s0 = t.begin + (uint64_t)it * per_iter + (uint64_t)threadIdx.x * kStartsPerThread;
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        uint2 h = make_uint2(0u, 0u);
+        uint64_t valid = 0ull;
+        if (s0 < t.end) {
+            const uint32_t* wp = base + (s0 >> 4);
+            q = __ldg(reinterpret_cast<const uint4*>(wp));
+            h = __ldg(reinterpret_cast<const uint2*>(wp + 4));
+            const uint64_t remain = t.end - s0;
+            valid = remain >= 64 ? ~0ull : ((1ull << remain) - 1ull);
+            if (mbase) {
+                const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mbase + (s0 >> 5)));
+                valid &= ~(((uint64_t)mv.y << 32) | mv.x);
+            }
         }
         // big-endian base order inside each word: first base in the top bits
         uint32_t f0 = __byte_perm(q.x, 0, 0x0123), f1 = __byte_perm(q.y, 0, 0x0123);
@@ -99,51 +168,67 @@ __global__ void __launch_bounds__(kSketchThreads)
 #pragma unroll 1
         for (int w = 0; w < 4; ++w) {
             const uint32_t v16 = (uint32_t)(valid >> (16 * w)) & 0xffffu;
-            if (v16) {
-                const uint32_t A = f0, B = f1, Cw = f2;
-                const uint32_t Ar = rc16(A), Br = rc16(B), Cr = WIDE ? rc16(Cw) : 0u;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    uint32_t klo, khi;
-                    if (!WIDE) {
-                        uint32_t fw = __funnelshift_l(B, A, 2 * i) >> narrow_shr;
-                        uint32_t rc = __funnelshift_r(Ar, Br, 2 * i) & narrow_mask;
-                        klo = min(fw, rc);
-                        khi = 0u;
-                    } else {
-                        uint32_t fhi = __funnelshift_l(B, A, 2 * i), flo = __funnelshift_l(Cw, B, 2 * i);
-                        flo = __funnelshift_r(flo, fhi, wide_shr);
-                        fhi >>= wide_shr;
-                        uint32_t rlo = __funnelshift_r(Ar, Br, 2 * i);
-                        uint32_t rhi = __funnelshift_r(Br, Cr, 2 * i) & wide_mask_hi;
-                        uint64_t f64 = mk64(flo, fhi), r64 = mk64(rlo, rhi);
-                        uint64_t c64 = f64 < r64 ? f64 : r64;
-                        klo = (uint32_t)c64;
-                        khi = (uint32_t)(c64 >> 32);
-                    }
-                    uint32_t idx, val;
-                    C::from_kmer(klo, khi, hc, p, idx, val);
-                    if (v16 & (1u << i)) {
-                        uint32_t r = load_cell<typename C::T, GLOBAL>(acc, idx);
-                        if (C::update(r, val) != r) cell_cas<ALGO>(acc, idx, val);
-                    }
+            const uint32_t A0 = f0, B0 = f1, C0 = f2;
+            const uint32_t Ar = rc16(A0), Br = rc16(B0), Cr = WIDE ? rc16(C0) : 0u;
+            // one k-mer: window extraction -> canonical -> hash -> cell update
+            auto one = [&](const int sh /* 2*i */, const uint32_t ok01) {
+                uint32_t klo, khi;
+                if (!WIDE) {
+                    const uint32_t fw = __funnelshift_l(B0, A0, sh) >> narrow_shr;
+                    const uint32_t rc = __funnelshift_r(Ar, Br, sh) & narrow_mask;
+                    klo = min(fw, rc);
+                    khi = 0u;
+                } else {
+                    uint32_t fhi = __funnelshift_l(B0, A0, sh), flo = __funnelshift_l(C0, B0, sh);
+                    flo = __funnelshift_r(flo, fhi, wide_shr);
+                    fhi >>= wide_shr;
+                    const uint32_t rlo = __funnelshift_r(Ar, Br, sh);
+                    const uint32_t rhi = __funnelshift_r(Br, Cr, sh) & wide_mask_hi;
+                    const uint64_t f64 = mk64(flo, fhi), r64 = mk64(rlo, rhi);
+                    const uint64_t c64 = f64 < r64 ? f64 : r64;
+                    klo = (uint32_t)c64;
+                    khi = (uint32_t)(c64 >> 32);
                 }
+                uint32_t idx, val;
+                if (GLOBAL) {
+                    C::from_kmer(klo, khi, hc, p, idx, val);
+                    global_update<ALGO>(gacc, idx, val, ok01 != 0u);
+                } else {
+                    C::from_kmer_smem(klo, khi, hc, p, idx, val);
+                    A::update(sbase, idx, val, ok01);
+                }
+            };
+            if (v16 == 0xffffu) {  // every start valid (the common case): straight-line, no checks
+#pragma unroll
+                for (int i = 0; i < 16; ++i) one(2 * i, 1u);
+            } else if (v16 != 0u) {  // record boundary / tile tail inside this block: rolled, checked
+#pragma unroll 1
+                for (int i = 0; i < 16; ++i) one(2 * i, (v16 >> i) & 1u);
             }
             f0 = f1; f1 = f2; f2 = f3; f3 = f4; f4 = f5;
         }
+        __syncwarp();
     }
 
     if (!GLOBAL) {
+        // flush: cells -> register bytes/halfwords -> merge the non-zero words into the genome's
+        // global accumulator (max for HLL/HMH, packed-domain OR-merge for ULL)
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < cell_words; i += kSketchThreads) {
-            const uint32_t v = sacc[i];
+        constexpr uint32_t per = 4 / C::kBytes;
+        for (uint32_t i = threadIdx.x; i < cell_words; i += blockDim.x) {
+            uint32_t v = 0u;
+#pragma unroll
+            for (uint32_t j = 0; j < per; ++j) {
+                const uint32_t c = i * per + j;
+                if (c < n_cells) v |= A::to_reg(sacc, c, p) << (j * 8 * C::kBytes);
+            }
             if (v == 0u) continue;
             uint32_t* gp = gacc + i;
             uint32_t old = *reinterpret_cast<volatile uint32_t*>(gp);
             for (;;) {
-                uint32_t nw = C::merge_word(old, v);
+                const uint32_t nw = C::merge_word(old, v);
                 if (nw == old) break;
-                uint32_t assumed = old;
+                const uint32_t assumed = old;
                 old = atomicCAS(gp, assumed, nw);
                 if (old == assumed) break;
             }
@@ -173,6 +258,19 @@ __global__ void build_invalid_mask_kernel(const SpanRecs* __restrict__ spans, co
     }
 }
 
+void plan_sketch(SketchParams& sp) {
+    sp.n_cells = sp.algo == HMH ? 16384u : (1u << sp.p);
+    const uint32_t cell_bytes = sp.algo == HMH ? 2u : 1u;
+    sp.cell_words = (sp.n_cells * cell_bytes + 3u) / 4u;
+    const uint64_t smem = (uint64_t)sp.n_cells * (sp.algo == ULL ? 8u : 4u);
+    sp.global_acc = smem > kMaxSmemAccBytes;
+    sp.smem_bytes = sp.global_acc ? 0u : (uint32_t)smem;
+    // 227 KiB of shared memory per SM: keep at least 32 warps resident whatever the accumulator size
+    if (sp.smem_bytes <= 24u * 1024u) sp.threads = 256;       // >= 8 CTAs by smem, register-limited
+    else if (sp.smem_bytes <= 72u * 1024u) sp.threads = 512;  // 3 CTAs x 16 warps
+    else sp.threads = 1024;                                    // 1 CTA x 32 warps
+}
+
 cudaError_t launch_build_invalid_mask(const SpanRecs* spans_dev, uint32_t n_spans, const uint64_t* rec_start_dev,
                                       uint32_t* mask_dev, int k, cudaStream_t st) {
     if (n_spans == 0) return cudaSuccess;
@@ -184,12 +282,12 @@ template <int ALGO, bool WIDE, bool GLOBAL>
 static cudaError_t launch_one(const SketchParams& sp, const uint32_t* packed, const uint32_t* mask,
                               const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st) {
     auto kern = sketch_kernel<ALGO, WIDE, GLOBAL>;
-    size_t smem = GLOBAL ? 0 : (size_t)sp.cell_words * 4;
+    size_t smem = GLOBAL ? 0 : (size_t)sp.smem_bytes;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<n_tiles, kSketchThreads, smem, st>>>(packed, mask, tiles, acc, sp.p, sp.k, sp.hc, sp.cell_words);
+    kern<<<n_tiles, sp.threads, smem, st>>>(packed, mask, tiles, acc, sp.p, sp.k, sp.hc, sp.cell_words, sp.n_cells);
     return cudaGetLastError();
 }
 
