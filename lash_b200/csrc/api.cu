@@ -260,9 +260,9 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
         }
         if (sp.n_bases >= (uint64_t)k) total_starts += sp.n_bases - k + 1;
     }
-    // chunk size: aim for ~8 CTAs per SM over the push, but keep chunks long enough to warm the
-    // private accumulator; always a multiple of the per-iteration CTA footprint.
-    const uint64_t target_tiles = (uint64_t)s->ctx->n_sm * 8;
+    // chunk size: aim for >= ~16 waves of CTAs over the push (a short tail), but keep chunks long
+    // enough to warm the private accumulator; always a multiple of the per-iteration CTA footprint.
+    const uint64_t target_tiles = (uint64_t)s->ctx->n_sm * 8 * 16;
     uint64_t chunk = (total_starts + target_tiles - 1) / target_tiles;
     chunk = std::max(chunk, s->min_chunk);
     const uint64_t kStartsPerIter = s->per_iter;

@@ -50,8 +50,11 @@ __device__ __forceinline__ uint64_t xxh3_rrmxmx8(uint64_t h) {
     lo ^= r49_lo ^ r24_lo;
     hi ^= r49_hi ^ r24_hi;
     h = mk64(lo, hi) * kPrimeMX2;
-    h ^= (h >> 35) + 8;
-    h *= kPrimeMX2;
+    // h ^= (h >> 35) + len: (h >> 35) < 2^29, so the +8 cannot carry into the high word
+    lo = (uint32_t)h;
+    hi = (uint32_t)(h >> 32);
+    lo ^= (hi >> 3) + 8u;
+    h = mk64(lo, hi) * kPrimeMX2;
     return h ^ (h >> 28);
 }
 
@@ -79,6 +82,18 @@ __device__ __forceinline__ void xxh3_128_le32(uint32_t w, const HashConsts& c, u
     out_hi = hi;
 }
 
+// bfind.u32: bit position of the most significant 1, 0xffffffff for 0 (SASS FLO, XU pipe)
+__device__ __forceinline__ uint32_t bfind32(uint32_t x) {
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+// shl.b32 clamps: shift amounts >= 32 give 0 (C's << would be undefined)
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t n) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
 __device__ __forceinline__ int clz64_parts(uint32_t lo, uint32_t hi) {
     return hi ? __clz(hi) : 32 + __clz(lo);  // __clz(0) == 32
 }

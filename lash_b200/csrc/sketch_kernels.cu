@@ -32,63 +32,111 @@ __device__ __forceinline__ uint32_t rc16(uint32_t f) {
 // Private (shared-memory) accumulators.  They are NOT kept in the byte/halfword register domain:
 // a sub-word read-modify-write needs a CAS loop, and a CAS loop inside the k-mer loop makes lanes
 // diverge for good.  Instead every cell is laid out so that ONE native 32-bit shared-memory atomic
-// (predicated on a plain-load filter) is the whole update:
-//   ULL  cell = 64-bit mask of seen update values u (two 32-bit words)  -> atomicOr;
-//        register = pack(mask) at flush time (exact: sequential add()s == pack(OR of 1<<u))
-//   HLL  cell = u32 rho                                                 -> atomicMax
-//   HMH  cell = u32 (lz<<10 | sig)                                      -> atomicMax
+// is the whole update, and a plain shared load filters out the (vast majority of) k-mers that
+// would not change it:
+//   ULL  cell = two 32-bit words of "seen nlz" bits -> atomicOr.  Word 0 bit j <=> nlz = 31-j was
+//        seen, word 1 bit j <=> nlz = 63-j (the bit index is the raw FLO result, no subtraction).
+//        At flush: nlz-mask M = brev(w0) | brev(w1) << 32, unpacked hash prefix = M << (p-1),
+//        register = ultraloglog pack(prefix)  (exact: sequential add()s == pack(OR of 1 << u)).
+//   HLL  cell = u32 rho                -> atomicMax
+//   HMH  cell = u32 (lz << 10 | sig)   -> atomicMax
+// Each algorithm has a FAST preparation that is exact whenever the top 32 bits it looks at are
+// non-zero (all but ~2^-32 of the hashes) and otherwise requests nothing wrong (ULL: no bit;
+// HLL/HMH: a lower bound of the true value), plus an EXACT update used for those rare hashes, for
+// blocks with invalid starts, and for the global-memory fallback.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
-// predicated shared-memory reductions: one ATOMS, no branch, no divergence
-__device__ __forceinline__ void red_or_if_nonzero(uint32_t saddr, uint32_t bits) {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q red.shared.or.b32 [%0], %1; }" ::"r"(saddr), "r"(bits) : "memory");
+__device__ __forceinline__ void red_or(uint32_t saddr, uint32_t bits) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(saddr), "r"(bits) : "memory");
 }
-__device__ __forceinline__ void red_max_if_greater(uint32_t saddr, uint32_t cur, uint32_t v) {
-    asm volatile("{ .reg .pred q; setp.lt.u32 q, %1, %2; @q red.shared.max.u32 [%0], %2; }" ::"r"(saddr), "r"(cur), "r"(v) : "memory");
+__device__ __forceinline__ void red_max(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 
 template <int ALGO>
 struct SmemAcc;
 
-// ULL cell: bit j of the 64-bit mask <=> an update with nlz == j was seen (j in [0, 64-p]);
-// the unpacked hash prefix of the register is mask' = bitreverse-free: bit (nlz + p - 1), i.e.
-// prefix = sum over seen nlz of 1 << (nlz + p - 1)  ==  mask << (p - 1).
 template <>
 struct SmemAcc<ULL> {
     static constexpr uint32_t kWordsPerCell = 2;
-    // val = nlz (see Cell<ULL>::from_kmer_nlz)
-    __device__ static __forceinline__ void update(uint32_t sbase, uint32_t idx, uint32_t nlz, uint32_t ok01) {
-        const uint32_t saddr = sbase + idx * 8u + ((nlz >> 5) << 2);
-        const uint32_t bit = ok01 << (nlz & 31u);
-        red_or_if_nonzero(saddr, ~lds_u32(saddr) & bit);
+    // fast: (address of word 0, bit to set [0 if the hash is a rare one], rare indicator word)
+    __device__ static __forceinline__ void prep(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t sbase,
+                                                uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
+        const uint64_t h = xxh3_64_le64(klo, khi, hc);
+        const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+        const uint32_t yh = __funnelshift_l(lo, hi, p);  // top 32 bits of h << p
+        saddr = sbase + (hi >> (32 - p)) * 8u;
+        v = shl_clamp(1u, bfind32(yh));                  // yh == 0 -> bfind = 0xffffffff -> v = 0
+        rare_word = yh;
+    }
+    __device__ static __forceinline__ uint32_t need(uint32_t cur, uint32_t v) { return ~cur & v; }
+    __device__ static __forceinline__ void apply(uint32_t saddr, uint32_t needv) { red_or(saddr, needv); }
+    __device__ static __forceinline__ void exact(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t sbase) {
+        const uint64_t h = xxh3_64_le64(klo, khi, hc);
+        const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+        const uint32_t yh = __funnelshift_l(lo, hi, p), yl = (lo << p) | ((1u << p) - 1u);
+        const uint32_t saddr = sbase + (hi >> (32 - p)) * 8u + (yh ? 0u : 4u);
+        const uint32_t bit = 1u << bfind32(yh ? yh : yl);
+        if (~lds_u32(saddr) & bit) red_or(saddr, bit);
     }
     __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int p) {
-        const uint32_t lo = acc[2u * cell], hi = acc[2u * cell + 1u];
-        if ((lo | hi) == 0u) return 0u;
-        const uint64_t m = mk64(lo, hi) << (p - 1);                 // unpacked hash prefix
-        const uint32_t u = 63u - (uint32_t)__clzll((long long)m);  // u >= p-1 >= 2
-        return (u << 2) | ((uint32_t)(m >> (u - 2u)) & 3u);         // ultraloglog pack()
+        const uint32_t w0 = acc[2u * cell], w1 = acc[2u * cell + 1u];
+        if ((w0 | w1) == 0u) return 0u;
+        const uint64_t m = mk64(__brev(w0), __brev(w1)) << (p - 1);  // unpacked hash prefix
+        const uint32_t u = 63u - (uint32_t)__clzll((long long)m);   // u >= p-1 >= 2
+        return (u << 2) | ((uint32_t)(m >> (u - 2u)) & 3u);          // ultraloglog pack()
     }
 };
 template <>
 struct SmemAcc<HLL> {
     static constexpr uint32_t kWordsPerCell = 1;
-    __device__ static __forceinline__ void update(uint32_t sbase, uint32_t idx, uint32_t v, uint32_t ok01) {
+    __device__ static __forceinline__ void prep(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t sbase,
+                                                uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
+        const uint64_t h = xxh3_64_le64(klo, khi, hc);
+        const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+        saddr = sbase + (lo & ((1u << p) - 1u)) * 4u;
+        v = 32u - bfind32(hi);  // rho = clz(hi) + 1 when hi != 0; hi == 0 -> 33 <= true rho (p <= 18)
+        rare_word = hi;
+    }
+    __device__ static __forceinline__ uint32_t need(uint32_t cur, uint32_t v) { return cur < v ? v : 0u; }
+    __device__ static __forceinline__ void apply(uint32_t saddr, uint32_t needv) { red_max(saddr, needv); }
+    __device__ static __forceinline__ void exact(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t sbase) {
+        uint32_t idx, rho;
+        Cell<HLL>::from_kmer(klo, khi, hc, p, idx, rho);
         const uint32_t saddr = sbase + idx * 4u;
-        red_max_if_greater(saddr, lds_u32(saddr), ok01 ? v : 0u);
+        if (lds_u32(saddr) < rho) red_max(saddr, rho);
     }
     __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int) { return acc[cell]; }
 };
 template <>
 struct SmemAcc<HMH> {
     static constexpr uint32_t kWordsPerCell = 1;
-    __device__ static __forceinline__ void update(uint32_t sbase, uint32_t idx, uint32_t v, uint32_t ok01) {
+    __device__ static __forceinline__ void prep(uint32_t klo, uint32_t /*khi*/, const HashConsts& hc, int /*p*/, uint32_t sbase,
+                                                uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
+        uint64_t hlo, hhi;
+        xxh3_128_le32(klo, hc, hlo, hhi);
+#if LASH_HMH_X_IS_HIGH64
+        const uint64_t x = hhi, y = hlo;
+#else
+        const uint64_t x = hlo, y = hhi;
+#endif
+        const uint32_t xlo = (uint32_t)x, xhi = (uint32_t)(x >> 32);
+        saddr = sbase + (xhi >> 18) * 4u;                     // x >> 50
+        const uint32_t th = __funnelshift_l(xlo, xhi, 14);     // top 32 bits of (x << 14) | 0x3fff
+        v = ((32u - bfind32(th)) << 10) | ((uint32_t)y & 1023u);  // th == 0 -> lz = 33 <= true lz
+        rare_word = th;
+    }
+    __device__ static __forceinline__ uint32_t need(uint32_t cur, uint32_t v) { return cur < v ? v : 0u; }
+    __device__ static __forceinline__ void apply(uint32_t saddr, uint32_t needv) { red_max(saddr, needv); }
+    __device__ static __forceinline__ void exact(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t sbase) {
+        uint32_t idx, val;
+        Cell<HMH>::from_kmer(klo, khi, hc, p, idx, val);
         const uint32_t saddr = sbase + idx * 4u;
-        red_max_if_greater(saddr, lds_u32(saddr), ok01 ? v : 0u);
+        if (lds_u32(saddr) < val) red_max(saddr, val);
     }
     __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int) { return acc[cell]; }
 };
@@ -96,9 +144,8 @@ struct SmemAcc<HMH> {
 // Global-accumulator fallback (2^p too large for shared memory): byte / halfword cells of the
 // genome's accumulator in HBM/L2, volatile-load filter + CAS on the containing word.
 template <int ALGO>
-__device__ __forceinline__ void global_update(uint32_t* gacc, uint32_t idx, uint32_t val, bool valid) {
+__device__ __forceinline__ void global_update(uint32_t* gacc, uint32_t idx, uint32_t val) {
     using C = Cell<ALGO>;
-    if (!valid) return;
     const uint32_t r = (uint32_t)(*reinterpret_cast<const volatile typename C::T*>(reinterpret_cast<typename C::T*>(gacc) + idx));
     if (C::update(r, val) == r) return;
     constexpr uint32_t per = 4 / C::kBytes;
@@ -116,13 +163,20 @@ __device__ __forceinline__ void global_update(uint32_t* gacc, uint32_t idx, uint
     }
 }
 
-template <int ALGO, bool WIDE, bool GLOBAL>
+// k-mer width classes: the reference's own dispatch is k<=14 / 16 / else (utils.rs:466-502); here the
+// split is by what fits one 32-bit word, with k == 16 (lash's default) special-cased because the
+// window IS the word (no shift, no mask).
+enum KMode : int { K16 = 0, KNARROW = 1, KWIDE = 2 };
+constexpr int kGroup = 16;  // k-mers whose atomics are deferred together (one 32-bit word of bases)
+
+template <int ALGO, int KM, bool GLOBAL>
 __global__ void __launch_bounds__(1024)
     sketch_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ inv_mask,
                   const SketchTile* __restrict__ tiles, uint32_t* __restrict__ acc_global, int p, int k, HashConsts hc,
                   uint32_t cell_words, uint32_t n_cells) {
     using C = Cell<ALGO>;
     using A = SmemAcc<ALGO>;
+    constexpr bool WIDE = KM == KWIDE;
     extern __shared__ uint32_t sacc[];
     const SketchTile t = tiles[blockIdx.x];
     uint32_t* gacc = acc_global + (size_t)t.genome * cell_words;
@@ -170,10 +224,13 @@ __global__ void __launch_bounds__(1024)
             const uint32_t v16 = (uint32_t)(valid >> (16 * w)) & 0xffffu;
             const uint32_t A0 = f0, B0 = f1, C0 = f2;
             const uint32_t Ar = rc16(A0), Br = rc16(B0), Cr = WIDE ? rc16(C0) : 0u;
-            // one k-mer: window extraction -> canonical -> hash -> cell update
-            auto one = [&](const int sh /* 2*i */, const uint32_t ok01) {
-                uint32_t klo, khi;
-                if (!WIDE) {
+            // canonical masked k-mer starting at base i of this word (sh = 2*i): funnel-shift windows
+            // of the forward stream and of the reverse-complemented stream, then min
+            auto kmer = [&](const int sh, uint32_t& klo, uint32_t& khi) {
+                if (KM == K16) {
+                    klo = min(__funnelshift_l(B0, A0, sh), __funnelshift_r(Ar, Br, sh));
+                    khi = 0u;
+                } else if (KM == KNARROW) {
                     const uint32_t fw = __funnelshift_l(B0, A0, sh) >> narrow_shr;
                     const uint32_t rc = __funnelshift_r(Ar, Br, sh) & narrow_mask;
                     klo = min(fw, rc);
@@ -189,21 +246,45 @@ __global__ void __launch_bounds__(1024)
                     klo = (uint32_t)c64;
                     khi = (uint32_t)(c64 >> 32);
                 }
-                uint32_t idx, val;
-                if (GLOBAL) {
-                    C::from_kmer(klo, khi, hc, p, idx, val);
-                    global_update<ALGO>(gacc, idx, val, ok01 != 0u);
-                } else {
-                    C::from_kmer_smem(klo, khi, hc, p, idx, val);
-                    A::update(sbase, idx, val, ok01);
+            };
+            // exact, checked, rolled path: partial validity, rare hashes, global accumulators
+            auto exact_block = [&](const uint32_t mask16) {
+#pragma unroll 1
+                for (int i = 0; i < 16; ++i) {
+                    if (!((mask16 >> i) & 1u)) continue;
+                    uint32_t klo, khi;
+                    kmer(2 * i, klo, khi);
+                    if (GLOBAL) {
+                        uint32_t idx, val;
+                        C::from_kmer(klo, khi, hc, p, idx, val);
+                        global_update<ALGO>(gacc, idx, val);
+                    } else {
+                        A::exact(klo, khi, hc, p, sbase);
+                    }
                 }
             };
-            if (v16 == 0xffffu) {  // every start valid (the common case): straight-line, no checks
+            if (GLOBAL || v16 != 0xffffu) {
+                if (v16 != 0u) exact_block(v16);
+            } else {
+                // every start valid (the common case): straight-line; the shared-memory atomics of the
+                // whole group are deferred behind ONE branch, so the hot path has no divergence
+                uint32_t addr[kGroup], need[kGroup];
+                uint32_t any = 0u, rare = 0xffffffffu;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) one(2 * i, 1u);
-            } else if (v16 != 0u) {  // record boundary / tile tail inside this block: rolled, checked
-#pragma unroll 1
-                for (int i = 0; i < 16; ++i) one(2 * i, (v16 >> i) & 1u);
+                for (int i = 0; i < kGroup; ++i) {
+                    uint32_t klo, khi, v, rw;
+                    kmer(2 * i, klo, khi);
+                    A::prep(klo, khi, hc, p, sbase, addr[i], v, rw);
+                    need[i] = A::need(lds_u32(addr[i]), v);
+                    any |= need[i];
+                    rare = min(rare, rw);
+                }
+                if (any) {
+#pragma unroll
+                    for (int i = 0; i < kGroup; ++i)
+                        if (need[i]) A::apply(addr[i], need[i]);
+                }
+                if (rare == 0u) exact_block(0xffffu);  // some hash had 32 leading zeros where it matters
             }
             f0 = f1; f1 = f2; f2 = f3; f3 = f4; f4 = f5;
         }
@@ -278,10 +359,10 @@ cudaError_t launch_build_invalid_mask(const SpanRecs* spans_dev, uint32_t n_span
     return cudaGetLastError();
 }
 
-template <int ALGO, bool WIDE, bool GLOBAL>
+template <int ALGO, int KM, bool GLOBAL>
 static cudaError_t launch_one(const SketchParams& sp, const uint32_t* packed, const uint32_t* mask,
                               const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st) {
-    auto kern = sketch_kernel<ALGO, WIDE, GLOBAL>;
+    auto kern = sketch_kernel<ALGO, KM, GLOBAL>;
     size_t smem = GLOBAL ? 0 : (size_t)sp.smem_bytes;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -294,13 +375,13 @@ static cudaError_t launch_one(const SketchParams& sp, const uint32_t* packed, co
 template <int ALGO>
 static cudaError_t launch_algo(const SketchParams& sp, const uint32_t* packed, const uint32_t* mask,
                                const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st) {
-    const bool wide = sp.k > 16;
     if (sp.global_acc) {
-        return wide ? launch_one<ALGO, true, true>(sp, packed, mask, tiles, n_tiles, acc, st)
-                    : launch_one<ALGO, false, true>(sp, packed, mask, tiles, n_tiles, acc, st);
+        return sp.k > 16 ? launch_one<ALGO, KWIDE, true>(sp, packed, mask, tiles, n_tiles, acc, st)
+                         : launch_one<ALGO, KNARROW, true>(sp, packed, mask, tiles, n_tiles, acc, st);
     }
-    return wide ? launch_one<ALGO, true, false>(sp, packed, mask, tiles, n_tiles, acc, st)
-                : launch_one<ALGO, false, false>(sp, packed, mask, tiles, n_tiles, acc, st);
+    if (sp.k > 16) return launch_one<ALGO, KWIDE, false>(sp, packed, mask, tiles, n_tiles, acc, st);
+    if (sp.k == 16) return launch_one<ALGO, K16, false>(sp, packed, mask, tiles, n_tiles, acc, st);
+    return launch_one<ALGO, KNARROW, false>(sp, packed, mask, tiles, n_tiles, acc, st);
 }
 
 cudaError_t launch_sketch(const SketchParams& sp, const uint32_t* packed_dev, const uint32_t* mask_dev,
