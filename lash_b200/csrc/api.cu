@@ -210,6 +210,7 @@ extern "C" int lash_sketch_open(lash_ctx* ctx, int algo, int p, int k, uint64_t 
     s->sp.k = k;
     s->sp.hc = make_hash_consts(seed);
     plan_sketch(s->sp);
+    s->sp.n_sm = ctx->n_sm;
     s->per_iter = (uint64_t)s->sp.threads * kStartsPerThread;
     // a CTA should see enough k-mers to warm its private accumulator (>= ~64 per cell)
     s->min_chunk = std::max<uint64_t>(s->per_iter, 64ull * s->sp.n_cells);
@@ -260,11 +261,11 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
         }
         if (sp.n_bases >= (uint64_t)k) total_starts += sp.n_bases - k + 1;
     }
-    // chunk size: aim for >= ~16 waves of CTAs over the push (a short tail), but keep chunks long
-    // enough to warm the private accumulator; always a multiple of the per-iteration CTA footprint.
-    const uint64_t target_tiles = (uint64_t)s->ctx->n_sm * 8 * 16;
+    // Tiles are the balancing granule of the persistent CTAs (each CTA takes a contiguous run of
+    // them): aim for ~32 tiles per resident CTA, never less than one CTA iteration.
+    const uint64_t target_tiles = (uint64_t)s->ctx->n_sm * 8 * 32;
     uint64_t chunk = (total_starts + target_tiles - 1) / target_tiles;
-    chunk = std::max(chunk, s->min_chunk);
+    chunk = std::max(chunk, s->per_iter);
     const uint64_t kStartsPerIter = s->per_iter;
     chunk = ((chunk + kStartsPerIter - 1) / kStartsPerIter) * kStartsPerIter;
 

@@ -16,6 +16,12 @@ struct HashConsts {
     uint32_t bf64_lo, bf64_hi;
     // 128-bit path: bitflip = (secret[16..24] ^ secret[24..32]) + seed'
     uint32_t bf128_lo, bf128_hi;
+    // 64-bit path for k-mers that fit 32 bits (k <= 16): the keyed word is (lo = bf64_lo,
+    // hi = kmer ^ bf64_hi), so the rotate-xor stage  h ^= rotl(h,49) ^ rotl(h,24)  splits into shifts
+    // of the k-mer alone plus seed-only constants (shifts distribute over xor):
+    //   new_lo = (kmer << 17) ^ (kmer >> 8) ^ nar_cl
+    //   new_hi = kmer ^ ((kmer >> 15) | (nar_ch & 0xfffe0000)) ^ ((kmer << 24) + (nar_ch & 0x1ffff))
+    uint32_t nar_cl, nar_ch;
 };
 
 constexpr uint64_t kSecretX_8_16 = 0xc73ab174c5ecd5a2ULL;   // readLE64(kSecret+8) ^ readLE64(kSecret+16)
@@ -35,6 +41,9 @@ inline HashConsts make_hash_consts(uint64_t seed) {
     c.bf64_hi = (uint32_t)(b64 >> 32);
     c.bf128_lo = (uint32_t)b128;
     c.bf128_hi = (uint32_t)(b128 >> 32);
+    const uint32_t L = c.bf64_lo, B = c.bf64_hi;
+    c.nar_cl = L ^ (L >> 15) ^ (L << 24) ^ (B << 17) ^ (B >> 8);
+    c.nar_ch = B ^ (B >> 15) ^ (B << 24) ^ (L << 17) ^ (L >> 8);
     return c;
 }
 
@@ -56,6 +65,32 @@ __device__ __forceinline__ uint64_t xxh3_rrmxmx8(uint64_t h) {
     lo ^= (hi >> 3) + 8u;
     h = mk64(lo, hi) * kPrimeMX2;
     return h ^ (h >> 28);
+}
+
+// tail of XXH3_rrmxmx after the rotate-xor stage, on halves
+__device__ __forceinline__ uint64_t xxh3_rrmxmx8_tail(uint32_t lo, uint32_t hi) {
+    uint64_t h = mk64(lo, hi) * kPrimeMX2;
+    lo = (uint32_t)h;
+    hi = (uint32_t)(h >> 32);
+    lo ^= (hi >> 3) + 8u;  // h ^= (h >> 35) + len, no carry into the high word
+    return mk64(lo, hi) * kPrimeMX2;   // caller applies the final h ^= h >> 28 (or only the part it needs)
+}
+// pre-xorshift hash (h before `h ^= h >> 28`) of a k-mer that fits 32 bits; see HashConsts::nar_*
+__device__ __forceinline__ uint64_t xxh3_64_narrow_pre(uint32_t kmer, const HashConsts& c) {
+    const uint32_t t2 = __funnelshift_r(kmer, c.nar_ch >> 17, 15);      // (kmer >> 15) | (nar_ch & 0xfffe0000)
+    const uint32_t t3 = kmer * (1u << 24) + (c.nar_ch & 0x1ffffu);      // disjoint bits: + is ^
+    const uint32_t hi = kmer ^ t2 ^ t3;
+    const uint32_t lo = (kmer * (1u << 17)) ^ (kmer >> 8) ^ c.nar_cl;
+    return xxh3_rrmxmx8_tail(lo, hi);
+}
+// pre-xorshift hash of a general 64-bit k-mer value
+__device__ __forceinline__ uint64_t xxh3_64_wide_pre(uint32_t v_lo, uint32_t v_hi, const HashConsts& c) {
+    uint32_t lo = v_hi ^ c.bf64_lo, hi = v_lo ^ c.bf64_hi;
+    const uint32_t r49_lo = __funnelshift_r(lo, hi, 15), r49_hi = __funnelshift_r(hi, lo, 15);
+    const uint32_t r24_lo = __funnelshift_l(hi, lo, 24), r24_hi = __funnelshift_l(lo, hi, 24);
+    lo ^= r49_lo ^ r24_lo;
+    hi ^= r49_hi ^ r24_hi;
+    return xxh3_rrmxmx8_tail(lo, hi);
 }
 
 // xxh3_64_with_seed(le64(v), seed); v given as two 32-bit halves.

@@ -34,6 +34,7 @@ struct SketchParams {
     uint32_t cell_words;  // 32-bit words per sketch in the register domain (global accumulator)
     uint32_t n_cells;     // registers per sketch
     uint32_t smem_bytes;  // private accumulator size (ULL 8 B, HLL/HMH 4 B per register)
+    int n_sm;             // SMs of the device (persistent grid sizing)
     uint32_t threads;     // CTA size: grows with smem_bytes so the SM keeps >= 32 warps resident
     bool global_acc;      // accumulator too large for shared memory: update global memory directly
 };

@@ -16,6 +16,8 @@
 //     32-bit shared atomic (OR of a seen-value bit for ULL, max for HLL/HMH) only when it would.
 //   * record boundaries (k-mers never span records, utils.rs:457-464) come from an
 //     "invalid start" bitmask built on device from rec_start[] by build_invalid_mask().
+#include <algorithm>
+
 #include "kernels.h"
 #include "registers.cuh"
 
@@ -64,12 +66,16 @@ template <>
 struct SmemAcc<ULL> {
     static constexpr uint32_t kWordsPerCell = 2;
     // fast: (address of word 0, bit to set [0 if the hash is a rare one], rare indicator word)
+    // g = hash BEFORE its last step h = g ^ (g >> 28).  Because p <= 26 that xorshift cannot reach
+    // the index bits (idx = g.hi >> (32-p)) and, for the top 32 bits of h << p, reduces to
+    // funnel(g, p) ^ (g.hi >> (28-p)) -- two ALU ops fewer than finishing the hash first.
+    template <bool NARROW>
     __device__ static __forceinline__ void prep(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t sbase,
                                                 uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
-        const uint64_t h = xxh3_64_le64(klo, khi, hc);
-        const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
-        const uint32_t yh = __funnelshift_l(lo, hi, p);  // top 32 bits of h << p
-        saddr = sbase + (hi >> (32 - p)) * 8u;
+        const uint64_t g = NARROW ? xxh3_64_narrow_pre(klo, hc) : xxh3_64_wide_pre(klo, khi, hc);
+        const uint32_t lo = (uint32_t)g, hi = (uint32_t)(g >> 32);
+        const uint32_t yh = __funnelshift_l(lo, hi, p) ^ (hi >> (28 - p));  // top 32 bits of h << p
+        saddr = sbase + __umulhi(hi, 1u << p) * 8u;       // (hi >> (32-p)) * 8 on the FMA pipe
         v = shl_clamp(1u, bfind32(yh));                  // yh == 0 -> bfind = 0xffffffff -> v = 0
         rare_word = yh;
     }
@@ -94,9 +100,11 @@ struct SmemAcc<ULL> {
 template <>
 struct SmemAcc<HLL> {
     static constexpr uint32_t kWordsPerCell = 1;
+    template <bool NARROW>
     __device__ static __forceinline__ void prep(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t sbase,
                                                 uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
-        const uint64_t h = xxh3_64_le64(klo, khi, hc);
+        const uint64_t g = NARROW ? xxh3_64_narrow_pre(klo, hc) : xxh3_64_wide_pre(klo, khi, hc);
+        const uint64_t h = g ^ (g >> 28);
         const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
         saddr = sbase + (lo & ((1u << p) - 1u)) * 4u;
         v = 32u - bfind32(hi);  // rho = clz(hi) + 1 when hi != 0; hi == 0 -> 33 <= true rho (p <= 18)
@@ -115,6 +123,7 @@ struct SmemAcc<HLL> {
 template <>
 struct SmemAcc<HMH> {
     static constexpr uint32_t kWordsPerCell = 1;
+    template <bool NARROW>
     __device__ static __forceinline__ void prep(uint32_t klo, uint32_t /*khi*/, const HashConsts& hc, int /*p*/, uint32_t sbase,
                                                 uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
         uint64_t hlo, hhi;
@@ -172,136 +181,33 @@ constexpr int kGroup = 16;  // k-mers whose atomics are deferred together (one 3
 template <int ALGO, int KM, bool GLOBAL>
 __global__ void __launch_bounds__(1024)
     sketch_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ inv_mask,
-                  const SketchTile* __restrict__ tiles, uint32_t* __restrict__ acc_global, int p, int k, HashConsts hc,
-                  uint32_t cell_words, uint32_t n_cells) {
+                  const SketchTile* __restrict__ tiles, uint32_t n_tiles, uint32_t* __restrict__ acc_global, int p, int k,
+                  HashConsts hc, uint32_t cell_words, uint32_t n_cells) {
     using C = Cell<ALGO>;
     using A = SmemAcc<ALGO>;
     constexpr bool WIDE = KM == KWIDE;
     extern __shared__ uint32_t sacc[];
-    const SketchTile t = tiles[blockIdx.x];
-    uint32_t* gacc = acc_global + (size_t)t.genome * cell_words;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sacc);
     if (!GLOBAL) {
         for (uint32_t i = threadIdx.x; i < n_cells * A::kWordsPerCell; i += blockDim.x) sacc[i] = 0u;
         __syncthreads();
     }
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sacc);
-    const uint32_t* base = packed + t.word_off;
-    const uint32_t* mbase = (t.mask_word_off != ~0ull) ? inv_mask + t.mask_word_off : nullptr;
-
-    // uniform shift amounts / masks
-    const uint32_t narrow_shr = WIDE ? 0u : (uint32_t)(32 - 2 * k);             // fwd >> (32-2k)
-    const uint32_t narrow_mask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
-    const uint32_t wide_shr = WIDE ? (uint32_t)(64 - 2 * k) : 0u;               // in [0,30]
-    const uint32_t wide_mask_hi = (k >= 32) ? 0xffffffffu : ((1u << ((2 * k - 32) & 31)) - 1u);
-
-    // The trip count is uniform over the CTA (out-of-range threads carry valid == 0), so the warp can
-    // be re-converged explicitly at the end of every iteration.
-    const uint64_t per_iter = (uint64_t)blockDim.x * kStartsPerThread;
-    const uint32_t n_iter = (uint32_t)((t.end - t.begin + per_iter - 1) / per_iter);
-    for (uint32_t it = 0; it < n_iter; ++it) {
-        const uint64_t s0 = t.begin + (uint64_t)it * per_iter + (uint64_t)threadIdx.x * kStartsPerThread;
-        uint4 q = make_uint4(0u, 0u, 0u, 0u);
-        uint2 h = make_uint2(0u, 0u);
-        uint64_t valid = 0ull;
-        if (s0 < t.end) {
-            const uint32_t* wp = base + (s0 >> 4);
-            q = __ldg(reinterpret_cast<const uint4*>(wp));
-            h = __ldg(reinterpret_cast<const uint2*>(wp + 4));
-            const uint64_t remain = t.end - s0;
-            valid = remain >= 64 ? ~0ull : ((1ull << remain) - 1ull);
-            if (mbase) {
-                const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mbase + (s0 >> 5)));
-                valid &= ~(((uint64_t)mv.y << 32) | mv.x);
-            }
-        }
-        // big-endian base order inside each word: first base in the top bits
-        uint32_t f0 = __byte_perm(q.x, 0, 0x0123), f1 = __byte_perm(q.y, 0, 0x0123);
-        uint32_t f2 = __byte_perm(q.z, 0, 0x0123), f3 = __byte_perm(q.w, 0, 0x0123);
-        uint32_t f4 = __byte_perm(h.x, 0, 0x0123), f5 = __byte_perm(h.y, 0, 0x0123);
-
-#pragma unroll 1
-        for (int w = 0; w < 4; ++w) {
-            const uint32_t v16 = (uint32_t)(valid >> (16 * w)) & 0xffffu;
-            const uint32_t A0 = f0, B0 = f1, C0 = f2;
-            const uint32_t Ar = rc16(A0), Br = rc16(B0), Cr = WIDE ? rc16(C0) : 0u;
-            // canonical masked k-mer starting at base i of this word (sh = 2*i): funnel-shift windows
-            // of the forward stream and of the reverse-complemented stream, then min
-            auto kmer = [&](const int sh, uint32_t& klo, uint32_t& khi) {
-                if (KM == K16) {
-                    klo = min(__funnelshift_l(B0, A0, sh), __funnelshift_r(Ar, Br, sh));
-                    khi = 0u;
-                } else if (KM == KNARROW) {
-                    const uint32_t fw = __funnelshift_l(B0, A0, sh) >> narrow_shr;
-                    const uint32_t rc = __funnelshift_r(Ar, Br, sh) & narrow_mask;
-                    klo = min(fw, rc);
-                    khi = 0u;
-                } else {
-                    uint32_t fhi = __funnelshift_l(B0, A0, sh), flo = __funnelshift_l(C0, B0, sh);
-                    flo = __funnelshift_r(flo, fhi, wide_shr);
-                    fhi >>= wide_shr;
-                    const uint32_t rlo = __funnelshift_r(Ar, Br, sh);
-                    const uint32_t rhi = __funnelshift_r(Br, Cr, sh) & wide_mask_hi;
-                    const uint64_t f64 = mk64(flo, fhi), r64 = mk64(rlo, rhi);
-                    const uint64_t c64 = f64 < r64 ? f64 : r64;
-                    klo = (uint32_t)c64;
-                    khi = (uint32_t)(c64 >> 32);
-                }
-            };
-            // exact, checked, rolled path: partial validity, rare hashes, global accumulators
-            auto exact_block = [&](const uint32_t mask16) {
-#pragma unroll 1
-                for (int i = 0; i < 16; ++i) {
-                    if (!((mask16 >> i) & 1u)) continue;
-                    uint32_t klo, khi;
-                    kmer(2 * i, klo, khi);
-                    if (GLOBAL) {
-                        uint32_t idx, val;
-                        C::from_kmer(klo, khi, hc, p, idx, val);
-                        global_update<ALGO>(gacc, idx, val);
-                    } else {
-                        A::exact(klo, khi, hc, p, sbase);
-                    }
-                }
-            };
-            if (GLOBAL || v16 != 0xffffu) {
-                if (v16 != 0u) exact_block(v16);
-            } else {
-                // every start valid (the common case): straight-line; the shared-memory atomics of the
-                // whole group are deferred behind ONE branch, so the hot path has no divergence
-                uint32_t addr[kGroup], need[kGroup];
-                uint32_t any = 0u, rare = 0xffffffffu;
-#pragma unroll
-                for (int i = 0; i < kGroup; ++i) {
-                    uint32_t klo, khi, v, rw;
-                    kmer(2 * i, klo, khi);
-                    A::prep(klo, khi, hc, p, sbase, addr[i], v, rw);
-                    need[i] = A::need(lds_u32(addr[i]), v);
-                    any |= need[i];
-                    rare = min(rare, rw);
-                }
-                if (any) {
-#pragma unroll
-                    for (int i = 0; i < kGroup; ++i)
-                        if (need[i]) A::apply(addr[i], need[i]);
-                }
-                if (rare == 0u) exact_block(0xffffu);  // some hash had 32 leading zeros where it matters
-            }
-            f0 = f1; f1 = f2; f2 = f3; f3 = f4; f4 = f5;
-        }
-        __syncwarp();
-    }
-
-    if (!GLOBAL) {
-        // flush: cells -> register bytes/halfwords -> merge the non-zero words into the genome's
-        // global accumulator (max for HLL/HMH, packed-domain OR-merge for ULL)
+    // cells -> register bytes/halfwords -> merge the non-zero words into the genome's global
+    // accumulator (max for HLL/HMH, packed-domain OR-merge for ULL); leaves the cells zeroed
+    auto flush = [&](uint32_t genome) {
         __syncthreads();
+        uint32_t* gacc = acc_global + (size_t)genome * cell_words;
         constexpr uint32_t per = 4 / C::kBytes;
         for (uint32_t i = threadIdx.x; i < cell_words; i += blockDim.x) {
             uint32_t v = 0u;
 #pragma unroll
             for (uint32_t j = 0; j < per; ++j) {
                 const uint32_t c = i * per + j;
-                if (c < n_cells) v |= A::to_reg(sacc, c, p) << (j * 8 * C::kBytes);
+                if (c < n_cells) {
+                    v |= A::to_reg(sacc, c, p) << (j * 8 * C::kBytes);
+#pragma unroll
+                    for (uint32_t z = 0; z < A::kWordsPerCell; ++z) sacc[c * A::kWordsPerCell + z] = 0u;
+                }
             }
             if (v == 0u) continue;
             uint32_t* gp = gacc + i;
@@ -314,7 +220,131 @@ __global__ void __launch_bounds__(1024)
                 if (old == assumed) break;
             }
         }
+        __syncthreads();
+    };
+
+    // uniform shift amounts / masks
+    const uint32_t narrow_shr = WIDE ? 0u : (uint32_t)(32 - 2 * k);             // fwd >> (32-2k)
+    const uint32_t narrow_mask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+    const uint32_t wide_shr = WIDE ? (uint32_t)(64 - 2 * k) : 0u;               // in [0,30]
+    const uint32_t wide_mask_hi = (k >= 32) ? 0xffffffffu : ((1u << ((2 * k - 32) & 31)) - 1u);
+
+    // Persistent CTAs: CTA c owns the contiguous tile range [c*T/G, (c+1)*T/G) of the (genome-ordered)
+    // tile list, so equal-cost tiles are balanced statically with no tail, and the private accumulator
+    // is carried across consecutive tiles of the same genome (one warm-up + one flush per genome a CTA
+    // touches instead of one per tile).
+    const uint32_t t_begin = (uint32_t)(((uint64_t)blockIdx.x * n_tiles) / gridDim.x);
+    const uint32_t t_end = (uint32_t)(((uint64_t)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+    uint32_t cur_genome = 0xffffffffu;
+    for (uint32_t ti = t_begin; ti < t_end; ++ti) {
+        const SketchTile t = tiles[ti];
+        if (t.genome != cur_genome) {
+            if (!GLOBAL && cur_genome != 0xffffffffu) flush(cur_genome);
+            cur_genome = t.genome;
+        }
+        uint32_t* gacc = acc_global + (size_t)t.genome * cell_words;
+        const uint32_t* base = packed + t.word_off;
+        const uint32_t* mbase = (t.mask_word_off != ~0ull) ? inv_mask + t.mask_word_off : nullptr;
+
+        // The trip count is uniform over the CTA (out-of-range threads carry valid == 0), so the warp can
+        // be re-converged explicitly at the end of every iteration.
+        const uint64_t per_iter = (uint64_t)blockDim.x * kStartsPerThread;
+        const uint32_t n_iter = (uint32_t)((t.end - t.begin + per_iter - 1) / per_iter);
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const uint64_t s0 = t.begin + (uint64_t)it * per_iter + (uint64_t)threadIdx.x * kStartsPerThread;
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            uint2 h = make_uint2(0u, 0u);
+            uint64_t valid = 0ull;
+            if (s0 < t.end) {
+                const uint32_t* wp = base + (s0 >> 4);
+                q = __ldg(reinterpret_cast<const uint4*>(wp));
+                h = __ldg(reinterpret_cast<const uint2*>(wp + 4));
+                const uint64_t remain = t.end - s0;
+                valid = remain >= 64 ? ~0ull : ((1ull << remain) - 1ull);
+                if (mbase) {
+                    const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mbase + (s0 >> 5)));
+                    valid &= ~(((uint64_t)mv.y << 32) | mv.x);
+                }
+            }
+            // big-endian base order inside each word: first base in the top bits
+            uint32_t f0 = __byte_perm(q.x, 0, 0x0123), f1 = __byte_perm(q.y, 0, 0x0123);
+            uint32_t f2 = __byte_perm(q.z, 0, 0x0123), f3 = __byte_perm(q.w, 0, 0x0123);
+            uint32_t f4 = __byte_perm(h.x, 0, 0x0123), f5 = __byte_perm(h.y, 0, 0x0123);
+
+    #pragma unroll 1
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t v16 = (uint32_t)(valid >> (16 * w)) & 0xffffu;
+                const uint32_t A0 = f0, B0 = f1, C0 = f2;
+                const uint32_t Ar = rc16(A0), Br = rc16(B0), Cr = WIDE ? rc16(C0) : 0u;
+                // canonical masked k-mer starting at base i of this word (sh = 2*i): funnel-shift windows
+                // of the forward stream and of the reverse-complemented stream, then min
+                auto kmer = [&](const int sh, uint32_t& klo, uint32_t& khi) {
+                    if (KM == K16) {
+                        klo = min(__funnelshift_l(B0, A0, sh), __funnelshift_r(Ar, Br, sh));
+                        khi = 0u;
+                    } else if (KM == KNARROW) {
+                        const uint32_t fw = __funnelshift_l(B0, A0, sh) >> narrow_shr;
+                        const uint32_t rc = __funnelshift_r(Ar, Br, sh) & narrow_mask;
+                        klo = min(fw, rc);
+                        khi = 0u;
+                    } else {
+                        uint32_t fhi = __funnelshift_l(B0, A0, sh), flo = __funnelshift_l(C0, B0, sh);
+                        flo = __funnelshift_r(flo, fhi, wide_shr);
+                        fhi >>= wide_shr;
+                        const uint32_t rlo = __funnelshift_r(Ar, Br, sh);
+                        const uint32_t rhi = __funnelshift_r(Br, Cr, sh) & wide_mask_hi;
+                        const uint64_t f64 = mk64(flo, fhi), r64 = mk64(rlo, rhi);
+                        const uint64_t c64 = f64 < r64 ? f64 : r64;
+                        klo = (uint32_t)c64;
+                        khi = (uint32_t)(c64 >> 32);
+                    }
+                };
+                // exact, checked, rolled path: partial validity, rare hashes, global accumulators
+                auto exact_block = [&](const uint32_t mask16) {
+    #pragma unroll 1
+                    for (int i = 0; i < 16; ++i) {
+                        if (!((mask16 >> i) & 1u)) continue;
+                        uint32_t klo, khi;
+                        kmer(2 * i, klo, khi);
+                        if (GLOBAL) {
+                            uint32_t idx, val;
+                            C::from_kmer(klo, khi, hc, p, idx, val);
+                            global_update<ALGO>(gacc, idx, val);
+                        } else {
+                            A::exact(klo, khi, hc, p, sbase);
+                        }
+                    }
+                };
+                if (GLOBAL || v16 != 0xffffu) {
+                    if (v16 != 0u) exact_block(v16);
+                } else {
+                    // every start valid (the common case): straight-line; the shared-memory atomics of the
+                    // whole group are deferred behind ONE branch, so the hot path has no divergence
+                    uint32_t addr[kGroup], need[kGroup];
+                    uint32_t any = 0u, rare = 0xffffffffu;
+    #pragma unroll
+                    for (int i = 0; i < kGroup; ++i) {
+                        uint32_t klo, khi, v, rw;
+                        kmer(2 * i, klo, khi);
+                        A::template prep<!WIDE>(klo, khi, hc, p, sbase, addr[i], v, rw);
+                        need[i] = A::need(lds_u32(addr[i]), v);
+                        any |= need[i];
+                        rare = min(rare, rw);
+                    }
+                    if (any) {
+    #pragma unroll
+                        for (int i = 0; i < kGroup; ++i)
+                            if (need[i]) A::apply(addr[i], need[i]);
+                    }
+                    if (rare == 0u) exact_block(0xffffu);  // some hash had 32 leading zeros where it matters
+                }
+                f0 = f1; f1 = f2; f2 = f3; f3 = f4; f4 = f5;
+            }
+            __syncwarp();
+        }
+
     }
+    if (!GLOBAL && cur_genome != 0xffffffffu) flush(cur_genome);
 }
 
 // One CTA per multi-record span: mark every k-mer start that would cross the END of a record
@@ -368,7 +398,12 @@ static cudaError_t launch_one(const SketchParams& sp, const uint32_t* packed, co
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<n_tiles, sp.threads, smem, st>>>(packed, mask, tiles, acc, sp.p, sp.k, sp.hc, sp.cell_words, sp.n_cells);
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)sp.threads, smem);
+    if (e != cudaSuccess) return e;
+    const uint32_t resident = (uint32_t)std::max(occ, 1) * (uint32_t)sp.n_sm;
+    const uint32_t grid = n_tiles < resident ? n_tiles : resident;  // one persistent CTA per resident slot
+    kern<<<grid, sp.threads, smem, st>>>(packed, mask, tiles, n_tiles, acc, sp.p, sp.k, sp.hc, sp.cell_words, sp.n_cells);
     return cudaGetLastError();
 }
 

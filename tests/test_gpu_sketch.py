@@ -138,3 +138,34 @@ def test_error_behaviour(gpu_ctx):
         b.add_genome(5, [b"ACGT" * 10])               # genome slot out of range
         with pytest.raises(LashError):
             sk.push_batch(b)
+
+
+@pytest.mark.parametrize("algo,p", [(ALGO_ULL, 10), (ALGO_ULL, 14), (ALGO_ULL, 3), (ALGO_ULL, 20), (ALGO_HLL, 14), (ALGO_HLL, 4),
+                                    (ALGO_HLL, 18)])
+def test_adversarial_hashes_with_32_or_more_leading_zeros(oracle, gpu_ctx, algo, p):
+    """The kernel's fast path looks at 32 bits of the hash; the remaining 2^-32 of hashes take an exact
+    slow path that random genomes never reach.  XXH3 on 8 bytes is invertible, so build 32-mers whose
+    hash has 32..(64-p) leading zeros where it matters and check registers bit for bit."""
+    from tools.xxh3_invert import adversarial_32mers
+    rng = np.random.default_rng(p)
+    targets = []
+    for _ in range(400):
+        if algo == ALGO_ULL:       # idx | 32+ zeros | tail
+            idx = int(rng.integers(0, 1 << p))
+            tail_bits = 64 - p - 32
+            tail = int(rng.integers(0, 1 << tail_bits)) >> int(rng.integers(0, tail_bits + 1))
+            targets.append((idx << (64 - p)) | tail)
+        else:                      # hi word zero; low p bits = index
+            lo = int(rng.integers(0, 1 << 32)) >> int(rng.integers(0, 33 - p))
+            targets.append((lo << p | int(rng.integers(0, 1 << p))) & 0xFFFFFFFF)
+    kmers = adversarial_32mers(targets, SEED)
+    assert len(kmers) > 100
+    # hide them in ordinary sequence: own records (exactly one k-mer each) and inside long records
+    filler = synth.genomes(1, 30_000, seed=p)[0][0]
+    g1 = [filler] + kmers
+    g2 = [filler[:5000] + b"N" + b"N".join(kmers[:50]) + b"N" + filler[5000:]]
+    regs = _check(oracle, gpu_ctx, algo, p, 32, [g1, g2, kmers])
+    if algo == ALGO_HLL:
+        assert regs[2].max() >= 33     # rho beyond what 32 bits can see
+    else:
+        assert (regs[2] >> 2).max() >= 31 + p   # update value u = nlz + p - 1 with nlz >= 32
