@@ -339,13 +339,23 @@ def run_graft(args):
                 sp[i - g0] = Span(i, (i - g0) * stride, GENOME_LEN, 0, 1, 0)
             pushes.append((g0 * stride, (g1 - g0) * stride, sp, g1 - g0))
 
+        trace = os.environ.get("LASH_BENCH_TRACE")
+
         def e2e_step():
+            t0 = time.perf_counter()
             check(L.lash_sketch_reset(sk._h))
+            t1 = time.perf_counter()
             for off, nb, sp, ns in pushes:
                 check(L.lash_sketch_push(sk._h, C.c_void_p(pin.value + off), nb, sp, ns, None, 0, None))
+            t2 = time.perf_counter()
             check(L.lash_sketch_fetch(sk._h, 0, n_g, host_regs_all.ctypes.data_as(C.c_void_p)))
+            t3 = time.perf_counter()
             check(L.lash_dist(ctx.handle, ALGO_ULL, P, K, EST_FGRA, MODEL, 0, host_regs_all.ctypes.data_as(C.c_void_p), n_g,
                               host_regs_all.ctypes.data_as(C.c_void_p), n_g, 1, tri_out.ctypes.data_as(C.c_void_p)))
+            t4 = time.perf_counter()
+            if trace:
+                print(f"[rank {rank}] e2e ms: reset {1e3*(t1-t0):.2f} pushes {1e3*(t2-t1):.2f} fetch(sync) {1e3*(t3-t2):.2f} "
+                      f"dist {1e3*(t4-t3):.2f}", file=sys.stderr, flush=True)
 
         for _ in range(2):
             e2e_step()

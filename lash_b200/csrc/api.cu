@@ -44,69 +44,6 @@ extern "C" int lash_gpu_device_count(void) {
     return n;
 }
 
-struct lash_ctx {
-    int device = 0;
-    int n_sm = 148;
-    cudaStream_t stream = nullptr;
-    double dist_ms = 0.0;
-    uint64_t dist_launches = 0;
-};
-
-extern "C" int lash_ctx_create(int device, lash_ctx** out) {
-    if (!out) return fail(LASH_E_INVALID, "lash_ctx_create: out is NULL");
-    int n = lash_gpu_device_count();
-    if (n <= 0) return fail(LASH_E_CUDA, "lash_ctx_create: no CUDA device visible (this library has no CPU fallback)");
-    if (device < 0 || device >= n) return fail(LASH_E_INVALID, "lash_ctx_create: device index out of range");
-    CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        return fail(LASH_E_CUDA, std::string("lash_ctx_create: device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
-                                     ", this build carries sm_100a code only");
-    lash_ctx* c = new (std::nothrow) lash_ctx();
-    if (!c) return fail(LASH_E_NOMEM, "lash_ctx_create: out of host memory");
-    c->device = device;
-    c->n_sm = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(ensure_tables());
-    *out = c;
-    return LASH_OK;
-}
-extern "C" int lash_ctx_destroy(lash_ctx* c) {
-    if (!c) return LASH_OK;
-    cudaSetDevice(c->device);
-    if (c->stream) cudaStreamDestroy(c->stream);
-    delete c;
-    return LASH_OK;
-}
-extern "C" int lash_ctx_device(const lash_ctx* c) { return c ? c->device : -1; }
-
-extern "C" int lash_host_alloc(size_t bytes, void** out) {
-    if (!out) return fail(LASH_E_INVALID, "lash_host_alloc: out is NULL");
-    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
-    return LASH_OK;
-}
-extern "C" int lash_host_free(void* p) {
-    if (p) CU(cudaFreeHost(p));
-    return LASH_OK;
-}
-
-static bool valid_algo_p(int algo, int p) {
-    if (algo == LASH_ALGO_HMH) return true;
-    if (algo == LASH_ALGO_HLL) return p >= 4 && p <= 18;   // streaming_algorithms threshold table range
-    if (algo == LASH_ALGO_ULL) return p >= 3 && p <= 26;   // ultraloglog::new range
-    return false;
-}
-extern "C" size_t lash_sketch_reg_bytes(int algo, int p) {
-    if (algo == LASH_ALGO_HMH) return 32768;
-    if (!valid_algo_p(algo, p)) return 0;
-    return (size_t)1 << p;
-}
-extern "C" uint64_t lash_sketch_padded_bytes(uint64_t n_bases) {
-    uint64_t b = (n_bases + 3) / 4;
-    return ((b + 15) / 16) * 16 + 16;
-}
-
 // ------------------------------------------------------------------------------------------------
 // growable device / pinned buffers
 // ------------------------------------------------------------------------------------------------
@@ -150,6 +87,75 @@ struct PinBuf {
         cap = 0;
     }
 };
+
+struct lash_ctx {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    double dist_ms = 0.0;
+    uint64_t dist_launches = 0;
+    // scratch of lash_dist / lash_dist_stream, kept across calls (cudaMalloc/cudaFree per call cost
+    // milliseconds of jitter on a 2.5 ms operation)
+    DevBuf d_ref, d_qry, d_card, d_out[2], d_flags;
+    PinBuf h_out[2];
+};
+
+extern "C" int lash_ctx_create(int device, lash_ctx** out) {
+    if (!out) return fail(LASH_E_INVALID, "lash_ctx_create: out is NULL");
+    int n = lash_gpu_device_count();
+    if (n <= 0) return fail(LASH_E_CUDA, "lash_ctx_create: no CUDA device visible (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(LASH_E_INVALID, "lash_ctx_create: device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(LASH_E_CUDA, std::string("lash_ctx_create: device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                     ", this build carries sm_100a code only");
+    lash_ctx* c = new (std::nothrow) lash_ctx();
+    if (!c) return fail(LASH_E_NOMEM, "lash_ctx_create: out of host memory");
+    c->device = device;
+    c->n_sm = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(ensure_tables());
+    *out = c;
+    return LASH_OK;
+}
+extern "C" int lash_ctx_destroy(lash_ctx* c) {
+    if (!c) return LASH_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    c->d_ref.release(); c->d_qry.release(); c->d_card.release(); c->d_out[0].release(); c->d_out[1].release();
+    c->d_flags.release(); c->h_out[0].release(); c->h_out[1].release();
+    delete c;
+    return LASH_OK;
+}
+extern "C" int lash_ctx_device(const lash_ctx* c) { return c ? c->device : -1; }
+
+extern "C" int lash_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(LASH_E_INVALID, "lash_host_alloc: out is NULL");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return LASH_OK;
+}
+extern "C" int lash_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return LASH_OK;
+}
+
+static bool valid_algo_p(int algo, int p) {
+    if (algo == LASH_ALGO_HMH) return true;
+    if (algo == LASH_ALGO_HLL) return p >= 4 && p <= 18;   // streaming_algorithms threshold table range
+    if (algo == LASH_ALGO_ULL) return p >= 3 && p <= 26;   // ultraloglog::new range
+    return false;
+}
+extern "C" size_t lash_sketch_reg_bytes(int algo, int p) {
+    if (algo == LASH_ALGO_HMH) return 32768;
+    if (!valid_algo_p(algo, p)) return 0;
+    return (size_t)1 << p;
+}
+extern "C" uint64_t lash_sketch_padded_bytes(uint64_t n_bases) {
+    uint64_t b = (n_bases + 3) / 4;
+    return ((b + 15) / 16) * 16 + 16;
+}
 
 // ------------------------------------------------------------------------------------------------
 // sketcher
@@ -552,12 +558,11 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
     const size_t esz = fp32 ? 4 : 8;
     const bool same = (ref_regs == qry_regs && n_ref == n_qry);
     cudaStream_t st = ctx->stream;
-    DevBuf d_ref, d_qry, d_card, d_out[2], d_flags;
-    PinBuf h_out[2];
+    DevBuf &d_ref = ctx->d_ref, &d_qry = ctx->d_qry, &d_card = ctx->d_card, &d_flags = ctx->d_flags;
+    DevBuf* d_out = ctx->d_out;
+    PinBuf* h_out = ctx->h_out;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done[2] = {nullptr, nullptr};
     auto cleanup = [&]() {
-        d_ref.release(); d_qry.release(); d_card.release(); d_out[0].release(); d_out[1].release(); d_flags.release();
-        h_out[0].release(); h_out[1].release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (int i = 0; i < 2; ++i) if (done[i]) cudaEventDestroy(done[i]);

@@ -24,113 +24,28 @@ namespace lash {
 
 
 constexpr int kDistThreads = 256;
-constexpr int kChunkWords = 256;  // 1 KiB of registers per sketch per stage
+constexpr int kChunkBytes = 1024;  // bytes of registers per sketch per stage
+
+// sentinel contribution of a register outside FGRA's table range [4p+4, 252): makes the running sum
+// explode (>= 2^600) so the pair is re-done by the exact path; normal sums are <= 2^26 * 0.85
+#define LASH_FGRA_SENTINEL 0x1p600
+#define LASH_FGRA_SENTINEL_TEST 0x1p500
 
 // ------------------------------------------------------------------------------------------------
-// per-pair accumulators
+// register-pair primitives (plain 32-bit integer ops; the byte-SIMD "video" intrinsics are emulated
+// with ~10 instructions each on sm_100 and were the bottleneck of the first version)
 // ------------------------------------------------------------------------------------------------
-struct SharedTables {
-    double* fgra_tab;    // [256] contribution of a merged register byte (0 outside [4p+4, 252))
-    uint64_t* ml_ret;    // [256] ML alpha contribution (scaled by 2^64) of a register byte
-};
+// ULL union of two register bytes == pack(unpack(a) | unpack(b))  (ultraloglog merge, utils.rs:260-262)
+__device__ __forceinline__ uint32_t ull_merge_fast(uint32_t a, uint32_t b) {
+    const uint32_t hi = max(a, b), lo = min(a, b);
+    const uint32_t d = min((hi >> 2) - (lo >> 2), 3u);
+    // 3-bit window (1,w1,w0) of the smaller register, 0 if it is empty (valid non-empty registers are >= 8)
+    const uint32_t x = (lo & 3u) | (min(lo, 4u) & 4u);
+    return hi | ((x >> d) & 3u);
+}
 
-struct HllAcc {
-    static constexpr int RM = 2, QM = 2;
-    static constexpr int kTableBytes = 0;
-    double sum;
-    uint32_t zero;
-    __device__ __forceinline__ void init() { sum = 0.0; zero = 0; }
-    __device__ __forceinline__ void add(uint32_t a, uint32_t b, const SharedTables&, int) {
-        const uint32_t m = __vmaxu4(a, b);
-        zero += __popc(__vcmpeq4(m, 0u)) >> 3;
-        sum += pow2neg(m & 0xffu);
-        sum += pow2neg((m >> 8) & 0xffu);
-        sum += pow2neg((m >> 16) & 0xffu);
-        sum += pow2neg(m >> 24);
-    }
-};
-
-struct FgraAcc {
-    static constexpr int RM = 2, QM = 2;
-    static constexpr int kTableBytes = 256 * 8;
-    double sum;
-    uint32_t c0, c4, c8, c10, w0, w1, w2, w3;
-    __device__ __forceinline__ void init() { sum = 0.0; c0 = c4 = c8 = c10 = w0 = w1 = w2 = w3 = 0; }
-    __device__ __forceinline__ void classify(uint32_t r, int off) {
-        const int r2 = (int)r - off;
-        c0 += (r2 < -8);
-        c4 += (r2 == -8);
-        c8 += (r2 == -4);
-        c10 += (r2 == -2);
-        w0 += (r == 252u);
-        w1 += (r == 253u);
-        w2 += (r == 254u);
-        w3 += (r == 255u);
-    }
-    __device__ __forceinline__ void add(uint32_t a, uint32_t b, const SharedTables& t, int p) {
-        const uint32_t m = ull_merge4(a, b);
-        sum += t.fgra_tab[m & 0xffu];
-        sum += t.fgra_tab[(m >> 8) & 0xffu];
-        sum += t.fgra_tab[(m >> 16) & 0xffu];
-        sum += t.fgra_tab[m >> 24];
-        // registers outside [4p+4, 252) contribute through counts, not through the table
-        const uint32_t off = 4u * p + 4u;
-        const uint32_t rel = __vsub4(m, off * 0x01010101u);
-        if (__vcmpgeu4(rel, (252u - off) * 0x01010101u)) {
-            classify(m & 0xffu, (int)off);
-            classify((m >> 8) & 0xffu, (int)off);
-            classify((m >> 16) & 0xffu, (int)off);
-            classify(m >> 24, (int)off);
-        }
-    }
-};
-
-struct MlAcc {
-    static constexpr int RM = 1, QM = 1;
-    static constexpr int kTableBytes = 256 * 8;
-    uint64_t S;
-    int b[66];
-    __device__ __forceinline__ void init() {
-        S = 0;
-#pragma unroll 1
-        for (int i = 0; i < 66; ++i) b[i] = 0;
-    }
-    __device__ __forceinline__ void one(uint32_t r, const SharedTables& t, int off) {
-        S += t.ml_ret[r];
-        const int r2 = (int)r - off;
-        if (r2 >= 0) {
-            const int k = r2 >> 2;
-            b[k] += (int)(r & 1u);
-            b[k + 1] += (int)((r >> 1) & 1u);
-            b[k + 2] += 1;
-        } else {
-            if (r2 == -2 || r2 == -8) b[0] += 1;
-            if (r2 == -2 || r2 == -4) b[1] += 1;
-        }
-    }
-    __device__ __forceinline__ void add(uint32_t a, uint32_t bb, const SharedTables& t, int p) {
-        const uint32_t m = ull_merge4(a, bb);
-        const int off = 4 * p + 4;
-        one(m & 0xffu, t, off);
-        one((m >> 8) & 0xffu, t, off);
-        one((m >> 16) & 0xffu, t, off);
-        one(m >> 24, t, off);
-    }
-};
-
-struct HmhAcc {
-    static constexpr int RM = 2, QM = 2;
-    static constexpr int kTableBytes = 0;
-    uint32_t C, N;
-    __device__ __forceinline__ void init() { C = N = 0; }
-    __device__ __forceinline__ void add(uint32_t a, uint32_t b, const SharedTables&, int) {
-        const uint32_t eq = __vcmpeq2(a, b) & __vcmpne2(a, 0u);
-        C += __popc(eq) >> 4;
-        N += __popc(__vcmpne2(a | b, 0u)) >> 4;
-    }
-};
-
-// ML alpha contribution of a register byte (hash4j contribute(), scaled by 2^64)
+// hash4j contribute(): alpha contribution (scaled by 2^64) of one register byte, and the bit pattern
+// W it adds to the b[] statistics: b[j] += bit j of W  (W = unpack(r) >> (p-1) for valid registers)
 __device__ __forceinline__ uint64_t ml_ret_of(uint32_t r, int p) {
     const int r2 = (int)r - 4 * p - 4;
     if (r2 < 0) {
@@ -145,32 +60,244 @@ __device__ __forceinline__ uint64_t ml_ret_of(uint32_t r, int p) {
     ret -= (uint64_t)((r >> 1) & 1u) << 62;
     return ret >> (k + p);
 }
+__device__ __forceinline__ uint64_t ml_w_of(uint32_t r, int p) {
+    const int r2 = (int)r - 4 * p - 4;
+    if (r2 < 0) {
+        uint64_t w = 0;
+        if (r2 == -2 || r2 == -8) w |= 1;
+        if (r2 == -2 || r2 == -4) w |= 2;
+        return w;
+    }
+    return (uint64_t)(4u | (r & 3u)) << (r2 >> 2);  // b[k] += y0, b[k+1] += y1, b[k+2] += 1
+}
+
+struct SharedTables {
+    const double* fgra_tab;    // [256] contribution of a merged register byte (sentinel outside [4p+4, 252))
+    const uint64_t* ml_ret;    // [256]
+    const uint32_t* ml_wlo;    // [256] low 32 bits of W
+    const double* hll_pow;     // [256] 2^-r
+};
+
+// carry-save adder on 32-bit bit-planes: (a + b + c) -> sum (weight 1) and carry (weight 2); 2 LOP3
+__device__ __forceinline__ void csa(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t u = a ^ b;
+    carry = (a & b) | (u & c);
+    sum = u ^ c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-pair accumulators.  add_group<N>() consumes N consecutive registers of both sketches (N = 16,
+// or 8 for the 8-register ULL p=3), ALWAYS in index order with one scalar FP64 accumulator.
+// ------------------------------------------------------------------------------------------------
+struct HllAcc {
+    using CT = uint8_t;
+    static constexpr int RM = 2, QM = 2;
+    static constexpr int kTableBytes = 256 * 8;
+    double sum;
+    uint32_t zero;
+    __device__ __forceinline__ void init() { sum = 0.0; zero = 0; }
+    template <int N>
+    __device__ __forceinline__ void add_group(const uint32_t* a, const uint32_t* b, const SharedTables& t) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const uint32_t m = max(a[i], b[i]);
+            zero += (m == 0u);
+            sum += t.hll_pow[m];
+        }
+    }
+};
+
+struct FgraAcc {
+    using CT = uint8_t;
+    static constexpr int RM = 2, QM = 2;
+    static constexpr int kTableBytes = 256 * 8;
+    double sum;
+    __device__ __forceinline__ void init() { sum = 0.0; }
+    template <int N>
+    __device__ __forceinline__ void add_group(const uint32_t* a, const uint32_t* b, const SharedTables& t) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) sum += t.fgra_tab[ull_merge_fast(a[i], b[i])];
+    }
+};
+
+constexpr int kMlPlanes = 27;  // counts up to 2^26 registers
+struct MlAcc {
+    using CT = uint8_t;
+    static constexpr int RM = 1, QM = 2;
+    static constexpr int kTableBytes = 256 * 8 + 256 * 4;
+    uint64_t S;
+    uint32_t mmax;                 // largest merged register seen (decides whether W fits 32 bits)
+    uint32_t pl[kMlPlanes];        // vertical (bit-sliced) counters of the low 32 bits of W
+    __device__ __forceinline__ void init() {
+        S = 0;
+        mmax = 0;
+#pragma unroll
+        for (int i = 0; i < kMlPlanes; ++i) pl[i] = 0u;
+    }
+    // add a bit-plane of weight 2^L into the vertical counter (ripple carry, nplanes is CTA-uniform)
+    template <int L>
+    __device__ __forceinline__ void ripple(uint32_t x, int nplanes) {
+#pragma unroll
+        for (int l = L; l < kMlPlanes; ++l) {
+            if (l < nplanes) {
+                const uint32_t c = pl[l] & x;
+                pl[l] ^= x;
+                x = c;
+            }
+        }
+    }
+    template <int N>
+    __device__ __forceinline__ void add_group(const uint32_t* a, const uint32_t* b, const SharedTables& t, int nplanes) {
+        uint32_t w[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const uint32_t m = ull_merge_fast(a[i], b[i]);
+            mmax = max(mmax, m);
+            S += t.ml_ret[m];
+            w[i] = t.ml_wlo[m];
+        }
+        // Harley-Seal: N one-bit words -> weights 1,2,4,(8) planes, then one ripple of the top carry
+        uint32_t t2a, t2b, t4a, t4b;
+        csa(t2a, pl[0], pl[0], w[0], w[1]);
+        csa(t2b, pl[0], pl[0], w[2], w[3]);
+        csa(t4a, pl[1], pl[1], t2a, t2b);
+        csa(t2a, pl[0], pl[0], w[4], w[5]);
+        csa(t2b, pl[0], pl[0], w[6], w[7]);
+        csa(t4b, pl[1], pl[1], t2a, t2b);
+        uint32_t t8a;
+        csa(t8a, pl[2], pl[2], t4a, t4b);
+        if (N == 8) {
+            ripple<3>(t8a, nplanes);
+        } else {
+            csa(t2a, pl[0], pl[0], w[8 % N], w[9 % N]);
+            csa(t2b, pl[0], pl[0], w[10 % N], w[11 % N]);
+            csa(t4a, pl[1], pl[1], t2a, t2b);
+            csa(t2a, pl[0], pl[0], w[12 % N], w[13 % N]);
+            csa(t2b, pl[0], pl[0], w[14 % N], w[15 % N]);
+            csa(t4b, pl[1], pl[1], t2a, t2b);
+            uint32_t t8b, t16;
+            csa(t8b, pl[2], pl[2], t4a, t4b);
+            csa(t16, pl[3], pl[3], t8a, t8b);
+            ripple<4>(t16, nplanes);
+        }
+    }
+};
+
+struct HmhAcc {
+    using CT = uint16_t;
+    static constexpr int RM = 2, QM = 2;
+    static constexpr int kTableBytes = 0;
+    uint32_t C, N;
+    __device__ __forceinline__ void init() { C = N = 0; }
+    template <int G>
+    __device__ __forceinline__ void add_group(const uint32_t* a, const uint32_t* b, const SharedTables&) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            C += (a[i] == b[i]) & (a[i] != 0u);   // hyperminhash similarity(): equal and non-empty
+            N += ((a[i] | b[i]) != 0u);
+        }
+    }
+};
 
 template <class ACC>
 __device__ __forceinline__ void build_tables(SharedTables& t, unsigned char* smem_tab, int p) {
-    t.fgra_tab = reinterpret_cast<double*>(smem_tab);
-    t.ml_ret = reinterpret_cast<uint64_t*>(smem_tab);
+    double* d = reinterpret_cast<double*>(smem_tab);
+    uint64_t* u = reinterpret_cast<uint64_t*>(smem_tab);
+    uint32_t* w = reinterpret_cast<uint32_t*>(smem_tab + 256 * 8);
+    t.fgra_tab = d;
+    t.hll_pow = d;
+    t.ml_ret = u;
+    t.ml_wlo = w;
     if (ACC::kTableBytes == 0) return;
     const int off = 4 * p + 4;
     for (int r = threadIdx.x; r < 256; r += blockDim.x) {
         if constexpr (std::is_same<ACC, FgraAcc>::value) {
-            t.fgra_tab[r] = (r >= off && r < 252) ? c_ull.reg[r - off] : 0.0;
+            d[r] = (r >= off && r < 252) ? c_ull.reg[r - off] : LASH_FGRA_SENTINEL;
+        } else if constexpr (std::is_same<ACC, MlAcc>::value) {
+            u[r] = ml_ret_of((uint32_t)r, p);
+            w[r] = (uint32_t)ml_w_of((uint32_t)r, p);
         } else {
-            t.ml_ret[r] = ml_ret_of((uint32_t)r, p);
+            d[r] = pow2neg((uint32_t)r);
         }
     }
 }
 
-// union cardinality from a finished accumulator
-__device__ __forceinline__ double finish_union(HllAcc& a, int p, uint32_t, bool* bias) { return hll_len(a.sum, a.zero, p, bias); }
-__device__ __forceinline__ double finish_union(FgraAcc& a, int p, uint32_t, bool* bias) {
+// ---- exact per-pair fallbacks (read the two sketches from global memory, index order) -----------
+// FGRA with small/large-range registers: counts + table sum, as get_distinct_count_estimate does
+__device__ __noinline__ double fgra_exact_pair(const uint8_t* a, const uint8_t* b, int p) {
+    const uint32_t m = 1u << p;
+    const int off = 4 * p + 4;
+    uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double sum = 0.0;
+    for (uint32_t i = 0; i < m; ++i) {
+        const uint32_t r = ull_merge1(a[i], b[i]);
+        const int r2 = (int)r - off;
+        if (r2 < 0) {
+            cnt[0] += (r2 < -8);
+            cnt[1] += (r2 == -8);
+            cnt[2] += (r2 == -4);
+            cnt[3] += (r2 == -2);
+        } else if (r < 252u) {
+            sum += c_ull.reg[r2];
+        } else {
+            cnt[4 + (r - 252u)] += 1;
+        }
+    }
+    return ull_fgra_finalize(sum, cnt, p);
+}
+// ML statistics with direct increments (used when W does not fit 32 bits: astronomically large sketches)
+__device__ __noinline__ double ml_exact_pair(const uint8_t* a, const uint8_t* b, int p) {
+    const uint32_t m = 1u << p;
+    int bb[66];
+    for (int i = 0; i < 66; ++i) bb[i] = 0;
+    uint64_t S = 0;
+    for (uint32_t i = 0; i < m; ++i) {
+        const uint32_t r = ull_merge1(a[i], b[i]);
+        S += ml_ret_of(r, p);
+        uint64_t w = ml_w_of(r, p);
+        while (w) {
+            const int j = __ffsll((long long)w) - 1;
+            bb[j] += 1;
+            w &= w - 1;
+        }
+    }
+    return ull_ml_finalize(S, bb, p, ull_merge1(a[0], b[0]));
+}
+
+// union cardinality from a finished accumulator; ga/gb = the two sketches in global memory
+__device__ __forceinline__ double finish_union(HllAcc& a, int p, const void*, const void*, bool* bias) {
+    return hll_len(a.sum, a.zero, p, bias);
+}
+__device__ __forceinline__ double finish_union(FgraAcc& a, int p, const void* ga, const void* gb, bool* bias) {
     *bias = false;
-    uint32_t cnt[8] = {a.c0, a.c4, a.c8, a.c10, a.w0, a.w1, a.w2, a.w3};
+    if (a.sum >= LASH_FGRA_SENTINEL_TEST)  // some merged register outside [4p+4, 252): NaN compares false
+        return fgra_exact_pair(reinterpret_cast<const uint8_t*>(ga), reinterpret_cast<const uint8_t*>(gb), p);
+    const uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     return ull_fgra_finalize(a.sum, cnt, p);
 }
-__device__ __forceinline__ double finish_union(MlAcc& a, int p, uint32_t reg0, bool* bias) {
+__device__ __forceinline__ double finish_union(MlAcc& a, int p, const void* ga, const void* gb, bool* bias) {
     *bias = false;
-    return ull_ml_finalize(a.S, a.b, p, reg0);
+    // W = (4|w) << k fits 32 bits iff k <= 29, i.e. merged register < 4p+4 + 4*30
+    if (a.mmax >= (uint32_t)(4 * p + 4 + 120))
+        return ml_exact_pair(reinterpret_cast<const uint8_t*>(ga), reinterpret_cast<const uint8_t*>(gb), p);
+    int bb[66];
+#pragma unroll 1
+    for (int j = 0; j < 66; ++j) bb[j] = 0;
+    uint32_t any = 0;
+#pragma unroll
+    for (int l = 0; l < kMlPlanes; ++l) any |= a.pl[l];
+    if (any) {
+        const int jlo = __ffs((int)any) - 1, jhi = 31 - __clz((int)any);
+        for (int j = jlo; j <= jhi; ++j) {
+            uint32_t c = 0;
+#pragma unroll
+            for (int l = 0; l < kMlPlanes; ++l) c |= ((a.pl[l] >> j) & 1u) << l;
+            bb[j] = (int)c;
+        }
+    }
+    const uint8_t* pa = reinterpret_cast<const uint8_t*>(ga);
+    const uint8_t* pb = reinterpret_cast<const uint8_t*>(gb);
+    return ull_ml_finalize(a.S, bb, p, ull_merge1(pa[0], pb[0]));
 }
 
 template <class ACC>
@@ -178,19 +305,29 @@ struct IsHmh { static constexpr bool value = false; };
 template <>
 struct IsHmh<HmhAcc> { static constexpr bool value = true; };
 
+template <class ACC, int G>
+__device__ __forceinline__ void acc_add(ACC& acc, const uint32_t* a, const uint32_t* b, const SharedTables& t, int nplanes) {
+    if constexpr (std::is_same<ACC, MlAcc>::value)
+        acc.template add_group<G>(a, b, t, nplanes);
+    else
+        acc.template add_group<G>(a, b, t);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4: distance tiles
 // ------------------------------------------------------------------------------------------------
-template <class ACC>
-__global__ void __launch_bounds__(kDistThreads) dist_kernel(DistParams dp, uint32_t cell_words, uint32_t chunk_words) {
+template <class ACC, int G>
+__global__ void __launch_bounds__(kDistThreads) dist_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk_bytes) {
+    using CT = typename ACC::CT;
     constexpr int RM = ACC::RM, QM = ACC::QM;
     constexpr int TR = 16 * RM, TQ = 16 * QM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SharedTables tabs;
     build_tables<ACC>(tabs, smem_raw, dp.p);
-    uint32_t* sref = reinterpret_cast<uint32_t*>(smem_raw + ACC::kTableBytes);
-    const uint32_t stride = chunk_words + 1;
-    uint32_t* sqry = sref + TR * stride;
+    unsigned char* sref = smem_raw + ACC::kTableBytes;
+    const uint32_t stride = chunk_bytes + 4;  // one pad word per row: 16 rows -> 16 banks
+    unsigned char* sqry = sref + TR * stride;
+    const int nplanes = dp.p + 1;
 
     const uint64_t row0 = dp.row_begin + (uint64_t)blockIdx.y * TR;
     const uint64_t col0 = (uint64_t)blockIdx.x * TQ;
@@ -205,35 +342,44 @@ __global__ void __launch_bounds__(kDistThreads) dist_kernel(DistParams dp, uint3
 #pragma unroll
         for (int b = 0; b < QM; ++b) acc[a][b].init();
 
-    const uint32_t* gref = reinterpret_cast<const uint32_t*>(dp.ref);
-    const uint32_t* gqry = reinterpret_cast<const uint32_t*>(dp.qry);
+    const unsigned char* gref = reinterpret_cast<const unsigned char*>(dp.ref);
+    const unsigned char* gqry = reinterpret_cast<const unsigned char*>(dp.qry);
+    const uint32_t chunk_words = chunk_bytes / 4;
 
-    for (uint32_t c0 = 0; c0 < cell_words; c0 += chunk_words) {
+    for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk_bytes) {
         __syncthreads();  // previous chunk fully consumed (also orders the table build)
         for (uint32_t e = threadIdx.x; e < (uint32_t)TR * chunk_words; e += kDistThreads) {
             const uint32_t r = e / chunk_words, w = e % chunk_words;
             const uint64_t gi = row0 + r;
-            sref[r * stride + w] = gi < dp.row_end ? __ldg(gref + gi * cell_words + c0 + w) : 0u;
+            const uint32_t v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint32_t*>(gref + gi * cell_bytes + c0) + w) : 0u;
+            *reinterpret_cast<uint32_t*>(sref + r * stride + 4 * w) = v;
         }
         for (uint32_t e = threadIdx.x; e < (uint32_t)TQ * chunk_words; e += kDistThreads) {
             const uint32_t r = e / chunk_words, w = e % chunk_words;
             const uint64_t gj = col0 + r;
-            sqry[r * stride + w] = gj < dp.n_qry ? __ldg(gqry + gj * cell_words + c0 + w) : 0u;
+            const uint32_t v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint32_t*>(gqry + gj * cell_bytes + c0) + w) : 0u;
+            *reinterpret_cast<uint32_t*>(sqry + r * stride + 4 * w) = v;
         }
         __syncthreads();
-        const uint32_t* pr = sref + ty * stride;
-        const uint32_t* pq = sqry + tx * stride;
-#pragma unroll 2
-        for (uint32_t w = 0; w < chunk_words; ++w) {
-            uint32_t ra[RM], qb[QM];
-#pragma unroll
-            for (int a = 0; a < RM; ++a) ra[a] = pr[a * 16 * stride + w];
-#pragma unroll
-            for (int b = 0; b < QM; ++b) qb[b] = pq[b * 16 * stride + w];
+        const CT* pr = reinterpret_cast<const CT*>(sref + ty * stride);
+        const CT* pq = reinterpret_cast<const CT*>(sqry + tx * stride);
+        const uint32_t row16 = 16u * stride / sizeof(CT);
+        const uint32_t n_el = chunk_bytes / sizeof(CT);
+#pragma unroll 1
+        for (uint32_t e = 0; e < n_el; e += G) {
+            uint32_t ra[RM][G], qb[QM][G];
 #pragma unroll
             for (int a = 0; a < RM; ++a)
 #pragma unroll
-                for (int b = 0; b < QM; ++b) acc[a][b].add(ra[a], qb[b], tabs, dp.p);
+                for (int i = 0; i < G; ++i) ra[a][i] = pr[a * row16 + e + i];
+#pragma unroll
+            for (int b = 0; b < QM; ++b)
+#pragma unroll
+                for (int i = 0; i < G; ++i) qb[b][i] = pq[b * row16 + e + i];
+#pragma unroll
+            for (int a = 0; a < RM; ++a)
+#pragma unroll
+                for (int b = 0; b < QM; ++b) acc_add<ACC, G>(acc[a][b], ra[a], qb[b], tabs, nplanes);
         }
     }
 
@@ -251,13 +397,7 @@ __global__ void __launch_bounds__(kDistThreads) dist_kernel(DistParams dp, uint3
                 s = fmax(sim, 0.0);
             } else {
                 bool bias;
-                // register 0 of the union is only needed by ML's S == 0 corner (all-empty vs saturated)
-                uint32_t reg0 = 0;
-                if constexpr (std::is_same<ACC, MlAcc>::value) {
-                    uint32_t ra0 = __ldg(gref + i * cell_words) & 0xffu, rb0 = __ldg(gqry + j * cell_words) & 0xffu;
-                    reg0 = ull_merge1(ra0, rb0);
-                }
-                const double U = finish_union(acc[a][b], dp.p, reg0, &bias);
+                const double U = finish_union(acc[a][b], dp.p, gref + i * cell_bytes, gqry + j * cell_bytes, &bias);
                 if (bias && dp.flags) atomicAdd(dp.flags, 1u);
                 const double ca = dp.card_ref[i], cb = dp.card_qry[j];
                 const double sim = (ca + cb - U) / U;
@@ -281,8 +421,8 @@ __global__ void __launch_bounds__(kDistThreads) dist_kernel(DistParams dp, uint3
 // One thread per sketch, registers walked in index order with the same accumulators as K4
 // (the union of a sketch with itself is the sketch).
 // ------------------------------------------------------------------------------------------------
-template <class ACC>
-__global__ void __launch_bounds__(128) card_kernel(const uint32_t* __restrict__ regs, uint64_t n, uint32_t cell_words, int p,
+template <class ACC, int G>
+__global__ void __launch_bounds__(128) card_kernel(const unsigned char* __restrict__ regs, uint64_t n, uint32_t cell_bytes, int p,
                                                    double* __restrict__ card, uint32_t* flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SharedTables tabs;
@@ -290,15 +430,23 @@ __global__ void __launch_bounds__(128) card_kernel(const uint32_t* __restrict__ 
     __syncthreads();
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t* g = regs + i * cell_words;
+    const unsigned char* g = regs + i * cell_bytes;
     ACC acc;
     acc.init();
-    for (uint32_t w = 0; w < cell_words; ++w) {
-        const uint32_t v = __ldg(g + w);
-        acc.add(v, v, tabs, p);
+    for (uint32_t e = 0; e < cell_bytes; e += G) {
+        uint32_t v[G];
+#pragma unroll
+        for (int k = 0; k < G / 4; ++k) {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(g + e) + k);
+            v[4 * k] = w & 0xffu;
+            v[4 * k + 1] = (w >> 8) & 0xffu;
+            v[4 * k + 2] = (w >> 16) & 0xffu;
+            v[4 * k + 3] = w >> 24;
+        }
+        acc_add<ACC, G>(acc, v, v, tabs, p + 1);
     }
     bool bias;
-    card[i] = finish_union(acc, p, __ldg(g) & 0xffu, &bias);
+    card[i] = finish_union(acc, p, g, g, &bias);
     if (bias && flags) atomicAdd(flags, 1u);
 }
 
@@ -348,15 +496,15 @@ cudaError_t ensure_tables() {
     return cudaMemcpyToSymbol(c_ull, &host, sizeof(UllConsts));
 }
 
-static uint32_t cell_words_of(int algo, int p) { return algo == HMH ? 8192u : (p >= 2 ? (1u << p) / 4u : 1u); }
+static uint32_t cell_bytes_of(int algo, int p) { return algo == HMH ? 32768u : (1u << p); }
 
-template <class ACC>
+template <class ACC, int G>
 static cudaError_t launch_dist_t(const DistParams& dp, cudaStream_t st) {
     constexpr int TR = 16 * ACC::RM, TQ = 16 * ACC::QM;
-    const uint32_t cw = cell_words_of(dp.algo, dp.p);
-    const uint32_t chunk = cw < (uint32_t)kChunkWords ? cw : (uint32_t)kChunkWords;
-    const size_t smem = ACC::kTableBytes + (size_t)(TR + TQ) * (chunk + 1) * 4;
-    auto kern = dist_kernel<ACC>;
+    const uint32_t cb = cell_bytes_of(dp.algo, dp.p);
+    const uint32_t chunk = cb < (uint32_t)kChunkBytes ? cb : (uint32_t)kChunkBytes;
+    const size_t smem = ACC::kTableBytes + (size_t)(TR + TQ) * (chunk + 4);
+    auto kern = dist_kernel<ACC, G>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint64_t rows = dp.row_end - dp.row_begin;
@@ -370,7 +518,7 @@ static cudaError_t launch_dist_t(const DistParams& dp, cudaStream_t st) {
         q.row_begin = dp.row_begin + y0 * TR;
         const uint64_t ny = (gy - y0) < 65535 ? (gy - y0) : 65535;
         dim3 grid((unsigned)gx, (unsigned)ny);
-        kern<<<grid, kDistThreads, smem, st>>>(q, cw, chunk);
+        kern<<<grid, kDistThreads, smem, st>>>(q, cb, chunk);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -380,18 +528,19 @@ static cudaError_t launch_dist_t(const DistParams& dp, cudaStream_t st) {
 cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launches) {
     if (dp.row_end <= dp.row_begin || dp.n_qry == 0) return cudaSuccess;
     if (n_launches) *n_launches += 1;
-    if (dp.algo == HLL) return launch_dist_t<HllAcc>(dp, st);
-    if (dp.algo == HMH) return launch_dist_t<HmhAcc>(dp, st);
-    if (dp.estimator == 0) return launch_dist_t<FgraAcc>(dp, st);
-    return launch_dist_t<MlAcc>(dp, st);
+    if (dp.algo == HLL) return launch_dist_t<HllAcc, 16>(dp, st);
+    if (dp.algo == HMH) return launch_dist_t<HmhAcc, 16>(dp, st);
+    const bool tiny = dp.p == 3;  // 8 registers per sketch
+    if (dp.estimator == 0) return tiny ? launch_dist_t<FgraAcc, 8>(dp, st) : launch_dist_t<FgraAcc, 16>(dp, st);
+    return tiny ? launch_dist_t<MlAcc, 8>(dp, st) : launch_dist_t<MlAcc, 16>(dp, st);
 }
 
-template <class ACC>
+template <class ACC, int G>
 static cudaError_t launch_card_t(int algo, int p, const void* regs, uint64_t n, double* card, uint32_t* flags,
                                  cudaStream_t st) {
-    const uint32_t cw = cell_words_of(algo, p);
+    const uint32_t cb = cell_bytes_of(algo, p);
     const unsigned grid = (unsigned)((n + 127) / 128);
-    card_kernel<ACC><<<grid, 128, ACC::kTableBytes, st>>>(reinterpret_cast<const uint32_t*>(regs), n, cw, p, card, flags);
+    card_kernel<ACC, G><<<grid, 128, ACC::kTableBytes, st>>>(reinterpret_cast<const unsigned char*>(regs), n, cb, p, card, flags);
     return cudaGetLastError();
 }
 
@@ -402,9 +551,13 @@ cudaError_t launch_cardinality(int algo, int p, int estimator, const void* regs,
         card_hmh_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(reinterpret_cast<const uint32_t*>(regs), n, card);
         return cudaGetLastError();
     }
-    if (algo == HLL) return launch_card_t<HllAcc>(algo, p, regs, n, card, flags, st);
-    if (estimator == 0) return launch_card_t<FgraAcc>(algo, p, regs, n, card, flags, st);
-    return launch_card_t<MlAcc>(algo, p, regs, n, card, flags, st);
+    if (algo == HLL) return launch_card_t<HllAcc, 16>(algo, p, regs, n, card, flags, st);
+    const bool tiny = p == 3;
+    if (estimator == 0)
+        return tiny ? launch_card_t<FgraAcc, 8>(algo, p, regs, n, card, flags, st)
+                    : launch_card_t<FgraAcc, 16>(algo, p, regs, n, card, flags, st);
+    return tiny ? launch_card_t<MlAcc, 8>(algo, p, regs, n, card, flags, st)
+                : launch_card_t<MlAcc, 16>(algo, p, regs, n, card, flags, st);
 }
 
 }  // namespace lash

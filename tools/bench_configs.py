@@ -1,0 +1,121 @@
+"""Kernel-level timings of the other BASELINE configs (not the bench.py headline): run on a GPU box.
+    python -m tools.bench_configs [--quick] > gpurun_out/configs.json
+Everything goes through the C ABI; torch builds the synthetic inputs in HBM and provides events."""
+import argparse
+import ctypes as C
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+import bench  # noqa: E402  (reuses the HBM genome generator)
+from lash_b200 import ALGO_HLL, ALGO_HMH, ALGO_ULL, EST_FGRA, EST_ML, ops  # noqa: E402
+from lash_b200.capi import Span, check, lib  # noqa: E402
+from lash_b200.pack import padded_bytes  # noqa: E402
+
+
+def sketch_case(ctx, name, algo, p, k, n_g, length, reps=5):
+    dev = torch.device("cuda", 0)
+    buf, stride = bench.make_packed_genomes(torch, dev, n_g, length, 42, 0)
+    spans = (Span * n_g)()
+    for i in range(n_g):
+        spans[i] = Span(i, i * stride, length, 0, 1, 0)
+    sk = ops.Sketcher(ctx, algo, p, k, 42, n_g)
+    stream = torch.cuda.Stream(dev)
+    sk.set_stream(stream.cuda_stream)
+    ts = []
+    for r in range(reps + 2):
+        sk.reset()
+        ms0, _ = sk.stats()
+        sk.push_raw(buf.data_ptr(), n_g * stride, spans, n_g, None, 0, dev=True)
+        ms1, _ = sk.stats()
+        if r >= 2:
+            ts.append(ms1 - ms0)
+    regs = sk.fetch()
+    sk.close()
+    ms = float(np.median(ts))
+    return {"case": name, "algo": algo, "p": p, "k": k, "genomes": n_g, "genome_len": length, "kernel_ms": ms,
+            "gbp_per_s": n_g * length / ms / 1e6}, regs
+
+
+def reads_case(ctx, name, p, k, n_reads, read_len, reps=3):
+    """config 4 shape: every 150 bp read is its own record of ONE sample -> boundary mask path."""
+    dev = torch.device("cuda", 0)
+    n_bases = n_reads * read_len
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    packed = torch.randint(0, 256, (padded_bytes(n_bases) + 64,), dtype=torch.uint8, device=dev, generator=g)
+    rec = (np.arange(n_reads + 1, dtype=np.uint64) * read_len)
+    spans = (Span * 1)(Span(0, 0, n_bases, 0, n_reads, 0))
+    sk = ops.Sketcher(ctx, ALGO_ULL, p, k, 42, 1)
+    stream = torch.cuda.Stream(dev)
+    sk.set_stream(stream.cuda_stream)
+    ts = []
+    for r in range(reps + 1):
+        sk.reset()
+        ms0, _ = sk.stats()
+        t0 = time.perf_counter()
+        sk.push_raw(packed.data_ptr(), padded_bytes(n_bases), spans, 1, rec.ctypes.data_as(C.c_void_p), len(rec), dev=True)
+        ms1, _ = sk.stats()
+        wall = time.perf_counter() - t0
+        if r >= 1:
+            ts.append((ms1 - ms0, wall * 1e3))
+    sk.close()
+    ms = float(np.median([a for a, _ in ts]))
+    return {"case": name, "algo": ALGO_ULL, "p": p, "k": k, "reads": n_reads, "read_len": read_len, "kernel_ms(mask+sketch)": ms,
+            "gbp_per_s": n_bases / ms / 1e6, "push_wall_ms_incl_8B_per_read_table_h2d": float(np.median([b for _, b in ts]))}
+
+
+def dist_case(ctx, name, algo, p, k, est, regs, reps=3):
+    n = regs.shape[0]
+    ts = []
+    for r in range(reps + 1):
+        d, w = ops.dist(ctx, algo, p, k, est, 1, False, regs, regs, triangular=True)
+        ms, _ = ops.dist_stats(ctx)
+        if r >= 1:
+            ts.append(ms)
+    ms = float(np.median(ts))
+    pairs = n * (n + 1) // 2
+    cells = regs.shape[1]
+    return {"case": name, "algo": algo, "p": p, "est": est, "n": n, "pairs": pairs, "kernel_ms": ms, "pairs_per_s": pairs / ms * 1e3,
+            "register_merges_per_s": pairs * cells / ms * 1e3, "warn": w}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    q = a.quick
+    out = []
+    with ops.Context(0) as ctx:
+        r, regs_ull10 = sketch_case(ctx, "C2 ULL p=10 k=16", ALGO_ULL, 10, 16, 200 if q else 1000, 5_000_000)
+        out.append(r)
+        r, regs_hll14 = sketch_case(ctx, "C3 HLL p=14 k=21", ALGO_HLL, 14, 21, 200 if q else 1000, 5_000_000)
+        out.append(r)
+        r, regs_hmh = sketch_case(ctx, "C1 HMH k=16", ALGO_HMH, 14, 16, 100 if q else 400, 2_000_000)
+        out.append(r)
+        r, _ = sketch_case(ctx, "ULL p=14 k=21 (genomes)", ALGO_ULL, 14, 21, 200 if q else 1000, 5_000_000)
+        out.append(r)
+        r, _ = sketch_case(ctx, "ULL p=10 k=31", ALGO_ULL, 10, 31, 200 if q else 1000, 5_000_000)
+        out.append(r)
+        r, _ = sketch_case(ctx, "ULL p=10 k=12", ALGO_ULL, 10, 12, 200 if q else 1000, 5_000_000)
+        out.append(r)
+        r, _ = sketch_case(ctx, "ULL p=18 k=21 (global accumulators)", ALGO_ULL, 18, 21, 50 if q else 200, 5_000_000)
+        out.append(r)
+        r, regs_small = sketch_case(ctx, "C5 inputs: ULL p=10 k=16 100 kbp", ALGO_ULL, 10, 16, 2000 if q else 8000, 100_000)
+        out.append(r)
+        out.append(reads_case(ctx, "C4 ULL p=14 k=21, 150 bp reads, one sample", 14, 21, 2_000_000 if q else 20_000_000, 150))
+        out.append(dist_case(ctx, "C2 dist FGRA 1000x1000", ALGO_ULL, 10, 16, EST_FGRA, regs_ull10))
+        out.append(dist_case(ctx, "C5 dist ML p=10 (n x n triangle)", ALGO_ULL, 10, 16, EST_ML, regs_small))
+        out.append(dist_case(ctx, "dist FGRA p=10 (n x n triangle)", ALGO_ULL, 10, 16, EST_FGRA, regs_small))
+        out.append(dist_case(ctx, "C3 dist HLL p=14", ALGO_HLL, 14, 21, 0, regs_hll14))
+        out.append(dist_case(ctx, "C1 dist HMH", ALGO_HMH, 14, 16, 0, regs_hmh))
+    for r in out:
+        print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()
