@@ -22,7 +22,7 @@ class LashError(RuntimeError):
 class Span(C.Structure):
     """struct lash_span"""
     _fields_ = [("genome", C.c_uint64), ("byte_off", C.c_uint64), ("n_bases", C.c_uint64), ("rec_first", C.c_uint64),
-                ("n_rec", C.c_uint32), ("reserved", C.c_uint32)]
+                ("n_rec", C.c_uint32), ("rec_len", C.c_uint32)]
 
 
 DIST_BLOCK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p)

@@ -249,12 +249,22 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
     uint64_t total_starts = 0;
     uint64_t mask_words = 0;
     uint32_t n_multi = 0;
+    uint64_t n_multi_recs = 0;
+    bool need_rec_table = false;
     for (uint32_t i = 0; i < n_spans; ++i) {
         const lash_span& sp = spans[i];
         if (sp.genome >= s->n_genomes) return fail(LASH_E_INVALID, "lash_sketch_push: span.genome out of range");
         if (sp.byte_off % 16) return fail(LASH_E_INVALID, "lash_sketch_push: span.byte_off must be a multiple of 16");
         if (sp.byte_off + (sp.n_bases + 3) / 4 > n_bytes) return fail(LASH_E_INVALID, "lash_sketch_push: span exceeds buffer");
-        if (sp.n_rec > 1) {
+        if (sp.n_rec > 1 && sp.rec_len != 0) {
+            // uniform record length (fixed-length reads): boundaries are arithmetic, no table
+            if ((uint64_t)sp.n_rec != (sp.n_bases + sp.rec_len - 1) / sp.rec_len)
+                return fail(LASH_E_INVALID, "lash_sketch_push: n_rec does not match n_bases / record length");
+            ++n_multi;
+            n_multi_recs += sp.n_rec;
+            mask_words += ((sp.n_bases + 63) / 64) * 2 + 2;
+        } else if (sp.n_rec > 1) {
+            need_rec_table = true;
             if (!rec_start || sp.rec_first + sp.n_rec + 1 > n_rec_entries)
                 return fail(LASH_E_INVALID, "lash_sketch_push: rec_start table too short");
             const uint64_t* rs = rec_start + sp.rec_first;
@@ -263,6 +273,7 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
             for (uint32_t r = 0; r < sp.n_rec; ++r)
                 if (rs[r] > rs[r + 1]) return fail(LASH_E_INVALID, "lash_sketch_push: rec_start not ascending");
             ++n_multi;
+            n_multi_recs += sp.n_rec;
             mask_words += ((sp.n_bases + 63) / 64) * 2 + 2;
         }
         if (sp.n_bases >= (uint64_t)k) total_starts += sp.n_bases - k + 1;
@@ -287,8 +298,9 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
             SpanRecs sr;
             sr.mask_word_off = mask_off;
             sr.rec_first = sp.rec_first;
+            sr.n_bases = sp.n_bases;
             sr.n_rec = sp.n_rec;
-            sr.pad = 0;
+            sr.uniform_len = sp.rec_len;
             mspans.push_back(sr);
             this_mask = mask_off;
             mask_off += ((sp.n_bases + 63) / 64) * 2 + 2;
@@ -324,7 +336,7 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
     }
     const size_t tiles_bytes = tiles.size() * sizeof(SketchTile);
     const size_t mspans_bytes = mspans.size() * sizeof(SpanRecs);
-    const size_t recs_bytes = n_multi ? n_rec_entries * sizeof(uint64_t) : 0;
+    const size_t recs_bytes = need_rec_table ? n_rec_entries * sizeof(uint64_t) : 0;
     const size_t off_mspans = (tiles_bytes + 15) / 16 * 16;
     const size_t off_recs = off_mspans + (mspans_bytes + 15) / 16 * 16;
     const size_t meta_bytes = off_recs + recs_bytes;
@@ -354,8 +366,8 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
     }
     CU(cudaEventRecord(sl.k_start, stream));
     if (n_multi) {
-        CU(launch_build_invalid_mask((const SpanRecs*)((char*)sl.meta.p + off_mspans), n_multi,
-                                     (const uint64_t*)((char*)sl.meta.p + off_recs), mask_dev, k, stream));
+        CU(launch_build_invalid_mask((const SpanRecs*)((char*)sl.meta.p + off_mspans), n_multi, n_multi_recs,
+                                     (const uint64_t*)((char*)sl.meta.p + off_recs), mask_dev, k, s->ctx->n_sm, stream));
         s->launches += 1;
     }
     if (!tiles.empty()) {

@@ -21,9 +21,10 @@ struct SketchTile {
 // A multi-record span, for the boundary-mask builder.
 struct SpanRecs {
     uint64_t mask_word_off;  // into the mask buffer
-    uint64_t rec_first;      // into rec_start[]
+    uint64_t rec_first;      // into rec_start[] (unused when uniform_len != 0)
+    uint64_t n_bases;        // bases in the span
     uint32_t n_rec;
-    uint32_t pad;
+    uint32_t uniform_len;    // != 0: every record has this many bases (the last may be shorter)
 };
 
 constexpr int kStartsPerThread = 64;  // one 16-byte load of packed bases per thread per iteration
@@ -44,8 +45,8 @@ constexpr uint32_t kMaxSmemAccBytes = 128 * 1024;
 // fills n_cells / smem_bytes / threads / global_acc from algo and p
 void plan_sketch(SketchParams& sp);
 
-cudaError_t launch_build_invalid_mask(const SpanRecs* spans_dev, uint32_t n_spans, const uint64_t* rec_start_dev,
-                                      uint32_t* mask_dev, int k, cudaStream_t st);
+cudaError_t launch_build_invalid_mask(const SpanRecs* spans_dev, uint32_t n_spans, uint64_t n_rec_total,
+                                      const uint64_t* rec_start_dev, uint32_t* mask_dev, int k, int n_sm, cudaStream_t st);
 cudaError_t launch_sketch(const SketchParams& sp, const uint32_t* packed_dev, const uint32_t* mask_dev,
                           const SketchTile* tiles_dev, uint32_t n_tiles, uint32_t* acc_dev, cudaStream_t st);
 

@@ -17,6 +17,7 @@
 //   * record boundaries (k-mers never span records, utils.rs:457-464) come from an
 //     "invalid start" bitmask built on device from rec_start[] by build_invalid_mask().
 #include <algorithm>
+#include <type_traits>
 
 #include "kernels.h"
 #include "registers.cuh"
@@ -315,28 +316,36 @@ __global__ void __launch_bounds__(1024)
                         }
                     }
                 };
-                if (GLOBAL || v16 != 0xffffu) {
-                    if (v16 != 0u) exact_block(v16);
-                } else {
-                    // every start valid (the common case): straight-line; the shared-memory atomics of the
-                    // whole group are deferred behind ONE branch, so the hot path has no divergence
+                // straight-line group: the shared-memory atomics of 16 k-mers are deferred behind ONE
+                // branch, so the hot path has no divergence.  CHECKED masks out starts that are invalid
+                // (record boundary inside the word, tile tail) -- every ~150 bases for short reads.
+                auto fast_block = [&](auto checked, const uint32_t mask16) {
+                    constexpr bool CHECKED = decltype(checked)::value;
                     uint32_t addr[kGroup], need[kGroup];
                     uint32_t any = 0u, rare = 0xffffffffu;
-    #pragma unroll
+#pragma unroll
                     for (int i = 0; i < kGroup; ++i) {
                         uint32_t klo, khi, v, rw;
                         kmer(2 * i, klo, khi);
                         A::template prep<!WIDE>(klo, khi, hc, p, sbase, addr[i], v, rw);
                         need[i] = A::need(lds_u32(addr[i]), v);
+                        if (CHECKED) need[i] = (mask16 & (1u << i)) ? need[i] : 0u;
                         any |= need[i];
                         rare = min(rare, rw);
                     }
                     if (any) {
-    #pragma unroll
+#pragma unroll
                         for (int i = 0; i < kGroup; ++i)
                             if (need[i]) A::apply(addr[i], need[i]);
                     }
-                    if (rare == 0u) exact_block(0xffffu);  // some hash had 32 leading zeros where it matters
+                    if (rare == 0u) exact_block(mask16);  // some hash had 32 leading zeros where it matters
+                };
+                if (GLOBAL) {
+                    if (v16 != 0u) exact_block(v16);
+                } else if (v16 == 0xffffu) {
+                    fast_block(std::false_type{}, 0xffffu);
+                } else if (v16 != 0u) {
+                    fast_block(std::true_type{}, v16);
                 }
                 f0 = f1; f1 = f2; f2 = f3; f3 = f4; f4 = f5;
             }
@@ -347,26 +356,49 @@ __global__ void __launch_bounds__(1024)
     if (!GLOBAL && cur_genome != 0xffffffffu) flush(cur_genome);
 }
 
-// One CTA per multi-record span: mark every k-mer start that would cross the END of a record
-// (or belongs to a record shorter than k).  Bit b of the span's mask <=> start position b.
-__global__ void build_invalid_mask_kernel(const SpanRecs* __restrict__ spans, const uint64_t* __restrict__ rec_start,
-                                          uint32_t* __restrict__ mask, int k) {
-    const SpanRecs s = spans[blockIdx.x];
-    const uint64_t* rs = rec_start + s.rec_first;
-    uint32_t* m = mask + s.mask_word_off;
-    for (uint32_t r = threadIdx.x; r < s.n_rec; r += blockDim.x) {
-        const uint64_t b = rs[r], e = rs[r + 1];
-        // starts in [max(b, e-k+1), e) are invalid
-        uint64_t lo = (e >= (uint64_t)(k - 1)) ? e - (uint64_t)(k - 1) : 0;
-        if (lo < b) lo = b;
-        for (uint64_t x = lo; x < e;) {
-            const uint32_t bit = (uint32_t)(x & 31);
-            const uint64_t n = min((uint64_t)(32 - bit), e - x);
-            const uint32_t bits = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << bit;
-            atomicOr(m + (x >> 5), bits);
-            x += n;
+// Mark every k-mer start that would cross the END of a record (or belongs to a record shorter than
+// k).  Bit b of a span's mask <=> start position b.  All threads of the grid stride over the records
+// of every multi-record span (a metagenome sample is ONE span with ~10^8 records).
+__global__ void build_invalid_mask_kernel(const SpanRecs* __restrict__ spans, uint32_t n_spans,
+                                          const uint64_t* __restrict__ rec_start, uint32_t* __restrict__ mask, int k) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+    for (uint32_t si = 0; si < n_spans; ++si) {
+        const SpanRecs s = spans[si];
+        const uint64_t* rs = rec_start + s.rec_first;
+        uint32_t* m = mask + s.mask_word_off;
+        for (uint64_t r = tid; r < s.n_rec; r += nthreads) {
+            uint64_t b, e;
+            if (s.uniform_len) {
+                b = r * (uint64_t)s.uniform_len;
+                e = min(b + (uint64_t)s.uniform_len, s.n_bases);
+            } else {
+                b = rs[r];
+                e = rs[r + 1];
+            }
+            // starts in [max(b, e-k+1), e) are invalid
+            uint64_t lo = (e >= (uint64_t)(k - 1)) ? e - (uint64_t)(k - 1) : 0;
+            if (lo < b) lo = b;
+            for (uint64_t x = lo; x < e;) {
+                const uint32_t bit = (uint32_t)(x & 31);
+                const uint64_t n = min((uint64_t)(32 - bit), e - x);
+                const uint32_t bits = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << bit;
+                atomicOr(m + (x >> 5), bits);
+                x += n;
+            }
         }
     }
+}
+
+cudaError_t launch_build_invalid_mask(const SpanRecs* spans_dev, uint32_t n_spans, uint64_t n_rec_total,
+                                      const uint64_t* rec_start_dev, uint32_t* mask_dev, int k, int n_sm, cudaStream_t st) {
+    if (n_spans == 0) return cudaSuccess;
+    uint64_t blocks = (n_rec_total + 255) / 256;
+    const uint64_t cap = (uint64_t)n_sm * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    build_invalid_mask_kernel<<<(unsigned)blocks, 256, 0, st>>>(spans_dev, n_spans, rec_start_dev, mask_dev, k);
+    return cudaGetLastError();
 }
 
 void plan_sketch(SketchParams& sp) {
@@ -380,13 +412,6 @@ void plan_sketch(SketchParams& sp) {
     if (sp.smem_bytes <= 24u * 1024u) sp.threads = 256;       // >= 8 CTAs by smem, register-limited
     else if (sp.smem_bytes <= 72u * 1024u) sp.threads = 512;  // 3 CTAs x 16 warps
     else sp.threads = 1024;                                    // 1 CTA x 32 warps
-}
-
-cudaError_t launch_build_invalid_mask(const SpanRecs* spans_dev, uint32_t n_spans, const uint64_t* rec_start_dev,
-                                      uint32_t* mask_dev, int k, cudaStream_t st) {
-    if (n_spans == 0) return cudaSuccess;
-    build_invalid_mask_kernel<<<n_spans, 256, 0, st>>>(spans_dev, rec_start_dev, mask_dev, k);
-    return cudaGetLastError();
 }
 
 template <int ALGO, int KM, bool GLOBAL>

@@ -84,6 +84,32 @@ def test_short_reads_many_records(oracle, gpu_ctx):
     _check(oracle, gpu_ctx, ALGO_ULL, 14, 21, [reads, reads[:1000]])
 
 
+def test_fixed_length_reads_without_boundary_table(oracle, gpu_ctx):
+    """lash_span.rec_len: fixed-length reads need no rec_start[] table; the last read may be shorter."""
+    import ctypes as C
+    from lash_b200.capi import Span
+    from lash_b200.pack import encode_record, pack_codes, padded_bytes
+    rng = np.random.default_rng(5)
+    for read_len, n_reads, tail, k in ((150, 3000, 0, 21), (100, 1001, 37, 31), (36, 500, 5, 16), (20, 64, 0, 21)):
+        reads = [synth.to_ascii(rng.integers(0, 4, size=read_len, dtype=np.uint8)) for _ in range(n_reads)]
+        if tail:
+            reads.append(synth.to_ascii(rng.integers(0, 4, size=tail, dtype=np.uint8)))
+        codes = np.concatenate([encode_record(r) for r in reads])
+        buf = np.zeros(padded_bytes(len(codes)), dtype=np.uint8)
+        pk = pack_codes(codes)
+        buf[: len(pk)] = pk
+        spans = (Span * 1)(Span(0, 0, len(codes), 0, len(reads), read_len))
+        with Sketcher(gpu_ctx, ALGO_ULL, 12, k, SEED, 1) as sk:
+            sk.push_raw(buf.ctypes.data, buf.nbytes, spans, 1, None, 0)
+            got = sk.fetch()
+        exp = oracle.sketch_genomes(ALGO_ULL, 12, k, SEED, [reads])
+        assert np.array_equal(got, exp), (read_len, n_reads, tail, k)
+    with Sketcher(gpu_ctx, ALGO_ULL, 12, 21, SEED, 1) as sk:   # n_rec must match ceil(n_bases / rec_len)
+        spans = (Span * 1)(Span(0, 0, 1000, 0, 3, 150))
+        with pytest.raises(LashError):
+            sk.push_raw(buf.ctypes.data, buf.nbytes, spans, 1, None, 0)
+
+
 def test_split_pushes_and_repeats_are_idempotent(oracle, gpu_ctx):
     """Register updates are commutative, associative and idempotent: the same genome pushed as one
     span, as many spans over several pushes, or twice, must give identical registers."""

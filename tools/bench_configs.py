@@ -41,7 +41,7 @@ def sketch_case(ctx, name, algo, p, k, n_g, length, reps=5):
             "gbp_per_s": n_g * length / ms / 1e6}, regs
 
 
-def reads_case(ctx, name, p, k, n_reads, read_len, reps=3):
+def reads_case(ctx, name, p, k, n_reads, read_len, reps=3, uniform=False):
     """config 4 shape: every 150 bp read is its own record of ONE sample -> boundary mask path."""
     dev = torch.device("cuda", 0)
     n_bases = n_reads * read_len
@@ -49,7 +49,7 @@ def reads_case(ctx, name, p, k, n_reads, read_len, reps=3):
     g.manual_seed(7)
     packed = torch.randint(0, 256, (padded_bytes(n_bases) + 64,), dtype=torch.uint8, device=dev, generator=g)
     rec = (np.arange(n_reads + 1, dtype=np.uint64) * read_len)
-    spans = (Span * 1)(Span(0, 0, n_bases, 0, n_reads, 0))
+    spans = (Span * 1)(Span(0, 0, n_bases, 0, n_reads, read_len if uniform else 0))
     sk = ops.Sketcher(ctx, ALGO_ULL, p, k, 42, 1)
     stream = torch.cuda.Stream(dev)
     sk.set_stream(stream.cuda_stream)
@@ -58,7 +58,10 @@ def reads_case(ctx, name, p, k, n_reads, read_len, reps=3):
         sk.reset()
         ms0, _ = sk.stats()
         t0 = time.perf_counter()
-        sk.push_raw(packed.data_ptr(), padded_bytes(n_bases), spans, 1, rec.ctypes.data_as(C.c_void_p), len(rec), dev=True)
+        if uniform:
+            sk.push_raw(packed.data_ptr(), padded_bytes(n_bases), spans, 1, None, 0, dev=True)
+        else:
+            sk.push_raw(packed.data_ptr(), padded_bytes(n_bases), spans, 1, rec.ctypes.data_as(C.c_void_p), len(rec), dev=True)
         ms1, _ = sk.stats()
         wall = time.perf_counter() - t0
         if r >= 1:
@@ -107,7 +110,9 @@ def main():
         out.append(r)
         r, regs_small = sketch_case(ctx, "C5 inputs: ULL p=10 k=16 100 kbp", ALGO_ULL, 10, 16, 2000 if q else 8000, 100_000)
         out.append(r)
-        out.append(reads_case(ctx, "C4 ULL p=14 k=21, 150 bp reads, one sample", 14, 21, 2_000_000 if q else 20_000_000, 150))
+        out.append(reads_case(ctx, "C4 ULL p=14 k=21, 150 bp reads, one sample (rec_start table)", 14, 21, 2_000_000 if q else 20_000_000, 150))
+        out.append(reads_case(ctx, "C4 ULL p=14 k=21, 150 bp reads, one sample (rec_len=150, no table)", 14, 21,
+                              2_000_000 if q else 20_000_000, 150, uniform=True))
         out.append(dist_case(ctx, "C2 dist FGRA 1000x1000", ALGO_ULL, 10, 16, EST_FGRA, regs_ull10))
         out.append(dist_case(ctx, "C5 dist ML p=10 (n x n triangle)", ALGO_ULL, 10, 16, EST_ML, regs_small))
         out.append(dist_case(ctx, "dist FGRA p=10 (n x n triangle)", ALGO_ULL, 10, 16, EST_FGRA, regs_small))
