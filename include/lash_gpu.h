@@ -44,6 +44,10 @@ extern "C" {
 /* Mash distance model (main.rs:415-423): 0 binomial, 1 poisson */
 #define LASH_MODEL_BINOMIAL 0
 #define LASH_MODEL_POISSON 1
+/* not a model: return `frac = 2s/(1+s)` itself (cast to T), i.e. exactly the value the reference's
+ * *_distance functions hand to emit() (utils.rs:176,277,364) -- lets a host keep print_dist /
+ * compute_distance (main.rs:415-471) unchanged */
+#define LASH_MODEL_FRAC 2
 
 /* error codes */
 #define LASH_OK 0

@@ -6,8 +6,8 @@ ctypes bindings (:mod:`lash_b200.capi`), the host-side 2-bit packer (:mod:`lash_
 mirror of the reference's sketch/dist operator interface (:mod:`lash_b200.ops`).
 There is no CPU fallback: importing works without a GPU, computing does not.
 """
-from .capi import (ALGO_HLL, ALGO_HMH, ALGO_ULL, EST_FGRA, EST_ML, MODEL_BINOMIAL, MODEL_POISSON, LashError, lib,
+from .capi import (ALGO_HLL, ALGO_HMH, ALGO_ULL, EST_FGRA, EST_ML, MODEL_BINOMIAL, MODEL_FRAC, MODEL_POISSON, LashError, lib,
                    lib_path)
 
-__all__ = ["ALGO_HLL", "ALGO_HMH", "ALGO_ULL", "EST_FGRA", "EST_ML", "MODEL_BINOMIAL", "MODEL_POISSON", "LashError",
+__all__ = ["ALGO_HLL", "ALGO_HMH", "ALGO_ULL", "EST_FGRA", "EST_ML", "MODEL_BINOMIAL", "MODEL_FRAC", "MODEL_POISSON", "LashError",
            "lib", "lib_path"]

@@ -9,7 +9,7 @@ _SO = os.path.join(_HERE, "_lib", "liblash_gpu.so")
 
 ALGO_HMH, ALGO_HLL, ALGO_ULL = 0, 1, 2
 EST_FGRA, EST_ML = 0, 1
-MODEL_BINOMIAL, MODEL_POISSON = 0, 1
+MODEL_BINOMIAL, MODEL_POISSON, MODEL_FRAC = 0, 1, 2
 W_HLL_BIAS_REGIME = 1
 
 

@@ -476,7 +476,7 @@ extern "C" int lash_sketch_close(lash_sketcher* s) {
 static int check_dist_args(int algo, int p, int k, int estimator, int model, uint64_t n_ref, uint64_t n_qry, int triangular) {
     if (!valid_algo_p(algo, p)) return fail(LASH_E_INVALID, "lash_dist: bad algorithm / precision");
     if (k < 1 || k > 32) return fail(LASH_E_INVALID, "k-mer length must be 1-32");
-    if (model != 0 && model != 1) return fail(LASH_E_INVALID, "model needs to be 0 or 1");  // main.rs:421
+    if (model != 0 && model != 1 && model != LASH_MODEL_FRAC) return fail(LASH_E_INVALID, "model needs to be 0 or 1");  // main.rs:421
     if (algo == LASH_ALGO_ULL && estimator != 0 && estimator != 1)
         return fail(LASH_E_INVALID, "estimator needs to be either fgra or ml");  // utils.rs:217
     if (triangular && n_ref != n_qry) return fail(LASH_E_INVALID, "lash_dist: triangular needs the same set on both sides");

@@ -34,11 +34,13 @@ __constant__ UllConsts c_ull;  // this header belongs to exactly one translation
 // ---------------------------------------------------------------- Mash distance, main.rs:415-423
 __device__ __forceinline__ double mash_distance_f64(double frac, int k, int model) {
     const double kk = (double)k;
+    if (model == 2) return frac;  // LASH_MODEL_FRAC: what the reference's emit() carries (utils.rs:176,277,364)
     if (model == 1) return fmin(-log(frac) / kk, 1.0);
     return 1.0 - pow(frac, 1.0 / kk);
 }
 __device__ __forceinline__ float mash_distance_f32(float frac, int k, int model) {
     const float kk = (float)k;
+    if (model == 2) return frac;
     if (model == 1) return fminf(-logf(frac) / kk, 1.0f);
     return 1.0f - powf(frac, 1.0f / kk);
 }

@@ -1,0 +1,114 @@
+// See pack.hpp.  Two implementations of the same byte -> (keep?, 2-bit code) map:
+//   scalar: 256-entry table (any x86-64 / any CPU)
+//   AVX2 + BMI2: 32 bytes per step -- pshufb classifies, shifts/xor code, pext gathers the 2-bit
+//   codes, pdep/pext squeezes out the deleted bytes (newlines, N, lowercase, IUPAC ...), so dirty
+//   input costs the same as clean input and there is no per-byte branch.
+#include "pack.hpp"
+
+#include <cstring>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace lashhost {
+
+namespace {
+
+struct Lut {
+    uint8_t code[256];  // 0..3, or 0xff when filter_out_n deletes the byte (utils.rs:36: only "ACTG" survive)
+    Lut() {
+        memset(code, 0xff, sizeof(code));
+        code[(unsigned)'A'] = 0;
+        code[(unsigned)'C'] = 1;
+        code[(unsigned)'G'] = 2;
+        code[(unsigned)'T'] = 3;
+    }
+};
+const Lut g_lut;
+
+uint64_t append_scalar(BaseStream& bs, const uint8_t* s, size_t n) {
+    uint64_t kept = 0;
+    size_t i = 0;
+    while (i < n) {
+        uint64_t v = 0;
+        unsigned cnt = 0;
+        const size_t e = (n - i) < 32 ? n : i + 32;
+        for (; i < e; ++i) {
+            const uint8_t c = g_lut.code[s[i]];
+            if (c != 0xff) {
+                v |= (uint64_t)c << (2 * cnt);
+                ++cnt;
+            }
+        }
+        if (cnt) bs.append64(v, cnt);
+        kept += cnt;
+    }
+    return kept;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2,bmi2,popcnt"))) uint64_t append_avx2(BaseStream& bs, const uint8_t* s, size_t n) {
+    // pshufb table indexed by the low nibble: the only byte with that nibble that survives the filter
+    // ('A' 0x41, 'C' 0x43, 'T' 0x54, 'G' 0x47); entry 0 is 0xff so that byte 0x00 cannot match itself,
+    // and bytes >= 0x80 make pshufb return 0, which never equals them.
+    const __m256i lut = _mm256_setr_epi8((char)0xff, 'A', 0, 'C', 'T', 0, 0, 'G', 0, 0, 0, 0, 0, 0, 0, 0,
+                                         (char)0xff, 'A', 0, 'C', 'T', 0, 0, 'G', 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i three = _mm256_set1_epi8(3);
+    uint64_t kept = 0;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i));
+        const uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, c), c));
+        // code = ((c >> 1) ^ (c >> 2)) & 3 : A 0, C 1, G 2, T 3 (bits leaking in from the neighbour byte are masked)
+        const __m256i code = _mm256_and_si256(_mm256_xor_si256(_mm256_srli_epi16(c, 1), _mm256_srli_epi16(c, 2)), three);
+        const uint64_t k = 0x0303030303030303ull;
+        const uint64_t all = _pext_u64((uint64_t)_mm256_extract_epi64(code, 0), k) |
+                             (_pext_u64((uint64_t)_mm256_extract_epi64(code, 1), k) << 16) |
+                             (_pext_u64((uint64_t)_mm256_extract_epi64(code, 2), k) << 32) |
+                             (_pext_u64((uint64_t)_mm256_extract_epi64(code, 3), k) << 48);
+        const uint64_t keep2 = _pdep_u64((uint64_t)m, 0x5555555555555555ull) * 3ull;  // both bits of every kept base
+        const unsigned cnt = (unsigned)_mm_popcnt_u32(m);
+        if (cnt) bs.append64(_pext_u64(all, keep2), cnt);
+        kept += cnt;
+    }
+    if (i < n) kept += append_scalar(bs, s + i, n - i);
+    return kept;
+}
+#endif
+
+}  // namespace
+
+bool pack_has_simd() {
+#if defined(__x86_64__)
+    static const bool ok = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("popcnt");
+    return ok;
+#else
+    return false;
+#endif
+}
+
+uint64_t BaseStream::append_filtered(const uint8_t* s, size_t n, bool use_simd) {
+#if defined(__x86_64__)
+    if (use_simd && pack_has_simd()) return append_avx2(*this, s, n);
+#endif
+    (void)use_simd;
+    return append_scalar(*this, s, n);
+}
+
+uint64_t BaseStream::finalize() {
+    const uint64_t padded = padded_bytes(n_);
+    const uint64_t words_used = (n_ + 31) / 32;
+    const uint64_t words_total = padded / 8;
+    // reverse the four 2-bit groups of every byte: LSB-first stream -> "first base in the high bits"
+    for (uint64_t i = 0; i < words_used; ++i) {
+        uint64_t x = w_[i];
+        x = ((x >> 4) & 0x0f0f0f0f0f0f0f0full) | ((x & 0x0f0f0f0f0f0f0f0full) << 4);
+        x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+        w_[i] = x;
+    }
+    for (uint64_t i = words_used; i < words_total; ++i) w_[i] = 0;
+    return padded;
+}
+
+}  // namespace lashhost

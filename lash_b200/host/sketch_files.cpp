@@ -1,0 +1,335 @@
+// sketch_files<S> (reference src/utils.rs:439-581) on top of the C ABI.
+//
+// Reference shape: files.par_iter().map(|file| { reader; sketch = S::new(p); for record { filter_out_n;
+// skip if shorter than k; k-mers -> add_kmer } sketch }).collect(), then S::save of every sketch into
+// one zstd stream + the names JSON.  "Each file is processed to completion in its own task."
+//
+// Here: the same "parallel by sample" -- a pool of host workers takes files one at a time (dynamic,
+// like rayon's work stealing) -- but a worker does no hashing: it parses, filters + 2-bit packs
+// (pack.cpp) into a pinned chunk and hands full chunks to the GPU (lash_sketch_push) while it fills
+// its second chunk.  Several small files share a chunk (one span each); a large record is split
+// across chunks with a (k-1)-base overlap so that every k-mer start is produced exactly once.
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <thread>
+
+#include "fastx.hpp"
+#include "lash_host.hpp"
+#include "pack.hpp"
+#include "sketch_io.hpp"
+
+namespace lash {
+
+using lashhost::BaseStream;
+using lashhost::FastxReader;
+
+namespace {
+
+constexpr uint64_t kDefaultChunk = 16ull << 20;
+constexpr size_t kFeed = 1u << 16;  // sequence bytes handed to the packer per call (room is checked per call)
+
+// serialises access to the (not thread-safe) sketcher handle
+struct Gpu {
+    lash_sketcher* sk = nullptr;
+    std::mutex mu;
+    std::atomic<uint64_t> pushes{0};
+    std::string err;  // first error
+    std::atomic<bool> failed{false};
+    void fail(const std::string& m) {
+        std::lock_guard<std::mutex> g(mu);
+        if (!failed.exchange(true)) err = m;
+    }
+};
+
+// One pinned chunk being filled: spans of (possibly several) genomes, their record tables
+class Chunk {
+  public:
+    bool alloc(uint64_t bytes) {
+        cap_ = bytes;
+        void* p = nullptr;
+        if (lash_host_alloc(bytes, &p) != LASH_OK) return false;
+        buf_ = static_cast<uint8_t*>(p);
+        return true;
+    }
+    void release() {
+        if (buf_) lash_host_free(buf_);
+        buf_ = nullptr;
+    }
+    bool empty() const { return spans_.empty() && !span_open_; }
+    uint64_t used() const { return off_; }
+    uint64_t cap() const { return cap_; }
+    // room (in bases) the current span can still take
+    uint64_t room() const { return bs_.room(); }
+    bool can_begin_span() const { return off_ + 4096 <= cap_; }
+
+    void begin_span(uint64_t genome) {
+        genome_ = genome;
+        bs_.attach(buf_ + off_, cap_ - off_);
+        rec_first_ = rec_start_.size();
+        rec_start_.push_back(0);
+        n_rec_ = 0;
+        uniform_len_ = 0;
+        uniform_ = true;
+        rec_begin_ = 0;
+        span_open_ = true;
+    }
+    void begin_record() { rec_begin_ = bs_.size(); }
+    uint64_t append(const uint8_t* s, size_t n) { return bs_.append_filtered(s, n); }
+    void push_base(unsigned c) { bs_.push_base(c); }
+    uint64_t record_len() const { return bs_.size() - rec_begin_; }
+    unsigned record_base(uint64_t i) const { return bs_.base_at(rec_begin_ + i); }
+    // utils.rs:460-462: a (filtered) record shorter than k contributes nothing -- it is dropped here
+    void end_record(int k) {
+        const uint64_t len = record_len();
+        if (len < (uint64_t)k) {
+            bs_.truncate(rec_begin_);
+            return;
+        }
+        close_record(len);
+    }
+    // first part of a record that continues in the next chunk; returns the bases to carry over
+    void split_record(int k, std::vector<uint8_t>& carry) {
+        const uint64_t len = record_len();
+        const uint64_t c = std::min<uint64_t>(len, (uint64_t)(k - 1));
+        carry.resize(c);
+        for (uint64_t i = 0; i < c; ++i) carry[i] = (uint8_t)record_base(len - c + i);
+        if (len < (uint64_t)k) bs_.truncate(rec_begin_);  // no k-mer starts here: the carry holds all of it
+        else close_record(len);
+    }
+    void end_span() {
+        const uint64_t n = bs_.size();
+        if (n == 0) {  // nothing kept: no span
+            rec_start_.resize(rec_first_);
+            span_open_ = false;
+            return;
+        }
+        lash_span sp;
+        sp.genome = genome_;
+        sp.byte_off = off_;
+        sp.n_bases = n;
+        sp.rec_first = rec_first_;
+        sp.n_rec = n_rec_;
+        sp.rec_len = 0;
+        if (n_rec_ <= 1) {
+            rec_start_.resize(rec_first_);  // one record: no table needed
+            sp.rec_first = 0;
+        } else if (uniform_ && uniform_len_ <= 0xffffffffull) {
+            // fixed-length reads: boundaries are arithmetic, no 8 B/read table over PCIe (lash_span.rec_len)
+            rec_start_.resize(rec_first_);
+            sp.rec_first = 0;
+            sp.rec_len = (uint32_t)uniform_len_;
+        }
+        spans_.push_back(sp);
+        off_ += bs_.finalize();
+        span_open_ = false;
+    }
+    // hand the chunk to the GPU; returns the ticket (0 = nothing to push)
+    bool submit(Gpu& gpu, uint64_t* ticket) {
+        *ticket = 0;
+        if (spans_.empty()) {
+            reset();
+            return true;
+        }
+        std::lock_guard<std::mutex> g(gpu.mu);
+        const int rc = lash_sketch_push(gpu.sk, buf_, off_, spans_.data(), (uint32_t)spans_.size(),
+                                        rec_start_.empty() ? nullptr : rec_start_.data(), rec_start_.size(), ticket);
+        if (rc != LASH_OK) {
+            if (!gpu.failed.exchange(true)) gpu.err = lash_gpu_last_error();
+            return false;
+        }
+        gpu.pushes.fetch_add(1);
+        return true;
+    }
+    void reset() {
+        spans_.clear();
+        rec_start_.clear();
+        off_ = 0;
+        span_open_ = false;
+    }
+
+  private:
+    void close_record(uint64_t len) {
+        // uniform = every record has the same length except possibly the last one (which may be shorter)
+        if (n_rec_ == 0) uniform_len_ = len;
+        else if (last_len_ != uniform_len_ || len > uniform_len_) uniform_ = false;
+        last_len_ = len;
+        rec_start_.push_back(bs_.size());
+        ++n_rec_;
+    }
+    uint8_t* buf_ = nullptr;
+    uint64_t cap_ = 0, off_ = 0;
+    BaseStream bs_;
+    std::vector<lash_span> spans_;
+    std::vector<uint64_t> rec_start_;
+    uint64_t genome_ = 0, rec_first_ = 0, rec_begin_ = 0, uniform_len_ = 0, last_len_ = 0;
+    uint32_t n_rec_ = 0;
+    bool uniform_ = true, span_open_ = false;
+};
+
+struct Worker {
+    Chunk chunk[2];
+    uint64_t ticket[2] = {0, 0};
+    int cur = 0;
+    uint64_t n_records = 0, n_in = 0, n_kept = 0;
+
+    // submit the current chunk and switch to the other one (waiting until its last copy has left the host)
+    bool rotate(Gpu& gpu) {
+        if (!chunk[cur].submit(gpu, &ticket[cur])) return false;
+        cur ^= 1;
+        if (ticket[cur]) {
+            std::lock_guard<std::mutex> g(gpu.mu);
+            if (lash_sketch_wait_copied(gpu.sk, ticket[cur]) != LASH_OK) {
+                if (!gpu.failed.exchange(true)) gpu.err = lash_gpu_last_error();
+                return false;
+            }
+            ticket[cur] = 0;
+        }
+        chunk[cur].reset();
+        return true;
+    }
+
+    bool sketch_file(Gpu& gpu, const std::string& path, uint64_t genome, int k, std::string& err) {
+        FastxReader rd;
+        if (!rd.open(path)) {
+            err = "Invalid input file " + path + ": " + rd.err();  // utils.rs:453 expect("Invalid input file")
+            return false;
+        }
+        if (!chunk[cur].can_begin_span() && !rotate(gpu)) return false;
+        chunk[cur].begin_span(genome);
+        std::vector<uint8_t> carry;
+        for (;;) {
+            FastxReader::Ev e = rd.next();
+            if (e.type == FastxReader::kEof) break;
+            if (e.type == FastxReader::kError) {
+                err = "Invalid input file " + path + ": " + rd.err();
+                return false;
+            }
+            if (e.type == FastxReader::kBegin) {
+                ++n_records;
+                chunk[cur].begin_record();
+            } else if (e.type == FastxReader::kEnd) {
+                chunk[cur].end_record(k);
+            } else {
+                n_in += e.n;
+                for (size_t off = 0; off < e.n;) {
+                    const size_t n = std::min(kFeed, e.n - off);
+                    if (chunk[cur].room() < n) {
+                        // chunk full in the middle of a record: close this part, continue in the other chunk
+                        chunk[cur].split_record(k, carry);
+                        chunk[cur].end_span();
+                        if (!rotate(gpu)) return false;
+                        chunk[cur].begin_span(genome);
+                        chunk[cur].begin_record();
+                        for (uint8_t c : carry) chunk[cur].push_base(c);
+                        if (chunk[cur].room() < n) {
+                            err = "staging chunk too small";
+                            return false;
+                        }
+                    }
+                    n_kept += chunk[cur].append(e.p + off, n);
+                    off += n;
+                }
+            }
+        }
+        chunk[cur].end_span();
+        return true;
+    }
+};
+
+}  // namespace
+
+Status sketch_files_impl(lash_ctx* ctx, int algo, std::optional<uint32_t> precision, const std::vector<std::string>& files,
+                         size_t kmer_length, const std::string* output_name, uint32_t threads, uint64_t seed, uint64_t chunk_bytes,
+                         void* regs_out, SketchFilesStats* stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!ctx) return Status{LASH_E_INVALID, "sketch_files: NULL ctx"};
+    if (kmer_length < 1 || kmer_length > 32) return Status{LASH_E_INVALID, "k-mer length must be 1-32"};  // utils.rs:500-502
+    int p = 14;
+    if (algo == LASH_ALGO_HLL || algo == LASH_ALGO_ULL) {
+        if (!precision) return Status{LASH_E_INVALID, algo == LASH_ALGO_HLL ? "HLL needs precision" : "ULL needs precision"};  // utils.rs:408,423
+        p = (int)*precision;
+    }
+    const size_t rb = lash_sketch_reg_bytes(algo, p);
+    if (rb == 0) return Status{LASH_E_INVALID, algo == LASH_ALGO_ULL ? "failed to create ULL" : "bad algorithm / precision"};
+    const uint64_t n_files = files.size();
+    std::vector<uint8_t> regs_local;
+    uint8_t* regs = static_cast<uint8_t*>(regs_out);
+    if (!regs) {
+        regs_local.resize(rb * n_files);
+        regs = regs_local.data();
+    }
+    SketchFilesStats st{};
+    if (n_files) {
+        if (chunk_bytes == 0) chunk_bytes = kDefaultChunk;
+        chunk_bytes = std::max<uint64_t>(chunk_bytes, 1u << 20) / 16 * 16;
+        uint32_t n_workers = threads ? threads : std::max(1u, std::thread::hardware_concurrency());
+        n_workers = (uint32_t)std::min<uint64_t>(n_workers, n_files);
+
+        Gpu gpu;
+        if (lash_sketch_open(ctx, algo, p, (int)kmer_length, seed, n_files, &gpu.sk) != LASH_OK)
+            return Status{LASH_E_CUDA, lash_gpu_last_error()};
+        std::vector<Worker> workers(n_workers);
+        bool alloc_ok = true;
+        for (auto& w : workers)
+            for (auto& c : w.chunk) alloc_ok = alloc_ok && c.alloc(chunk_bytes);
+        std::atomic<uint64_t> next_file{0};
+        if (alloc_ok) {
+            auto run = [&](Worker& w) {
+                for (;;) {
+                    const uint64_t f = next_file.fetch_add(1);
+                    if (f >= n_files || gpu.failed.load()) break;
+                    std::string err;
+                    if (!w.sketch_file(gpu, files[f], f, (int)kmer_length, err)) {
+                        if (!err.empty()) gpu.fail(err);
+                        break;
+                    }
+                }
+                if (!gpu.failed.load()) {
+                    uint64_t t;
+                    w.chunk[w.cur].submit(gpu, &t);
+                }
+            };
+            std::vector<std::thread> pool;
+            for (uint32_t i = 1; i < n_workers; ++i) pool.emplace_back(run, std::ref(workers[i]));
+            run(workers[0]);
+            for (auto& t : pool) t.join();
+        } else {
+            gpu.fail(std::string("pinned staging allocation failed: ") + lash_gpu_last_error());
+        }
+        int rc = LASH_OK;
+        if (!gpu.failed.load()) rc = lash_sketch_fetch(gpu.sk, 0, n_files, regs);
+        else lash_sketch_sync(gpu.sk);  // chunks must not be freed under an in-flight copy
+        std::string gerr = rc != LASH_OK ? lash_gpu_last_error() : "";
+        uint64_t launches = 0;
+        lash_sketch_stats(gpu.sk, &st.gpu_kernel_ms, &launches);
+        for (auto& w : workers) {
+            st.n_records += w.n_records;
+            st.n_bases_in += w.n_in;
+            st.n_bases_kept += w.n_kept;
+            for (auto& c : w.chunk) c.release();
+        }
+        st.n_pushes = gpu.pushes.load();
+        lash_sketch_close(gpu.sk);
+        if (gpu.failed.load()) {
+            const bool input = gpu.err.rfind("Invalid input file", 0) == 0;
+            return Status{input ? LASH_HOST_E_FORMAT : LASH_E_CUDA, gpu.err};
+        }
+        if (rc != LASH_OK) return Status{rc, gerr};
+    }
+    if (output_name) {
+        // write sketches (utils.rs:566-575) and names (utils.rs:577-580)
+        std::string err;
+        if (!lashhost::write_sketches(*output_name + "_sketches.bin", algo, p, regs, n_files, (int)threads, err))
+            return Status{LASH_HOST_E_IO, err};
+        if (!lashhost::write_file(*output_name + "_files.json", lashhost::json_pretty_string_array(files), err))
+            return Status{LASH_HOST_E_IO, err};
+    }
+    st.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = st;
+    return Status{};
+}
+
+}  // namespace lash

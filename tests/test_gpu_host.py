@@ -1,0 +1,257 @@
+"""End-to-end parity of the C++ host layer on a GPU: FASTA/FASTQ files -> sketch_files<S> ->
+{out}_sketches.bin / _files.json / _parameters.json -> `dist` -> TSV / --dm text, against the CPU
+oracle fed with the same records.  Mirrors what an integration test of the reference's
+`lash sketch` + `lash dist` (src/main.rs:179-613) would check.
+
+Bar: registers bit-exact; distances as text equal to the oracle's `{:.6}` text except where the
+1e-12 relative difference between CUDA and glibc log/pow straddles a rounding boundary of the 6th
+decimal (at most 1 unit in the last printed place, and rare)."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from lash_b200 import ALGO_HLL, ALGO_HMH, ALGO_ULL, hostapi
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_fasta(path, records, width=70, gz=False):
+    opener = gzip.open if gz else open
+    with opener(path, "wb") as f:
+        for i, s in enumerate(records):
+            f.write(b">rec%d some description\n" % i)
+            for o in range(0, len(s), width):
+                f.write(s[o:o + width] + b"\n")
+
+
+def _write_fastq(path, records):
+    with open(path, "wb") as f:
+        for i, s in enumerate(records):
+            f.write(b"@read%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
+
+
+def _oname(algo):
+    return {ALGO_HMH: "HMH", ALGO_HLL: "HLL", ALGO_ULL: "ULL"}[algo]
+
+
+@pytest.mark.parametrize("algo,p,k", [(ALGO_ULL, 10, 16), (ALGO_HLL, 12, 21), (ALGO_HMH, 14, 16), (ALGO_ULL, 14, 31), (ALGO_ULL, 8, 5)])
+def test_sketch_files_matches_oracle_on_dirty_fasta(oracle, gpu_ctx, tmp_path, algo, p, k):
+    """Per-file record loop of utils.rs:457-503 on multi-record, multi-line, dirty, gzipped and
+    short files -- several files per staging chunk."""
+    genomes = [synth.dirty_genome(60_000 + 7919 * g, k, seed=g + 1) for g in range(6)]
+    genomes.append([b"ACGT" * 3])                       # one tiny record (shorter than k for most k)
+    genomes.append([b"NNNN", b"acgt"])                  # nothing survives the filter: an empty sketch
+    genomes += synth.genomes(2, 300_000, seed=9)
+    files = []
+    for g, recs in enumerate(genomes):
+        path = str(tmp_path / f"g{g}.fa{'.gz' if g % 3 == 1 else ''}")
+        _write_fasta(path, recs, width=60 + g, gz=(g % 3 == 1))
+        files.append(path)
+    regs, st = hostapi.sketch_files_regs(gpu_ctx, algo, p, k, 42, files, threads=3)
+    exp = oracle.sketch_genomes(getattr(oracle, _oname(algo)), p, k, 42, genomes, threads=4)
+    assert np.array_equal(regs, exp)
+    assert st.n_records == sum(len(g) for g in genomes)
+    assert not regs[7].any()
+
+
+@pytest.mark.parametrize("k", [16, 21, 32])
+def test_large_records_split_across_staging_chunks(oracle, gpu_ctx, tmp_path, k):
+    """A record larger than a staging chunk is cut with a (k-1)-base overlap: every k-mer start
+    exactly once (chunk = 1 MiB = 4 Mbp; records of 9 and 5 Mbp, plus small ones around them)."""
+    rng = np.random.default_rng(k)
+    recs = [synth.to_ascii(rng.integers(0, 4, size=n, dtype=np.uint8)) for n in (1000, 9_000_000, k - 1, 5_000_000, 3 * k)]
+    recs[1] = recs[1][:4_100_000] + b"N" * 50 + recs[1][4_100_050:]     # dirt right where a chunk boundary falls
+    path = str(tmp_path / "big.fa")
+    _write_fasta(path, recs, width=80)
+    other = str(tmp_path / "small.fa")
+    _write_fasta(other, [recs[0]])
+    for algo, p in ((ALGO_ULL, 12), (ALGO_HMH, 14)):
+        regs, st = hostapi.sketch_files_regs(gpu_ctx, algo, p, k, 7, [other, path, other], threads=2, chunk_bytes=1 << 20)
+        exp = oracle.sketch_genomes(getattr(oracle, _oname(algo)), p, k, 7, [[recs[0]], recs, [recs[0]]], threads=3)
+        assert st.n_pushes >= 4
+        assert np.array_equal(regs, exp)
+
+
+def test_fastq_reads_uniform_and_ragged(oracle, gpu_ctx, tmp_path):
+    """config 4 shape: 150 bp reads of one sample.  Equal-length reads take the table-free
+    rec_len path, ragged reads (and reads that lose bases to the filter) the rec_start table."""
+    rng = np.random.default_rng(4)
+    genome = synth.to_ascii(rng.integers(0, 4, size=400_000, dtype=np.uint8))
+    starts = rng.integers(0, len(genome) - 150, size=20_000)
+    uniform = [genome[s:s + 150] for s in starts]
+    ragged = [genome[s:s + int(n)] for s, n in zip(starts, rng.integers(1, 151, size=len(starts)))]
+    dirty = [r[:40] + b"N" + r[41:] if i % 7 == 0 else r for i, r in enumerate(uniform)]
+    cases = {"uniform": uniform, "ragged": ragged, "dirty": dirty}
+    files = []
+    for name, reads in cases.items():
+        path = str(tmp_path / f"{name}.fq")
+        _write_fastq(path, reads)
+        files.append(path)
+    regs, st = hostapi.sketch_files_regs(gpu_ctx, ALGO_ULL, 14, 21, 42, files, threads=2)
+    exp = oracle.sketch_genomes(oracle.ULL, 14, 21, 42, list(cases.values()), threads=3)
+    assert np.array_equal(regs, exp)
+    assert st.n_records == 3 * len(starts)
+
+
+def test_many_small_files_share_chunks(oracle, gpu_ctx, tmp_path):
+    genomes = synth.genomes(300, 20_000, seed=5)
+    files = []
+    for g, recs in enumerate(genomes):
+        path = str(tmp_path / f"s{g}.fa")
+        _write_fasta(path, recs)
+        files.append(path)
+    regs, st = hostapi.sketch_files_regs(gpu_ctx, ALGO_ULL, 10, 16, 42, files, threads=4)
+    assert st.n_pushes <= 8          # not one push per file
+    assert np.array_equal(regs, oracle.sketch_genomes(oracle.ULL, 10, 16, 42, genomes, threads=4))
+
+
+def test_sketch_files_error_behaviour(gpu_ctx, tmp_path):
+    good = str(tmp_path / "ok.fa")
+    _write_fasta(good, [b"ACGT" * 100])
+    bad = str(tmp_path / "bad.fa")
+    open(bad, "wb").write(b"this is not a sequence file\n")
+    with pytest.raises(hostapi.HostError, match="Invalid input file"):      # utils.rs:453
+        hostapi.sketch_files_regs(gpu_ctx, ALGO_ULL, 10, 16, 42, [good, bad])
+    with pytest.raises(hostapi.HostError, match="Invalid input file"):
+        hostapi.sketch_files_regs(gpu_ctx, ALGO_ULL, 10, 16, 42, [str(tmp_path / "missing.fa")])
+    with pytest.raises(hostapi.HostError, match="k-mer length must be 1-32"):  # utils.rs:500-502
+        hostapi.sketch_files_regs(gpu_ctx, ALGO_ULL, 10, 33, 42, [good])
+    with pytest.raises(hostapi.HostError):                                   # UltraLogLog::new(p) Err
+        hostapi.sketch_files_regs(gpu_ctx, ALGO_ULL, 2, 16, 42, [good])
+    regs, _ = hostapi.sketch_files_regs(gpu_ctx, ALGO_ULL, 10, 16, 42, [])
+    assert regs.shape == (0, 1024)
+
+
+def _parse_list(path):
+    lines = open(path).read().split("\n")
+    assert lines[0] == "Reference\tQuery\tDistance" and lines[-1] == ""
+    return [tuple(ln.split("\t")) for ln in lines[1:-1]]
+
+
+def _expected_text(oracle, algo, p, k, est, model, fp32, regs_r, regs_q, names_r, names_q, tri):
+    d = oracle.dist(getattr(oracle, _oname(algo)), p, k, est, model, fp32, regs_r, regs_q)
+    rows = []
+    for i, rn in enumerate(names_r):
+        for j, qn in enumerate(names_q):
+            if tri and j > i:
+                continue
+            v = 0.0 if rn == qn else float(d[i, j])
+            rows.append((rn, qn, v))
+    return rows
+
+
+def _assert_text_rows(got, exp):
+    assert len(got) == len(exp)
+    off = 0
+    for (gr, gq, gd), (er, eq, ev) in zip(got, exp):
+        assert (gr, gq) == (er, eq)
+        et = "%.6f" % ev
+        if gd != et:
+            assert abs(float(gd) - ev) <= 1.0000001e-6, (gr, gq, gd, et)
+            off += 1
+    assert off <= max(1, len(exp) // 200)
+
+
+@pytest.mark.parametrize("algo,p,k,estimator", [(ALGO_ULL, 10, 16, "fgra"), (ALGO_ULL, 10, 16, "ml"), (ALGO_HLL, 12, 21, "fgra"),
+                                                (ALGO_HMH, 14, 16, "fgra")])
+@pytest.mark.parametrize("fused", [True, False])
+def test_sketch_then_dist_end_to_end(oracle, gpu_ctx, tmp_path, algo, p, k, estimator, fused):
+    """`lash sketch` + `lash dist` on files: same prefix on both sides (same_files: lower triangle
+    incl. diagonal, main.rs:404 + utils.rs:158-160) and a different query set (full matrix)."""
+    genomes = synth.genomes(9, 150_000, seed=21)
+    files = []
+    for g, recs in enumerate(genomes):
+        path = str(tmp_path / f"genome_{g}.fasta")
+        _write_fasta(path, recs)
+        files.append(path)
+    ref_prefix, qry_prefix = str(tmp_path / "refs"), str(tmp_path / "qrys")
+    hostapi.sketch_files(gpu_ctx, algo, p, k, 42, files, ref_prefix, threads=2)
+    hostapi.sketch_files(gpu_ctx, algo, p, k, 42, files[2:6], qry_prefix, threads=2)
+    for suffix in ("_sketches.bin", "_files.json", "_parameters.json"):
+        assert os.path.exists(ref_prefix + suffix)
+    O = getattr(oracle, _oname(algo))
+    regs = oracle.sketch_genomes(O, p, k, 42, genomes, threads=4)
+    on_disk, _ = hostapi.read_sketches(ref_prefix + "_sketches.bin", algo, len(files))
+    assert np.array_equal(on_disk, regs)
+    est = 1 if estimator == "ml" else 0
+    for model in (1, 0):
+        for fp32 in (False, True):
+            out = str(tmp_path / f"self_{model}_{int(fp32)}.tsv")
+            hostapi.dist(gpu_ctx, ref_prefix, ref_prefix, out, estimator, model, dm=False, fp32=fp32, threads=3, fused=fused)
+            exp = _expected_text(oracle, algo, p, k, est, model, fp32, regs, regs, files, files, tri=True)
+            _assert_text_rows([(r, q, d) for r, q, d in _parse_list(out)], exp)
+    out = str(tmp_path / "cross.tsv")
+    hostapi.dist(gpu_ctx, ref_prefix, qry_prefix, out, estimator, 1, dm=False, fp32=False, threads=2, fused=fused)
+    exp = _expected_text(oracle, algo, p, k, est, 1, False, regs, regs[2:6], files, files[2:6], tri=False)
+    _assert_text_rows(_parse_list(out), exp)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_dm_matrix_layout(oracle, gpu_ctx, tmp_path, fused):
+    """--dm (main.rs:438-467): header row of "\\t{query}", then "\\n{ref}" + "\\t{:.6}" cells, no final newline."""
+    genomes = synth.genomes(5, 100_000, seed=3)
+    files = []
+    for g, recs in enumerate(genomes):
+        path = str(tmp_path / f"m{g}.fa")
+        _write_fasta(path, recs)
+        files.append(path)
+    a, b = str(tmp_path / "A"), str(tmp_path / "B")
+    hostapi.sketch_files(gpu_ctx, ALGO_ULL, 10, 16, 42, files, a)
+    hostapi.sketch_files(gpu_ctx, ALGO_ULL, 10, 16, 42, files[1:4], b)
+    regs = oracle.sketch_genomes(oracle.ULL, 10, 16, 42, genomes, threads=4)
+    out = str(tmp_path / "dm.txt")
+    hostapi.dist(gpu_ctx, a, b, out, "fgra", 1, dm=True, fused=fused)
+    text = open(out).read()
+    lines = text.split("\n")
+    assert not text.endswith("\n")
+    assert lines[0] == "".join("\t" + q for q in files[1:4])
+    exp = _expected_text(oracle, ALGO_ULL, 10, 16, 0, 1, False, regs, regs[1:4], files, files[1:4], tri=False)
+    got = []
+    for ln, rn in zip(lines[1:], files):
+        cells = ln.split("\t")
+        assert cells[0] == rn and len(cells) == 4
+        got += [(rn, qn, c) for qn, c in zip(files[1:4], cells[1:])]
+    _assert_text_rows(got, exp)
+    # same files: lower-triangular rows
+    hostapi.dist(gpu_ctx, a, a, out, "fgra", 1, dm=True, fused=fused)
+    lines = open(out).read().split("\n")
+    assert [len(ln.split("\t")) for ln in lines[1:]] == [2, 3, 4, 5, 6]
+    assert lines[1].split("\t")[1] == "0.000000"
+
+
+def test_dist_command_error_behaviour_and_name_rules(oracle, gpu_ctx, tmp_path):
+    genomes = synth.genomes(3, 60_000, seed=8)
+    files = []
+    for g, recs in enumerate(genomes):
+        path = str(tmp_path / f"e{g}.fa")
+        _write_fasta(path, recs)
+        files.append(path)
+    u16, u21, h16 = str(tmp_path / "u16"), str(tmp_path / "u21"), str(tmp_path / "h16")
+    hostapi.sketch_files(gpu_ctx, ALGO_ULL, 10, 16, 42, files, u16)
+    hostapi.sketch_files(gpu_ctx, ALGO_ULL, 10, 21, 42, files, u21)
+    hostapi.sketch_files(gpu_ctx, ALGO_HLL, 10, 16, 42, files, h16)
+    out = str(tmp_path / "o.tsv")
+    with pytest.raises(hostapi.HostError, match="same k"):                 # main.rs:363
+        hostapi.dist(gpu_ctx, u16, u21, out)
+    with pytest.raises(hostapi.HostError, match="Algorithms do not match"):  # main.rs:366
+        hostapi.dist(gpu_ctx, u16, h16, out)
+    with pytest.raises(hostapi.HostError, match="fgra or ml"):              # utils.rs:217
+        hostapi.dist(gpu_ctx, u16, u16, out, estimator="bogus")
+    with pytest.raises(hostapi.HostError, match="model needs to be 0 or 1"):  # main.rs:421
+        hostapi.dist(gpu_ctx, u16, u16, out, model=2)
+    with pytest.raises(hostapi.HostError, match="There should be 3 files"):  # main.rs:330-336
+        hostapi.dist(gpu_ctx, str(tmp_path / "nothing_here"), u16, out)
+    # a name listed twice collapses to one entry holding the LAST sketch (HashMap insert, utils.rs:219);
+    # an identical sketch under a DIFFERENT name is not forced to 0 (main.rs:452 compares names): -ln(1)/k = -0
+    dup = str(tmp_path / "dup")
+    alias = str(tmp_path / "alias.fa")
+    _write_fasta(alias, genomes[1])
+    hostapi.sketch_files(gpu_ctx, ALGO_ULL, 10, 16, 42, [files[0], files[1], files[0], alias], dup)
+    hostapi.dist(gpu_ctx, dup, dup, out, fused=False)
+    rows = _parse_list(out)
+    assert [(r, q) for r, q, _ in rows] == [(files[0], files[0]), (files[1], files[0]), (files[1], files[1]),
+                                           (alias, files[0]), (alias, files[1]), (alias, alias)]
+    assert rows[4][2] == "-0.000000" and rows[5][2] == "0.000000"

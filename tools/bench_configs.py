@@ -17,6 +17,9 @@ from lash_b200.capi import Span, check, lib  # noqa: E402
 from lash_b200.pack import padded_bytes  # noqa: E402
 
 
+PROFILE = False  # --profile: exactly one launch per case (the run is under ncu, which replays it anyway)
+
+
 def sketch_case(ctx, name, algo, p, k, n_g, length, reps=5):
     dev = torch.device("cuda", 0)
     buf, stride = bench.make_packed_genomes(torch, dev, n_g, length, 42, 0)
@@ -27,12 +30,14 @@ def sketch_case(ctx, name, algo, p, k, n_g, length, reps=5):
     stream = torch.cuda.Stream(dev)
     sk.set_stream(stream.cuda_stream)
     ts = []
-    for r in range(reps + 2):
+    warm = 0 if PROFILE else 2
+    reps = 1 if PROFILE else reps
+    for r in range(reps + warm):
         sk.reset()
         ms0, _ = sk.stats()
         sk.push_raw(buf.data_ptr(), n_g * stride, spans, n_g, None, 0, dev=True)
         ms1, _ = sk.stats()
-        if r >= 2:
+        if r >= warm:
             ts.append(ms1 - ms0)
     regs = sk.fetch()
     sk.close()
@@ -54,7 +59,9 @@ def reads_case(ctx, name, p, k, n_reads, read_len, reps=3, uniform=False):
     stream = torch.cuda.Stream(dev)
     sk.set_stream(stream.cuda_stream)
     ts = []
-    for r in range(reps + 1):
+    warm = 0 if PROFILE else 1
+    reps = 1 if PROFILE else reps
+    for r in range(reps + warm):
         sk.reset()
         ms0, _ = sk.stats()
         t0 = time.perf_counter()
@@ -64,7 +71,7 @@ def reads_case(ctx, name, p, k, n_reads, read_len, reps=3, uniform=False):
             sk.push_raw(packed.data_ptr(), padded_bytes(n_bases), spans, 1, rec.ctypes.data_as(C.c_void_p), len(rec), dev=True)
         ms1, _ = sk.stats()
         wall = time.perf_counter() - t0
-        if r >= 1:
+        if r >= warm:
             ts.append((ms1 - ms0, wall * 1e3))
     sk.close()
     ms = float(np.median([a for a, _ in ts]))
@@ -75,10 +82,12 @@ def reads_case(ctx, name, p, k, n_reads, read_len, reps=3, uniform=False):
 def dist_case(ctx, name, algo, p, k, est, regs, reps=3):
     n = regs.shape[0]
     ts = []
-    for r in range(reps + 1):
+    warm = 0 if PROFILE else 1
+    reps = 1 if PROFILE else reps
+    for r in range(reps + warm):
         d, w = ops.dist(ctx, algo, p, k, est, 1, False, regs, regs, triangular=True)
         ms, _ = ops.dist_stats(ctx)
-        if r >= 1:
+        if r >= warm:
             ts.append(ms)
     ms = float(np.median(ts))
     pairs = n * (n + 1) // 2
@@ -90,8 +99,11 @@ def dist_case(ctx, name, algo, p, k, est, regs, reps=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="one launch per case, quick sizes (for ncu)")
     a = ap.parse_args()
-    q = a.quick
+    global PROFILE
+    PROFILE = a.profile
+    q = a.quick or a.profile
     out = []
     with ops.Context(0) as ctx:
         r, regs_ull10 = sketch_case(ctx, "C2 ULL p=10 k=16", ALGO_ULL, 10, 16, 200 if q else 1000, 5_000_000)
