@@ -301,13 +301,28 @@ def run_graft(args):
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
     # ALU-pipe bound (the real limiter): 148 SMs x 64 INT lanes/clk
     int_peak = 148 * 64 * sm_mhz * 1e6
+    # issue-slot bound: 4 schedulers/SM x 1 warp-instruction/clk x 32 lanes; instructions per k-mer come from the
+    # committed ncu capture of this kernel (smsp__inst_executed x 32 / k-mers), traffic from its dram__bytes
+    kname = "lash::sketch_kernel<ULL,narrow,smem>"
+    cap = {}
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kname, {})
+    except Exception:
+        pass
+    traffic = cap.get("dram_bytes_per_base")
+    ipk = cap.get("warp_inst_x32_per_kmer")
+    issue_peak = 148 * 4 * 32 * sm_mhz * 1e6
+    kps = kmers / (sk_kernel_ms * 1e-3)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "lash::sketch_kernel<ULL,narrow,smem>",
+                "traffic": traffic * bases_rank if traffic else None, "traffic_source": cap.get("capture"),
+                "peak_source": peak_src, "kernel": kname,
                 "kernel_ms": sk_kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
                 "note": "0.25 B/base streamed once; the kernel is integer-pipe bound, not HBM bound (see int_pipe)",
-                "int_pipe": {"kmers_per_s": kmers / (sk_kernel_ms * 1e-3), "alu_lane_ops_peak_per_s": int_peak,
+                "int_pipe": {"kmers_per_s": kps, "alu_lane_ops_peak_per_s": int_peak,
                              "sm_mhz_used": sm_mhz,
-                             "alu_instr_per_kmer_at_peak": int_peak / (kmers / (sk_kernel_ms * 1e-3))}}
+                             "alu_instr_per_kmer_at_peak": int_peak / kps,
+                             "issue_lane_ops_peak_per_s": issue_peak, "instr_per_kmer_ncu": ipk,
+                             "issue_frac": (kps * ipk / issue_peak) if ipk else None}}
 
     # ---- parity spot check against the oracle (checker only) -------------------------------------
     parity = None
@@ -390,6 +405,11 @@ def run_graft(args):
                                   "triangular FGRA dist, oracle/lash_oracle.c on all host cores",
                         "sketch_gbp_per_s": bases / ts / 1e9, "dist_pairs_per_s": pairs / td}
 
+    # ---- from FASTA text through the C++ host layer (rank 0, N=1 only; bounded sample) ----------------
+    ingest = None
+    if rank == 0 and world == 1 and not args.no_ingest:
+        ingest = fasta_ingest_leg(ctx, buf, stride, min(n_g, 64))
+
     if rank == 0:
         line = {
             "metric": "kmer_sketch_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
@@ -402,7 +422,7 @@ def run_graft(args):
             "phases_ms_last_step": {"sketch": sk_ms, "gather": ga_ms, "cardinality+dist": di_ms},
             "dist": {"metric": "all_vs_all_pairs_per_s", "value": n_pairs_all / (di_ms * 1e-3), "unit": "pairs/s", "pairs": n_pairs_all,
                      "register_merges_per_s": n_pairs_all * rb / (di_ms * 1e-3)},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "fasta_ingest": ingest, "clocks": clocks,
             "gpu_launches": int(args.steps * 3), "parity_spot_check": parity, "hll_bias_flags": int(flags.item()),
         }
         print(json.dumps(line), flush=True)
@@ -410,6 +430,41 @@ def run_graft(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def fasta_ingest_leg(ctx, buf, stride, n_files: int):
+    """The widened path: 80-column FASTA text on tmpfs -> C++ host layer (mmap, AVX2 filter + 2-bit
+    pack, pinned chunks, lash_sketch_push) -> registers.  A bounded sample (n_files genomes of the bench workload);
+    `pack_only` is the same parse + pack with the chunks dropped (host ceiling, no GPU)."""
+    import shutil
+    import tempfile
+
+    from lash_b200 import ALGO_ULL, hostapi
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    d = tempfile.mkdtemp(prefix="lash_bench_", dir=base)
+    try:
+        files = []
+        for i in range(n_files):
+            packed = buf[i * stride: i * stride + (GENOME_LEN + 3) // 4].cpu().numpy()
+            a = np.frombuffer(unpack_to_ascii(packed, GENOME_LEN), dtype=np.uint8)
+            body = np.concatenate([a[: GENOME_LEN // 80 * 80].reshape(-1, 80),
+                                   np.full((GENOME_LEN // 80, 1), 10, dtype=np.uint8)], axis=1).tobytes() + a[GENOME_LEN // 80 * 80:].tobytes() + b"\n"
+            path = os.path.join(d, f"g{i}.fa")
+            with open(path, "wb") as f:
+                f.write(b">genome_%d\n" % i + body)
+            files.append(path)
+        cores = os.cpu_count() or 1
+        best, best_dry, st = 1e30, 1e30, None
+        for _ in range(3):
+            regs, st = hostapi.sketch_files_regs(ctx, ALGO_ULL, P, K, SEED, files, threads=cores)
+            best = min(best, st.seconds_total)
+            best_dry = min(best_dry, hostapi.pack_files_dry(files, K, threads=cores).seconds_total)
+        return {"value": n_files * GENOME_LEN / best / 1e9, "unit": "Gbp/s", "files": n_files, "bytes_of_fasta": int(n_files * (GENOME_LEN + GENOME_LEN // 80 + 12)),
+                "host_threads": cores, "pushes": int(st.n_pushes), "gpu_kernel_ms": st.gpu_kernel_ms,
+                "pack_only_gbp_per_s": n_files * GENOME_LEN / best_dry / 1e9, "simd_packer": bool(hostapi.lib().lash_host_pack_has_simd()),
+                "note": "FASTA text (tmpfs) -> lash::sketch_files<Ull> (C++ host) -> registers on host; best of 3"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def _as_tensor(torch, ptr: int, nbytes: int, device):
@@ -429,6 +484,7 @@ def main():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the FASTA -> C++ host -> GPU leg")
     ap.add_argument("--genomes", type=int, default=N_GENOMES, help="genomes per GPU (default = the BASELINE config; other values are for profiling)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -57,7 +57,7 @@ int lash_host_pack_has_simd(void);
  * One host worker per file at a time ("parallel by sample"), each parsing + packing into pinned
  * chunks that are pushed to the GPU (lash_sketch_push) while the next chunk is parsed.
  * regs_out: n_files * lash_sketch_reg_bytes(algo, p) bytes, in list order.
- * chunk_bytes: pinned staging chunk per worker buffer (0 = default 16 MiB). */
+ * chunk_bytes: pinned staging chunk per worker buffer (0 = sized from the input, 1..16 MiB). */
 typedef struct lash_sketch_files_stats {
     uint64_t n_records;      /* records seen (all files) */
     uint64_t n_bases_in;     /* sequence bytes read, before filter_out_n */
@@ -74,6 +74,13 @@ int lash_host_sketch_files_regs(lash_ctx* ctx, int algo, int p, int k, uint64_t 
  * utils.rs:566-575) and {output_name}_files.json (utils.rs:577-580). */
 int lash_host_sketch_files(lash_ctx* ctx, int algo, int p, int k, uint64_t seed, const char* const* files,
                            uint64_t n_files, const char* output_name, int threads, lash_sketch_files_stats* stats);
+/* Measurement aid: the same parse + filter + pack over the files, chunks dropped instead of pushed
+ * (no GPU work, no registers) -- the host ingest ceiling bench.py reports next to the end-to-end rate. */
+int lash_host_pack_files_dry(const char* const* files, uint64_t n_files, int k, int threads, uint64_t chunk_bytes,
+                             lash_sketch_files_stats* stats);
+/* sketch_files keeps its pinned staging blocks (up to 1 GiB) for the next call, because page-locking costs more
+ * than sketching a small batch; this returns them to the driver. */
+int lash_host_release_pinned(void);
 /* {output_name}_parameters.json as the `sketch` sub-command writes it (main.rs:249-276). */
 int lash_host_write_parameters(const char* output_name, int algo, int p, int k, uint64_t seed);
 
@@ -96,7 +103,7 @@ int lash_host_dist(lash_ctx* ctx, const char* ref_prefix, const char* query_pref
                    const char* estimator, int model, int dm, int fp32, int threads, int fused);
 
 /* Rust's `{:.6}` for f64 / f32 (main.rs:459,465): exact decimal expansion, round-half-even.
- * Writes at most 32 bytes (no terminator) and returns the length. */
+ * Writes at most 32 bytes for |v| < 2^20, at most 330 otherwise (no terminator); returns the length. */
 int lash_host_format_fixed6_f64(double v, char* out);
 int lash_host_format_fixed6_f32(float v, char* out);
 

@@ -67,12 +67,21 @@ __device__ __forceinline__ uint64_t xxh3_rrmxmx8(uint64_t h) {
     return h ^ (h >> 28);
 }
 
+// 32-bit add the optimiser cannot widen: written in C, `lo ^ ((hi >> 3) + 8u)` next to mk64() is re-fused by
+// the front end into a 64-bit add and lowered with a carry into the high word (LEA.HI.P + IMAD.X + LOP3:
+// two wasted instructions per hash) although (h >> 35) + 8 < 2^30 can never carry.
+__device__ __forceinline__ uint32_t add32_opaque(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("add.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
 // tail of XXH3_rrmxmx after the rotate-xor stage, on halves
 __device__ __forceinline__ uint64_t xxh3_rrmxmx8_tail(uint32_t lo, uint32_t hi) {
     uint64_t h = mk64(lo, hi) * kPrimeMX2;
     lo = (uint32_t)h;
     hi = (uint32_t)(h >> 32);
-    lo ^= (hi >> 3) + 8u;  // h ^= (h >> 35) + len, no carry into the high word
+    lo ^= add32_opaque(hi >> 3, 8u);  // h ^= (h >> 35) + len, no carry into the high word
     return mk64(lo, hi) * kPrimeMX2;   // caller applies the final h ^= h >> 28 (or only the part it needs)
 }
 // pre-xorshift hash (h before `h ^= h >> 28`) of a k-mer that fits 32 bits; see HashConsts::nar_*

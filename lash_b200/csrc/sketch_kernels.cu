@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(1024)
                 auto fast_block = [&](auto checked, const uint32_t mask16) {
                     constexpr bool CHECKED = decltype(checked)::value;
                     uint32_t addr[kGroup], need[kGroup];
-                    uint32_t any = 0u, rare = 0xffffffffu;
+                    uint32_t any = 0u, rare = 0xffffffffu, rw_prev = 0xffffffffu;
 #pragma unroll
                     for (int i = 0; i < kGroup; ++i) {
                         uint32_t klo, khi, v, rw;
@@ -331,7 +331,8 @@ __global__ void __launch_bounds__(1024)
                         need[i] = A::need(lds_u32(addr[i]), v);
                         if (CHECKED) need[i] = (mask16 & (1u << i)) ? need[i] : 0u;
                         any |= need[i];
-                        rare = min(rare, rw);
+                        if (i & 1) rare = __vimin3_u32(rare, rw_prev, rw);  // one VIMNMX3 per two k-mers
+                        else rw_prev = rw;
                     }
                     if (any) {
 #pragma unroll
@@ -340,11 +341,15 @@ __global__ void __launch_bounds__(1024)
                     }
                     if (rare == 0u) exact_block(mask16);  // some hash had 32 leading zeros where it matters
                 };
+                // The choice between the two straight-line blocks is made per WARP, not per lane: with short reads
+                // nearly every warp holds some lane with a record boundary in its 16 starts, and a per-lane choice
+                // would run both ~500-instruction blocks back to back with half the lanes idle in each (ncu: 15 of 32
+                // active lanes, 252 Gbp/s on 150 bp reads).  Lanes without a valid start ride along with mask 0.
                 if (GLOBAL) {
                     if (v16 != 0u) exact_block(v16);
-                } else if (v16 == 0xffffu) {
+                } else if (__all_sync(0xffffffffu, v16 == 0xffffu)) {
                     fast_block(std::false_type{}, 0xffffu);
-                } else if (v16 != 0u) {
+                } else if (__any_sync(0xffffffffu, v16 != 0u)) {
                     fast_block(std::true_type{}, v16);
                 }
                 f0 = f1; f1 = f2; f2 = f3; f3 = f4; f4 = f5;

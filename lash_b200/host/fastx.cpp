@@ -4,16 +4,27 @@
 
 namespace lashhost {
 
+FastxReader::~FastxReader() { unmap_file(map_, map_len_); }
+
 bool FastxReader::open(const std::string& path, size_t buf_bytes) {
     err_.clear();
-    src_ = open_source(path, err_);
-    if (!src_) {
-        state_ = kStFailed;
-        return false;
-    }
-    buf_.resize(buf_bytes < 4096 ? 4096 : buf_bytes);
+    unmap_file(map_, map_len_);
+    map_ = nullptr;
+    map_len_ = 0;
     pos_ = end_ = 0;
     eof_ = false;
+    // uncompressed regular files are parsed in place (page cache mapped read-only, no copy)
+    if (map_plain_file(path, &map_, &map_len_)) {
+        end_ = map_len_;
+        eof_ = true;
+    } else {
+        src_ = open_source(path, err_);
+        if (!src_) {
+            state_ = kStFailed;
+            return false;
+        }
+        buf_.resize(buf_bytes < 4096 ? 4096 : buf_bytes);
+    }
     at_line_start_ = true;
     fa_open_ = false;
     state_ = kStStart;
@@ -46,7 +57,7 @@ static inline size_t strip_cr(const uint8_t* b, size_t from, size_t to) { return
 
 FastxReader::Ev FastxReader::next() {
     for (;;) {
-        uint8_t* b = buf_.data();
+        const uint8_t* b = map_ ? map_ : buf_.data();
         switch (state_) {
             case kStFailed:
                 return Ev{kError, nullptr, 0};
@@ -54,7 +65,7 @@ FastxReader::Ev FastxReader::next() {
                 return Ev{kEof, nullptr, 0};
             case kStStart: {
                 if (pos_ == end_ && !fill()) return fail(err_.empty() ? "Invalid input file: empty file" : err_);
-                b = buf_.data();
+                b = map_ ? map_ : buf_.data();
                 if (b[pos_] == '>') state_ = kStFaHeader;
                 else if (b[pos_] == '@') state_ = kStFqRecord;
                 else return fail("Invalid input file: first byte is neither '>' (FASTA) nor '@' (FASTQ)");

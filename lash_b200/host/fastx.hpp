@@ -23,6 +23,10 @@ class FastxReader {
         size_t n;          //         (FASTA: may contain '\n' / '\r'; they are not bases)
     };
 
+    FastxReader() = default;
+    ~FastxReader();
+    FastxReader(const FastxReader&) = delete;
+    FastxReader& operator=(const FastxReader&) = delete;
     bool open(const std::string& path, size_t buf_bytes = 4u << 20);
     Ev next();
     // 1 record, 0 end of file, -1 error
@@ -39,6 +43,8 @@ class FastxReader {
     enum State { kStStart, kStFaHeader, kStFaSeq, kStFqRecord, kStFqSeq, kStFqEnd, kStDone, kStFailed };
     std::unique_ptr<ByteSource> src_;
     std::vector<uint8_t> buf_;
+    const uint8_t* map_ = nullptr;  // whole file mapped (uncompressed input); buf_ / src_ unused then
+    size_t map_len_ = 0;
     size_t pos_ = 0, end_ = 0;
     bool eof_ = false;
     bool at_line_start_ = true;  // FASTA: the byte before pos_ was '\n' (or pos_ is the start of the data)

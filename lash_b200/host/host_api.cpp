@@ -100,6 +100,18 @@ extern "C" int lash_host_sketch_files(lash_ctx* ctx, int algo, int p, int k, uin
                                                seed, 0, nullptr, stats));
 }
 
+extern "C" int lash_host_pack_files_dry(const char* const* files, uint64_t n_files, int k, int threads, uint64_t chunk_bytes,
+                                        lash_sketch_files_stats* stats) {
+    if (!files && n_files) return fail(LASH_E_INVALID, "lash_host_pack_files_dry: NULL argument");
+    if (k < 1) return fail(LASH_E_INVALID, "k-mer length must be 1-32");
+    return from_status(lash::pack_files_dry(to_vec(files, n_files), (size_t)k, (uint32_t)std::max(threads, 0), chunk_bytes, stats));
+}
+
+extern "C" int lash_host_release_pinned(void) {
+    lash::release_pinned();
+    return 0;
+}
+
 extern "C" int lash_host_write_parameters(const char* output_name, int algo, int p, int k, uint64_t seed) {
     if (!output_name) return fail(LASH_E_INVALID, "lash_host_write_parameters: NULL argument");
     // main.rs:249-276: every value is a string; serde_json's Map is a BTreeMap, i.e. keys come out sorted

@@ -2,6 +2,8 @@
 
 #include <dlfcn.h>
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -417,6 +419,33 @@ std::unique_ptr<ByteSource> open_source(const std::string& path, std::string& er
         return std::make_unique<ZstdSource>(std::move(raw), api);
     }
     return raw;
+}
+
+bool map_plain_file(const std::string& path, const uint8_t** data, size_t* size) {
+    const int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return false;
+    struct stat sb;
+    uint8_t m[6] = {0, 0, 0, 0, 0, 0};
+    bool ok = fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0 && ::pread(fd, m, 6, 0) > 0;
+    const bool compressed = (m[0] == 0x1f && m[1] == 0x8b) || (m[0] == 'B' && m[1] == 'Z' && m[2] == 'h') ||
+                            (m[0] == 0xfd && m[1] == '7' && m[2] == 'z' && m[3] == 'X' && m[4] == 'Z' && m[5] == 0) ||
+                            (m[0] == 0x28 && m[1] == 0xb5 && m[2] == 0x2f && m[3] == 0xfd);
+    ok = ok && !compressed;
+    void* p = MAP_FAILED;
+    if (ok) {
+        const size_t len = (size_t)sb.st_size;
+        p = mmap(nullptr, len, PROT_READ, MAP_PRIVATE | (len <= (256u << 20) ? MAP_POPULATE : 0), fd, 0);
+        if (p != MAP_FAILED) {
+            madvise(p, len, MADV_SEQUENTIAL);
+            *data = static_cast<const uint8_t*>(p);
+            *size = len;
+        }
+    }
+    ::close(fd);
+    return ok && p != MAP_FAILED;
+}
+void unmap_file(const uint8_t* data, size_t size) {
+    if (data) munmap(const_cast<uint8_t*>(data), size);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -25,6 +25,10 @@ class ByteSource {
 // Opens `path`, sniffs the compression, returns a decoding source (nullptr + err on failure).
 std::unique_ptr<ByteSource> open_source(const std::string& path, std::string& err);
 
+// Maps an UNCOMPRESSED regular file read-only (false: compressed, empty, not mappable -> use open_source).
+bool map_plain_file(const std::string& path, const uint8_t** data, size_t* size);
+void unmap_file(const uint8_t* data, size_t size);
+
 // ---- zstd (streaming, run-time bound) --------------------------------------------------------------
 struct ZstdApi;
 const ZstdApi* zstd_api(std::string& err);  // nullptr when libzstd.so.1 cannot be loaded

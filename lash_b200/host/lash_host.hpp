@@ -46,6 +46,13 @@ Status sketch_files_impl(lash_ctx* ctx, int algo, std::optional<uint32_t> precis
                          size_t kmer_length, const std::string* output_name, uint32_t threads, uint64_t seed,
                          uint64_t chunk_bytes, void* regs_out, SketchFilesStats* stats);
 
+// host ingest ceiling: the same parse + filter + pack, chunks dropped instead of pushed (no GPU work)
+Status pack_files_dry(const std::vector<std::string>& files, size_t kmer_length, uint32_t threads, uint64_t chunk_bytes,
+                      SketchFilesStats* stats);
+
+// return the cached pinned staging blocks of sketch_files to the driver
+void release_pinned();
+
 template <class S>
 Status sketch_files(lash_ctx* ctx, std::optional<uint32_t> precision, const std::vector<std::string>& files, size_t kmer_length,
                     const std::string& output_name, uint32_t threads, uint64_t seed, SketchFilesStats* stats = nullptr) {

@@ -55,6 +55,16 @@ __attribute__((target("avx2,bmi2,popcnt"))) uint64_t append_avx2(BaseStream& bs,
     const __m256i lut = _mm256_setr_epi8((char)0xff, 'A', 0, 'C', 'T', 0, 0, 'G', 0, 0, 0, 0, 0, 0, 0, 0,
                                          (char)0xff, 'A', 0, 'C', 'T', 0, 0, 'G', 0, 0, 0, 0, 0, 0, 0, 0);
     const __m256i three = _mm256_set1_epi8(3);
+    const __m256i w14 = _mm256_set1_epi16(0x0401);       // byte pairs  -> c0 + 4 c1
+    const __m256i w116 = _mm256_set1_epi32(0x00100001);  // word pairs  -> (c0 + 4 c1) + 16 (c2 + 4 c3): 4 bases per byte
+    const __m256i low_bytes = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                               0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    // the partially filled last word lives in a register for the whole call
+    uint64_t* w = bs.words();
+    const uint64_t n0 = bs.size();
+    uint64_t idx = n0 >> 5;
+    unsigned bit = (unsigned)(n0 & 31) * 2;
+    uint64_t acc = bit ? w[idx] : 0;
     uint64_t kept = 0;
     size_t i = 0;
     for (; i + 32 <= n; i += 32) {
@@ -62,16 +72,23 @@ __attribute__((target("avx2,bmi2,popcnt"))) uint64_t append_avx2(BaseStream& bs,
         const uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, c), c));
         // code = ((c >> 1) ^ (c >> 2)) & 3 : A 0, C 1, G 2, T 3 (bits leaking in from the neighbour byte are masked)
         const __m256i code = _mm256_and_si256(_mm256_xor_si256(_mm256_srli_epi16(c, 1), _mm256_srli_epi16(c, 2)), three);
-        const uint64_t k = 0x0303030303030303ull;
-        const uint64_t all = _pext_u64((uint64_t)_mm256_extract_epi64(code, 0), k) |
-                             (_pext_u64((uint64_t)_mm256_extract_epi64(code, 1), k) << 16) |
-                             (_pext_u64((uint64_t)_mm256_extract_epi64(code, 2), k) << 32) |
-                             (_pext_u64((uint64_t)_mm256_extract_epi64(code, 3), k) << 48);
+        const __m256i g = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(code, w14), w116), low_bytes);
+        const uint64_t all = (uint64_t)(uint32_t)_mm256_cvtsi256_si32(g) |
+                             ((uint64_t)(uint32_t)_mm_cvtsi128_si32(_mm256_extracti128_si256(g, 1)) << 32);
         const uint64_t keep2 = _pdep_u64((uint64_t)m, 0x5555555555555555ull) * 3ull;  // both bits of every kept base
+        const uint64_t v = _pext_u64(all, keep2);                                       // deleted bytes squeezed out
         const unsigned cnt = (unsigned)_mm_popcnt_u32(m);
-        if (cnt) bs.append64(_pext_u64(all, keep2), cnt);
+        acc |= v << bit;
+        const unsigned nbits = bit + 2 * cnt;
+        w[idx] = acc;
+        const bool carry = nbits >= 64;
+        idx += carry;
+        acc = carry ? (v >> 1) >> (63 - bit) : acc;  // == v >> (64 - bit), and 0 when bit == 0
+        bit = nbits & 63;
         kept += cnt;
     }
+    if (bit) w[idx] = acc;
+    bs.set_size(n0 + kept);
     if (i < n) kept += append_scalar(bs, s + i, n - i);
     return kept;
 }

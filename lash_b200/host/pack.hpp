@@ -21,6 +21,8 @@ class BaseStream {
         n_ = 0;
     }
     uint64_t size() const { return n_; }
+    uint64_t* words() { return w_; }
+    void set_size(uint64_t n) { n_ = n; }  // after the caller wrote words() itself, keeping the invariants of append64
     // bases that can still be appended (leaves room for the spill word and the 16-byte ABI pad)
     uint64_t room() const {
         const uint64_t usable = cap_ > 48 ? (cap_ - 48) * 4 : 0;

@@ -9,8 +9,11 @@
 // (pack.cpp) into a pinned chunk and hands full chunks to the GPU (lash_sketch_push) while it fills
 // its second chunk.  Several small files share a chunk (one span each); a large record is split
 // across chunks with a (k-1)-base overlap so that every k-mer start is produced exactly once.
+#include <sys/stat.h>
+
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -31,6 +34,57 @@ namespace {
 constexpr uint64_t kDefaultChunk = 16ull << 20;
 constexpr size_t kFeed = 1u << 16;  // sequence bytes handed to the packer per call (room is checked per call)
 
+// Pinned staging blocks are kept across calls: page-locking is slow (cudaHostAlloc runs at ~1-3 GB/s, so the
+// 16 workers x 2 x 16 MiB of a default call cost more than sketching a few hundred Mbp) and a host that sketches
+// batch after batch should pay it once.  lash_host_release_pinned() returns the blocks to the driver.
+class PinnedPool {
+  public:
+    void* get(uint64_t bytes, uint64_t* got) {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            auto it = free_.lower_bound(bytes);
+            if (it != free_.end() && it->first <= 2 * bytes) {
+                void* p = it->second;
+                *got = it->first;
+                pooled_ -= it->first;
+                free_.erase(it);
+                return p;
+            }
+        }
+        void* p = nullptr;
+        if (lash_host_alloc(bytes, &p) != LASH_OK) return nullptr;
+        *got = bytes;
+        return p;
+    }
+    void put(void* p, uint64_t bytes) {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            if (pooled_ + bytes <= kMaxPooled) {
+                free_.emplace(bytes, p);
+                pooled_ += bytes;
+                return;
+            }
+        }
+        lash_host_free(p);
+    }
+    void clear() {
+        std::lock_guard<std::mutex> g(mu_);
+        for (auto& kv : free_) lash_host_free(kv.second);
+        free_.clear();
+        pooled_ = 0;
+    }
+
+  private:
+    static constexpr uint64_t kMaxPooled = 1ull << 30;
+    std::mutex mu_;
+    std::multimap<uint64_t, void*> free_;
+    uint64_t pooled_ = 0;
+};
+PinnedPool& pinned_pool() {
+    static PinnedPool* pool = new PinnedPool();  // never destroyed: the CUDA runtime may be gone at exit
+    return *pool;
+}
+
 // serialises access to the (not thread-safe) sketcher handle
 struct Gpu {
     lash_sketcher* sk = nullptr;
@@ -47,15 +101,24 @@ struct Gpu {
 // One pinned chunk being filled: spans of (possibly several) genomes, their record tables
 class Chunk {
   public:
-    bool alloc(uint64_t bytes) {
+    // pinned: staging for lash_sketch_push; !pinned: plain memory for the parse+pack dry run (no GPU involved)
+    bool alloc(uint64_t bytes, bool pinned = true) {
         cap_ = bytes;
+        pinned_ = pinned;
         void* p = nullptr;
-        if (lash_host_alloc(bytes, &p) != LASH_OK) return false;
+        if (pinned) {
+            p = pinned_pool().get(bytes, &block_);
+            if (!p) return false;
+        } else if (posix_memalign(&p, 64, bytes) != 0) {
+            return false;
+        }
         buf_ = static_cast<uint8_t*>(p);
         return true;
     }
+    bool allocated() const { return buf_ != nullptr; }
     void release() {
-        if (buf_) lash_host_free(buf_);
+        if (buf_ && pinned_) pinned_pool().put(buf_, block_);
+        else if (buf_) free(buf_);
         buf_ = nullptr;
     }
     bool empty() const { return spans_.empty() && !span_open_; }
@@ -129,7 +192,8 @@ class Chunk {
     // hand the chunk to the GPU; returns the ticket (0 = nothing to push)
     bool submit(Gpu& gpu, uint64_t* ticket) {
         *ticket = 0;
-        if (spans_.empty()) {
+        if (spans_.empty() || !gpu.sk) {  // nothing to push, or dry run
+            if (!spans_.empty()) gpu.pushes.fetch_add(1);
             reset();
             return true;
         }
@@ -160,13 +224,13 @@ class Chunk {
         ++n_rec_;
     }
     uint8_t* buf_ = nullptr;
-    uint64_t cap_ = 0, off_ = 0;
+    uint64_t cap_ = 0, off_ = 0, block_ = 0;
     BaseStream bs_;
     std::vector<lash_span> spans_;
     std::vector<uint64_t> rec_start_;
     uint64_t genome_ = 0, rec_first_ = 0, rec_begin_ = 0, uniform_len_ = 0, last_len_ = 0;
     uint32_t n_rec_ = 0;
-    bool uniform_ = true, span_open_ = false;
+    bool uniform_ = true, span_open_ = false, pinned_ = true;
 };
 
 struct Worker {
@@ -179,6 +243,10 @@ struct Worker {
     bool rotate(Gpu& gpu) {
         if (!chunk[cur].submit(gpu, &ticket[cur])) return false;
         cur ^= 1;
+        if (!chunk[cur].allocated() && !chunk[cur].alloc(chunk[cur ^ 1].cap(), gpu.sk != nullptr)) {  // second buffer on first need
+            gpu.fail(std::string("pinned staging allocation failed: ") + lash_gpu_last_error());
+            return false;
+        }
         if (ticket[cur]) {
             std::lock_guard<std::mutex> g(gpu.mu);
             if (lash_sketch_wait_copied(gpu.sk, ticket[cur]) != LASH_OK) {
@@ -239,7 +307,71 @@ struct Worker {
     }
 };
 
+// Staging chunk size when the caller does not choose: about half of a worker's share of the packed input
+// (input bytes / 4), between 1 and 16 MiB -- small jobs do not page-lock memory they will never fill.
+uint64_t auto_chunk_bytes(const std::vector<std::string>& files, uint32_t n_workers) {
+    uint64_t total = 0;
+    for (const auto& f : files) {
+        struct stat sb;
+        if (stat(f.c_str(), &sb) == 0 && S_ISREG(sb.st_mode)) total += (uint64_t)sb.st_size;
+        if (total > (1ull << 36)) break;
+    }
+    const uint64_t per_worker = total / 4 / std::max(1u, n_workers);
+    const uint64_t want = ((per_worker / 2 + (1u << 20) - 1) >> 20) << 20;
+    return std::min<uint64_t>(std::max<uint64_t>(want, 1u << 20), kDefaultChunk);
+}
+
 }  // namespace
+
+void release_pinned() { pinned_pool().clear(); }
+
+// Parse + filter + pack every file exactly as sketch_files does, but drop the chunks instead of pushing
+// them: the host-side ingest ceiling (no GPU, no sketch -- a measurement aid for bench.py).
+Status pack_files_dry(const std::vector<std::string>& files, size_t kmer_length, uint32_t threads, uint64_t chunk_bytes,
+                      SketchFilesStats* stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (kmer_length < 1 || kmer_length > 32) return Status{LASH_E_INVALID, "k-mer length must be 1-32"};
+    const uint64_t n_files = files.size();
+    SketchFilesStats st{};
+    if (n_files) {
+        if (chunk_bytes == 0) chunk_bytes = kDefaultChunk;
+        uint32_t n_workers = threads ? threads : std::max(1u, std::thread::hardware_concurrency());
+        n_workers = (uint32_t)std::min<uint64_t>(n_workers, n_files);
+        Gpu gpu;  // sk == nullptr: submit() only counts
+        std::vector<Worker> workers(n_workers);
+        for (auto& w : workers)
+            if (!w.chunk[0].alloc(chunk_bytes, false)) return Status{LASH_E_NOMEM, "staging allocation failed"};
+        std::atomic<uint64_t> next_file{0};
+        auto run = [&](Worker& w) {
+            for (;;) {
+                const uint64_t f = next_file.fetch_add(1);
+                if (f >= n_files || gpu.failed.load()) break;
+                std::string err;
+                if (!w.sketch_file(gpu, files[f], f, (int)kmer_length, err)) {
+                    gpu.fail(err);
+                    break;
+                }
+            }
+            uint64_t t;
+            w.chunk[w.cur].submit(gpu, &t);
+        };
+        std::vector<std::thread> pool;
+        for (uint32_t i = 1; i < n_workers; ++i) pool.emplace_back(run, std::ref(workers[i]));
+        run(workers[0]);
+        for (auto& t : pool) t.join();
+        for (auto& w : workers) {
+            st.n_records += w.n_records;
+            st.n_bases_in += w.n_in;
+            st.n_bases_kept += w.n_kept;
+            for (auto& c : w.chunk) c.release();
+        }
+        st.n_pushes = gpu.pushes.load();
+        if (gpu.failed.load()) return Status{LASH_HOST_E_FORMAT, gpu.err};
+    }
+    st.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = st;
+    return Status{};
+}
 
 Status sketch_files_impl(lash_ctx* ctx, int algo, std::optional<uint32_t> precision, const std::vector<std::string>& files,
                          size_t kmer_length, const std::string* output_name, uint32_t threads, uint64_t seed, uint64_t chunk_bytes,
@@ -263,18 +395,17 @@ Status sketch_files_impl(lash_ctx* ctx, int algo, std::optional<uint32_t> precis
     }
     SketchFilesStats st{};
     if (n_files) {
-        if (chunk_bytes == 0) chunk_bytes = kDefaultChunk;
-        chunk_bytes = std::max<uint64_t>(chunk_bytes, 1u << 20) / 16 * 16;
         uint32_t n_workers = threads ? threads : std::max(1u, std::thread::hardware_concurrency());
         n_workers = (uint32_t)std::min<uint64_t>(n_workers, n_files);
+        if (chunk_bytes == 0) chunk_bytes = auto_chunk_bytes(files, n_workers);
+        chunk_bytes = std::max<uint64_t>(chunk_bytes, 1u << 20) / 16 * 16;
 
         Gpu gpu;
         if (lash_sketch_open(ctx, algo, p, (int)kmer_length, seed, n_files, &gpu.sk) != LASH_OK)
             return Status{LASH_E_CUDA, lash_gpu_last_error()};
         std::vector<Worker> workers(n_workers);
         bool alloc_ok = true;
-        for (auto& w : workers)
-            for (auto& c : w.chunk) alloc_ok = alloc_ok && c.alloc(chunk_bytes);
+        for (auto& w : workers) alloc_ok = alloc_ok && w.chunk[0].alloc(chunk_bytes);  // chunk[1]: on first rotate
         std::atomic<uint64_t> next_file{0};
         if (alloc_ok) {
             auto run = [&](Worker& w) {

@@ -35,6 +35,8 @@ PROTOTYPES = {
     "lash_host_pack_has_simd": (i32, []),
     "lash_host_sketch_files_regs": (i32, [vp, i32, i32, i32, u64, C.POINTER(cp), u64, i32, u64, vp, C.POINTER(SketchFilesStats)]),
     "lash_host_sketch_files": (i32, [vp, i32, i32, i32, u64, C.POINTER(cp), u64, cp, i32, C.POINTER(SketchFilesStats)]),
+    "lash_host_pack_files_dry": (i32, [C.POINTER(cp), u64, i32, i32, u64, C.POINTER(SketchFilesStats)]),
+    "lash_host_release_pinned": (i32, []),
     "lash_host_write_parameters": (i32, [cp, i32, i32, i32, u64]),
     "lash_host_write_sketches": (i32, [cp, i32, i32, vp, u64, i32]),
     "lash_host_read_sketches": (i32, [cp, i32, C.POINTER(i32), u64, vp]),
@@ -120,6 +122,13 @@ def sketch_files_regs(ctx, algo: int, p: int, k: int, seed: int, files: Sequence
     check(lib().lash_host_sketch_files_regs(ctx.handle, algo, p, k, seed & (2**64 - 1), _files_arg(files), len(files), threads,
                                             chunk_bytes, out.ctypes.data_as(vp), C.byref(st)))
     return out, st
+
+
+def pack_files_dry(files: Sequence[str], k: int, threads: int = 0, chunk_bytes: int = 0) -> SketchFilesStats:
+    """Parse + filter + pack only (no GPU): the host ingest ceiling."""
+    st = SketchFilesStats()
+    check(lib().lash_host_pack_files_dry(_files_arg(files), len(files), k, threads, chunk_bytes, C.byref(st)))
+    return st
 
 
 def sketch_files(ctx, algo: int, p: int, k: int, seed: int, files: Sequence[str], output_name: str, threads: int = 0) -> SketchFilesStats:

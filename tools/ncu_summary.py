@@ -35,7 +35,10 @@ def main():
     rep, out = sys.argv[1], sys.argv[2]
     units = float(sys.argv[3]) if len(sys.argv) > 3 else None
     unit_name = sys.argv[4] if len(sys.argv) > 4 else "units"
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):  # already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`)
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, unit = rows[0], rows[1]
     res = []

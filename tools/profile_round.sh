@@ -10,7 +10,7 @@ tag=${1:-rXX}
 out=gpurun_out
 mkdir -p $out
 NCU="ncu --clock-control none"
-B="python bench.py --genomes 400 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+B="python bench.py --genomes 400 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ingest"
 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $out/${tag}_launches.csv $B > $out/${tag}_launches.log 2>&1
 $NCU --set full --import-source on -k regex:sketch_kernel --launch-skip 3 -c 1 -f -o $out/${tag}_sketch_ull10_k16 $B > $out/${tag}_ncu1.log 2>&1
 $NCU --set full --import-source on -k regex:dist_kernel --launch-skip 3 -c 1 -f -o $out/${tag}_dist_fgra $B > $out/${tag}_ncu2.log 2>&1
