@@ -140,6 +140,16 @@ int lash_sketch_set_stream(lash_sketcher* s, void* stream);
 int lash_sketch_stats(lash_sketcher* s, double* kernel_ms, uint64_t* launches);
 int lash_sketch_close(lash_sketcher* s);
 
+/* Fold sketches: dst[i] = merge(dst[i], src[i]) for n_sketches register arrays of the same (algo, p) --
+ * register-wise max for HLL / HMH (HyperLogLog::union), pack(unpack(a) | unpack(b)) for ULL
+ * (UltraLogLog::merge, utils.rs:260-262; NOT a byte max).  This is the one exchange step when a SINGLE
+ * sample is sketched in shares (config "100 Gbp of reads -> one sketch": every GPU sketches its share of the
+ * reads, the world x reg_bytes accumulators are all-gathered and folded).  _dev: device pointers, enqueued on
+ * `stream` (NULL = the context's stream), not synchronised.  Host variant: dst_regs is updated in place. */
+int lash_sketch_merge_dev(lash_ctx* ctx, int algo, int p, void* dst_dev, const void* src_dev, uint64_t n_sketches,
+                          void* stream);
+int lash_sketch_merge(lash_ctx* ctx, int algo, int p, void* dst_regs, const void* src_regs, uint64_t n_sketches);
+
 /* ------------------------------------------------------------------------------------------------
  * Distance.  Replaces the par_iter bodies of utils.rs:150-180 / 248-285 / 342-370 and
  * compute_distance (main.rs:415-423): for every (reference i, query j) pair

@@ -51,6 +51,8 @@ PROTOTYPES = {
     "lash_sketch_set_stream": (i32, [vp, vp]),
     "lash_sketch_stats": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
     "lash_sketch_close": (i32, [vp]),
+    "lash_sketch_merge_dev": (i32, [vp, i32, i32, vp, vp, u64, vp]),
+    "lash_sketch_merge": (i32, [vp, i32, i32, vp, vp, u64]),
     "lash_dist": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, u64, vp, u64, i32, vp]),
     "lash_dist_dev": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, u64, vp, u64, vp, vp, i32, u64, u64, vp, vp, vp]),
     "lash_cardinality_dev": (i32, [vp, i32, i32, i32, vp, u64, vp, vp]),

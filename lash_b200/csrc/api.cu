@@ -96,7 +96,7 @@ struct lash_ctx {
     uint64_t dist_launches = 0;
     // scratch of lash_dist / lash_dist_stream, kept across calls (cudaMalloc/cudaFree per call cost
     // milliseconds of jitter on a 2.5 ms operation)
-    DevBuf d_ref, d_qry, d_card, d_out[2], d_flags;
+    DevBuf d_ref, d_qry, d_card, d_out[2], d_flags, d_regmin;
     PinBuf h_out[2];
 };
 
@@ -125,7 +125,7 @@ extern "C" int lash_ctx_destroy(lash_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_ref.release(); c->d_qry.release(); c->d_card.release(); c->d_out[0].release(); c->d_out[1].release();
-    c->d_flags.release(); c->h_out[0].release(); c->h_out[1].release();
+    c->d_flags.release(); c->d_regmin.release(); c->h_out[0].release(); c->h_out[1].release();
     delete c;
     return LASH_OK;
 }
@@ -470,6 +470,39 @@ extern "C" int lash_sketch_close(lash_sketcher* s) {
     return LASH_OK;
 }
 
+extern "C" int lash_sketch_merge_dev(lash_ctx* ctx, int algo, int p, void* dst_dev, const void* src_dev, uint64_t n_sketches,
+                                     void* stream) {
+    if (!ctx) return fail(LASH_E_INVALID, "lash_sketch_merge_dev: NULL ctx");
+    if (!valid_algo_p(algo, p)) return fail(LASH_E_INVALID, "lash_sketch_merge_dev: bad algorithm / precision");
+    if (n_sketches == 0) return LASH_OK;
+    if (!dst_dev || !src_dev) return fail(LASH_E_INVALID, "lash_sketch_merge_dev: NULL device pointer");
+    const size_t rb = lash_sketch_reg_bytes(algo, p);
+    if ((rb * n_sketches) % 4 || ((uintptr_t)dst_dev | (uintptr_t)src_dev) % 4)
+        return fail(LASH_E_INVALID, "lash_sketch_merge_dev: register arrays must be 4-byte aligned and a multiple of 4 bytes");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_merge(algo, (uint32_t*)dst_dev, (const uint32_t*)src_dev, rb * n_sketches / 4, ctx->n_sm,
+                    stream ? (cudaStream_t)stream : ctx->stream));
+    return LASH_OK;
+}
+extern "C" int lash_sketch_merge(lash_ctx* ctx, int algo, int p, void* dst_regs, const void* src_regs, uint64_t n_sketches) {
+    if (!ctx) return fail(LASH_E_INVALID, "lash_sketch_merge: NULL ctx");
+    if (!valid_algo_p(algo, p)) return fail(LASH_E_INVALID, "lash_sketch_merge: bad algorithm / precision");
+    if (n_sketches == 0) return LASH_OK;
+    if (!dst_regs || !src_regs) return fail(LASH_E_INVALID, "lash_sketch_merge: NULL argument");
+    const size_t bytes = lash_sketch_reg_bytes(algo, p) * n_sketches;
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->d_ref.reserve((bytes + 3) / 4 * 4));
+    CU(ctx->d_qry.reserve((bytes + 3) / 4 * 4));
+    CU(cudaMemsetAsync(ctx->d_ref.p, 0, (bytes + 3) / 4 * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_qry.p, 0, (bytes + 3) / 4 * 4, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_ref.p, dst_regs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_qry.p, src_regs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_merge(algo, (uint32_t*)ctx->d_ref.p, (const uint32_t*)ctx->d_qry.p, (bytes + 3) / 4, ctx->n_sm, ctx->stream));
+    CU(cudaMemcpyAsync(dst_regs, ctx->d_ref.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LASH_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // distance
 // ------------------------------------------------------------------------------------------------
@@ -480,6 +513,18 @@ static int check_dist_args(int algo, int p, int k, int estimator, int model, uin
     if (algo == LASH_ALGO_ULL && estimator != 0 && estimator != 1)
         return fail(LASH_E_INVALID, "estimator needs to be either fgra or ml");  // utils.rs:217
     if (triangular && n_ref != n_qry) return fail(LASH_E_INVALID, "lash_dist: triangular needs the same set on both sides");
+    return LASH_OK;
+}
+
+// smallest non-empty register of both sets, for the FGRA pair-table kernel (dist_kernels.cu)
+static int prepare_regmin(lash_ctx* ctx, DistParams& dp, size_t rb, cudaStream_t st) {
+    if (dp.algo != LASH_ALGO_ULL || dp.estimator != LASH_EST_FGRA) return LASH_OK;
+    CU(ctx->d_regmin.reserve(4));
+    uint32_t* w = (uint32_t*)ctx->d_regmin.p;
+    CU(cudaMemsetAsync(w, 0xff, 4, st));
+    CU(launch_regmin(dp.ref, rb * dp.n_ref, w, ctx->n_sm, st));
+    if (dp.qry != dp.ref) CU(launch_regmin(dp.qry, rb * dp.n_qry, w, ctx->n_sm, st));
+    dp.regmin = w;
     return LASH_OK;
 }
 
@@ -546,6 +591,8 @@ extern "C" int lash_dist_dev(lash_ctx* ctx, int algo, int p, int k, int estimato
     dp.packed_tri = triangular ? 1 : 0;
     dp.out_row0 = 0;
     dp.flags = flags_dev;
+    rc = prepare_regmin(ctx, dp, lash_sketch_reg_bytes(algo, p), stream ? (cudaStream_t)stream : ctx->stream);
+    if (rc) return rc;
     uint32_t nl = 0;
     CU(launch_dist(dp, stream ? (cudaStream_t)stream : ctx->stream, &nl));
     ctx->dist_launches += nl;
@@ -615,6 +662,11 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
     dp.triangular = triangular ? 1 : 0;
     dp.ref = d_ref.p; dp.qry = qdev; dp.n_ref = n_ref; dp.n_qry = n_qry;
     dp.card_ref = card_r; dp.card_qry = card_q; dp.flags = (uint32_t*)d_flags.p;
+    rc = prepare_regmin(ctx, dp, rb, st);
+    if (rc) {
+        cleanup();
+        return rc;
+    }
 
     if (!cb) {
         // whole result on device, one D2H

@@ -13,7 +13,10 @@
 // oracle's; only pow/log in the per-pair epilogue can differ from a host libm by an ulp.
 // The union itself never exists in memory: HLL = __vmaxu4, ULL = packed-domain OR-merge of four
 // registers per 32-bit word (ull_merge4), HMH = SIMD halfword equality / non-zero counts.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <string>
 #include <type_traits>
 
 #include "estimators.cuh"
@@ -417,6 +420,153 @@ __global__ void __launch_bounds__(kDistThreads) dist_kernel(DistParams dp, uint3
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4b: FGRA distance tiles through a PAIR table.
+//
+// dist_kernel<FgraAcc> spends ~12 ALU instructions per register pair on the packed-domain merge
+// (ncu: ALU pipe 91 % busy, everything else idle).  Here the merge is looked up instead: register bytes
+// are recoded at staging time to c = 0 (empty) or r - (4p-4) + 1 (1..126; 127 = "outside the table"),
+// and a CTA-private table T[ca][cb] = REGISTER_CONTRIBUTIONS[merge(ra, rb)] (128 x 128 doubles =
+// 128 KiB of shared memory) turns one register pair into  address add + LDS.64 + DADD.  Entries whose
+// merged register needs FGRA's small/large-range treatment, and code 127, hold the same 2^600 sentinel
+// as dist_kernel, so those pairs are redone by the exact per-pair path; every other pair adds exactly the
+// same doubles in exactly the same (register index) order as before -- results are bit-identical.
+// A warp owns 2 reference rows (uniform across lanes -> shared loads broadcast) x 64 query columns.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTabN = 128;
+constexpr int kTabThreads = 512;
+constexpr int kTabTR = 32, kTabTQ = 64;   // pairs tile of a CTA
+constexpr int kTabChunk = 256;            // registers per sketch per stage
+
+__device__ __forceinline__ uint32_t fgra_code(uint32_t r, uint32_t base) {
+    const uint32_t c = min(r - base + 1u, 127u);  // r < base wraps to a huge value -> 127
+    return r ? c : 0u;
+}
+
+__global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* T = reinterpret_cast<double*>(smem_raw);
+    const uint32_t a_stride = chunk + 4;                 // u32 elements per reference row (+16 B pad)
+    const uint32_t b_stride = chunk + 8;                 // u16 elements per query row (+16 B pad)
+    uint32_t* sa = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTabN * kTabN * 8);
+    uint16_t* sb = reinterpret_cast<uint16_t*>(sa + (size_t)kTabTR * a_stride);
+
+    const uint64_t row0 = dp.row_begin + (uint64_t)blockIdx.y * kTabTR;
+    const uint64_t col0 = (uint64_t)blockIdx.x * kTabTQ;
+    if (row0 >= dp.row_end) return;
+    const uint64_t row_hi = min(row0 + kTabTR, dp.row_end);
+    if (dp.triangular && col0 > row_hi - 1) return;
+
+    // ---- pair table -------------------------------------------------------------------------------
+    // The 126 register values the table covers start at the smallest non-empty register of the two sets
+    // (regmin_kernel), not at the smallest possible one: sketches of large inputs (10^11 k-mers at p = 14)
+    // have no register anywhere near 4p-4 but plenty above 4p-4+126, and would all take the exact path.
+    const int p = dp.p;
+    const uint32_t off = (uint32_t)(4 * p + 4);
+    uint32_t base = (uint32_t)(4 * p - 4);
+    if (dp.regmin) {
+        const uint32_t mn = __ldg(dp.regmin);
+        if (mn != 0xffffffffu) base = max(base, mn & ~3u);
+    }
+    for (uint32_t e = threadIdx.x; e < (uint32_t)(kTabN * kTabN); e += kTabThreads) {
+        const uint32_t ca = e >> 7, cb = e & 127u;
+        double v = LASH_FGRA_SENTINEL;
+        if (ca != 127u && cb != 127u) {
+            const uint32_t ra = ca ? ca + base - 1u : 0u, rb = cb ? cb + base - 1u : 0u;
+            const uint32_t m = ull_merge1(ra, rb);
+            if (m >= off && m < 252u) v = c_ull.reg[m - off];
+        }
+        T[e] = v;
+    }
+
+    const uint32_t ty = threadIdx.x >> 5, tx = threadIdx.x & 31u;  // ty is warp-uniform
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    const unsigned char* gref = reinterpret_cast<const unsigned char*>(dp.ref);
+    const unsigned char* gqry = reinterpret_cast<const unsigned char*>(dp.qry);
+    const uint32_t chunk_words = chunk / 4;
+    const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(T);
+
+    for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk) {
+        __syncthreads();  // previous chunk consumed (first pass: orders the table build)
+        // stage + recode: reference side as byte offsets of the table ROW (code << 10), query side as byte
+        // offsets inside a row (code << 3)
+        for (uint32_t e = threadIdx.x; e < (uint32_t)kTabTR * chunk_words; e += kTabThreads) {
+            const uint32_t r = e / chunk_words, w = e % chunk_words;
+            const uint64_t gi = row0 + r;
+            const uint32_t v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint32_t*>(gref + gi * cell_bytes + c0) + w) : 0u;
+            uint4 o;
+            o.x = fgra_code(v & 0xffu, base) << 10;
+            o.y = fgra_code((v >> 8) & 0xffu, base) << 10;
+            o.z = fgra_code((v >> 16) & 0xffu, base) << 10;
+            o.w = fgra_code(v >> 24, base) << 10;
+            *reinterpret_cast<uint4*>(sa + r * a_stride + 4 * w) = o;
+        }
+        for (uint32_t e = threadIdx.x; e < (uint32_t)kTabTQ * chunk_words; e += kTabThreads) {
+            const uint32_t r = e / chunk_words, w = e % chunk_words;
+            const uint64_t gj = col0 + r;
+            const uint32_t v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint32_t*>(gqry + gj * cell_bytes + c0) + w) : 0u;
+            uint2 o;
+            o.x = (fgra_code(v & 0xffu, base) << 3) | (fgra_code((v >> 8) & 0xffu, base) << 19);
+            o.y = (fgra_code((v >> 16) & 0xffu, base) << 3) | (fgra_code(v >> 24, base) << 19);
+            *reinterpret_cast<uint2*>(sb + r * b_stride + 4 * w) = o;
+        }
+        __syncthreads();
+        const uint32_t* pa0 = sa + ty * a_stride;
+        const uint32_t* pa1 = sa + (ty + 16) * a_stride;
+        const uint16_t* pb0 = sb + tx * b_stride;
+        const uint16_t* pb1 = sb + (tx + 32) * b_stride;
+#pragma unroll 1
+        for (uint32_t e = 0; e < chunk; e += 8) {
+            const uint4 a0l = *reinterpret_cast<const uint4*>(pa0 + e), a0h = *reinterpret_cast<const uint4*>(pa0 + e + 4);
+            const uint4 a1l = *reinterpret_cast<const uint4*>(pa1 + e), a1h = *reinterpret_cast<const uint4*>(pa1 + e + 4);
+            const uint4 b0 = *reinterpret_cast<const uint4*>(pb0 + e);
+            const uint4 b1 = *reinterpret_cast<const uint4*>(pb1 + e);
+            const uint32_t a0[8] = {a0l.x, a0l.y, a0l.z, a0l.w, a0h.x, a0h.y, a0h.z, a0h.w};
+            const uint32_t a1[8] = {a1l.x, a1l.y, a1l.z, a1l.w, a1h.x, a1h.y, a1h.z, a1h.w};
+            const uint32_t b0w[4] = {b0.x, b0.y, b0.z, b0.w}, b1w[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t q0 = (i & 1) ? (b0w[i >> 1] >> 16) : (b0w[i >> 1] & 0xffffu);
+                const uint32_t q1 = (i & 1) ? (b1w[i >> 1] >> 16) : (b1w[i >> 1] & 0xffffu);
+                const uint32_t r0 = tbase + a0[i], r1 = tbase + a1[i];
+                double t00, t01, t10, t11;
+                asm("ld.shared.f64 %0, [%1];" : "=d"(t00) : "r"(r0 + q0));
+                asm("ld.shared.f64 %0, [%1];" : "=d"(t01) : "r"(r0 + q1));
+                asm("ld.shared.f64 %0, [%1];" : "=d"(t10) : "r"(r1 + q0));
+                asm("ld.shared.f64 %0, [%1];" : "=d"(t11) : "r"(r1 + q1));
+                acc[0][0] += t00;
+                acc[0][1] += t01;
+                acc[1][0] += t10;
+                acc[1][1] += t11;
+            }
+        }
+    }
+
+    // epilogue: identical to dist_kernel<FgraAcc>
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const uint64_t i = row0 + ty + 16 * a, j = col0 + tx + 32 * b;
+            if (i >= dp.row_end || j >= dp.n_qry) continue;
+            if (dp.triangular && j > i) continue;
+            FgraAcc fa;
+            fa.sum = acc[a][b];
+            bool bias;
+            const double U = finish_union(fa, dp.p, gref + i * cell_bytes, gqry + j * cell_bytes, &bias);
+            const double ca = dp.card_ref[i], cb = dp.card_qry[j];
+            const double sim = (ca + cb - U) / U;
+            const double s = sim < 0.0 ? 0.0 : sim;  // utils.rs:274: NaN propagates
+            const double frac = 2.0 * s / (1.0 + s);
+            const uint64_t o = dp.packed_tri ? (i * (i + 1) / 2 + j) : ((i - dp.out_row0) * dp.n_qry + j);
+            if (dp.fp32)
+                reinterpret_cast<float*>(dp.out)[o] = mash_distance_f32((float)frac, dp.k, dp.model);
+            else
+                reinterpret_cast<double*>(dp.out)[o] = mash_distance_f64(frac, dp.k, dp.model);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: per-sketch cardinality (utils.rs:213-219, 314-316; hyperminhash cardinality())
 // One thread per sketch, registers walked in index order with the same accumulators as K4
 // (the union of a sketch with itself is the sketch).
@@ -525,9 +675,61 @@ static cudaError_t launch_dist_t(const DistParams& dp, cudaStream_t st) {
     return cudaSuccess;
 }
 
+// smallest non-zero register byte of an array (atomicMin into *out, which the caller presets to 0xffffffff)
+__global__ void regmin_kernel(const uint32_t* __restrict__ regs, uint64_t n_words, uint32_t* out) {
+    uint32_t m = 0xffu;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+        const uint32_t w = __ldg(regs + i);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t r = (w >> (8 * b)) & 0xffu;
+            m = r ? min(m, r) : m;
+        }
+    }
+    m = __reduce_min_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m != 0xffu) atomicMin(out, m);
+}
+cudaError_t launch_regmin(const void* regs, uint64_t n_bytes, uint32_t* out_dev, int n_sm, cudaStream_t st) {
+    const uint64_t n_words = n_bytes / 4;
+    if (n_words == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_words + 255) / 256, (uint64_t)n_sm * 8);
+    regmin_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(regs), n_words, out_dev);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_dist_fgra_tab(const DistParams& dp, cudaStream_t st) {
+    const uint32_t cb = cell_bytes_of(dp.algo, dp.p);
+    const uint32_t chunk = cb < (uint32_t)kTabChunk ? cb : (uint32_t)kTabChunk;
+    const size_t smem = (size_t)kTabN * kTabN * 8 + (size_t)kTabTR * (chunk + 4) * 4 + (size_t)kTabTQ * (chunk + 8) * 2;
+    cudaError_t e = cudaFuncSetAttribute(dist_fgra_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint64_t rows = dp.row_end - dp.row_begin;
+    const uint64_t gy = (rows + kTabTR - 1) / kTabTR;
+    uint64_t ncols = dp.n_qry;
+    if (dp.triangular && dp.row_end < ncols) ncols = dp.row_end;
+    const uint64_t gx = (ncols + kTabTQ - 1) / kTabTQ;
+    for (uint64_t y0 = 0; y0 < gy; y0 += 65535) {
+        DistParams q = dp;
+        q.row_begin = dp.row_begin + y0 * kTabTR;
+        const uint64_t ny = (gy - y0) < 65535 ? (gy - y0) : 65535;
+        dim3 grid((unsigned)gx, (unsigned)ny);
+        dist_fgra_tab_kernel<<<grid, kTabThreads, smem, st>>>(q, cb, chunk);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launches) {
     if (dp.row_end <= dp.row_begin || dp.n_qry == 0) return cudaSuccess;
     if (n_launches) *n_launches += 1;
+    // LASH_FGRA_KERNEL=merge selects the ALU-merge kernel (A/B measurements); default is the pair-table kernel
+    static const bool fgra_merge = [] {
+        const char* v = getenv("LASH_FGRA_KERNEL");
+        return v && std::string(v) == "merge";
+    }();
+    if (dp.algo == ULL && dp.estimator == 0 && !fgra_merge) return launch_dist_fgra_tab(dp, st);
     if (dp.algo == HLL) return launch_dist_t<HllAcc, 16>(dp, st);
     if (dp.algo == HMH) return launch_dist_t<HmhAcc, 16>(dp, st);
     const bool tiny = dp.p == 3;  // 8 registers per sketch

@@ -50,6 +50,9 @@ cudaError_t launch_build_invalid_mask(const SpanRecs* spans_dev, uint32_t n_span
 cudaError_t launch_sketch(const SketchParams& sp, const uint32_t* packed_dev, const uint32_t* mask_dev,
                           const SketchTile* tiles_dev, uint32_t n_tiles, uint32_t* acc_dev, cudaStream_t st);
 
+// dst[i] = merge(dst[i], src[i]) over 32-bit words of register arrays
+cudaError_t launch_merge(int algo, uint32_t* dst, const uint32_t* src, uint64_t n_words, int n_sm, cudaStream_t st);
+
 struct DistParams {
     int algo, p, k, estimator, model, fp32, triangular;
     const void* ref;
@@ -63,7 +66,11 @@ struct DistParams {
     int packed_tri;
     uint64_t out_row0;
     uint32_t* flags;  // optional bias-regime counter
+    // optional (ULL FGRA pair-table kernel): device word holding the smallest non-empty register of both sets
+    const uint32_t* regmin = nullptr;
 };
+// atomicMin of the smallest non-zero register byte into *out_dev (preset to 0xffffffff by the caller)
+cudaError_t launch_regmin(const void* regs, uint64_t n_bytes, uint32_t* out_dev, int n_sm, cudaStream_t st);
 cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launches);
 cudaError_t launch_cardinality(int algo, int p, int estimator, const void* regs, uint64_t n, double* card,
                                uint32_t* flags, cudaStream_t st);

@@ -406,6 +406,27 @@ cudaError_t launch_build_invalid_mask(const SpanRecs* spans_dev, uint32_t n_span
     return cudaGetLastError();
 }
 
+// Fold `src` sketches into `dst` register-wise (same algorithm and precision): max for HLL / HMH
+// (HyperLogLog::union, hyperminhash merge), pack(unpack(a) | unpack(b)) for ULL (UltraLogLog::merge,
+// utils.rs:260-262).  Used when ONE sample is sketched in shares (several GPUs, several passes).
+template <int ALGO>
+__global__ void merge_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n_words) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride)
+        dst[i] = Cell<ALGO>::merge_word(dst[i], __ldg(src + i));
+}
+cudaError_t launch_merge(int algo, uint32_t* dst, const uint32_t* src, uint64_t n_words, int n_sm, cudaStream_t st) {
+    if (n_words == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_words + 255) / 256, (uint64_t)n_sm * 8);
+    switch (algo) {
+        case HMH: merge_kernel<HMH><<<grid, 256, 0, st>>>(dst, src, n_words); break;
+        case HLL: merge_kernel<HLL><<<grid, 256, 0, st>>>(dst, src, n_words); break;
+        case ULL: merge_kernel<ULL><<<grid, 256, 0, st>>>(dst, src, n_words); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 void plan_sketch(SketchParams& sp) {
     sp.n_cells = sp.algo == HMH ? 16384u : (1u << sp.p);
     const uint32_t cell_bytes = sp.algo == HMH ? 2u : 1u;

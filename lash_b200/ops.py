@@ -149,6 +149,16 @@ def sketch_genomes(ctx: Context, algo: int, p: int, k: int, seed: int, genomes: 
     return regs[: len(genomes)]
 
 
+def merge(ctx: Context, algo: int, p: int, dst: np.ndarray, src: np.ndarray) -> np.ndarray:
+    """UltraLogLog::merge / HyperLogLog::union / hyperminhash merge of register arrays (returns a new array)."""
+    out = np.ascontiguousarray(dst, dtype=reg_dtype(algo)).copy()
+    src = np.ascontiguousarray(src, dtype=reg_dtype(algo))
+    assert out.shape == src.shape
+    n = out.shape[0] if out.ndim == 2 else 1
+    check(lib().lash_sketch_merge(ctx.handle, algo, p, out.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), n))
+    return out
+
+
 def cardinality(ctx: Context, algo: int, p: int, estimator: int, regs: np.ndarray) -> np.ndarray:
     regs = np.ascontiguousarray(regs, dtype=reg_dtype(algo))
     out = np.empty(regs.shape[0], dtype=np.float64)

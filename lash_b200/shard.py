@@ -45,3 +45,11 @@ def pair_count(rows: tuple[int, int], n_qry: int, triangular: bool) -> int:
     if triangular:
         return e * (e + 1) // 2 - b * (b + 1) // 2
     return (e - b) * n_qry
+
+
+def read_shard(n_records: int, rank: int, world: int) -> tuple[int, int]:
+    """[begin, end) records of ONE sample that rank `rank` sketches (config "100 Gbp of reads -> one
+    sketch per sample").  Every rank folds the world's partial sketches afterwards (all-gather of
+    world x reg_bytes, then lash_sketch_merge_dev): registers are order-free, so any partition of the
+    records gives the same sketch."""
+    return (n_records * rank) // world, (n_records * (rank + 1)) // world

@@ -171,6 +171,34 @@ def test_saturated_ull_registers_large_range_path(oracle, gpu_ctx):
         np.testing.assert_allclose(got[m], exp[m], rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("p", [10, 14])
+def test_huge_cardinality_ull_sketches_stay_on_the_table_path(oracle, gpu_ctx, p):
+    """Sketches of very large inputs (config 4: 10^11 k-mers -> ~2^22 hashes per register at p=14) have no
+    register near 4p-4; the FGRA pair table is anchored at the smallest register present, so they are
+    neither wrong nor pushed to the per-pair exact path.  A mixed set (one small sketch among them) and
+    an out-of-window register exercise the sentinel -> exact fallback."""
+    rng = np.random.default_rng(p)
+    m = 1 << p
+    n = 12
+    def simulated(log2_per_reg, rows):
+        # max nlz of 2^log2 hashes: Gumbel-like; u = p - 1 + nlz, two random sub-bits
+        nlz = np.clip(np.floor(log2_per_reg - np.log2(-np.log(rng.random((rows, m))))), 0, 60 - p).astype(np.int64)
+        return (4 * (nlz + p - 1) + rng.integers(0, 4, size=(rows, m))).astype(np.uint8)
+    big = simulated(22.0, n)
+    big[1] = big[0]
+    big[1, ::7] = np.maximum(big[1, ::7], big[2, ::7])          # a near-duplicate pair (large Jaccard)
+    for regs in (big, np.concatenate([big[:6], simulated(6.0, 3), simulated(14.0, 3)])):
+        regs = regs.copy()
+        regs[5, 3] = 251                                         # far above any window: exact per-pair path
+        exp = oracle.dist(ALGO_ULL, p, 21, EST_FGRA, MODEL_POISSON, False, regs, regs)
+        frac = oracle.dist(ALGO_ULL, p, 21, EST_FGRA, 2, False, regs, regs)
+        got, _ = ops.dist(gpu_ctx, ALGO_ULL, p, 21, EST_FGRA, MODEL_POISSON, False, regs, regs)
+        _assert_close_f64(got, exp, frac, 21, f"huge-cardinality p={p}")
+        tri, _ = ops.dist(gpu_ctx, ALGO_ULL, p, 21, EST_FGRA, MODEL_POISSON, False, regs, regs, triangular=True)
+        il = np.tril_indices(len(regs))
+        np.testing.assert_array_equal(tri, got[il])
+
+
 def test_ull_merge_in_packed_domain_is_exhaustively_correct(oracle, gpu_ctx):
     """ULL union is pack(unpack(a)|unpack(b)), not max(a,b).  Every ordered pair of valid register
     bytes for p=8 goes through the kernel's SIMD merge; the union's ML statistics are integers, so

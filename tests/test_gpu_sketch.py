@@ -195,3 +195,29 @@ def test_adversarial_hashes_with_32_or_more_leading_zeros(oracle, gpu_ctx, algo,
         assert regs[2].max() >= 33     # rho beyond what 32 bits can see
     else:
         assert (regs[2] >> 2).max() >= 31 + p   # update value u = nlz + p - 1 with nlz >= 32
+
+
+@pytest.mark.parametrize("algo,p", [(ALGO_ULL, 10), (ALGO_ULL, 14), (ALGO_ULL, 3), (ALGO_HLL, 12), (ALGO_HMH, 14)])
+def test_merge_of_shares_equals_sketch_of_the_whole(oracle, gpu_ctx, algo, p):
+    """One sample sketched in shares (several GPUs / passes) and folded with lash_sketch_merge must equal
+    the sketch of all its records: UltraLogLog::merge (utils.rs:260-262; not a byte max),
+    HyperLogLog::union and the hyperminhash register max."""
+    from lash_b200 import ops
+    k = 16
+    parts_a = [synth.dirty_genome(40_000 + 1000 * g, k, seed=100 + g) for g in range(5)]
+    parts_b = [synth.dirty_genome(30_000 + 1500 * g, k, seed=200 + g) for g in range(5)]
+    parts_b[3] = []                                                  # an empty share
+    ra = sketch_genomes(gpu_ctx, algo, p, k, SEED, parts_a)
+    rb = sketch_genomes(gpu_ctx, algo, p, k, SEED, parts_b)
+    merged = ops.merge(gpu_ctx, algo, p, ra, rb)
+    whole = oracle.sketch_genomes(algo, p, k, SEED, [a + b for a, b in zip(parts_a, parts_b)], threads=4)
+    assert np.array_equal(merged, whole)
+    if algo == ALGO_ULL:
+        exp = np.stack([oracle.ull_merge(x, y, p) for x, y in zip(ra, rb)])
+        assert np.array_equal(merged, exp)
+        if p >= 10:
+            assert not np.array_equal(merged, np.maximum(ra, rb))   # ULL merge is not max
+    else:
+        assert np.array_equal(merged, np.maximum(ra, rb))
+    assert np.array_equal(ops.merge(gpu_ctx, algo, p, merged, merged), merged)      # idempotent
+    assert np.array_equal(ops.merge(gpu_ctx, algo, p, rb, ra), merged)              # commutative

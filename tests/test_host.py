@@ -137,12 +137,64 @@ def test_sharding_covers_everything_once_world_size_2():
     assert regs == list(range(64))
 
 
+def _sample_worker(rank, world, port, q):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import oracle as O
+    from lash_b200 import shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(77)
+    genome = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=60_000)].tobytes()
+    starts = rng.integers(0, len(genome) - 150, size=3001)
+    reads = [genome[s:s + 150] for s in starts]
+    out = {}
+    for name, algo, p in (("ull", O.ULL, 12), ("hll", O.HLL, 10), ("hmh", O.HMH, 14)):
+        b, e = shard.read_shard(len(reads), rank, world)
+        regs = O.sketch_genomes(algo, p, 21, 42, [reads[b:e]])[0]
+        mine = torch.from_numpy(regs.view(np.uint8).copy())     # registers travel as bytes (gloo has no u16)
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)                      # the path's one exchange step for a single sample
+        parts = [t.numpy().view(regs.dtype) for t in parts]
+        acc = parts[0].copy()
+        for part in parts[1:]:                             # what lash_sketch_merge_dev does on the GPU
+            acc = O.ull_merge(acc, part, p) if algo == O.ULL else np.maximum(acc, part)
+        whole = O.sketch_genomes(algo, p, 21, 42, [reads])[0]
+        out[name] = bool(np.array_equal(acc, whole))
+    if rank == 0:
+        q.put(out)
+    dist.destroy_process_group()
+
+
+def test_single_sample_in_shares_world_size_2():
+    """N>1 path for ONE sample (config 4) on CPU (gloo, world_size 2): reads are split by
+    shard.read_shard, partial sketches all-gathered and folded with the sketch's own merge
+    (ULL: pack(unpack|unpack), HLL/HMH: max) -- the result equals the sketch of all reads."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_sample_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out == {"ull": True, "hll": True, "hmh": True}
+
+
 def test_shard_functions_edge_cases():
     from lash_b200 import shard
     for world in (1, 2, 3, 4, 8):
         for n in (0, 1, 5, 8, 1000):
             got = sorted(g for r in range(world) for g in shard.genome_shard([10] * n, r, world))
             assert got == list(range(n))
+            cuts = [shard.read_shard(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n and all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             for tri in (False, True):
                 rows = [shard.row_shard(n, r, world, tri) for r in range(world)]
                 assert rows[0][0] == 0 and rows[-1][1] == n
