@@ -96,11 +96,85 @@ def dist_case(ctx, name, algo, p, k, est, regs, reps=3):
             "register_merges_per_s": pairs * cells / ms * 1e3, "warn": w}
 
 
+def c5_full(ctx, n=100_000, length=100_000, est=EST_ML):
+    """BASELINE configs[4] at full size on ONE GPU: n ULL p=10 sketches (made by the sketch kernel from n random
+    `length`-bp genomes), all-vs-all ML, lower triangle, f64, streamed to the host in row blocks (--dm shape)."""
+    dev = torch.device("cuda", 0)
+    stride = padded_bytes(length)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    buf = torch.randint(0, 256, (n * stride + 64,), dtype=torch.uint8, device=dev, generator=g)
+    spans = (Span * n)()
+    for i in range(n):
+        spans[i] = Span(i, i * stride, length, 0, 1, 0)
+    sk = ops.Sketcher(ctx, ALGO_ULL, 10, 16, 42, n)
+    t0 = time.perf_counter()
+    sk.push_raw(buf.data_ptr(), n * stride, spans, n, None, 0, dev=True)
+    regs = sk.fetch()
+    t_sketch = time.perf_counter() - t0
+    k_ms, _ = sk.stats()
+    sk.close()
+    del buf
+    torch.cuda.empty_cache()
+    seen = {"rows": 0, "blocks": 0, "checksum": 0.0}
+
+    def on_block(row0, block):
+        seen["rows"] += block.shape[0]
+        seen["blocks"] += 1
+        seen["checksum"] += float(block[0, 0])
+
+    t0 = time.perf_counter()
+    w = ops.dist_stream(ctx, ALGO_ULL, 10, 16, est, 1, False, regs, regs, True, 0, on_block)
+    wall = time.perf_counter() - t0
+    ms, launches = ops.dist_stats(ctx)
+    pairs = n * (n + 1) // 2
+    return {"case": f"C5 FULL: {n} x {n} ULL p=10 {'ML' if est == EST_ML else 'FGRA'} triangle, f64, streamed in row blocks to pinned host memory",
+            "n": n, "pairs": pairs, "sketch_wall_s": t_sketch, "sketch_kernel_ms": k_ms, "sketch_gbp_per_s_kernel": n * length / k_ms / 1e6,
+            "dist_wall_s": wall, "dist_kernel_ms": ms, "pairs_per_s_wall": pairs / wall, "pairs_per_s_kernel": pairs / ms * 1e3,
+            "d2h_bytes": n * n * 8, "blocks": seen["blocks"], "rows_delivered": seen["rows"], "launches": launches, "warn": w}
+
+
+def c4_full(ctx, total_gbp=100, chunk_reads=26_666_667, read_len=150):
+    """BASELINE configs[3] shape: `total_gbp` Gbp of 150 bp reads of ONE sample -> one ULL p=14 k=21 sketch; a 4 Gbp
+    chunk of packed reads resident in HBM is pushed repeatedly (fixed-length records: no boundary table)."""
+    dev = torch.device("cuda", 0)
+    n_bases = chunk_reads * read_len
+    g = torch.Generator(device=dev)
+    g.manual_seed(9)
+    packed = torch.randint(0, 256, (padded_bytes(n_bases) + 64,), dtype=torch.uint8, device=dev, generator=g)
+    spans = (Span * 1)(Span(0, 0, n_bases, 0, chunk_reads, read_len))
+    sk = ops.Sketcher(ctx, ALGO_ULL, 14, 21, 42, 1)
+    stream = torch.cuda.Stream(dev)
+    sk.set_stream(stream.cuda_stream)
+    n_push = int(round(total_gbp * 1e9 / n_bases))
+    sk.push_raw(packed.data_ptr(), padded_bytes(n_bases), spans, 1, None, 0, dev=True)  # warm-up
+    sk.sync()
+    ms0, _ = sk.stats()
+    t0 = time.perf_counter()
+    for _ in range(n_push):
+        sk.push_raw(packed.data_ptr(), padded_bytes(n_bases), spans, 1, None, 0, dev=True)
+    sk.sync()
+    wall = time.perf_counter() - t0
+    ms1, _ = sk.stats()
+    regs = sk.fetch()
+    sk.close()
+    return {"case": f"C4 FULL: {n_push} x {n_bases / 1e9:.2f} Gbp of {read_len} bp reads -> one ULL p=14 k=21 sketch (HBM-resident chunk re-pushed)",
+            "bases": n_push * n_bases, "kernel_ms(mask+sketch)": ms1 - ms0, "wall_s": wall, "gbp_per_s_kernel": n_push * n_bases / (ms1 - ms0) / 1e6,
+            "gbp_per_s_wall": n_push * n_bases / wall / 1e9, "nonzero_registers": int((regs != 0).sum())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--profile", action="store_true", help="one launch per case, quick sizes (for ncu)")
+    ap.add_argument("--full", action="store_true", help="only the full-size C4 / C5 runs (tens of seconds of GPU time)")
     a = ap.parse_args()
+    if a.full:
+        with ops.Context(0) as ctx:
+            print(json.dumps(c4_full(ctx)), flush=True)
+            print(json.dumps(c5_full(ctx, est=EST_FGRA)), flush=True)
+            print(json.dumps(c5_full(ctx, est=EST_ML)), flush=True)
+        return
     global PROFILE
     PROFILE = a.profile
     q = a.quick or a.profile
