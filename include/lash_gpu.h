@@ -191,6 +191,12 @@ int lash_dist_stream(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
                      uint64_t n_ref, const void* qry_regs, uint64_t n_qry, int triangular, uint64_t rows_per_block,
                      lash_dist_block_cb cb, void* user);
 
+/* Same for reference rows [row_begin, row_end) only: the output tiling of the N x M matrix across GPUs / processes
+ * (each takes a row range, e.g. lash_b200/shard.py::row_shard; every one uploads both register arrays). */
+int lash_dist_stream_rows(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_regs,
+                          uint64_t n_ref, const void* qry_regs, uint64_t n_qry, int triangular, uint64_t row_begin,
+                          uint64_t row_end, uint64_t rows_per_block, lash_dist_block_cb cb, void* user);
+
 /* Kernel time (ms) and launches of the last lash_dist / lash_dist_stream call on this ctx. */
 int lash_dist_stats(lash_ctx* ctx, double* kernel_ms, uint64_t* launches);
 

@@ -102,6 +102,12 @@ int lash_host_read_sketches(const char* path, int algo, int* p_inout, uint64_t n
 int lash_host_dist(lash_ctx* ctx, const char* ref_prefix, const char* query_prefix, const char* output_file,
                    const char* estimator, int model, int dm, int fp32, int threads, int fused);
 
+/* One process per GPU: process `rank` of `world` computes and writes only its range of reference rows (cut so that
+ * pair counts are equal) into "<output_file>.part<rank, 4 digits>"; rank 0's part carries the header line; the parts
+ * concatenated in rank order are byte for byte the file lash_host_dist(fused) writes.  world == 1: plain output_file. */
+int lash_host_dist_rows(lash_ctx* ctx, const char* ref_prefix, const char* query_prefix, const char* output_file,
+                        const char* estimator, int model, int dm, int fp32, int threads, int rank, int world);
+
 /* Rust's `{:.6}` for f64 / f32 (main.rs:459,465): exact decimal expansion, round-half-even.
  * Writes at most 32 bytes for |v| < 2^20, at most 330 otherwise (no terminator); returns the length. */
 int lash_host_format_fixed6_f64(double v, char* out);

@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_lib", "liblash_gpu.so")
+# LASH_GPU_LIB: load a tuning build of the same library (tools/, never the tests)
+_SO = os.environ.get("LASH_GPU_LIB") or os.path.join(_HERE, "_lib", "liblash_gpu.so")
 
 ALGO_HMH, ALGO_HLL, ALGO_ULL = 0, 1, 2
 EST_FGRA, EST_ML = 0, 1
@@ -58,6 +59,7 @@ PROTOTYPES = {
     "lash_cardinality_dev": (i32, [vp, i32, i32, i32, vp, u64, vp, vp]),
     "lash_cardinality": (i32, [vp, i32, i32, i32, vp, u64, vp]),
     "lash_dist_stream": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, u64, vp, u64, i32, u64, DIST_BLOCK_CB, vp]),
+    "lash_dist_stream_rows": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, u64, vp, u64, i32, u64, u64, u64, DIST_BLOCK_CB, vp]),
     "lash_dist_stats": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
 }
 

@@ -602,7 +602,7 @@ extern "C" int lash_dist_dev(lash_ctx* ctx, int algo, int p, int k, int estimato
 // shared body of lash_dist / lash_dist_stream: upload, cardinalities, row blocks
 static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_regs,
                      uint64_t n_ref, const void* qry_regs, uint64_t n_qry, int triangular, void* out, uint64_t rows_per_block,
-                     lash_dist_block_cb cb, void* user) {
+                     lash_dist_block_cb cb, void* user, uint64_t row_begin = 0, uint64_t row_end = ~0ull) {
     if (!ctx) return fail(LASH_E_INVALID, "lash_dist: NULL ctx");
     int rc = check_dist_args(algo, p, k, estimator, model, n_ref, n_qry, triangular);
     if (rc) return rc;
@@ -708,8 +708,9 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
         int buf = 0;
         int cb_rc = 0;
         uint64_t nblocks = 0;
-        for (uint64_t r0 = 0; r0 < n_ref && cb_rc == 0; r0 += rows_per_block, buf ^= 1, ++nblocks) {
-            const uint64_t r1 = std::min(n_ref, r0 + rows_per_block);
+        if (row_end > n_ref) row_end = n_ref;
+        for (uint64_t r0 = row_begin; r0 < row_end && cb_rc == 0; r0 += rows_per_block, buf ^= 1, ++nblocks) {
+            const uint64_t r1 = std::min(row_end, r0 + rows_per_block);
             if (nblocks >= 2) CUC(cudaEventSynchronize(copied[buf]));  // device buffer free again (its D2H finished)
             dp.row_begin = r0; dp.row_end = r1; dp.out = d_out[buf].p; dp.packed_tri = 0; dp.out_row0 = r0;
             CUC(cudaEventRecord(kstart, st));
@@ -766,6 +767,15 @@ extern "C" int lash_dist_stream(lash_ctx* ctx, int algo, int p, int k, int estim
                                 lash_dist_block_cb cb, void* user) {
     if (!cb) return fail(LASH_E_INVALID, "lash_dist_stream: callback is NULL");
     return dist_host(ctx, algo, p, k, estimator, model, fp32, ref_regs, n_ref, qry_regs, n_qry, triangular, nullptr, rows_per_block, cb, user);
+}
+extern "C" int lash_dist_stream_rows(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_regs,
+                                     uint64_t n_ref, const void* qry_regs, uint64_t n_qry, int triangular, uint64_t row_begin,
+                                     uint64_t row_end, uint64_t rows_per_block, lash_dist_block_cb cb, void* user) {
+    if (!cb) return fail(LASH_E_INVALID, "lash_dist_stream_rows: callback is NULL");
+    if (row_begin > row_end || row_end > n_ref) return fail(LASH_E_INVALID, "lash_dist_stream_rows: bad row range");
+    if (row_begin == row_end) return LASH_OK;
+    return dist_host(ctx, algo, p, k, estimator, model, fp32, ref_regs, n_ref, qry_regs, n_qry, triangular, nullptr, rows_per_block, cb,
+                     user, row_begin, row_end);
 }
 extern "C" int lash_dist_stats(lash_ctx* ctx, double* kernel_ms, uint64_t* launches) {
     if (!ctx) return fail(LASH_E_INVALID, "lash_dist_stats: NULL ctx");

@@ -179,8 +179,28 @@ __device__ __forceinline__ void global_update(uint32_t* gacc, uint32_t idx, uint
 enum KMode : int { K16 = 0, KNARROW = 1, KWIDE = 2 };
 constexpr int kGroup = 16;  // k-mers whose atomics are deferred together (one 32-bit word of bases)
 
-template <int ALGO, int KM, bool GLOBAL>
-__global__ void __launch_bounds__(1024)
+// CTA size is a template parameter so that the register budget follows it.  Measured on B200 (tools/variant_sweep):
+// ~80 registers with 24 resident warps per SM beats 64 registers with 32 warps (+4 % at C2) and everything
+// tighter (48 / 40 registers spill) -- the 16-k-mer deferred group wants the registers more than the SM wants warps.
+//   accumulator <= LASH_SMALL_SMEM_KB (24 KiB) : 256-thread CTAs, LASH_MINB_256 (3) of them per SM
+//   larger                                      : ONE CTA of LASH_TB_BIG (768) threads per SM -- every resident CTA
+//                                                 is one more private accumulator to warm up and flush, which costs
+//                                                 more than it hides once the accumulator is tens of KiB
+#ifndef LASH_MINB_256
+#define LASH_MINB_256 3
+#endif
+#ifndef LASH_TB_BIG
+#define LASH_TB_BIG 768
+#endif
+#ifndef LASH_SMALL_SMEM_KB
+#define LASH_SMALL_SMEM_KB 24
+#endif
+constexpr int kTbSmall = 256, kTbBig = LASH_TB_BIG;
+template <int TB>
+struct MinBlocks { static constexpr int value = TB == kTbSmall ? LASH_MINB_256 : 1; };
+
+template <int ALGO, int KM, bool GLOBAL, int TB>
+__global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
     sketch_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ inv_mask,
                   const SketchTile* __restrict__ tiles, uint32_t n_tiles, uint32_t* __restrict__ acc_global, int p, int k,
                   HashConsts hc, uint32_t cell_words, uint32_t n_cells) {
@@ -434,16 +454,13 @@ void plan_sketch(SketchParams& sp) {
     const uint64_t smem = (uint64_t)sp.n_cells * (sp.algo == ULL ? 8u : 4u);
     sp.global_acc = smem > kMaxSmemAccBytes;
     sp.smem_bytes = sp.global_acc ? 0u : (uint32_t)smem;
-    // 227 KiB of shared memory per SM: keep at least 32 warps resident whatever the accumulator size
-    if (sp.smem_bytes <= 24u * 1024u) sp.threads = 256;       // >= 8 CTAs by smem, register-limited
-    else if (sp.smem_bytes <= 72u * 1024u) sp.threads = 512;  // 3 CTAs x 16 warps
-    else sp.threads = 1024;                                    // 1 CTA x 32 warps
+    sp.threads = sp.smem_bytes <= LASH_SMALL_SMEM_KB * 1024u ? (uint32_t)kTbSmall : (uint32_t)kTbBig;
 }
 
-template <int ALGO, int KM, bool GLOBAL>
-static cudaError_t launch_one(const SketchParams& sp, const uint32_t* packed, const uint32_t* mask,
-                              const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st) {
-    auto kern = sketch_kernel<ALGO, KM, GLOBAL>;
+template <int ALGO, int KM, bool GLOBAL, int TB>
+static cudaError_t launch_tb(const SketchParams& sp, const uint32_t* packed, const uint32_t* mask,
+                             const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st) {
+    auto kern = sketch_kernel<ALGO, KM, GLOBAL, TB>;
     size_t smem = GLOBAL ? 0 : (size_t)sp.smem_bytes;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -456,6 +473,12 @@ static cudaError_t launch_one(const SketchParams& sp, const uint32_t* packed, co
     const uint32_t grid = n_tiles < resident ? n_tiles : resident;  // one persistent CTA per resident slot
     kern<<<grid, sp.threads, smem, st>>>(packed, mask, tiles, n_tiles, acc, sp.p, sp.k, sp.hc, sp.cell_words, sp.n_cells);
     return cudaGetLastError();
+}
+template <int ALGO, int KM, bool GLOBAL>
+static cudaError_t launch_one(const SketchParams& sp, const uint32_t* packed, const uint32_t* mask,
+                              const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st) {
+    if (GLOBAL || sp.threads == (uint32_t)kTbSmall) return launch_tb<ALGO, KM, GLOBAL, kTbSmall>(sp, packed, mask, tiles, n_tiles, acc, st);
+    return launch_tb<ALGO, KM, false, kTbBig>(sp, packed, mask, tiles, n_tiles, acc, st);
 }
 
 template <int ALGO>

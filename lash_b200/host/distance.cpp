@@ -139,8 +139,22 @@ int block_trampoline(void* user, uint64_t row0, uint64_t n_rows, const void* blo
 }
 }  // namespace
 
+std::pair<uint64_t, uint64_t> row_shard(uint64_t n_rows, int rank, int world, bool triangular) {
+    auto cut = [&](int r) -> uint64_t {
+        if (r <= 0) return 0;
+        if (r >= world) return n_rows;
+        if (!triangular) return n_rows * (uint64_t)r / (uint64_t)world;
+        const double total = (double)n_rows * ((double)n_rows + 1.0) / 2.0;
+        const double x = (std::sqrt(1.0 + 8.0 * total * (double)r / (double)world) - 1.0) / 2.0;
+        const double rx = std::nearbyint(x);
+        return rx < 0 ? 0 : (rx > (double)n_rows ? n_rows : (uint64_t)rx);
+    };
+    return {cut(rank), cut(rank + 1)};
+}
+
 Status distance_blocks(lash_ctx* ctx, int algo, int k, int estimator, int model, bool fp32, const DistInputs& in, bool same_files,
-                       const std::function<void(uint64_t row0, uint64_t n_rows, const void* block)>& on_block) {
+                       const std::function<void(uint64_t row0, uint64_t n_rows, const void* block)>& on_block, uint64_t row_begin,
+                       uint64_t row_end) {
     const uint64_t n_ref = in.ref_names.size(), n_qry = in.qry_names.size();
     if (n_ref == 0 || n_qry == 0) return Status{};
     // same_files (main.rs:404) means both sides were loaded from the same files: the triangle rule of
@@ -151,8 +165,10 @@ Status distance_blocks(lash_ctx* ctx, int algo, int k, int estimator, int model,
     const uint64_t esz = fp32 ? 4 : 8;
     uint64_t rows = std::max<uint64_t>(1, (64ull << 20) / (n_qry * esz));
     const void* q = (same_files && n_ref == n_qry) ? in.ref_regs.data() : in.qry_regs.data();
-    const int rc = lash_dist_stream(ctx, algo, in.p, k, estimator, model, fp32 ? 1 : 0, in.ref_regs.data(), n_ref, q, n_qry, tri ? 1 : 0,
-                                    rows, block_trampoline, &bc);
+    if (row_end > n_ref) row_end = n_ref;
+    if (row_begin >= row_end) return Status{};
+    const int rc = lash_dist_stream_rows(ctx, algo, in.p, k, estimator, model, fp32 ? 1 : 0, in.ref_regs.data(), n_ref, q, n_qry,
+                                         tri ? 1 : 0, row_begin, row_end, rows, block_trampoline, &bc);
     if (rc < 0) return Status{rc, lash_gpu_last_error()};
     return Status{rc, rc > 0 ? "some pairs fell in the HLL++ bias-table regime (see lash_gpu.h)" : ""};
 }
@@ -254,9 +270,9 @@ void format_rows(std::string& out, const T* block, uint64_t row0, uint64_t r0, u
 template <class T>
 Status run_dist(lash_ctx* ctx, int algo, int k, const std::string& estimator, uint64_t model, bool dm, bool same_files, int threads,
                 bool fused, const std::vector<std::string>& reference_names, const std::string& ref_bin,
-                const std::vector<std::string>& query_names, const std::string& query_bin, OutFile& file) {
+                const std::vector<std::string>& query_names, const std::string& query_bin, OutFile& file, int rank, int world) {
     Status wst;
-    if (!fused) {
+    if (!fused && world == 1) {
         // the reference's own structure: *_distance(..., emit) with emit = print_dist (main.rs:474-606)
         std::string sink;
         PrintDist<T> print(sink, dm, (size_t)k, model);
@@ -293,7 +309,8 @@ Status run_dist(lash_ctx* ctx, int algo, int k, const std::string& estimator, ui
         auto it = by_name.find(in.ref_names[i]);
         if (it != by_name.end()) same_name_cols[i] = it->second;
     }
-    if (dm) {
+    const std::pair<uint64_t, uint64_t> rows = row_shard(in.ref_names.size(), rank, world, tri);
+    if (dm && rank == 0) {
         std::string hdr;
         for (const auto& q : in.qry_names) {
             hdr.push_back('\t');
@@ -320,7 +337,8 @@ Status run_dist(lash_ctx* ctx, int algo, int k, const std::string& estimator, ui
                              for (auto& th : pool) th.join();
                              for (unsigned t = 0; t < use; ++t)
                                  if (!file.write(parts[t])) wst = Status{LASH_HOST_E_IO, "Error writing to file"};
-                         });
+                         },
+                         rows.first, rows.second);
     if (!st.ok()) return st;
     return wst.ok() ? st : wst;
 }
@@ -328,8 +346,10 @@ Status run_dist(lash_ctx* ctx, int algo, int k, const std::string& estimator, ui
 }  // namespace
 
 Status dist_command(lash_ctx* ctx, const std::string& ref_prefix, const std::string& query_prefix, const std::string& output_file,
-                    const std::string& estimator, uint64_t model, bool dm, bool fp32, int threads, bool fused) {
+                    const std::string& estimator, uint64_t model, bool dm, bool fp32, int threads, bool fused, int rank, int world) {
     if (!ctx) return Status{LASH_E_INVALID, "dist: NULL ctx"};
+    if (world < 1 || rank < 0 || rank >= world) return Status{LASH_E_INVALID, "dist: rank / world out of range"};
+    if (world > 1 && !fused) return Status{LASH_E_INVALID, "dist: row sharding needs the fused writer"};
     if (model != 0 && model != 1) return Status{LASH_E_INVALID, "model needs to be 0 or 1"};  // main.rs:421
     std::map<std::string, std::string> ref_files, query_files;
     Status st = find_files(ref_prefix, ref_files);
@@ -365,13 +385,19 @@ Status dist_command(lash_ctx* ctx, const std::string& ref_prefix, const std::str
     const bool same_files = query_files["files"] == ref_files["files"];  // main.rs:404
 
     OutFile file;
-    if (!file.open(output_file, err)) return Status{LASH_HOST_E_IO, err};
-    if (!dm && !file.write("Reference\tQuery\tDistance\n")) return Status{LASH_HOST_E_IO, "Error writing to file"};  // main.rs:409-412
+    std::string out_path = output_file;
+    if (world > 1) {
+        char suffix[16];
+        snprintf(suffix, sizeof(suffix), ".part%04d", rank);
+        out_path += suffix;
+    }
+    if (!file.open(out_path, err)) return Status{LASH_HOST_E_IO, err};
+    if (!dm && rank == 0 && !file.write("Reference\tQuery\tDistance\n")) return Status{LASH_HOST_E_IO, "Error writing to file"};  // main.rs:409-412
     if (fp32)
         return run_dist<float>(ctx, algo, (int)k, estimator, model, dm, same_files, threads, fused, reference_names, ref_files["sketches"],
-                               query_names, query_files["sketches"], file);
+                               query_names, query_files["sketches"], file, rank, world);
     return run_dist<double>(ctx, algo, (int)k, estimator, model, dm, same_files, threads, fused, reference_names, ref_files["sketches"],
-                            query_names, query_files["sketches"], file);
+                            query_names, query_files["sketches"], file, rank, world);
 }
 
 }  // namespace lash

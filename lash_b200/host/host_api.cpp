@@ -154,6 +154,14 @@ extern "C" int lash_host_dist(lash_ctx* ctx, const char* ref_prefix, const char*
                                           dm != 0, fp32 != 0, threads, fused != 0));
 }
 
+extern "C" int lash_host_dist_rows(lash_ctx* ctx, const char* ref_prefix, const char* query_prefix, const char* output_file,
+                                   const char* estimator, int model, int dm, int fp32, int threads, int rank, int world) {
+    if (!ref_prefix || !query_prefix || !output_file) return fail(LASH_E_INVALID, "lash_host_dist_rows: NULL argument");
+    if (model < 0) return fail(LASH_E_INVALID, "model needs to be 0 or 1");
+    return from_status(lash::dist_command(ctx, ref_prefix, query_prefix, output_file, estimator ? estimator : "fgra", (uint64_t)model,
+                                          dm != 0, fp32 != 0, threads, true, rank, world));
+}
+
 extern "C" int lash_host_format_fixed6_f64(double v, char* out) {
     std::string s;
     lash::append_fixed6(s, v);

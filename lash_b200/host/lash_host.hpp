@@ -22,6 +22,7 @@
 #include <optional>
 #include <string>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "../../include/lash_host.h"
@@ -72,8 +73,13 @@ struct DistInputs {
 };
 Status load_dist_inputs(int algo, const std::vector<std::string>& reference_names, const std::string& ref_sketch_file,
                         const std::vector<std::string>& query_names, const std::string& query_sketch_file, DistInputs& in);
+// reference rows [row_begin, row_end) only (row_end = ~0: all) -- one process per GPU takes one row range
 Status distance_blocks(lash_ctx* ctx, int algo, int k, int estimator, int model, bool fp32, const DistInputs& in, bool same_files,
-                       const std::function<void(uint64_t row0, uint64_t n_rows, const void* block)>& on_block);
+                       const std::function<void(uint64_t row0, uint64_t n_rows, const void* block)>& on_block,
+                       uint64_t row_begin = 0, uint64_t row_end = ~0ull);
+// [begin, end) reference rows of process `rank` of `world`; triangular: cut so that every process gets the same
+// number of pairs (rows [0, x) of a lower triangle hold x(x+1)/2 of them) -- same cuts as lash_b200/shard.py::row_shard
+std::pair<uint64_t, uint64_t> row_shard(uint64_t n_rows, int rank, int world, bool triangular);
 
 template <class T, class F>
 Status distance_generic(lash_ctx* ctx, int algo, const std::string* estimator, const std::vector<std::string>& reference_names,
@@ -194,7 +200,10 @@ class PrintDist {
 };
 
 // `lash dist` (main.rs:279-613); see lash_host_dist in include/lash_host.h for the arguments
+// rank / world: this process writes only its row range, into "<output_file>.part<rank, 4 digits>" when world > 1
+// (rank 0's part carries the header); the parts concatenated in rank order are the single-process file.
 Status dist_command(lash_ctx* ctx, const std::string& ref_prefix, const std::string& query_prefix, const std::string& output_file,
-                    const std::string& estimator, uint64_t model, bool dm, bool fp32, int threads, bool fused);
+                    const std::string& estimator, uint64_t model, bool dm, bool fp32, int threads, bool fused, int rank = 0,
+                    int world = 1);
 
 }  // namespace lash

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "lash_host_write_sketches": (i32, [cp, i32, i32, vp, u64, i32]),
     "lash_host_read_sketches": (i32, [cp, i32, C.POINTER(i32), u64, vp]),
     "lash_host_dist": (i32, [vp, cp, cp, cp, cp, i32, i32, i32, i32, i32]),
+    "lash_host_dist_rows": (i32, [vp, cp, cp, cp, cp, i32, i32, i32, i32, i32, i32]),
     "lash_host_format_fixed6_f64": (i32, [C.c_double, C.c_char_p]),
     "lash_host_format_fixed6_f32": (i32, [C.c_float, C.c_char_p]),
 }
@@ -161,6 +162,12 @@ def dist(ctx, ref_prefix: str, query_prefix: str, output_file: str, estimator: s
          fp32: bool = False, threads: int = 1, fused: bool = True) -> int:
     return check(lib().lash_host_dist(ctx.handle, os.fsencode(ref_prefix), os.fsencode(query_prefix), os.fsencode(output_file),
                                       estimator.encode(), model, int(dm), int(fp32), threads, int(fused)))
+
+
+def dist_rows(ctx, ref_prefix: str, query_prefix: str, output_file: str, rank: int, world: int, estimator: str = "fgra",
+              model: int = 1, dm: bool = False, fp32: bool = False, threads: int = 1) -> int:
+    return check(lib().lash_host_dist_rows(ctx.handle, os.fsencode(ref_prefix), os.fsencode(query_prefix), os.fsencode(output_file),
+                                           estimator.encode(), model, int(dm), int(fp32), threads, rank, world))
 
 
 def format_fixed6(v: float, fp32: bool = False) -> str:

@@ -255,3 +255,70 @@ def test_dist_command_error_behaviour_and_name_rules(oracle, gpu_ctx, tmp_path):
     assert [(r, q) for r, q, _ in rows] == [(files[0], files[0]), (files[1], files[0]), (files[1], files[1]),
                                            (alias, files[0]), (alias, files[1]), (alias, alias)]
     assert rows[4][2] == "-0.000000" and rows[5][2] == "0.000000"
+
+
+def test_cli_binary_mirrors_lash_sketch_and_dist(oracle, tmp_path):
+    """`lash-b200 sketch` / `lash-b200 dist`: the reference's flags and defaults (main.rs:26-177), its three
+    output files, its TSV -- driven as a user would, from a list file in the working directory."""
+    import json
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lash_b200", "_lib", "lash-b200")
+    genomes = synth.genomes(5, 80_000, seed=13)
+    names = []
+    for g, recs in enumerate(genomes):
+        _write_fasta(str(tmp_path / f"c{g}.fna"), recs)
+        names.append(f"c{g}.fna")
+    (tmp_path / "list.txt").write_text("\n".join(names[:3]) + "\n\n   \n" + "\n".join(names[3:]) + "\n")   # blank lines are skipped
+    run = lambda *a: subprocess.run([exe, *a], cwd=tmp_path, capture_output=True, text=True)
+    r = run("sketch", "-f", "list.txt", "-o", "db", "-a", "ull", "-p", "10", "-t", "2")       # k, seed: defaults 16 / 42
+    assert r.returncode == 0, r.stderr
+    assert json.load(open(tmp_path / "db_files.json")) == names
+    assert json.load(open(tmp_path / "db_parameters.json")) == {"algorithm": "ull", "k": "16", "molecule": "nucleotide", "precision": "10", "seed": "42"}
+    regs = oracle.sketch_genomes(oracle.ULL, 10, 16, 42, genomes, threads=4)
+    on_disk, p = hostapi.read_sketches(str(tmp_path / "db_sketches.bin"), ALGO_ULL, 5)
+    assert p == 10 and np.array_equal(on_disk, regs)
+    for extra, fused in ((), True), (("--mirror",), False):
+        r = run("dist", "-q", "db", "-r", "db", "-o", "d.tsv", *extra)                       # estimator fgra, model 1: defaults
+        assert r.returncode == 0, r.stderr
+        exp = _expected_text(oracle, ALGO_ULL, 10, 16, 0, 1, False, regs, regs, names, names, tri=True)
+        _assert_text_rows(_parse_list(str(tmp_path / "d.tsv")), exp)
+    r = run("dist", "--query", "db", "--reference", "db", "--output_file", "m.txt", "--dm", "--fp32", "-e", "ml", "-m", "0")
+    assert r.returncode == 0, r.stderr
+    lines = open(tmp_path / "m.txt").read().split("\n")
+    assert lines[0] == "".join("\t" + n for n in names) and [ln.split("\t")[0] for ln in lines[1:]] == names
+    d = oracle.dist(oracle.ULL, 10, 16, oracle.ML, 0, True, regs, regs)
+    assert lines[3].split("\t")[1:] == ["%.6f" % float(d[2, j]) if j != 2 else "0.000000" for j in range(3)]
+    r = run("sketch", "-f", "list.txt", "-a", "minhash")
+    assert r.returncode != 0 and "Algorithm must be either hmh, ull, or hll" in r.stderr      # main.rs:245
+    r = run("sketch", "-f", "list.txt", "-a", "hll", "-k", "40")
+    assert r.returncode != 0 and "k-mer length must be 1-32" in r.stderr                      # utils.rs:501
+    r = run("dist", "-q", "db", "-r", "nothing")
+    assert r.returncode != 0 and "There should be 3 files" in r.stderr                         # main.rs:330
+
+
+@pytest.mark.parametrize("dm", [False, True])
+@pytest.mark.parametrize("same", [True, False])
+def test_row_sharded_dist_parts_concatenate_to_the_single_file(gpu_ctx, tmp_path, dm, same):
+    """One process per GPU: rank r of world w writes its reference-row range to <out>.part000r; the parts in
+    rank order are byte for byte the single-process file (triangular cuts balance pairs, not rows)."""
+    genomes = synth.genomes(23, 30_000, seed=17)
+    files = []
+    for g, recs in enumerate(genomes):
+        path = str(tmp_path / f"r{g}.fa")
+        _write_fasta(path, recs)
+        files.append(path)
+    a, b = str(tmp_path / "A"), str(tmp_path / "B")
+    hostapi.sketch_files(gpu_ctx, ALGO_ULL, 10, 16, 42, files, a)
+    hostapi.sketch_files(gpu_ctx, ALGO_ULL, 10, 16, 42, files[5:12], b)
+    q = a if same else b
+    single = str(tmp_path / "single.out")
+    hostapi.dist(gpu_ctx, a, q, single, dm=dm, threads=2, fused=True)
+    for world in (2, 3, 8):
+        out = str(tmp_path / f"sharded{world}.out")
+        for rank in range(world):
+            hostapi.dist_rows(gpu_ctx, a, q, out, rank, world, dm=dm, threads=2)
+        joined = b"".join(open(f"{out}.part{r:04d}", "rb").read() for r in range(world))
+        assert joined == open(single, "rb").read()
+        sizes = [os.path.getsize(f"{out}.part{r:04d}") for r in range(world)]
+        if same and world == 2 and not dm:
+            assert abs(sizes[0] - sizes[1]) < 0.25 * max(sizes)       # pairs, not rows, are balanced
