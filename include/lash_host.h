@@ -112,6 +112,9 @@ int lash_host_dist_rows(lash_ctx* ctx, const char* ref_prefix, const char* query
  * Writes at most 32 bytes for |v| < 2^20, at most 330 otherwise (no terminator); returns the length. */
 int lash_host_format_fixed6_f64(double v, char* out);
 int lash_host_format_fixed6_f32(float v, char* out);
+/* The bulk writer's formatter (fast path + exact fallback; same text): n values, '\n' after each; `out` needs 341
+ * bytes per value in the worst case.  Returns the bytes written. */
+size_t lash_host_format_fixed6_bulk(const double* v, size_t n, char* out);
 
 #ifdef __cplusplus
 }

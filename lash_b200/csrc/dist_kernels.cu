@@ -159,6 +159,46 @@ struct MlAcc {
             S += t.ml_ret[m];
             w[i] = t.ml_wlo[m];
         }
+        add_w<N>(w, nplanes);
+    }
+    // unconditional ripple through every plane from L up (no per-plane range test: 2 LOP3 per plane)
+    template <int L>
+    __device__ __forceinline__ void ripple_all(uint32_t x) {
+#pragma unroll
+        for (int l = L; l < kMlPlanes; ++l) {
+            const uint32_t c = pl[l] & x;
+            pl[l] ^= x;
+            x = c;
+        }
+    }
+    // Harley-Seal step over 8 patterns: planes 0..2 absorb them, the weight-8 carry is returned
+    __device__ __forceinline__ uint32_t csa8(const uint32_t* w) {
+        uint32_t t2a, t2b, t4a, t4b, t8;
+        csa(t2a, pl[0], pl[0], w[0], w[1]);
+        csa(t2b, pl[0], pl[0], w[2], w[3]);
+        csa(t4a, pl[1], pl[1], t2a, t2b);
+        csa(t2a, pl[0], pl[0], w[4], w[5]);
+        csa(t2b, pl[0], pl[0], w[6], w[7]);
+        csa(t4b, pl[1], pl[1], t2a, t2b);
+        csa(t8, pl[2], pl[2], t4a, t4b);
+        return t8;
+    }
+    // eight weight-8 carries (64 patterns) -> planes 3..5, then ONE ripple from plane 6: the ripple, which costs
+    // 2 ops per plane, runs once per 64 registers instead of once per 8 or 16
+    __device__ __forceinline__ void fold64(const uint32_t* t8) {
+        uint32_t t16a, t16b, t32a, t32b, t64;
+        csa(t16a, pl[3], pl[3], t8[0], t8[1]);
+        csa(t16b, pl[3], pl[3], t8[2], t8[3]);
+        csa(t32a, pl[4], pl[4], t16a, t16b);
+        csa(t16a, pl[3], pl[3], t8[4], t8[5]);
+        csa(t16b, pl[3], pl[3], t8[6], t8[7]);
+        csa(t32b, pl[4], pl[4], t16a, t16b);
+        csa(t64, pl[5], pl[5], t32a, t32b);
+        ripple_all<6>(t64);
+    }
+    // fold N bit patterns W (b[j] += bit j of W) into the vertical counters
+    template <int N>
+    __device__ __forceinline__ void add_w(const uint32_t* w, int nplanes) {
         // Harley-Seal: N one-bit words -> weights 1,2,4,(8) planes, then one ripple of the top carry
         uint32_t t2a, t2b, t4a, t4b;
         csa(t2a, pl[0], pl[0], w[0], w[1]);
@@ -567,6 +607,148 @@ __global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParam
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4c: ML distance tiles through pair tables (same idea as K4b; everything here is integer, so any
+// evaluation order is exact).  R[ca][cb] = contribution of merge(ra, rb) to the wrapping 64-bit sum S,
+// W[ca][cb] = the bit pattern it adds to the b[] statistics (fits 32 bits for every code the table covers:
+// codes 1..126 <-> registers 4p-4 .. 4p+121 <-> bit positions <= 31).  A register outside the table marks its
+// whole sketch (a flag per staged row, set at recoding time) and pairs with a marked sketch take the exact
+// per-pair path, so the inner loop carries no range check at all:
+//     2 address ops + LDS.64 + LDS.32 + 64-bit add + ~2.7 carry-save ops per register pair  (K4: ~21, of which the
+//     per-16-registers ripple through all counter planes was the largest part; here it runs once per 64 registers).
+// A warp owns ONE reference row (uniform -> broadcast loads) x 64 query columns, two per lane.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMlTabThreads = 512;
+constexpr int kMlTabTR = 16, kMlTabTQ = 64;
+constexpr int kMlTabChunk = 128;
+
+__global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* R = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* W = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTabN * kTabN * 8);
+    const uint32_t a_stride = chunk + 4;   // u32 per reference row
+    const uint32_t b_stride = chunk + 8;   // u16 per query row
+    uint32_t* sa = W + kTabN * kTabN;
+    uint16_t* sb = reinterpret_cast<uint16_t*>(sa + (size_t)kMlTabTR * a_stride);
+    uint32_t* sflag = reinterpret_cast<uint32_t*>(sb + (size_t)kMlTabTQ * b_stride);  // [TR + TQ] "has a register outside the table"
+
+    const uint64_t row0 = dp.row_begin + (uint64_t)blockIdx.y * kMlTabTR;
+    const uint64_t col0 = (uint64_t)blockIdx.x * kMlTabTQ;
+    if (row0 >= dp.row_end) return;
+    const uint64_t row_hi = min(row0 + kMlTabTR, dp.row_end);
+    if (dp.triangular && col0 > row_hi - 1) return;
+
+    const int p = dp.p;
+    const uint32_t base = (uint32_t)(4 * p - 4);
+    for (uint32_t e = threadIdx.x; e < (uint32_t)(kTabN * kTabN); e += kMlTabThreads) {
+        const uint32_t ca = e >> 7, cb = e & 127u;
+        const uint32_t ra = (ca && ca != 127u) ? ca + base - 1u : 0u, rb = (cb && cb != 127u) ? cb + base - 1u : 0u;
+        const uint32_t m = ull_merge1(ra, rb);
+        R[e] = ml_ret_of(m, p);
+        W[e] = (uint32_t)ml_w_of(m, p);
+    }
+    if (threadIdx.x < kMlTabTR + kMlTabTQ) sflag[threadIdx.x] = 0u;
+
+    const uint32_t ty = threadIdx.x >> 5, tx = threadIdx.x & 31u;  // ty: the warp's reference row
+    MlAcc acc[2];
+    acc[0].init();
+    acc[1].init();
+    const int nplanes = p + 1;
+    const unsigned char* gref = reinterpret_cast<const unsigned char*>(dp.ref);
+    const unsigned char* gqry = reinterpret_cast<const unsigned char*>(dp.qry);
+    const uint32_t chunk_words = chunk / 4;
+    const uint32_t rbase = (uint32_t)__cvta_generic_to_shared(R), wbase = (uint32_t)__cvta_generic_to_shared(W);
+
+    for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk) {
+        __syncthreads();
+        // stage + recode: reference side code << 9, query side code << 2 (W offsets; R offsets are twice that)
+        for (uint32_t e = threadIdx.x; e < (uint32_t)kMlTabTR * chunk_words; e += kMlTabThreads) {
+            const uint32_t r = e / chunk_words, w = e % chunk_words;
+            const uint64_t gi = row0 + r;
+            const uint32_t v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint32_t*>(gref + gi * cell_bytes + c0) + w) : 0u;
+            const uint32_t c0_ = fgra_code(v & 0xffu, base), c1_ = fgra_code((v >> 8) & 0xffu, base);
+            const uint32_t c2_ = fgra_code((v >> 16) & 0xffu, base), c3_ = fgra_code(v >> 24, base);
+            if (max(max(c0_, c1_), max(c2_, c3_)) == 127u) atomicOr(&sflag[r], 1u);
+            *reinterpret_cast<uint4*>(sa + r * a_stride + 4 * w) = make_uint4(c0_ << 9, c1_ << 9, c2_ << 9, c3_ << 9);
+        }
+        for (uint32_t e = threadIdx.x; e < (uint32_t)kMlTabTQ * chunk_words; e += kMlTabThreads) {
+            const uint32_t r = e / chunk_words, w = e % chunk_words;
+            const uint64_t gj = col0 + r;
+            const uint32_t v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint32_t*>(gqry + gj * cell_bytes + c0) + w) : 0u;
+            const uint32_t c0_ = fgra_code(v & 0xffu, base), c1_ = fgra_code((v >> 8) & 0xffu, base);
+            const uint32_t c2_ = fgra_code((v >> 16) & 0xffu, base), c3_ = fgra_code(v >> 24, base);
+            if (max(max(c0_, c1_), max(c2_, c3_)) == 127u) atomicOr(&sflag[kMlTabTR + r], 1u);
+            *reinterpret_cast<uint2*>(sb + r * b_stride + 4 * w) = make_uint2((c0_ << 2) | (c1_ << 18), (c2_ << 2) | (c3_ << 18));
+        }
+        __syncthreads();
+        const uint32_t* pa = sa + ty * a_stride;
+        const uint16_t* pb0 = sb + tx * b_stride;
+        const uint16_t* pb1 = sb + (tx + 32) * b_stride;
+        // 8 registers x 2 pairs: table lookups, S, and the Harley-Seal step; returns the two weight-8 carries
+        auto step8 = [&](uint32_t e, uint32_t& c0, uint32_t& c1) {
+            const uint4 al = *reinterpret_cast<const uint4*>(pa + e), ah = *reinterpret_cast<const uint4*>(pa + e + 4);
+            const uint4 b0 = *reinterpret_cast<const uint4*>(pb0 + e);
+            const uint4 b1 = *reinterpret_cast<const uint4*>(pb1 + e);
+            const uint32_t a[8] = {al.x, al.y, al.z, al.w, ah.x, ah.y, ah.z, ah.w};
+            const uint32_t b0w[4] = {b0.x, b0.y, b0.z, b0.w}, b1w[4] = {b1.x, b1.y, b1.z, b1.w};
+            uint32_t w0[8], w1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t q0 = (i & 1) ? (b0w[i >> 1] >> 16) : (b0w[i >> 1] & 0xffffu);
+                const uint32_t q1 = (i & 1) ? (b1w[i >> 1] >> 16) : (b1w[i >> 1] & 0xffffu);
+                const uint32_t aw = wbase + a[i], ar = rbase + 2u * a[i];
+                uint64_t r0v, r1v;
+                asm("ld.shared.u64 %0, [%1];" : "=l"(r0v) : "r"(ar + 2u * q0));
+                asm("ld.shared.u64 %0, [%1];" : "=l"(r1v) : "r"(ar + 2u * q1));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(w0[i]) : "r"(aw + q0));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"(aw + q1));
+                acc[0].S += r0v;
+                acc[1].S += r1v;
+            }
+            c0 = acc[0].csa8(w0);
+            c1 = acc[1].csa8(w1);
+        };
+        if (chunk >= 64u) {
+#pragma unroll 1
+            for (uint32_t e = 0; e < chunk; e += 64) {
+                uint32_t c0[8], c1[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) step8(e + 8u * g, c0[g], c1[g]);
+                acc[0].fold64(c0);
+                acc[1].fold64(c1);
+            }
+        } else {  // sketches of 8 .. 32 registers (p = 3 .. 5)
+#pragma unroll 1
+            for (uint32_t e = 0; e < chunk; e += 8) {
+                uint32_t c0, c1;
+                step8(e, c0, c1);
+                acc[0].ripple_all<3>(c0);
+                acc[1].ripple_all<3>(c1);
+            }
+        }
+    }
+    __syncthreads();  // sflag complete (set during the last staging pass at the latest)
+
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const uint64_t i = row0 + ty, j = col0 + tx + 32 * b;
+        if (i >= dp.row_end || j >= dp.n_qry) continue;
+        if (dp.triangular && j > i) continue;
+        if (sflag[ty] | sflag[kMlTabTR + tx + 32 * b]) acc[b].mmax = 255u;  // -> exact per-pair path in finish_union
+        bool bias;
+        const double U = finish_union(acc[b], dp.p, gref + i * cell_bytes, gqry + j * cell_bytes, &bias);
+        const double ca = dp.card_ref[i], cb = dp.card_qry[j];
+        const double sim = (ca + cb - U) / U;
+        const double s = sim < 0.0 ? 0.0 : sim;  // utils.rs:274: NaN propagates
+        const double frac = 2.0 * s / (1.0 + s);
+        const uint64_t o = dp.packed_tri ? (i * (i + 1) / 2 + j) : ((i - dp.out_row0) * dp.n_qry + j);
+        if (dp.fp32)
+            reinterpret_cast<float*>(dp.out)[o] = mash_distance_f32((float)frac, dp.k, dp.model);
+        else
+            reinterpret_cast<double*>(dp.out)[o] = mash_distance_f64(frac, dp.k, dp.model);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: per-sketch cardinality (utils.rs:213-219, 314-316; hyperminhash cardinality())
 // One thread per sketch, registers walked in index order with the same accumulators as K4
 // (the union of a sketch with itself is the sketch).
@@ -721,15 +903,40 @@ static cudaError_t launch_dist_fgra_tab(const DistParams& dp, cudaStream_t st) {
     return cudaSuccess;
 }
 
+static cudaError_t launch_dist_ml_tab(const DistParams& dp, cudaStream_t st) {
+    const uint32_t cb = cell_bytes_of(dp.algo, dp.p);
+    const uint32_t chunk = cb < (uint32_t)kMlTabChunk ? cb : (uint32_t)kMlTabChunk;
+    const size_t smem = (size_t)kTabN * kTabN * 12 + (size_t)kMlTabTR * (chunk + 4) * 4 + (size_t)kMlTabTQ * (chunk + 8) * 2 +
+                        (size_t)(kMlTabTR + kMlTabTQ) * 4;
+    cudaError_t e = cudaFuncSetAttribute(dist_ml_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint64_t rows = dp.row_end - dp.row_begin;
+    const uint64_t gy = (rows + kMlTabTR - 1) / kMlTabTR;
+    uint64_t ncols = dp.n_qry;
+    if (dp.triangular && dp.row_end < ncols) ncols = dp.row_end;
+    const uint64_t gx = (ncols + kMlTabTQ - 1) / kMlTabTQ;
+    for (uint64_t y0 = 0; y0 < gy; y0 += 65535) {
+        DistParams q = dp;
+        q.row_begin = dp.row_begin + y0 * kMlTabTR;
+        const uint64_t ny = (gy - y0) < 65535 ? (gy - y0) : 65535;
+        dim3 grid((unsigned)gx, (unsigned)ny);
+        dist_ml_tab_kernel<<<grid, kMlTabThreads, smem, st>>>(q, cb, chunk);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launches) {
     if (dp.row_end <= dp.row_begin || dp.n_qry == 0) return cudaSuccess;
     if (n_launches) *n_launches += 1;
-    // LASH_FGRA_KERNEL=merge selects the ALU-merge kernel (A/B measurements); default is the pair-table kernel
+    // LASH_FGRA_KERNEL=merge selects the ALU-merge kernels K4 for ULL (A/B measurements); default: pair-table kernels K4b / K4c
     static const bool fgra_merge = [] {
         const char* v = getenv("LASH_FGRA_KERNEL");
         return v && std::string(v) == "merge";
     }();
     if (dp.algo == ULL && dp.estimator == 0 && !fgra_merge) return launch_dist_fgra_tab(dp, st);
+    if (dp.algo == ULL && dp.estimator == 1 && !fgra_merge) return launch_dist_ml_tab(dp, st);
     if (dp.algo == HLL) return launch_dist_t<HllAcc, 16>(dp, st);
     if (dp.algo == HMH) return launch_dist_t<HmhAcc, 16>(dp, st);
     const bool tiny = dp.p == 3;  // 8 registers per sketch

@@ -292,11 +292,14 @@ __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
             uint32_t f2 = __byte_perm(q.z, 0, 0x0123), f3 = __byte_perm(q.w, 0, 0x0123);
             uint32_t f4 = __byte_perm(h.x, 0, 0x0123), f5 = __byte_perm(h.y, 0, 0x0123);
 
+            // reverse complements of the words are carried across the four word steps (each word is the "B" of one
+            // step and the "A" of the next; wide k-mers also look one word further)
+            uint32_t rcA = rc16(f0), rcB = WIDE ? rc16(f1) : 0u;
     #pragma unroll 1
             for (int w = 0; w < 4; ++w) {
                 const uint32_t v16 = (uint32_t)(valid >> (16 * w)) & 0xffffu;
                 const uint32_t A0 = f0, B0 = f1, C0 = f2;
-                const uint32_t Ar = rc16(A0), Br = rc16(B0), Cr = WIDE ? rc16(C0) : 0u;
+                const uint32_t Ar = rcA, Br = WIDE ? rcB : rc16(B0), Cr = WIDE ? rc16(C0) : 0u;
                 // canonical masked k-mer starting at base i of this word (sh = 2*i): funnel-shift windows
                 // of the forward stream and of the reverse-complemented stream, then min
                 auto kmer = [&](const int sh, uint32_t& klo, uint32_t& khi) {
@@ -372,6 +375,8 @@ __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
                 } else if (__any_sync(0xffffffffu, v16 != 0u)) {
                     fast_block(std::true_type{}, v16);
                 }
+                rcA = Br;
+                rcB = Cr;
                 f0 = f1; f1 = f2; f2 = f3; f3 = f4; f4 = f5;
             }
             __syncwarp();

@@ -6,6 +6,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cerrno>
 #include <cstdio>
 #include <cstring>
@@ -78,6 +79,57 @@ static void fixed6(std::string& out, double v) {
 }
 void append_fixed6(std::string& out, double v) { fixed6(out, v); }
 void append_fixed6(std::string& out, float v) { fixed6(out, (double)v); }  // f32 -> f64 is exact
+
+// Bulk-writer variant of the same formatting, into a raw buffer (>= 340 bytes of room).  For |v| < 1024 the product
+// v * 1e6 is off by < 6e-8 from the exact value, so its ties-to-even rounding IS the exact answer unless it lies
+// within 2e-7 of a half-integer; only those (and huge / non-finite values) take the exact 128-bit path above.
+static const char kDigitPairs[] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263"
+    "646566676869707172737475767778798081828384858687888990919293949596979899";
+static inline char* fmt6(char* p, double v) {
+    const double av = std::fabs(v);
+    if (av < 1024.0) {
+        const double x = av * 1e6;
+        const double r = std::nearbyint(x);
+        if (std::fabs(std::fabs(x - r) - 0.5) > 2e-7) {
+            if (std::signbit(v)) *p++ = '-';
+            const uint32_t q = (uint32_t)r;
+            uint32_t ip = q / 1000000u;
+            const uint32_t fr = q - ip * 1000000u;
+            if (ip >= 10u) {
+                char tmp[4];
+                int n = 0;
+                while (ip) {
+                    tmp[n++] = (char)('0' + ip % 10u);
+                    ip /= 10u;
+                }
+                while (n) *p++ = tmp[--n];
+            } else {
+                *p++ = (char)('0' + ip);
+            }
+            const uint32_t a = fr / 10000u, bc = fr - a * 10000u, b = bc / 100u, c = bc - b * 100u;
+            p[0] = '.';
+            memcpy(p + 1, kDigitPairs + 2 * a, 2);
+            memcpy(p + 3, kDigitPairs + 2 * b, 2);
+            memcpy(p + 5, kDigitPairs + 2 * c, 2);
+            return p + 7;
+        }
+    }
+    std::string slow;
+    fixed6(slow, v);
+    memcpy(p, slow.data(), slow.size());
+    return p + slow.size();
+}
+
+// the bulk writer's formatter, '\n'-separated (test hook behind lash_host_format_fixed6_bulk)
+size_t format_fixed6_bulk(const double* v, size_t n, char* out) {
+    char* p = out;
+    for (size_t i = 0; i < n; ++i) {
+        p = fmt6(p, v[i]);
+        *p++ = '\n';
+    }
+    return (size_t)(p - out);
+}
 
 // ------------------------------------------------------------------------------------------------
 // inputs
@@ -219,51 +271,84 @@ class OutFile {
         return fd_ >= 0;
     }
     bool write(const std::string& s) {
+        const bool ok = write_at(pos_, s.data(), s.size());
+        pos_ += s.size();
+        return ok;
+    }
+    // positional write (thread-safe: several formatter threads store their parts concurrently)
+    bool write_at(uint64_t at, const char* p, size_t n) const {
         size_t off = 0;
-        while (off < s.size()) {
-            long w = ::write(fd_, s.data() + off, s.size() - off);
+        while (off < n) {
+            long w = ::pwrite(fd_, p + off, n - off, (off_t)(at + off));
             if (w < 0 && errno == EINTR) continue;
             if (w < 0) return false;
             off += (size_t)w;
         }
         return true;
     }
+    uint64_t pos() const { return pos_; }
+    void advance(uint64_t n) { pos_ += n; }
 
   private:
     int fd_ = -1;
+    uint64_t pos_ = 0;
+};
+
+// growable raw text buffer of one formatter thread (capacity survives across blocks)
+struct TextBuf {
+    std::vector<char> mem;
+    size_t n = 0;
+    char* room(size_t need) {
+        if (n + need > mem.size()) mem.resize(std::max(mem.size() * 2, n + need + (1u << 20)));
+        return mem.data() + n;
+    }
 };
 
 // format rows [r0, r1) of a block into `out` (fused path: values are final distances)
 template <class T>
-void format_rows(std::string& out, const T* block, uint64_t row0, uint64_t r0, uint64_t r1, uint64_t nq, bool tri, bool dm,
-                 const std::vector<std::string>& ref_names, const std::vector<std::string>& qry_names,
+void format_rows(TextBuf& out, const T* block, uint64_t row0, uint64_t r0, uint64_t r1, uint64_t nq, bool tri, bool dm,
+                 const std::vector<std::string>& ref_names, const std::vector<std::string>& qry_names, size_t max_qry_name,
                  const std::vector<std::vector<uint32_t>>& same_name_cols) {
     for (uint64_t r = r0; r < r1; ++r) {
         const uint64_t i = row0 + r;
         const uint64_t cols = tri ? i + 1 : nq;
         const T* v = block + r * nq;
         const std::vector<uint32_t>& zeros = same_name_cols[i];
+        const std::string& rn = ref_names[i];
         size_t zi = 0;
+        // worst case per cell: '\t' + 340 (a huge value through the exact path) is absurd for distances; reserve the
+        // common bound and re-check inside for the exact-path cells
+        const size_t per_cell = dm ? 16 : rn.size() + max_qry_name + 18;
+        char* p = out.room(rn.size() + 2 + cols * per_cell + 400);
         if (dm && cols) {
-            out.push_back('\n');
-            out += ref_names[i];
+            *p++ = '\n';
+            memcpy(p, rn.data(), rn.size());
+            p += rn.size();
         }
         for (uint64_t j = 0; j < cols; ++j) {
             T d = v[j];
             while (zi < zeros.size() && zeros[zi] < j) ++zi;
             if (zi < zeros.size() && zeros[zi] == j) d = (T)0;  // name equality => 0 (main.rs:452-453)
+            if (!(std::fabs((double)d) < 1024.0)) {                  // inf / NaN / huge: may need up to 340 bytes
+                out.n = (size_t)(p - out.mem.data());
+                p = out.room((cols - j) * per_cell + 800);
+            }
             if (!dm) {
-                out += ref_names[i];
-                out.push_back('\t');
-                out += qry_names[j];
-                out.push_back('\t');
-                append_fixed6(out, d);
-                out.push_back('\n');
+                memcpy(p, rn.data(), rn.size());
+                p += rn.size();
+                *p++ = '\t';
+                const std::string& qn = qry_names[j];
+                memcpy(p, qn.data(), qn.size());
+                p += qn.size();
+                *p++ = '\t';
+                p = fmt6(p, (double)d);
+                *p++ = '\n';
             } else {
-                out.push_back('\t');
-                append_fixed6(out, d);
+                *p++ = '\t';
+                p = fmt6(p, (double)d);
             }
         }
+        out.n = (size_t)(p - out.mem.data());
     }
 }
 
@@ -319,26 +404,46 @@ Status run_dist(lash_ctx* ctx, int algo, int k, const std::string& estimator, ui
         if (!file.write(hdr)) return Status{LASH_HOST_E_IO, "Error writing columns for matrix output"};
     }
     const unsigned nt = (unsigned)std::max(1, threads);
-    std::vector<std::string> parts(nt);
+    std::vector<TextBuf> parts(nt);
+    size_t max_qry_name = 0;
+    for (const auto& q : in.qry_names) max_qry_name = std::max(max_qry_name, q.size());
+    std::atomic<bool> io_ok{true};
     st = distance_blocks(ctx, algo, k, est, (int)model, std::is_same<T, float>::value, in, same_files,
                          [&](uint64_t row0, uint64_t n_rows, const void* block) {
                              const T* b = static_cast<const T*>(block);
                              const unsigned use = (unsigned)std::min<uint64_t>(nt, n_rows);
-                             std::vector<std::thread> pool;
-                             for (unsigned t = 0; t < use; ++t) {
-                                 const uint64_t r0 = n_rows * t / use, r1 = n_rows * (t + 1) / use;
-                                 parts[t].clear();
-                                 auto job = [&, t, r0, r1] {
-                                     format_rows<T>(parts[t], b, row0, r0, r1, nq, tri, dm, in.ref_names, in.qry_names, same_name_cols);
+                             // each worker formats its rows, learns its file offset from its predecessor (sizes are known
+                             // only after formatting) and stores its part itself: formatting AND the copies into the page
+                             // cache run in parallel, the file is still written in row order
+                             std::vector<std::atomic<int64_t>> start(use + 1);
+                             for (auto& a : start) a.store(-1, std::memory_order_relaxed);
+                             start[0].store((int64_t)file.pos(), std::memory_order_release);
+                             auto job = [&](unsigned t) {
+                                 // triangular rows grow with i: cut the block so that workers get equal CELLS
+                                 auto cut = [&](unsigned x) -> uint64_t {
+                                     if (!tri) return n_rows * x / use;
+                                     const double lo = (double)row0, hi = (double)(row0 + n_rows);
+                                     const double area = (hi * (hi + 1) - lo * (lo + 1)) * (double)x / (double)use + lo * (lo + 1);
+                                     const double rr = (std::sqrt(1.0 + 4.0 * area) - 1.0) / 2.0 - lo;
+                                     const uint64_t c = rr <= 0 ? 0 : (uint64_t)std::llround(rr);
+                                     return x == use ? n_rows : std::min<uint64_t>(c, n_rows);
                                  };
-                                 if (t + 1 < use) pool.emplace_back(job);
-                                 else job();
-                             }
+                                 const uint64_t r0 = cut(t), r1 = std::max(cut(t + 1), r0);
+                                 parts[t].n = 0;
+                                 format_rows<T>(parts[t], b, row0, r0, r1, nq, tri, dm, in.ref_names, in.qry_names, max_qry_name, same_name_cols);
+                                 int64_t at;
+                                 while ((at = start[t].load(std::memory_order_acquire)) < 0) std::this_thread::yield();
+                                 start[t + 1].store(at + (int64_t)parts[t].n, std::memory_order_release);
+                                 if (!file.write_at((uint64_t)at, parts[t].mem.data(), parts[t].n)) io_ok.store(false);
+                             };
+                             std::vector<std::thread> pool;
+                             for (unsigned t = 1; t < use; ++t) pool.emplace_back(job, t);
+                             job(0);
                              for (auto& th : pool) th.join();
-                             for (unsigned t = 0; t < use; ++t)
-                                 if (!file.write(parts[t])) wst = Status{LASH_HOST_E_IO, "Error writing to file"};
+                             file.advance((uint64_t)(start[use].load() - start[0].load()));
                          },
                          rows.first, rows.second);
+    if (!io_ok.load()) wst = Status{LASH_HOST_E_IO, "Error writing to file"};
     if (!st.ok()) return st;
     return wst.ok() ? st : wst;
 }

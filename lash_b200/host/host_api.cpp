@@ -168,6 +168,9 @@ extern "C" int lash_host_format_fixed6_f64(double v, char* out) {
     memcpy(out, s.data(), s.size());
     return (int)s.size();
 }
+extern "C" size_t lash_host_format_fixed6_bulk(const double* v, size_t n, char* out) {
+    return (v && out) ? lash::format_fixed6_bulk(v, n, out) : 0;
+}
 extern "C" int lash_host_format_fixed6_f32(float v, char* out) {
     std::string s;
     lash::append_fixed6(s, v);

@@ -153,6 +153,8 @@ inline T compute_distance(T frac, size_t kmer_length, uint8_t equation) {
 // Rust `{:.6}` (exact, round-half-even); appends to out
 void append_fixed6(std::string& out, double v);
 void append_fixed6(std::string& out, float v);
+// the bulk writer's fast path of the same formatting ('\n' after each value; out: 341 bytes per value); returns bytes written
+size_t format_fixed6_bulk(const double* v, size_t n, char* out);
 
 // main.rs:429-471: the emit callback that writes the TSV list / the --dm matrix
 template <class T>

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "lash_host_dist_rows": (i32, [vp, cp, cp, cp, cp, i32, i32, i32, i32, i32, i32]),
     "lash_host_format_fixed6_f64": (i32, [C.c_double, C.c_char_p]),
     "lash_host_format_fixed6_f32": (i32, [C.c_float, C.c_char_p]),
+    "lash_host_format_fixed6_bulk": (sz, [vp, sz, vp]),
 }
 
 _lib = None
@@ -168,6 +169,14 @@ def dist_rows(ctx, ref_prefix: str, query_prefix: str, output_file: str, rank: i
               model: int = 1, dm: bool = False, fp32: bool = False, threads: int = 1) -> int:
     return check(lib().lash_host_dist_rows(ctx.handle, os.fsencode(ref_prefix), os.fsencode(query_prefix), os.fsencode(output_file),
                                            estimator.encode(), model, int(dm), int(fp32), threads, rank, world))
+
+
+def format_fixed6_bulk(values: np.ndarray) -> list[str]:
+    """The fused writer's formatter over an array (fast path + exact fallback)."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    buf = np.zeros(341 * max(len(v), 1), dtype=np.uint8)
+    n = lib().lash_host_format_fixed6_bulk(v.ctypes.data_as(vp), len(v), buf.ctypes.data_as(vp))
+    return buf[:n].tobytes().decode().split("\n")[:-1]
 
 
 def format_fixed6(v: float, fp32: bool = False) -> str:

@@ -155,6 +155,14 @@ def test_fixed6_is_rusts_format(oracle):
         assert hostapi.format_fixed6(v) == "%.6f" % v, v
     for v in list(rng.random(5000).astype(np.float32)) + [np.float32(0.1), np.float32(1e-7), np.float32(0.0000005)]:
         assert hostapi.format_fixed6(float(v), fp32=True) == "%.6f" % float(v)
+    # the bulk writer's fast path gives the same text, including values a hair from a rounding boundary
+    half = (np.arange(0, 4000, dtype=np.float64) + 0.5) * 1e-6
+    near = np.concatenate([half, np.nextafter(half, 0), np.nextafter(half, 1), half * (1 + 3e-13), half * (1 - 3e-13)])
+    bulk_in = np.concatenate([np.array(vals, dtype=np.float64), near, rng.random(200000), -rng.random(100), rng.random(1000) * 1500,
+                              np.array([np.nan, np.inf, -np.inf, -0.0, 1023.9999995, 1024.0, 1e300])])
+    got = hostapi.format_fixed6_bulk(bulk_in)
+    exp = ["NaN" if np.isnan(v) else "%.6f" % v for v in bulk_in]
+    assert got == exp
     assert hostapi.format_fixed6(float("nan")) == "NaN" and hostapi.format_fixed6(float("inf")) == "inf"
     assert hostapi.format_fixed6(float("-inf")) == "-inf" and hostapi.format_fixed6(-0.0) == "-0.000000"
 

@@ -163,12 +163,63 @@ def c4_full(ctx, total_gbp=100, chunk_reads=26_666_667, read_len=150):
             "gbp_per_s_wall": n_push * n_bases / wall / 1e9, "nonzero_registers": int((regs != 0).sum())}
 
 
+def writer_case(ctx, n=20_000, threads=0):
+    """`lash dist` end to end on files (SURVEY.md 8f-2): n ULL p=10 sketches on disk -> lash::dist_command (fused kernel
+    epilogue + parallel `{:.6}` formatter) -> text on tmpfs; --dm matrix (lower triangle) and the TSV list."""
+    import json as js
+    import os
+    import shutil
+    import tempfile
+
+    from lash_b200 import hostapi
+    threads = threads or (os.cpu_count() or 1)
+    dev = torch.device("cuda", 0)
+    length = 50_000
+    stride = padded_bytes(length)
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    buf = torch.randint(0, 256, (n * stride + 64,), dtype=torch.uint8, device=dev, generator=g)
+    spans = (Span * n)()
+    for i in range(n):
+        spans[i] = Span(i, i * stride, length, 0, 1, 0)
+    sk = ops.Sketcher(ctx, ALGO_ULL, 10, 16, 42, n)
+    sk.push_raw(buf.data_ptr(), n * stride, spans, n, None, 0, dev=True)
+    regs = sk.fetch()
+    sk.close()
+    d = tempfile.mkdtemp(prefix="lash_writer_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    out = []
+    try:
+        prefix = os.path.join(d, "db")
+        hostapi.write_sketches(prefix + "_sketches.bin", ALGO_ULL, 10, regs, threads=threads)
+        open(prefix + "_files.json", "w").write(js.dumps([f"genome_{i:06d}.fna" for i in range(n)], indent=2))
+        hostapi.check(hostapi.lib().lash_host_write_parameters(prefix.encode(), ALGO_ULL, 10, 16, 42))
+        for dm in (True, False):
+            path = os.path.join(d, "dist.out")
+            t0 = time.perf_counter()
+            hostapi.dist(ctx, prefix, prefix, path, "fgra", 1, dm=dm, threads=threads, fused=True)
+            wall = time.perf_counter() - t0
+            cells = n * (n + 1) // 2
+            out.append({"case": f"lash dist on files: {n} x {n} ULL p=10 FGRA, {'--dm matrix' if dm else 'TSV list'}, fused + {threads} formatter threads, tmpfs",
+                        "cells": cells, "wall_s": wall, "cells_per_s": cells / wall, "bytes_written": os.path.getsize(path),
+                        "text_gb_per_s": os.path.getsize(path) / wall / 1e9})
+            os.remove(path)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--profile", action="store_true", help="one launch per case, quick sizes (for ncu)")
+    ap.add_argument("--writer", action="store_true", help="only the file -> dist -> text writer case")
     ap.add_argument("--full", action="store_true", help="only the full-size C4 / C5 runs (tens of seconds of GPU time)")
     a = ap.parse_args()
+    if a.writer:
+        with ops.Context(0) as ctx:
+            for r in writer_case(ctx):
+                print(json.dumps(r), flush=True)
+        return
     if a.full:
         with ops.Context(0) as ctx:
             print(json.dumps(c4_full(ctx)), flush=True)
