@@ -518,9 +518,12 @@ static int check_dist_args(int algo, int p, int k, int estimator, int model, uin
 
 // smallest non-empty register of both sets, for the FGRA pair-table kernel (dist_kernels.cu)
 static int prepare_regmin(lash_ctx* ctx, DistParams& dp, size_t rb, cudaStream_t st) {
-    if (dp.algo != LASH_ALGO_ULL || dp.estimator != LASH_EST_FGRA) return LASH_OK;
-    CU(ctx->d_regmin.reserve(4));
+    dp.n_sm = ctx->n_sm;
+    if (dp.algo != LASH_ALGO_ULL) return LASH_OK;
+    CU(ctx->d_regmin.reserve(8));
     uint32_t* w = (uint32_t*)ctx->d_regmin.p;
+    dp.tile_counter = w + 1;  // word 1: tile counter of the persistent pair-table kernels (zeroed per launch)
+    if (dp.estimator != LASH_EST_FGRA) return LASH_OK;
     CU(cudaMemsetAsync(w, 0xff, 4, st));
     CU(launch_regmin(dp.ref, rb * dp.n_ref, w, ctx->n_sm, st));
     if (dp.qry != dp.ref) CU(launch_regmin(dp.qry, rb * dp.n_qry, w, ctx->n_sm, st));

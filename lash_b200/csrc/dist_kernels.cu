@@ -482,19 +482,25 @@ __device__ __forceinline__ uint32_t fgra_code(uint32_t r, uint32_t base) {
     return r ? c : 0u;
 }
 
-__global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk) {
+// Persistent CTAs (one per SM: the table fills most of its shared memory) fetch tiles from a global counter, so the
+// table is built once per SM instead of once per tile and tiles above the diagonal cost one atomic.
+__device__ __forceinline__ bool next_tile(const DistParams& dp, uint32_t* s_tile, uint64_t n_tiles, uint64_t iter, uint64_t& t) {
+    __syncthreads();  // the previous tile is finished everywhere (its staging buffers and flags may be reused)
+    if (threadIdx.x == 0) *s_tile = dp.tile_counter ? atomicAdd(dp.tile_counter, 1u) : (uint32_t)(blockIdx.x + iter * gridDim.x);
+    __syncthreads();
+    t = *s_tile;
+    return t < n_tiles;
+}
+
+__global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk,
+                                                                       uint32_t tiles_x, uint32_t tiles_y) {
+    __shared__ uint32_t s_tile;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* T = reinterpret_cast<double*>(smem_raw);
     const uint32_t a_stride = chunk + 4;                 // u32 elements per reference row (+16 B pad)
     const uint32_t b_stride = chunk + 8;                 // u16 elements per query row (+16 B pad)
     uint32_t* sa = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTabN * kTabN * 8);
     uint16_t* sb = reinterpret_cast<uint16_t*>(sa + (size_t)kTabTR * a_stride);
-
-    const uint64_t row0 = dp.row_begin + (uint64_t)blockIdx.y * kTabTR;
-    const uint64_t col0 = (uint64_t)blockIdx.x * kTabTQ;
-    if (row0 >= dp.row_end) return;
-    const uint64_t row_hi = min(row0 + kTabTR, dp.row_end);
-    if (dp.triangular && col0 > row_hi - 1) return;
 
     // ---- pair table -------------------------------------------------------------------------------
     // The 126 register values the table covers start at the smallest non-empty register of the two sets
@@ -519,11 +525,19 @@ __global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParam
     }
 
     const uint32_t ty = threadIdx.x >> 5, tx = threadIdx.x & 31u;  // ty is warp-uniform
-    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     const unsigned char* gref = reinterpret_cast<const unsigned char*>(dp.ref);
     const unsigned char* gqry = reinterpret_cast<const unsigned char*>(dp.qry);
     const uint32_t chunk_words = chunk / 4;
     const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(T);
+    const uint64_t n_tiles = (uint64_t)tiles_x * tiles_y;
+
+    uint64_t tile;
+    for (uint64_t iter = 0; next_tile(dp, &s_tile, n_tiles, iter, tile); ++iter) {
+    const uint64_t row0 = dp.row_begin + (tile / tiles_x) * kTabTR;
+    const uint64_t col0 = (tile % tiles_x) * kTabTQ;
+    const uint64_t row_hi = min(row0 + kTabTR, dp.row_end);
+    if (dp.triangular && col0 > row_hi - 1) continue;  // tile entirely above the diagonal (CTA-uniform)
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 
     for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk) {
         __syncthreads();  // previous chunk consumed (first pass: orders the table build)
@@ -604,6 +618,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParam
                 reinterpret_cast<double*>(dp.out)[o] = mash_distance_f64(frac, dp.k, dp.model);
         }
     }
+    }  // tiles
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -621,7 +636,9 @@ constexpr int kMlTabThreads = 512;
 constexpr int kMlTabTR = 16, kMlTabTQ = 64;
 constexpr int kMlTabChunk = 128;
 
-__global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk) {
+__global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk,
+                                                                       uint32_t tiles_x, uint32_t tiles_y) {
+    __shared__ uint32_t s_tile;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* R = reinterpret_cast<uint64_t*>(smem_raw);
     uint32_t* W = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTabN * kTabN * 8);
@@ -630,12 +647,6 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
     uint32_t* sa = W + kTabN * kTabN;
     uint16_t* sb = reinterpret_cast<uint16_t*>(sa + (size_t)kMlTabTR * a_stride);
     uint32_t* sflag = reinterpret_cast<uint32_t*>(sb + (size_t)kMlTabTQ * b_stride);  // [TR + TQ] "has a register outside the table"
-
-    const uint64_t row0 = dp.row_begin + (uint64_t)blockIdx.y * kMlTabTR;
-    const uint64_t col0 = (uint64_t)blockIdx.x * kMlTabTQ;
-    if (row0 >= dp.row_end) return;
-    const uint64_t row_hi = min(row0 + kMlTabTR, dp.row_end);
-    if (dp.triangular && col0 > row_hi - 1) return;
 
     const int p = dp.p;
     const uint32_t base = (uint32_t)(4 * p - 4);
@@ -646,17 +657,23 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
         R[e] = ml_ret_of(m, p);
         W[e] = (uint32_t)ml_w_of(m, p);
     }
-    if (threadIdx.x < kMlTabTR + kMlTabTQ) sflag[threadIdx.x] = 0u;
-
     const uint32_t ty = threadIdx.x >> 5, tx = threadIdx.x & 31u;  // ty: the warp's reference row
-    MlAcc acc[2];
-    acc[0].init();
-    acc[1].init();
-    const int nplanes = p + 1;
     const unsigned char* gref = reinterpret_cast<const unsigned char*>(dp.ref);
     const unsigned char* gqry = reinterpret_cast<const unsigned char*>(dp.qry);
     const uint32_t chunk_words = chunk / 4;
     const uint32_t rbase = (uint32_t)__cvta_generic_to_shared(R), wbase = (uint32_t)__cvta_generic_to_shared(W);
+    const uint64_t n_tiles = (uint64_t)tiles_x * tiles_y;
+
+    uint64_t tile;
+    for (uint64_t iter = 0; next_tile(dp, &s_tile, n_tiles, iter, tile); ++iter) {
+    const uint64_t row0 = dp.row_begin + (tile / tiles_x) * kMlTabTR;
+    const uint64_t col0 = (tile % tiles_x) * kMlTabTQ;
+    const uint64_t row_hi = min(row0 + kMlTabTR, dp.row_end);
+    if (dp.triangular && col0 > row_hi - 1) continue;  // tile entirely above the diagonal (CTA-uniform)
+    if (threadIdx.x < kMlTabTR + kMlTabTQ) sflag[threadIdx.x] = 0u;  // ordered before the staging by its first barrier
+    MlAcc acc[2];
+    acc[0].init();
+    acc[1].init();
 
     for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk) {
         __syncthreads();
@@ -746,6 +763,7 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
         else
             reinterpret_cast<double*>(dp.out)[o] = mash_distance_f64(frac, dp.k, dp.model);
     }
+    }  // tiles
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -891,16 +909,14 @@ static cudaError_t launch_dist_fgra_tab(const DistParams& dp, cudaStream_t st) {
     uint64_t ncols = dp.n_qry;
     if (dp.triangular && dp.row_end < ncols) ncols = dp.row_end;
     const uint64_t gx = (ncols + kTabTQ - 1) / kTabTQ;
-    for (uint64_t y0 = 0; y0 < gy; y0 += 65535) {
-        DistParams q = dp;
-        q.row_begin = dp.row_begin + y0 * kTabTR;
-        const uint64_t ny = (gy - y0) < 65535 ? (gy - y0) : 65535;
-        dim3 grid((unsigned)gx, (unsigned)ny);
-        dist_fgra_tab_kernel<<<grid, kTabThreads, smem, st>>>(q, cb, chunk);
-        e = cudaGetLastError();
+    if (gx * gy > 0xffffffffull) return cudaErrorInvalidValue;
+    if (dp.tile_counter) {
+        e = cudaMemsetAsync(dp.tile_counter, 0, 4, st);
         if (e != cudaSuccess) return e;
     }
-    return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>(gx * gy, (uint64_t)dp.n_sm);
+    dist_fgra_tab_kernel<<<grid, kTabThreads, smem, st>>>(dp, cb, chunk, (uint32_t)gx, (uint32_t)gy);
+    return cudaGetLastError();
 }
 
 static cudaError_t launch_dist_ml_tab(const DistParams& dp, cudaStream_t st) {
@@ -915,16 +931,14 @@ static cudaError_t launch_dist_ml_tab(const DistParams& dp, cudaStream_t st) {
     uint64_t ncols = dp.n_qry;
     if (dp.triangular && dp.row_end < ncols) ncols = dp.row_end;
     const uint64_t gx = (ncols + kMlTabTQ - 1) / kMlTabTQ;
-    for (uint64_t y0 = 0; y0 < gy; y0 += 65535) {
-        DistParams q = dp;
-        q.row_begin = dp.row_begin + y0 * kMlTabTR;
-        const uint64_t ny = (gy - y0) < 65535 ? (gy - y0) : 65535;
-        dim3 grid((unsigned)gx, (unsigned)ny);
-        dist_ml_tab_kernel<<<grid, kMlTabThreads, smem, st>>>(q, cb, chunk);
-        e = cudaGetLastError();
+    if (gx * gy > 0xffffffffull) return cudaErrorInvalidValue;
+    if (dp.tile_counter) {
+        e = cudaMemsetAsync(dp.tile_counter, 0, 4, st);
         if (e != cudaSuccess) return e;
     }
-    return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>(gx * gy, (uint64_t)dp.n_sm);
+    dist_ml_tab_kernel<<<grid, kMlTabThreads, smem, st>>>(dp, cb, chunk, (uint32_t)gx, (uint32_t)gy);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launches) {

@@ -68,6 +68,10 @@ struct DistParams {
     uint32_t* flags;  // optional bias-regime counter
     // optional (ULL FGRA pair-table kernel): device word holding the smallest non-empty register of both sets
     const uint32_t* regmin = nullptr;
+    // optional (pair-table kernels): device word the persistent CTAs draw tile indices from (zeroed by the launcher);
+    // nullptr: static round-robin over the grid
+    uint32_t* tile_counter = nullptr;
+    int n_sm = 148;
 };
 // atomicMin of the smallest non-zero register byte into *out_dev (preset to 0xffffffff by the caller)
 cudaError_t launch_regmin(const void* regs, uint64_t n_bytes, uint32_t* out_dev, int n_sm, cudaStream_t st);
