@@ -460,6 +460,141 @@ __global__ void __launch_bounds__(kDistThreads) dist_kernel(DistParams dp, uint3
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4h: HLL distance tiles without a table or a per-register zero test.
+//
+// dist_kernel<HllAcc> spends, per register pair, a byte extract, a max, a zero test + add, an LDS.64 of 2^-r and the
+// DADD (ncu: shared-memory and issue bound, 2.0 T register pairs/s).  Here the registers are recoded ONCE, at staging
+// time, into the high word of the double 2^-r  (v = 0x3FF00000 - (r << 20); the low word of a power of two is 0), so
+//     2^-max(ra, rb) = hiloint2double(min(va, vb), 0)      -- one VIMNMX, then the DADD, per register pair,
+// the same doubles added in the same (register index) order as dist_kernel / the scalar CPU loop -> bit-identical sums.
+// The zero count (HLL++ linear counting, streaming_algorithms len()) only matters where BOTH sketches have an empty
+// register at the same index; staging records, per chunk, whether any reference row and any query column of the tile
+// holds an empty register at all, and only such chunks run the loop variant that also counts (v == 0x3FF00000).
+// A warp owns 4 reference rows (warp-uniform -> broadcast LDS.128) x 64 query columns, two per lane.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHllThreads = 256;
+constexpr int kHllRM = 4, kHllQM = 2;
+constexpr int kHllTR = (kHllThreads / 32) * kHllRM, kHllTQ = 32 * kHllQM;  // 32 x 64 pairs per CTA
+constexpr int kHllChunk = 128;                                            // registers per sketch per stage
+constexpr uint32_t kHllOne = 0x3FF00000u;                                 // high word of 2^-0
+
+__device__ __forceinline__ uint4 hll_recode(uint32_t w) {
+    return make_uint4(kHllOne - (w & 0xffu) * 0x100000u, kHllOne - ((w >> 8) & 0xffu) * 0x100000u,
+                      kHllOne - ((w >> 16) & 0xffu) * 0x100000u, kHllOne - (w >> 24) * 0x100000u);
+}
+// any zero byte in w?  (exact for all byte values)
+__device__ __forceinline__ bool has_zero_byte(uint32_t w) { return ((w - 0x01010101u) & ~w & 0x80808080u) != 0u; }
+
+template <bool COUNT_ZERO>
+__device__ __forceinline__ void hll_chunk(double (&sum)[kHllRM][kHllQM], uint32_t (&zero)[kHllRM][kHllQM], const uint32_t* pa,
+                                          const uint32_t* pb, uint32_t a_row, uint32_t b_row32, uint32_t chunk) {
+#pragma unroll 2
+    for (uint32_t e = 0; e < chunk; e += 4) {
+        uint4 a[kHllRM], b[kHllQM];
+#pragma unroll
+        for (int r = 0; r < kHllRM; ++r) a[r] = *reinterpret_cast<const uint4*>(pa + r * a_row + e);
+#pragma unroll
+        for (int c = 0; c < kHllQM; ++c) b[c] = *reinterpret_cast<const uint4*>(pb + c * b_row32 + e);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int r = 0; r < kHllRM; ++r) {
+                const uint32_t av = j == 0 ? a[r].x : j == 1 ? a[r].y : j == 2 ? a[r].z : a[r].w;
+#pragma unroll
+                for (int c = 0; c < kHllQM; ++c) {
+                    const uint32_t bv = j == 0 ? b[c].x : j == 1 ? b[c].y : j == 2 ? b[c].z : b[c].w;
+                    const uint32_t m = min(av, bv);
+                    if (COUNT_ZERO) zero[r][c] += (m == kHllOne);
+                    sum[r][c] += __hiloint2double((int)m, 0);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kHllThreads, 3) dist_hll_fast_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_zero[2][2];                    // [chunk parity][ref, qry]: an empty register was staged
+    const uint32_t stride = chunk + 4;                   // u32 per staged row (+16 B pad: conflict-free LDS.128)
+    uint32_t* sa = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* sb = sa + (size_t)kHllTR * stride;
+
+    const uint64_t row0 = dp.row_begin + (uint64_t)blockIdx.y * kHllTR;
+    const uint64_t col0 = (uint64_t)blockIdx.x * kHllTQ;
+    if (row0 >= dp.row_end) return;
+    const uint64_t row_hi = min(row0 + kHllTR, dp.row_end);
+    if (dp.triangular && col0 > row_hi - 1) return;      // tile entirely above the diagonal
+
+    const uint32_t wy = threadIdx.x >> 5, tx = threadIdx.x & 31u;
+    const unsigned char* gref = reinterpret_cast<const unsigned char*>(dp.ref);
+    const unsigned char* gqry = reinterpret_cast<const unsigned char*>(dp.qry);
+    const uint32_t chunk_words = chunk / 4;                                                // powers of two, both
+    const uint32_t cw_shift = 31u - __clz(chunk_words), cell_shift = 31u - __clz(cell_bytes);
+
+    double sum[kHllRM][kHllQM];
+    uint32_t zero[kHllRM][kHllQM];
+#pragma unroll
+    for (int r = 0; r < kHllRM; ++r)
+#pragma unroll
+        for (int c = 0; c < kHllQM; ++c) sum[r][c] = 0.0, zero[r][c] = 0u;
+    if (threadIdx.x < 2) s_zero[0][threadIdx.x] = 0u;
+
+    uint32_t par = 0;
+    for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk, par ^= 1u) {
+        __syncthreads();  // previous chunk consumed; s_zero[par] was cleared during the previous staging pass (or above)
+        if (threadIdx.x < 2) s_zero[par ^ 1u][threadIdx.x] = 0u;
+        bool za = false, zb = false;
+        for (uint32_t e = threadIdx.x; e < ((uint32_t)kHllTR << cw_shift); e += kHllThreads) {
+            const uint32_t r = e >> cw_shift, w = e & (chunk_words - 1u);
+            const uint64_t gi = row0 + r;
+            // rows past the end are staged as "register 255" (never empty, never read back)
+            const uint32_t v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint32_t*>(gref + (gi << cell_shift) + c0) + w) : 0xffffffffu;
+            za |= has_zero_byte(v);
+            *reinterpret_cast<uint4*>(sa + r * stride + 4 * w) = hll_recode(v);
+        }
+        for (uint32_t e = threadIdx.x; e < ((uint32_t)kHllTQ << cw_shift); e += kHllThreads) {
+            const uint32_t r = e >> cw_shift, w = e & (chunk_words - 1u);
+            const uint64_t gj = col0 + r;
+            const uint32_t v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint32_t*>(gqry + (gj << cell_shift) + c0) + w) : 0xffffffffu;
+            zb |= has_zero_byte(v);
+            *reinterpret_cast<uint4*>(sb + r * stride + 4 * w) = hll_recode(v);
+        }
+        if (za) s_zero[par][0] = 1u;
+        if (zb) s_zero[par][1] = 1u;
+        __syncthreads();
+        const uint32_t* pa = sa + (wy * kHllRM) * stride;
+        const uint32_t* pb = sb + tx * stride;
+        if (s_zero[par][0] & s_zero[par][1])  // CTA-uniform
+            hll_chunk<true>(sum, zero, pa, pb, stride, 32u * stride, chunk);
+        else
+            hll_chunk<false>(sum, zero, pa, pb, stride, 32u * stride, chunk);
+    }
+
+    // epilogue: identical to dist_kernel<HllAcc>
+#pragma unroll
+    for (int a = 0; a < kHllRM; ++a) {
+#pragma unroll
+        for (int b = 0; b < kHllQM; ++b) {
+            const uint64_t i = row0 + wy * kHllRM + a, j = col0 + tx + 32 * b;
+            if (i >= dp.row_end || j >= dp.n_qry) continue;
+            if (dp.triangular && j > i) continue;
+            bool bias;
+            const double U = hll_len(sum[a][b], zero[a][b], dp.p, &bias);
+            if (bias && dp.flags) atomicAdd(dp.flags, 1u);
+            const double ca = dp.card_ref[i], cb = dp.card_qry[j];
+            const double sim = (ca + cb - U) / U;
+            const double s = fmax(sim, 0.0);  // f64::max: NaN -> 0 (utils.rs:362)
+            const double frac = 2.0 * s / (1.0 + s);
+            const uint64_t o = dp.packed_tri ? (i * (i + 1) / 2 + j) : ((i - dp.out_row0) * dp.n_qry + j);
+            if (dp.fp32)
+                reinterpret_cast<float*>(dp.out)[o] = mash_distance_f32((float)frac, dp.k, dp.model);
+            else
+                reinterpret_cast<double*>(dp.out)[o] = mash_distance_f64(frac, dp.k, dp.model);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4b: FGRA distance tiles through a PAIR table.
 //
 // dist_kernel<FgraAcc> spends ~12 ALU instructions per register pair on the packed-domain merge
@@ -919,6 +1054,28 @@ static cudaError_t launch_dist_fgra_tab(const DistParams& dp, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static cudaError_t launch_dist_hll_fast(const DistParams& dp, cudaStream_t st) {
+    const uint32_t cb = cell_bytes_of(dp.algo, dp.p);
+    const uint32_t chunk = cb < (uint32_t)kHllChunk ? cb : (uint32_t)kHllChunk;
+    const size_t smem = (size_t)(kHllTR + kHllTQ) * (chunk + 4) * 4;
+    cudaError_t e = cudaFuncSetAttribute(dist_hll_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint64_t rows = dp.row_end - dp.row_begin;
+    const uint64_t gy = (rows + kHllTR - 1) / kHllTR;
+    uint64_t ncols = dp.n_qry;
+    if (dp.triangular && dp.row_end < ncols) ncols = dp.row_end;  // nothing right of the diagonal
+    const uint64_t gx = (ncols + kHllTQ - 1) / kHllTQ;
+    for (uint64_t y0 = 0; y0 < gy; y0 += 65535) {  // grid.y is limited to 65535: walk row bands
+        DistParams q = dp;
+        q.row_begin = dp.row_begin + y0 * kHllTR;
+        const uint64_t ny = (gy - y0) < 65535 ? (gy - y0) : 65535;
+        dist_hll_fast_kernel<<<dim3((unsigned)gx, (unsigned)ny), kHllThreads, smem, st>>>(q, cb, chunk);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 static cudaError_t launch_dist_ml_tab(const DistParams& dp, cudaStream_t st) {
     const uint32_t cb = cell_bytes_of(dp.algo, dp.p);
     const uint32_t chunk = cb < (uint32_t)kMlTabChunk ? cb : (uint32_t)kMlTabChunk;
@@ -951,7 +1108,12 @@ cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launc
     }();
     if (dp.algo == ULL && dp.estimator == 0 && !fgra_merge) return launch_dist_fgra_tab(dp, st);
     if (dp.algo == ULL && dp.estimator == 1 && !fgra_merge) return launch_dist_ml_tab(dp, st);
-    if (dp.algo == HLL) return launch_dist_t<HllAcc, 16>(dp, st);
+    // LASH_HLL_KERNEL=table selects K4 (LDS.64 table of 2^-r + per-register zero test) for A/B measurements; default K4h
+    static const bool hll_table = [] {
+        const char* v = getenv("LASH_HLL_KERNEL");
+        return v && std::string(v) == "table";
+    }();
+    if (dp.algo == HLL) return hll_table ? launch_dist_t<HllAcc, 16>(dp, st) : launch_dist_hll_fast(dp, st);
     if (dp.algo == HMH) return launch_dist_t<HmhAcc, 16>(dp, st);
     const bool tiny = dp.p == 3;  // 8 registers per sketch
     if (dp.estimator == 0) return tiny ? launch_dist_t<FgraAcc, 8>(dp, st) : launch_dist_t<FgraAcc, 16>(dp, st);

@@ -253,3 +253,45 @@ def test_reference_style_emit_interface(oracle, gpu_ctx):
     ops.hll_distance(gpu_ctx, 10, 16, MODEL_POISSON, False, ["x", "y"], oracle.sketch_genomes(ALGO_HLL, 10, 16, 42, synth.genomes(2, 50_000)),
                      ["y", "z"], oracle.sketch_genomes(ALGO_HLL, 10, 16, 42, synth.genomes(2, 50_000, seed=1)), False, False, rows.append)
     assert len(rows) == 2 and rows[1][0][:2] == ("y", "y") and rows[1][0][2] == 0.0 and rows[0][0][2] > 0.0
+
+
+@pytest.mark.parametrize("p,n_ref,n_qry", [(4, 5, 9), (7, 37, 101), (12, 70, 33), (14, 40, 67)])
+def test_hll_recoded_kernel_ragged_tiles_and_mixed_empties(oracle, gpu_ctx, p, n_ref, n_qry):
+    """K4h (registers recoded to the high word of 2^-r, zero count only in chunks where both sides hold an empty
+    register): simulated sketches from nearly empty (linear counting) to huge, tiles that are not multiples of
+    32 x 64, chunks with empties on one side only.  The HLL sum is +,*,/ of exact powers of two in register
+    order on both sides, so everything up to frac is bit-identical; the poisson distance adds one log."""
+    rng = np.random.default_rng(100 + p)
+    m = 1 << p
+
+    def simulated(log2_per_reg, rows):
+        if log2_per_reg < 0:                                     # sparse: a fraction 2^log2 of the registers is hit once
+            hit = rng.random((rows, m)) < 2.0 ** log2_per_reg
+            return (hit * np.clip(rng.geometric(0.5, size=(rows, m)), 1, 64 - p + 1)).astype(np.uint8)
+        rho = np.clip(np.floor(log2_per_reg - np.log2(-np.log(rng.random((rows, m))))) + 1, 1, 64 - p + 1)
+        return rho.astype(np.uint8)
+
+    def mixed(n):
+        kinds = [-3.0, -0.5, 2.0, 9.0, 22.0]
+        rows = [simulated(kinds[i % len(kinds)], 1)[0] for i in range(n)]
+        rows[0][:] = 0                                           # a completely empty sketch
+        if n > 3:
+            rows[3][: m // 2] = 0                                # empties in the first half only
+        return np.stack(rows)
+
+    ref, qry = mixed(n_ref), mixed(n_qry)
+    exp, flags = oracle.dist(ALGO_HLL, p, 21, 0, MODEL_POISSON, False, ref, qry, return_flags=True)
+    frac_exp = oracle.dist(ALGO_HLL, p, 21, 0, 2, False, ref, qry)
+    got, w = ops.dist(gpu_ctx, ALGO_HLL, p, 21, 0, MODEL_POISSON, False, ref, qry)
+    frac_got, _ = ops.dist(gpu_ctx, ALGO_HLL, p, 21, 0, 2, False, ref, qry)
+    assert (w == W_HLL_BIAS_REGIME) == bool(flags.any())
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+    ok = ~np.isnan(exp)
+    # frac = 2s/(1+s) with s from exact sums and a bit-exact raw estimate; linear counting adds one log (glibc vs CUDA)
+    np.testing.assert_allclose(frac_got[ok], frac_exp[ok], rtol=1e-13, atol=1e-300)
+    _assert_close_f64(np.where(ok, got, 0), np.where(ok, exp, 0), np.nan_to_num(frac_exp), 21, f"hll recoded p={p}")
+    # triangular / row-streamed forms of the same kernel agree with the dense one bit for bit
+    sq = np.concatenate([ref, qry])[: min(n_ref + n_qry, 90)]
+    dense, _ = ops.dist(gpu_ctx, ALGO_HLL, p, 21, 0, MODEL_POISSON, False, sq, sq)
+    tri, _ = ops.dist(gpu_ctx, ALGO_HLL, p, 21, 0, MODEL_POISSON, False, sq, sq, triangular=True)
+    np.testing.assert_array_equal(tri, dense[np.tril_indices(len(sq))])
