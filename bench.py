@@ -263,7 +263,8 @@ def run_graft(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    kernel_ms0, _ = sk.stats()
+    kernel_ms0, sk_launches0 = sk.stats()
+    _, dist_launches0 = ops.dist_stats(ctx)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -282,8 +283,11 @@ def run_graft(args):
     phase[1] = ev[1].elapsed_time(ev[2])   # gather
     phase[2] = ev[2].elapsed_time(ev[3])   # cardinality + dist
     clocks = sampler.stop() if rank == 0 else None
-    kernel_ms, _ = sk.stats()              # library-side CUDA events around the sketch kernel launches
+    kernel_ms, sk_launches = sk.stats()    # library-side CUDA events around the sketch kernel launches
     kernel_ms -= kernel_ms0                # timed steps only
+    # kernels of liblash_gpu.so launched inside the timed region on this rank, counted by the library itself:
+    # per step sketch_kernel + card_kernel + regmin_kernel + dist_fgra_tab_kernel
+    gpu_launches = int(sk_launches - sk_launches0) + int(ops.dist_stats(ctx)[1] - dist_launches0)
     t = torch.tensor([total_ms, phase[0], phase[1], phase[2]], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -355,6 +359,26 @@ def run_graft(args):
             pushes.append((g0 * stride, (g1 - g0) * stride, sp, g1 - g0))
 
         trace = os.environ.get("LASH_BENCH_TRACE")
+        # N>1: the host-side exchange step.  Every rank's host registers go up once more into a device tensor, are
+        # all-gathered over NCCL, and come back as ONE host array of all n_all sketches, which lash_dist_stream_rows
+        # (host buffers in, pinned host blocks out) turns into this rank's row range of the all-vs-all triangle.
+        if world > 1:
+            t_local = torch.empty(n_g * rb, dtype=torch.uint8, device=device)
+            t_all = torch.empty(n_all * rb, dtype=torch.uint8, device=device)
+            host_all_t = torch.empty(n_all * rb, dtype=torch.uint8, pin_memory=True)
+            host_all = host_all_t.numpy()
+            host_local_t = torch.from_numpy(host_regs_all.reshape(-1))
+            blocks = {"n": 0, "bytes": 0, "sum": 0.0}
+
+            def _cb(user, row0, nrows, ptr):
+                # the block sits in pinned host memory owned by the library: this IS the device->host read of the result
+                r1 = int(row0) + int(nrows)
+                blocks["n"] += 1
+                blocks["bytes"] += int(nrows) * min(n_all, r1) * 8
+                blocks["sum"] += C.cast(ptr, C.POINTER(C.c_double))[0]
+                return 0
+
+            cb = capi.DIST_BLOCK_CB(_cb)
 
         def e2e_step():
             t0 = time.perf_counter()
@@ -365,8 +389,16 @@ def run_graft(args):
             t2 = time.perf_counter()
             check(L.lash_sketch_fetch(sk._h, 0, n_g, host_regs_all.ctypes.data_as(C.c_void_p)))
             t3 = time.perf_counter()
-            check(L.lash_dist(ctx.handle, ALGO_ULL, P, K, EST_FGRA, MODEL, 0, host_regs_all.ctypes.data_as(C.c_void_p), n_g,
-                              host_regs_all.ctypes.data_as(C.c_void_p), n_g, 1, tri_out.ctypes.data_as(C.c_void_p)))
+            if world == 1:
+                check(L.lash_dist(ctx.handle, ALGO_ULL, P, K, EST_FGRA, MODEL, 0, host_regs_all.ctypes.data_as(C.c_void_p), n_g,
+                                  host_regs_all.ctypes.data_as(C.c_void_p), n_g, 1, tri_out.ctypes.data_as(C.c_void_p)))
+            else:
+                t_local.copy_(host_local_t)
+                dist.all_gather_into_tensor(t_all, t_local)
+                host_all_t.copy_(t_all)                         # synchronous D2H into pinned memory
+                blocks["n"] = blocks["bytes"] = 0
+                check(L.lash_dist_stream_rows(ctx.handle, ALGO_ULL, P, K, EST_FGRA, MODEL, 0, host_all.ctypes.data_as(C.c_void_p), n_all,
+                                              host_all.ctypes.data_as(C.c_void_p), n_all, 1, rows[0], rows[1], 0, cb, None))
             t4 = time.perf_counter()
             if trace:
                 print(f"[rank {rank}] e2e ms: reset {1e3*(t1-t0):.2f} pushes {1e3*(t2-t1):.2f} fetch(sync) {1e3*(t3-t2):.2f} "
@@ -384,16 +416,23 @@ def run_graft(args):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_ms = float(te.item()) * 1e3 / args.steps
-        h2d = n_bytes + n_g * rb
-        d2h = n_g * rb + tri_out.nbytes
+        if world == 1:
+            h2d = n_bytes + n_g * rb
+            d2h = n_g * rb + tri_out.nbytes
+        else:   # rank 0's bytes: packed bases, local registers up again for the all-gather, all registers up for dist
+            h2d = n_bytes + n_g * rb + n_all * rb
+            d2h = n_g * rb + n_all * rb + blocks["bytes"]
         if rank == 0:
             e2e_parity = bool(np.array_equal(host_regs_all[:2], regs_view.view(n_g, rb)[:2].cpu().numpy()))
             parity = parity and e2e_parity
         check(L.lash_host_free(pin))
         e2e = {"value": (bases_rank * world) / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
-               "note": "per rank: 1000 genomes pushed from pinned host memory in 50-genome slices (double-buffered H2D), registers "
-                       "fetched to host, lash_dist on host registers (per-rank 1000x1000 triangle), result copied back"}
+               "note": (f"per rank: {n_g} genomes pushed from pinned host memory in {per_push}-genome slices (double-buffered H2D), "
+                        "registers fetched to host, " +
+                        ("lash_dist on host registers (packed triangle copied back)" if world == 1 else
+                         f"host registers all-gathered over NCCL (up, gather, down), lash_dist_stream_rows on the {n_all} host "
+                         "sketches for this rank's row range of the triangle (pinned row blocks delivered to a callback)"))}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -423,7 +462,7 @@ def run_graft(args):
             "dist": {"metric": "all_vs_all_pairs_per_s", "value": n_pairs_all / (di_ms * 1e-3), "unit": "pairs/s", "pairs": n_pairs_all,
                      "register_merges_per_s": n_pairs_all * rb / (di_ms * 1e-3)},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "fasta_ingest": ingest, "clocks": clocks,
-            "gpu_launches": int(args.steps * 3), "parity_spot_check": parity, "hll_bias_flags": int(flags.item()),
+            "gpu_launches": gpu_launches, "parity_spot_check": parity, "hll_bias_flags": int(flags.item()),
         }
         print(json.dumps(line), flush=True)
     sk.close()

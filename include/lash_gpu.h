@@ -197,7 +197,9 @@ int lash_dist_stream_rows(lash_ctx* ctx, int algo, int p, int k, int estimator, 
                           uint64_t n_ref, const void* qry_regs, uint64_t n_qry, int triangular, uint64_t row_begin,
                           uint64_t row_end, uint64_t rows_per_block, lash_dist_block_cb cb, void* user);
 
-/* Kernel time (ms) and launches of the last lash_dist / lash_dist_stream call on this ctx. */
+/* Kernel time (ms) and kernel launches (cardinality, register minimum, distance tiles) of the last lash_dist /
+ * lash_dist_stream call on this ctx; the launch count also accumulates over lash_cardinality_dev / lash_dist_dev calls
+ * (those are not timed by the library: the caller owns the stream). */
 int lash_dist_stats(lash_ctx* ctx, double* kernel_ms, uint64_t* launches);
 
 #ifdef __cplusplus

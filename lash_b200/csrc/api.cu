@@ -527,6 +527,7 @@ static int prepare_regmin(lash_ctx* ctx, DistParams& dp, size_t rb, cudaStream_t
     CU(cudaMemsetAsync(w, 0xff, 4, st));
     CU(launch_regmin(dp.ref, rb * dp.n_ref, w, ctx->n_sm, st));
     if (dp.qry != dp.ref) CU(launch_regmin(dp.qry, rb * dp.n_qry, w, ctx->n_sm, st));
+    ctx->dist_launches += dp.qry != dp.ref ? 2 : 1;
     dp.regmin = w;
     return LASH_OK;
 }
@@ -538,6 +539,7 @@ extern "C" int lash_cardinality_dev(lash_ctx* ctx, int algo, int p, int estimato
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     CU(launch_cardinality(algo, algo == LASH_ALGO_HMH ? 14 : p, estimator, regs_dev, n, card_dev, nullptr, st));
+    ctx->dist_launches += 1;
     return LASH_OK;
 }
 
@@ -728,7 +730,10 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
                 pend.valid = false;
             }
             CUC(cudaStreamWaitEvent(st2, kdone[buf], 0));
-            CUC(cudaMemcpyAsync(h_out[buf].p, d_out[buf].p, (r1 - r0) * n_qry * esz, cudaMemcpyDeviceToHost, st2));
+            // triangular: nothing right of column r1-1 is defined in this block -> copy only the columns below the diagonal
+            // (same pitch on both sides, so the block keeps its dense [n_rows][n_qry] addressing)
+            const uint64_t ncols = triangular ? std::min<uint64_t>(n_qry, r1) : n_qry;
+            CUC(cudaMemcpy2DAsync(h_out[buf].p, n_qry * esz, d_out[buf].p, n_qry * esz, ncols * esz, r1 - r0, cudaMemcpyDeviceToHost, st2));
             CUC(cudaEventRecord(copied[buf], st2));
             CUC(cudaEventSynchronize(kdone[buf]));
             float ms = 0.f;

@@ -903,52 +903,80 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
 
 // ------------------------------------------------------------------------------------------------
 // K3: per-sketch cardinality (utils.rs:213-219, 314-316; hyperminhash cardinality())
-// One thread per sketch, registers walked in index order with the same accumulators as K4
+// One lane per sketch walks the registers in index order with the same accumulators as K4
 // (the union of a sketch with itself is the sketch).
 // ------------------------------------------------------------------------------------------------
+constexpr int kCardWarps = 4;        // sketches per CTA
+constexpr int kCardChunk = 1024;     // bytes of one sketch staged per pass
+
+// A warp owns one sketch: all lanes stage it through shared memory (coalesced 16-byte loads), lane 0 walks the staged
+// bytes in index order.  (One THREAD per sketch reading global memory directly -- the first version -- spent its time
+// waiting on its own strided loads: 0.44 ms for 200 HLL p=14 sketches.)
 template <class ACC, int G>
-__global__ void __launch_bounds__(128) card_kernel(const unsigned char* __restrict__ regs, uint64_t n, uint32_t cell_bytes, int p,
-                                                   double* __restrict__ card, uint32_t* flags) {
+__global__ void __launch_bounds__(kCardWarps * 32) card_kernel(const unsigned char* __restrict__ regs, uint64_t n, uint32_t cell_bytes, int p,
+                                                               double* __restrict__ card, uint32_t* flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SharedTables tabs;
     build_tables<ACC>(tabs, smem_raw, p);
     __syncthreads();
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint64_t i = (uint64_t)blockIdx.x * kCardWarps + warp;
     if (i >= n) return;
+    uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw + ((ACC::kTableBytes + 15) & ~15) + warp * kCardChunk);
     const unsigned char* g = regs + i * cell_bytes;
+    const uint32_t chunk = cell_bytes < (uint32_t)kCardChunk ? cell_bytes : (uint32_t)kCardChunk;
     ACC acc;
     acc.init();
-    for (uint32_t e = 0; e < cell_bytes; e += G) {
-        uint32_t v[G];
+    for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk) {
+        __syncwarp();
+        for (uint32_t w = lane; w < chunk / 4; w += 32) stage[w] = __ldg(reinterpret_cast<const uint32_t*>(g + c0) + w);
+        __syncwarp();
+        if (lane == 0) {
+            for (uint32_t e = 0; e < chunk; e += G) {
+                uint32_t v[G];
 #pragma unroll
-        for (int k = 0; k < G / 4; ++k) {
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(g + e) + k);
-            v[4 * k] = w & 0xffu;
-            v[4 * k + 1] = (w >> 8) & 0xffu;
-            v[4 * k + 2] = (w >> 16) & 0xffu;
-            v[4 * k + 3] = w >> 24;
+                for (int k = 0; k < G / 4; ++k) {
+                    const uint32_t w = stage[e / 4 + k];
+                    v[4 * k] = w & 0xffu;
+                    v[4 * k + 1] = (w >> 8) & 0xffu;
+                    v[4 * k + 2] = (w >> 16) & 0xffu;
+                    v[4 * k + 3] = w >> 24;
+                }
+                acc_add<ACC, G>(acc, v, v, tabs, p + 1);
+            }
         }
-        acc_add<ACC, G>(acc, v, v, tabs, p + 1);
     }
-    bool bias;
-    card[i] = finish_union(acc, p, g, g, &bias);
-    if (bias && flags) atomicAdd(flags, 1u);
+    if (lane == 0) {
+        bool bias;
+        card[i] = finish_union(acc, p, g, g, &bias);
+        if (bias && flags) atomicAdd(flags, 1u);
+    }
 }
 
-__global__ void __launch_bounds__(128) card_hmh_kernel(const uint32_t* __restrict__ regs, uint64_t n, double* __restrict__ card) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kCardWarps * 32) card_hmh_kernel(const uint32_t* __restrict__ regs, uint64_t n, double* __restrict__ card) {
+    __shared__ uint32_t s_stage[kCardWarps][kCardChunk / 4];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint64_t i = (uint64_t)blockIdx.x * kCardWarps + warp;
     if (i >= n) return;
     const uint32_t* g = regs + i * 8192u;
+    uint32_t* stage = s_stage[warp];
     double sum = 0.0, ez = 0.0;
-    for (uint32_t w = 0; w < 8192u; ++w) {
-        const uint32_t v = __ldg(g + w);
-        const uint32_t l0 = (v & 0xffffu) >> 10, l1 = v >> 26;
-        if (l0 == 0) ez += 1.0;
-        sum += pow2neg(l0);
-        if (l1 == 0) ez += 1.0;
-        sum += pow2neg(l1);
+    for (uint32_t w0 = 0; w0 < 8192u; w0 += kCardChunk / 4) {
+        __syncwarp();
+        for (uint32_t w = lane; w < kCardChunk / 4; w += 32) stage[w] = __ldg(g + w0 + w);
+        __syncwarp();
+        if (lane == 0) {
+            for (uint32_t w = 0; w < kCardChunk / 4; ++w) {
+                const uint32_t v = stage[w];
+                const uint32_t l0 = (v & 0xffffu) >> 10, l1 = v >> 26;
+                if (l0 == 0) ez += 1.0;
+                sum += pow2neg(l0);
+                if (l1 == 0) ez += 1.0;
+                sum += pow2neg(l1);
+            }
+        }
     }
-    card[i] = hmh_cardinality_from(sum, ez);
+    if (lane == 0) card[i] = hmh_cardinality_from(sum, ez);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1124,8 +1152,9 @@ template <class ACC, int G>
 static cudaError_t launch_card_t(int algo, int p, const void* regs, uint64_t n, double* card, uint32_t* flags,
                                  cudaStream_t st) {
     const uint32_t cb = cell_bytes_of(algo, p);
-    const unsigned grid = (unsigned)((n + 127) / 128);
-    card_kernel<ACC, G><<<grid, 128, ACC::kTableBytes, st>>>(reinterpret_cast<const unsigned char*>(regs), n, cb, p, card, flags);
+    const unsigned grid = (unsigned)((n + kCardWarps - 1) / kCardWarps);
+    const size_t smem = ((ACC::kTableBytes + 15) & ~15) + (size_t)kCardWarps * kCardChunk;
+    card_kernel<ACC, G><<<grid, kCardWarps * 32, smem, st>>>(reinterpret_cast<const unsigned char*>(regs), n, cb, p, card, flags);
     return cudaGetLastError();
 }
 
@@ -1133,7 +1162,7 @@ cudaError_t launch_cardinality(int algo, int p, int estimator, const void* regs,
                                uint32_t* flags, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     if (algo == HMH) {
-        card_hmh_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(reinterpret_cast<const uint32_t*>(regs), n, card);
+        card_hmh_kernel<<<(unsigned)((n + kCardWarps - 1) / kCardWarps), kCardWarps * 32, 0, st>>>(reinterpret_cast<const uint32_t*>(regs), n, card);
         return cudaGetLastError();
     }
     if (algo == HLL) return launch_card_t<HllAcc, 16>(algo, p, regs, n, card, flags, st);
