@@ -254,8 +254,10 @@ def main():
         out.append(dist_case(ctx, "C5 dist ML p=10 (n x n triangle)", ALGO_ULL, 10, 16, EST_ML, regs_small))
         out.append(dist_case(ctx, "dist FGRA p=10 (n x n triangle)", ALGO_ULL, 10, 16, EST_FGRA, regs_small))
         out.append(dist_case(ctx, "C3 dist HLL p=14", ALGO_HLL, 14, 21, 0, regs_hll14))
-        if not q:  # the same sketches four times over: enough tiles to fill the GPU (timing only)
-            out.append(dist_case(ctx, "C3 dist HLL p=14 (4000 sketches)", ALGO_HLL, 14, 21, 0, np.tile(regs_hll14, (4, 1))))
+        if not a.quick:  # the same sketches several times over: enough tiles to fill the GPU (timing only)
+            n_big = 2000 if q else 4000
+            out.append(dist_case(ctx, f"C3 dist HLL p=14 ({n_big} sketches)", ALGO_HLL, 14, 21, 0,
+                                 np.tile(regs_hll14, (n_big // regs_hll14.shape[0], 1))))
         out.append(dist_case(ctx, "C1 dist HMH", ALGO_HMH, 14, 16, 0, regs_hmh))
     for r in out:
         print(json.dumps(r))

@@ -27,6 +27,10 @@ KEYS = [
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_shared_atom.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+    "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_pipe_fp64.sum", "smsp__inst_executed_pipe_alu.sum",
+    "smsp__inst_executed_pipe_fma.sum", "smsp__inst_executed_pipe_lsu.sum", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+    "lts__t_bytes.sum", "sm__cycles_active.avg",
     "sm__cycles_elapsed.avg.per_second",
 ]
 
