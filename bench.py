@@ -493,15 +493,19 @@ def fasta_ingest_leg(ctx, buf, stride, n_files: int):
                 f.write(b">genome_%d\n" % i + body)
             files.append(path)
         cores = os.cpu_count() or 1
-        best, best_dry, st = 1e30, 1e30, None
-        for _ in range(3):
-            regs, st = hostapi.sketch_files_regs(ctx, ALGO_ULL, P, K, SEED, files, threads=cores)
-            best = min(best, st.seconds_total)
+        best, best_dry, st, runs = 1e30, 1e30, None, []
+        for _ in range(5):
+            regs, s1 = hostapi.sketch_files_regs(ctx, ALGO_ULL, P, K, SEED, files, threads=cores)
+            runs.append({"total_ms": round(s1.seconds_total * 1e3, 2), "open_ms": round(s1.seconds_open * 1e3, 2),
+                         "workers_ms": round(s1.seconds_workers * 1e3, 2), "drain_ms": round(s1.seconds_drain * 1e3, 2)})
+            if s1.seconds_total < best:
+                best, st = s1.seconds_total, s1
             best_dry = min(best_dry, hostapi.pack_files_dry(files, K, threads=cores).seconds_total)
         return {"value": n_files * GENOME_LEN / best / 1e9, "unit": "Gbp/s", "files": n_files, "bytes_of_fasta": int(n_files * (GENOME_LEN + GENOME_LEN // 80 + 12)),
                 "host_threads": cores, "pushes": int(st.n_pushes), "gpu_kernel_ms": st.gpu_kernel_ms,
                 "pack_only_gbp_per_s": n_files * GENOME_LEN / best_dry / 1e9, "simd_packer": bool(hostapi.lib().lash_host_pack_has_simd()),
-                "note": "FASTA text (tmpfs) -> lash::sketch_files<Ull> (C++ host) -> registers on host; best of 3"}
+                "runs": runs,
+                "note": "FASTA text (tmpfs) -> lash::sketch_files<Ull> (C++ host) -> registers on host; best of 5 (every run listed)"}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 

@@ -65,6 +65,9 @@ typedef struct lash_sketch_files_stats {
     uint64_t n_pushes;       /* lash_sketch_push calls */
     double seconds_total;    /* wall time of the call */
     double gpu_kernel_ms;    /* sum of sketch kernel time (lash_sketch_stats) */
+    double seconds_open;     /* lash_sketch_open + first pinned staging chunks (page-locking when the pool is cold) */
+    double seconds_workers;  /* parse + pack + push, all workers, until the last one joined */
+    double seconds_drain;    /* lash_sketch_fetch (waits for the last kernels) + close */
 } lash_sketch_files_stats;
 
 int lash_host_sketch_files_regs(lash_ctx* ctx, int algo, int p, int k, uint64_t seed, const char* const* files,

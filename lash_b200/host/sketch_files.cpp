@@ -407,6 +407,8 @@ Status sketch_files_impl(lash_ctx* ctx, int algo, std::optional<uint32_t> precis
         bool alloc_ok = true;
         for (auto& w : workers) alloc_ok = alloc_ok && w.chunk[0].alloc(chunk_bytes);  // chunk[1]: on first rotate
         std::atomic<uint64_t> next_file{0};
+        const auto t_open = std::chrono::steady_clock::now();
+        st.seconds_open = std::chrono::duration<double>(t_open - t0).count();
         if (alloc_ok) {
             auto run = [&](Worker& w) {
                 for (;;) {
@@ -430,6 +432,8 @@ Status sketch_files_impl(lash_ctx* ctx, int algo, std::optional<uint32_t> precis
         } else {
             gpu.fail(std::string("pinned staging allocation failed: ") + lash_gpu_last_error());
         }
+        const auto t_joined = std::chrono::steady_clock::now();
+        st.seconds_workers = std::chrono::duration<double>(t_joined - t_open).count();
         int rc = LASH_OK;
         if (!gpu.failed.load()) rc = lash_sketch_fetch(gpu.sk, 0, n_files, regs);
         else lash_sketch_sync(gpu.sk);  // chunks must not be freed under an in-flight copy
@@ -444,6 +448,7 @@ Status sketch_files_impl(lash_ctx* ctx, int algo, std::optional<uint32_t> precis
         }
         st.n_pushes = gpu.pushes.load();
         lash_sketch_close(gpu.sk);
+        st.seconds_drain = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_joined).count();
         if (gpu.failed.load()) {
             const bool input = gpu.err.rfind("Invalid input file", 0) == 0;
             return Status{input ? LASH_HOST_E_FORMAT : LASH_E_CUDA, gpu.err};

@@ -22,7 +22,8 @@ E_IO, E_FORMAT, E_PARAMS = -10, -11, -12
 class SketchFilesStats(C.Structure):
     """struct lash_sketch_files_stats"""
     _fields_ = [("n_records", C.c_uint64), ("n_bases_in", C.c_uint64), ("n_bases_kept", C.c_uint64), ("n_pushes", C.c_uint64),
-                ("seconds_total", C.c_double), ("gpu_kernel_ms", C.c_double)]
+                ("seconds_total", C.c_double), ("gpu_kernel_ms", C.c_double), ("seconds_open", C.c_double),
+                ("seconds_workers", C.c_double), ("seconds_drain", C.c_double)]
 
 
 u64, i32, vp, sz, cp = C.c_uint64, C.c_int, C.c_void_p, C.c_size_t, C.c_char_p
