@@ -322,6 +322,8 @@ def run_graft(args):
                 "peak_source": peak_src, "kernel": kname,
                 "kernel_ms": sk_kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
                 "note": "0.25 B/base streamed once; the kernel is integer-pipe bound, not HBM bound (see int_pipe)",
+                # the resource that actually binds this kernel (SM integer pipe) and the fraction of it in use
+                "binding": "sm_integer_issue", "binding_frac": (kps * ipk / issue_peak) if ipk else None,
                 "int_pipe": {"kmers_per_s": kps, "alu_lane_ops_peak_per_s": int_peak,
                              "sm_mhz_used": sm_mhz,
                              "alu_instr_per_kmer_at_peak": int_peak / kps,
