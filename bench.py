@@ -197,6 +197,8 @@ def run_graft(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    # one process per GPU: run (and allocate pinned staging memory) on the CPUs next to this rank's GPU
+    numa_cpus = lib().lash_bind_thread_to_device(local) if os.environ.get("LASH_NUMA_BIND", "1") != "0" else 0
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
@@ -459,7 +461,8 @@ def run_graft(args):
             "config": {"workload": f"configs[1]: ULL p={P} k={K} seed={SEED} sketch of {n_g} synthetic {GENOME_LEN} bp genomes per GPU + "
                                    f"FGRA all-vs-all dist (poisson, f64, lower triangle) over all {n_all} sketches",
                        "genomes_per_gpu": n_g, "genome_len": GENOME_LEN, "l2": "inputs (1.25 GB/GPU) larger than L2; no flush needed",
-                       "parallelism": f"genome shards x{world}; dist rows tiled x{world}; one NCCL all-gather of sketches" if world > 1 else "single GPU"},
+                       "parallelism": f"genome shards x{world}; dist rows tiled x{world}; one NCCL all-gather of sketches" if world > 1 else "single GPU",
+                       "host_binding": (f"rank pinned to its GPU's {numa_cpus} local CPUs" if numa_cpus > 0 else "none")},
             "phases_ms_last_step": {"sketch": sk_ms, "gather": ga_ms, "cardinality+dist": di_ms},
             "dist": {"metric": "all_vs_all_pairs_per_s", "value": n_pairs_all / (di_ms * 1e-3), "unit": "pairs/s", "pairs": n_pairs_all,
                      "register_merges_per_s": n_pairs_all * rb / (di_ms * 1e-3)},

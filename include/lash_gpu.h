@@ -71,6 +71,12 @@ int lash_gpu_device_count(void);
 int lash_ctx_create(int device, lash_ctx** out);
 int lash_ctx_destroy(lash_ctx* ctx);
 int lash_ctx_device(const lash_ctx* ctx);
+/* Multi-GPU hosts (one process or thread per GPU): pin the CALLING thread to the CPUs next to `device` (the sysfs
+ * local_cpulist of its PCI function, intersected with the CPUs the process may use).  Call it before lash_host_alloc /
+ * lash_ctx_create: pinned staging memory lands on the NUMA node of the allocating thread, and a rank whose staging
+ * memory sits on the far socket pays the inter-socket link for every H2D byte.  Returns the number of CPUs in the new
+ * mask (> 0), or < 0 when the box exposes no such information (single-socket boxes: harmless to ignore). */
+int lash_bind_thread_to_device(int device);
 
 /* Pinned host memory for the packer (so lash_sketch_push copies are truly asynchronous). */
 int lash_host_alloc(size_t bytes, void** out);

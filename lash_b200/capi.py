@@ -37,6 +37,7 @@ PROTOTYPES = {
     "lash_ctx_create": (i32, [i32, C.POINTER(vp)]),
     "lash_ctx_destroy": (i32, [vp]),
     "lash_ctx_device": (i32, [vp]),
+    "lash_bind_thread_to_device": (i32, [i32]),
     "lash_host_alloc": (i32, [sz, C.POINTER(vp)]),
     "lash_host_free": (i32, [vp]),
     "lash_sketch_reg_bytes": (sz, [i32, i32]),

@@ -3,6 +3,7 @@
 // stream double-buffering, launches.  No CPU fallback anywhere: every entry point either runs the
 // CUDA kernels or returns an error.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -130,6 +131,55 @@ extern "C" int lash_ctx_destroy(lash_ctx* c) {
     return LASH_OK;
 }
 extern "C" int lash_ctx_device(const lash_ctx* c) { return c ? c->device : -1; }
+
+// Pin the calling thread to the CPUs next to `device` (sysfs local_cpulist of its PCI function).  Pinned staging
+// memory is placed on the NUMA node of the thread that allocates it; on a two-socket box with one process per GPU,
+// ranks whose staging memory sits on the far socket share the inter-socket link for every H2D byte.
+static bool parse_cpulist(const std::string& text, cpu_set_t* set) {
+    CPU_ZERO(set);
+    int n = 0;
+    size_t i = 0;
+    while (i < text.size()) {
+        while (i < text.size() && !isdigit((unsigned char)text[i])) ++i;
+        if (i >= text.size()) break;
+        long a = strtol(text.c_str() + i, nullptr, 10);
+        while (i < text.size() && isdigit((unsigned char)text[i])) ++i;
+        long b = a;
+        if (i < text.size() && text[i] == '-') {
+            ++i;
+            b = strtol(text.c_str() + i, nullptr, 10);
+            while (i < text.size() && isdigit((unsigned char)text[i])) ++i;
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) {
+            CPU_SET((int)c, set);
+            ++n;
+        }
+    }
+    return n > 0;
+}
+extern "C" int lash_bind_thread_to_device(int device) {
+    int n = lash_gpu_device_count();
+    if (device < 0 || device >= n) return fail(LASH_E_INVALID, "lash_bind_thread_to_device: device index out of range");
+    char bus[32] = {0};
+    CU(cudaDeviceGetPCIBusId(bus, sizeof(bus), device));
+    std::string id(bus);
+    for (auto& ch : id) ch = (char)tolower((unsigned char)ch);
+    const std::string path = "/sys/bus/pci/devices/" + id + "/local_cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return fail(LASH_E_STATE, "lash_bind_thread_to_device: cannot read " + path);
+    char buf[4096];
+    const size_t got = fread(buf, 1, sizeof(buf) - 1, f);
+    fclose(f);
+    buf[got] = 0;
+    cpu_set_t want, have, both;
+    if (!parse_cpulist(buf, &want)) return fail(LASH_E_STATE, "lash_bind_thread_to_device: empty local_cpulist (no NUMA information)");
+    // stay inside the CPUs this process is allowed to use (containers, taskset)
+    if (sched_getaffinity(0, sizeof(have), &have) != 0) return fail(LASH_E_STATE, "lash_bind_thread_to_device: sched_getaffinity failed");
+    CPU_AND(&both, &want, &have);
+    if (CPU_COUNT(&both) == 0) return fail(LASH_E_STATE, "lash_bind_thread_to_device: none of the device-local CPUs is available to this process");
+    if (sched_setaffinity(0, sizeof(both), &both) != 0) return fail(LASH_E_STATE, "lash_bind_thread_to_device: sched_setaffinity failed");
+    return CPU_COUNT(&both);
+}
 
 extern "C" int lash_host_alloc(size_t bytes, void** out) {
     if (!out) return fail(LASH_E_INVALID, "lash_host_alloc: out is NULL");

@@ -1,8 +1,28 @@
-"""PCIe probe: pinned H2D / D2H bandwidth on this box (context for bench.py's e2e number)."""
+"""PCIe probe: pinned H2D / D2H bandwidth on this box (context for bench.py's e2e number).
+    python tools/h2d_probe.py                                   # one GPU
+    torchrun --nproc-per-node N tools/h2d_probe.py [--bind]     # N GPUs copying at the same time; --bind pins each rank
+                                                                # to its GPU's local CPUs first (lash_bind_thread_to_device)
+"""
 import json
-import torch
+import os
+import sys
 
-out = {}
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+rank = int(os.environ.get("RANK", "0"))
+world = int(os.environ.get("WORLD_SIZE", "1"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+bound = 0
+if "--bind" in sys.argv:
+    from lash_b200.capi import lib
+    bound = lib().lash_bind_thread_to_device(local)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+out = {"rank": rank, "world": world, "bound_cpus": bound, "cpus_allowed": len(os.sched_getaffinity(0))}
 for mb in (64, 1250):
     n = mb * 1000 * 1000
     h = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -10,6 +30,9 @@ for mb in (64, 1250):
     for name, (src, dst) in {"h2d": (h, d), "d2h": (d, h)}.items():
         best = 0.0
         for _ in range(5):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             dst.copy_(src, non_blocking=True)
@@ -17,4 +40,6 @@ for mb in (64, 1250):
             torch.cuda.synchronize()
             best = max(best, n / (e0.elapsed_time(e1) * 1e-3) / 1e9)
         out[f"{name}_{mb}MB_GBps"] = round(best, 2)
-print(json.dumps(out))
+print(json.dumps(out), flush=True)
+if world > 1:
+    dist.destroy_process_group()
