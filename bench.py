@@ -51,12 +51,12 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.mark_at = index, None, [], 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -65,6 +65,10 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def mark(self):
+        """Samples before this point (sampler start-up, warm-up steps) are not part of the timed region."""
+        self.mark_at = len(self.lines)
 
     def stop(self) -> dict:
         if not self.proc:
@@ -77,7 +81,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines[self.mark_at:] or self.lines
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -235,11 +240,17 @@ def run_graft(args):
 
     regs_view = _as_tensor(torch, regs_local, n_g * rb, device)   # the sketcher's accumulators, no copy
 
+    cpu_trace = [] if os.environ.get("LASH_BENCH_TRACE") else None
+
     def step(timed_events=None):
+        c0 = time.perf_counter()
         if timed_events:
             timed_events[0].record(stream)
         sk.reset()                                                  # async clear on the stream
+        c1 = time.perf_counter()
         sk.push_raw(buf.data_ptr(), n_bytes, spans, n_g, None, 0, dev=True)
+        if cpu_trace is not None:
+            cpu_trace.append((c0, c1, time.perf_counter()))
         if timed_events:
             timed_events[1].record(stream)
         if world > 1:
@@ -262,24 +273,33 @@ def run_graft(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    # the clock sampler (an nvidia-smi child) starts BEFORE the warm-up: spawning it next to the first timed step
+    # delayed that step by ~1.5 ms (seen with LASH_BENCH_TRACE); only samples taken after mark() are reported
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     kernel_ms0, sk_launches0 = sk.stats()
     _, dist_launches0 = ops.dist_stats(ctx)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     t_start = torch.cuda.Event(enable_timing=True)
     t_stop = torch.cuda.Event(enable_timing=True)
     phase = np.zeros(3)
     barrier()
+    trace_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)] if os.environ.get("LASH_BENCH_TRACE") else None
     t_start.record(stream)
     for it in range(args.steps):
-        step(ev)
+        step(trace_ev[it] if trace_ev else ev)
         # phase events are read after the loop for the last step only (no sync inside the loop)
     t_stop.record(stream)
     barrier()
+    if trace_ev:
+        ev = trace_ev[-1]
+        print(f"[rank {rank}] host ms per step (reset, push) of the last {args.steps} steps: " +
+              "; ".join(f"{1e3*(b-a):.3f} {1e3*(c-b):.3f}" for a, b, c in cpu_trace[-args.steps:]), file=sys.stderr, flush=True)
+        print(f"[rank {rank}] resident steps, ms from t_start (begin, sketch done, gather done, dist done): " +
+              "; ".join(" ".join(f"{t_start.elapsed_time(e):.3f}" for e in evs) for evs in trace_ev), file=sys.stderr, flush=True)
     total_ms = t_start.elapsed_time(t_stop)
     phase[0] = ev[0].elapsed_time(ev[1])   # sketch (last step)
     phase[1] = ev[1].elapsed_time(ev[2])   # gather

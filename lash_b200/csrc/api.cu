@@ -6,6 +6,8 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -239,6 +241,8 @@ struct lash_sketcher {
     uint64_t launches = 0;
     uint64_t min_chunk = 0;
     uint64_t per_iter = 0;  // k-mer starts one CTA iteration covers
+    std::vector<SketchTile> plan_tiles;  // host-side tile plan of the current push (capacity reused across pushes)
+    std::vector<SpanRecs> plan_mspans;
     cudaStream_t ext_stream = nullptr;  // caller-provided stream (lash_sketch_set_stream)
 };
 
@@ -300,6 +304,8 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
     if (n_spans && (!spans || !packed)) return fail(LASH_E_INVALID, "lash_sketch_push: NULL buffer");
     CU(cudaSetDevice(s->ctx->device));
     const int k = s->sp.k;
+    static const bool trace = getenv("LASH_TRACE_PUSH") != nullptr;
+    const auto tp0 = std::chrono::steady_clock::now();
 
     // ---- validate + plan tiles (host) --------------------------------------------------------
     uint64_t total_starts = 0;
@@ -342,9 +348,13 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
     const uint64_t kStartsPerIter = s->per_iter;
     chunk = ((chunk + kStartsPerIter - 1) / kStartsPerIter) * kStartsPerIter;
 
-    std::vector<SketchTile> tiles;
-    std::vector<SpanRecs> mspans;
-    tiles.reserve(n_spans * 2);
+    // plan buffers live in the sketcher: a fresh 1.4 MB vector per push cost ~1 ms of page faults + regrowth (seen
+    // with LASH_TRACE_PUSH on the GPU box), which is exposed whenever the GPU is not already busy with an older push
+    std::vector<SketchTile>& tiles = s->plan_tiles;
+    std::vector<SpanRecs>& mspans = s->plan_mspans;
+    tiles.clear();
+    mspans.clear();
+    tiles.reserve(total_starts / chunk + 2 * (size_t)n_spans + 16);
     mspans.reserve(n_multi);
     uint64_t mask_off = 0;
     for (uint32_t i = 0; i < n_spans; ++i) {
@@ -380,6 +390,7 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
     }
     if (tiles.size() > 0x7fffffffull) return fail(LASH_E_INVALID, "lash_sketch_push: too many tiles in one push");
 
+    const auto tp1 = std::chrono::steady_clock::now();
     // ---- stage ---------------------------------------------------------------------------------
     const uint64_t ticket = s->next_ticket++;
     Slot& sl = s->slot[ticket % kSlots];
@@ -418,6 +429,7 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
         packed_dev = (const uint32_t*)sl.packed.p;
     }
     CU(cudaEventRecord(sl.copied, stream));
+    const auto tp2 = std::chrono::steady_clock::now();
     uint32_t* mask_dev = nullptr;
     if (n_multi) {
         CU(sl.mask.reserve(mask_off * 4));
@@ -435,6 +447,12 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
         s->launches += 1;
     }
     CU(cudaEventRecord(sl.k_stop, stream));
+    if (trace) {
+        const auto tp3 = std::chrono::steady_clock::now();
+        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "[lash push] %zu tiles: plan %.0f us, slot wait + uploads %.0f us, launches %.0f us\n", tiles.size(),
+                us(tp0, tp1), us(tp1, tp2), us(tp2, tp3));
+    }
     sl.timing_pending = true;
     sl.used = true;
     sl.ticket = ticket;
