@@ -617,6 +617,14 @@ __device__ __forceinline__ uint32_t fgra_code(uint32_t r, uint32_t base) {
     return r ? c : 0u;
 }
 
+// one table entry: low word from the first plane, high word from the second (two conflict-free LDS.32)
+__device__ __forceinline__ double tab_lookup(uint32_t saddr, uint32_t plane_bytes) {
+    uint32_t lo, hi;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(saddr));
+    asm("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(saddr + plane_bytes));
+    return __hiloint2double((int)hi, (int)lo);
+}
+
 // Persistent CTAs (one per SM: the table fills most of its shared memory) fetch tiles from a global counter, so the
 // table is built once per SM instead of once per tile and tiles above the diagonal cost one atomic.
 __device__ __forceinline__ bool next_tile(const DistParams& dp, uint32_t* s_tile, uint64_t n_tiles, uint64_t iter, uint64_t& t) {
@@ -631,7 +639,13 @@ __global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParam
                                                                        uint32_t tiles_x, uint32_t tiles_y) {
     __shared__ uint32_t s_tile;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* T = reinterpret_cast<double*>(smem_raw);
+    // The table is stored as two planes of 32-bit words (low halves, then high halves) and read with two LDS.32: a warp
+    // reads ONE table row (the reference register is warp-uniform), so with 4-byte entries the bank is the query code
+    // mod 32 and the ~28 codes a sketch set actually uses (7-8 register levels x 4) never collide.  As one plane of
+    // doubles (LDS.64: 16 banks per half-warp) codes 16 apart -- same sub-bits, 4 levels apart -- collided: 12 % extra
+    // wavefronts on sketches of related genomes, ~80 % on unrelated ones (lanes then hold many distinct codes).
+    uint32_t* T = reinterpret_cast<uint32_t*>(smem_raw);
+    constexpr uint32_t kPlane = (uint32_t)kTabN * kTabN * 4u;  // bytes per plane
     const uint32_t a_stride = chunk + 4;                 // u32 elements per reference row (+16 B pad)
     const uint32_t b_stride = chunk + 8;                 // u16 elements per query row (+16 B pad)
     uint32_t* sa = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTabN * kTabN * 8);
@@ -656,7 +670,8 @@ __global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParam
             const uint32_t m = ull_merge1(ra, rb);
             if (m >= off && m < 252u) v = c_ull.reg[m - off];
         }
-        T[e] = v;
+        T[e] = (uint32_t)__double2loint(v);
+        T[e + kTabN * kTabN] = (uint32_t)__double2hiint(v);
     }
 
     const uint32_t ty = threadIdx.x >> 5, tx = threadIdx.x & 31u;  // ty is warp-uniform
@@ -676,17 +691,17 @@ __global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParam
 
     for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk) {
         __syncthreads();  // previous chunk consumed (first pass: orders the table build)
-        // stage + recode: reference side as byte offsets of the table ROW (code << 10), query side as byte
-        // offsets inside a row (code << 3)
+        // stage + recode: reference side as byte offsets of the table ROW (code << 9: 128 words), query side as byte
+        // offsets inside a row (code << 2)
         for (uint32_t e = threadIdx.x; e < (uint32_t)kTabTR * chunk_words; e += kTabThreads) {
             const uint32_t r = e / chunk_words, w = e % chunk_words;
             const uint64_t gi = row0 + r;
             const uint32_t v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint32_t*>(gref + gi * cell_bytes + c0) + w) : 0u;
             uint4 o;
-            o.x = fgra_code(v & 0xffu, base) << 10;
-            o.y = fgra_code((v >> 8) & 0xffu, base) << 10;
-            o.z = fgra_code((v >> 16) & 0xffu, base) << 10;
-            o.w = fgra_code(v >> 24, base) << 10;
+            o.x = fgra_code(v & 0xffu, base) << 9;
+            o.y = fgra_code((v >> 8) & 0xffu, base) << 9;
+            o.z = fgra_code((v >> 16) & 0xffu, base) << 9;
+            o.w = fgra_code(v >> 24, base) << 9;
             *reinterpret_cast<uint4*>(sa + r * a_stride + 4 * w) = o;
         }
         for (uint32_t e = threadIdx.x; e < (uint32_t)kTabTQ * chunk_words; e += kTabThreads) {
@@ -694,8 +709,8 @@ __global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParam
             const uint64_t gj = col0 + r;
             const uint32_t v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint32_t*>(gqry + gj * cell_bytes + c0) + w) : 0u;
             uint2 o;
-            o.x = (fgra_code(v & 0xffu, base) << 3) | (fgra_code((v >> 8) & 0xffu, base) << 19);
-            o.y = (fgra_code((v >> 16) & 0xffu, base) << 3) | (fgra_code(v >> 24, base) << 19);
+            o.x = (fgra_code(v & 0xffu, base) << 2) | (fgra_code((v >> 8) & 0xffu, base) << 18);
+            o.y = (fgra_code((v >> 16) & 0xffu, base) << 2) | (fgra_code(v >> 24, base) << 18);
             *reinterpret_cast<uint2*>(sb + r * b_stride + 4 * w) = o;
         }
         __syncthreads();
@@ -717,15 +732,10 @@ __global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParam
                 const uint32_t q0 = (i & 1) ? (b0w[i >> 1] >> 16) : (b0w[i >> 1] & 0xffffu);
                 const uint32_t q1 = (i & 1) ? (b1w[i >> 1] >> 16) : (b1w[i >> 1] & 0xffffu);
                 const uint32_t r0 = tbase + a0[i], r1 = tbase + a1[i];
-                double t00, t01, t10, t11;
-                asm("ld.shared.f64 %0, [%1];" : "=d"(t00) : "r"(r0 + q0));
-                asm("ld.shared.f64 %0, [%1];" : "=d"(t01) : "r"(r0 + q1));
-                asm("ld.shared.f64 %0, [%1];" : "=d"(t10) : "r"(r1 + q0));
-                asm("ld.shared.f64 %0, [%1];" : "=d"(t11) : "r"(r1 + q1));
-                acc[0][0] += t00;
-                acc[0][1] += t01;
-                acc[1][0] += t10;
-                acc[1][1] += t11;
+                acc[0][0] += tab_lookup(r0 + q0, kPlane);
+                acc[0][1] += tab_lookup(r0 + q1, kPlane);
+                acc[1][0] += tab_lookup(r1 + q0, kPlane);
+                acc[1][1] += tab_lookup(r1 + q1, kPlane);
             }
         }
     }
