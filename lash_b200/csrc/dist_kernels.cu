@@ -124,24 +124,28 @@ struct FgraAcc {
 };
 
 constexpr int kMlPlanes = 27;  // counts up to 2^26 registers
-struct MlAcc {
+// NPL = bit planes of the vertical counters: a count never exceeds the 2^p registers of a sketch, so p + 1 planes are
+// enough; the pair-table kernel is instantiated for 12 / 16 / 27 planes (15 fewer planes = 30 fewer live registers and
+// 30 fewer LOP3 per ripple for the two accumulators of a thread at p <= 11).
+template <int NPL>
+struct MlAccT {
     using CT = uint8_t;
     static constexpr int RM = 1, QM = 2;
     static constexpr int kTableBytes = 256 * 8 + 256 * 4;
     uint64_t S;
     uint32_t mmax;                 // largest merged register seen (decides whether W fits 32 bits)
-    uint32_t pl[kMlPlanes];        // vertical (bit-sliced) counters of the low 32 bits of W
+    uint32_t pl[NPL];              // vertical (bit-sliced) counters of the low 32 bits of W
     __device__ __forceinline__ void init() {
         S = 0;
         mmax = 0;
 #pragma unroll
-        for (int i = 0; i < kMlPlanes; ++i) pl[i] = 0u;
+        for (int i = 0; i < NPL; ++i) pl[i] = 0u;
     }
     // add a bit-plane of weight 2^L into the vertical counter (ripple carry, nplanes is CTA-uniform)
     template <int L>
     __device__ __forceinline__ void ripple(uint32_t x, int nplanes) {
 #pragma unroll
-        for (int l = L; l < kMlPlanes; ++l) {
+        for (int l = L; l < NPL; ++l) {
             if (l < nplanes) {
                 const uint32_t c = pl[l] & x;
                 pl[l] ^= x;
@@ -165,7 +169,7 @@ struct MlAcc {
     template <int L>
     __device__ __forceinline__ void ripple_all(uint32_t x) {
 #pragma unroll
-        for (int l = L; l < kMlPlanes; ++l) {
+        for (int l = L; l < NPL; ++l) {
             const uint32_t c = pl[l] & x;
             pl[l] ^= x;
             x = c;
@@ -225,6 +229,7 @@ struct MlAcc {
         }
     }
 };
+using MlAcc = MlAccT<kMlPlanes>;
 
 struct HmhAcc {
     using CT = uint16_t;
@@ -318,7 +323,8 @@ __device__ __forceinline__ double finish_union(FgraAcc& a, int p, const void* ga
     const uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     return ull_fgra_finalize(a.sum, cnt, p);
 }
-__device__ __forceinline__ double finish_union(MlAcc& a, int p, const void* ga, const void* gb, bool* bias) {
+template <int NPL>
+__device__ __forceinline__ double finish_union(MlAccT<NPL>& a, int p, const void* ga, const void* gb, bool* bias) {
     *bias = false;
     // W = (4|w) << k fits 32 bits iff k <= 29, i.e. merged register < 4p+4 + 4*30
     if (a.mmax >= (uint32_t)(4 * p + 4 + 120))
@@ -328,13 +334,13 @@ __device__ __forceinline__ double finish_union(MlAcc& a, int p, const void* ga, 
     for (int j = 0; j < 66; ++j) bb[j] = 0;
     uint32_t any = 0;
 #pragma unroll
-    for (int l = 0; l < kMlPlanes; ++l) any |= a.pl[l];
+    for (int l = 0; l < NPL; ++l) any |= a.pl[l];
     if (any) {
         const int jlo = __ffs((int)any) - 1, jhi = 31 - __clz((int)any);
         for (int j = jlo; j <= jhi; ++j) {
             uint32_t c = 0;
 #pragma unroll
-            for (int l = 0; l < kMlPlanes; ++l) c |= ((a.pl[l] >> j) & 1u) << l;
+            for (int l = 0; l < NPL; ++l) c |= ((a.pl[l] >> j) & 1u) << l;
             bb[j] = (int)c;
         }
     }
@@ -781,6 +787,7 @@ constexpr int kMlTabThreads = 512;
 constexpr int kMlTabTR = 16, kMlTabTQ = 64;
 constexpr int kMlTabChunk = 128;
 
+template <int NPL>
 __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk,
                                                                        uint32_t tiles_x, uint32_t tiles_y) {
     __shared__ uint32_t s_tile;
@@ -816,7 +823,7 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
     const uint64_t row_hi = min(row0 + kMlTabTR, dp.row_end);
     if (dp.triangular && col0 > row_hi - 1) continue;  // tile entirely above the diagonal (CTA-uniform)
     if (threadIdx.x < kMlTabTR + kMlTabTQ) sflag[threadIdx.x] = 0u;  // ordered before the staging by its first barrier
-    MlAcc acc[2];
+    MlAccT<NPL> acc[2];
     acc[0].init();
     acc[1].init();
 
@@ -883,8 +890,8 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
             for (uint32_t e = 0; e < chunk; e += 8) {
                 uint32_t c0, c1;
                 step8(e, c0, c1);
-                acc[0].ripple_all<3>(c0);
-                acc[1].ripple_all<3>(c1);
+                acc[0].template ripple_all<3>(c0);
+                acc[1].template ripple_all<3>(c1);
             }
         }
     }
@@ -1119,7 +1126,8 @@ static cudaError_t launch_dist_ml_tab(const DistParams& dp, cudaStream_t st) {
     const uint32_t chunk = cb < (uint32_t)kMlTabChunk ? cb : (uint32_t)kMlTabChunk;
     const size_t smem = (size_t)kTabN * kTabN * 12 + (size_t)kMlTabTR * (chunk + 4) * 4 + (size_t)kMlTabTQ * (chunk + 8) * 2 +
                         (size_t)(kMlTabTR + kMlTabTQ) * 4;
-    cudaError_t e = cudaFuncSetAttribute(dist_ml_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = dp.p <= 11 ? dist_ml_tab_kernel<12> : dp.p <= 15 ? dist_ml_tab_kernel<16> : dist_ml_tab_kernel<kMlPlanes>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint64_t rows = dp.row_end - dp.row_begin;
     const uint64_t gy = (rows + kMlTabTR - 1) / kMlTabTR;
@@ -1132,7 +1140,7 @@ static cudaError_t launch_dist_ml_tab(const DistParams& dp, cudaStream_t st) {
         if (e != cudaSuccess) return e;
     }
     const unsigned grid = (unsigned)std::min<uint64_t>(gx * gy, (uint64_t)dp.n_sm);
-    dist_ml_tab_kernel<<<grid, kMlTabThreads, smem, st>>>(dp, cb, chunk, (uint32_t)gx, (uint32_t)gy);
+    kern<<<grid, kMlTabThreads, smem, st>>>(dp, cb, chunk, (uint32_t)gx, (uint32_t)gy);
     return cudaGetLastError();
 }
 

@@ -150,6 +150,13 @@ __device__ inline double ull_fgra_finalize(double sum, const uint32_t* cnt, int 
 }
 
 // ---------------------------------------------------------------- ULL ML (Ertl 2017 Alg. 8 as in hash4j)
+// 2^k for |k| <= 1022, built from bits.  x * pow2i(k) is ldexp(x, k) exactly (one correctly rounded operation either
+// way); the library ldexp / ilogb are calls with denormal handling and showed up in the per-pair epilogue.
+__device__ __forceinline__ double pow2i(int k) { return __hiloint2double((1023 + k) << 20, 0); }
+__device__ __forceinline__ int ilogb_pos(double x) {
+    const int e = (__double2hiint(x) >> 20) & 0x7ff;
+    return (e == 0 || e == 0x7ff) ? ilogb(x) : e - 1023;  // normal numbers: the exponent field
+}
 __device__ inline double ull_solve_ml(double a, const int* b, int n, double eps) {
     if (a == 0.0) return __longlong_as_double(0x7ff0000000000000LL);
     int kMax = n;
@@ -157,12 +164,12 @@ __device__ inline double ull_solve_ml(double a, const int* b, int n, double eps)
     if (kMax < 0) return 0.0;
     int kMin = kMax;
     long long s1 = b[kMax];
-    double s2 = ldexp((double)b[kMax], kMax);
+    double s2 = (double)b[kMax] * pow2i(kMax);
     for (int k = kMax - 1; k >= 0; --k) {
         int t = b[k];
         if (t > 0) {
             s1 += t;
-            s2 += ldexp((double)t, k);
+            s2 += (double)t * pow2i(k);
             kMin = k;
         }
     }
@@ -173,9 +180,9 @@ __device__ inline double ull_solve_ml(double a, const int* b, int n, double eps)
         x = log1p(s2 / a) * ((double)s1 / s2);
     double dx = x;
     while (dx > x * eps) {
-        int kappa = ilogb(x) + 2;
+        int kappa = ilogb_pos(x) + 2;
         int sh = (kMax > kappa ? kMax : kappa) + 1;
-        double xp = ldexp(x, -sh);
+        double xp = x * pow2i(-sh);
         double xp2 = xp * xp;
         double h = xp - xp2 / 3.0 + (xp2 * xp2) * (1.0 / 45.0 - xp2 / 472.5);
         for (int k = kappa - 1; k >= kMax; --k) {

@@ -16,7 +16,7 @@ n = int(args[1]) if len(args) > 1 else 2000
 p = int(args[2]) if len(args) > 2 else (14 if kind == "hll" else 10)
 rng = np.random.default_rng(7)
 m = 1 << p
-lvl = np.clip(np.floor(12.0 - np.log2(-np.log(rng.random((n, m))))), 0, 40).astype(np.int64)   # max nlz of ~4000 hashes
+lvl = np.clip(np.floor(12.0 - np.log2(-np.log(rng.random((n, m))))), 0, 30).astype(np.int64)   # max nlz of ~4000 hashes (clipped: no register outside the pair tables)
 if kind.startswith("ull"):
     regs = (4 * (lvl + p - 1) + rng.integers(0, 4, size=(n, m))).astype(np.uint8)
     algo, est = ALGO_ULL, (EST_ML if kind == "ull-ml" else EST_FGRA)
