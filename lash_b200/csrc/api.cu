@@ -99,7 +99,7 @@ struct lash_ctx {
     uint64_t dist_launches = 0;
     // scratch of lash_dist / lash_dist_stream, kept across calls (cudaMalloc/cudaFree per call cost
     // milliseconds of jitter on a 2.5 ms operation)
-    DevBuf d_ref, d_qry, d_card, d_out[2], d_flags, d_regmin;
+    DevBuf d_ref, d_qry, d_card, d_out[2], d_flags, d_regmin, d_ml;
     PinBuf h_out[2];
 };
 
@@ -128,7 +128,7 @@ extern "C" int lash_ctx_destroy(lash_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_ref.release(); c->d_qry.release(); c->d_card.release(); c->d_out[0].release(); c->d_out[1].release();
-    c->d_flags.release(); c->d_regmin.release(); c->h_out[0].release(); c->h_out[1].release();
+    c->d_flags.release(); c->d_regmin.release(); c->d_ml.release(); c->h_out[0].release(); c->h_out[1].release();
     delete c;
     return LASH_OK;
 }
@@ -615,6 +615,39 @@ static int prepare_regmin(lash_ctx* ctx, DistParams& dp, size_t rb, cudaStream_t
     return LASH_OK;
 }
 
+// ULL ML: scratch for the two-kernel form (tile kernel stores the pair statistics, ml_finish_kernel solves).  Called
+// right before launch_dist, once dp's row range and output addressing are final.  Falls back to the fused kernel
+// (ml_scratch = nullptr) when the scratch would be larger than LASH_ML_SCRATCH_MAX_MB (default 16384) or cannot be
+// allocated, or when LASH_ML_KERNEL=fused asks for it (A/B measurements).
+static void setup_ml_scratch(lash_ctx* ctx, DistParams& dp) {
+    dp.ml_scratch = nullptr;
+    if (dp.algo != LASH_ALGO_ULL || dp.estimator != LASH_EST_ML || dp.row_end <= dp.row_begin) return;
+    static const bool fused = [] { const char* v = getenv("LASH_ML_KERNEL"); return v && std::string(v) == "fused"; }();
+    static const uint64_t max_bytes = [] {
+        const char* v = getenv("LASH_ML_SCRATCH_MAX_MB");
+        return (uint64_t)(v ? strtoull(v, nullptr, 10) : 16384ull) << 20;
+    }();
+    if (fused) return;
+    uint64_t o_base, o_end;
+    if (dp.packed_tri) {
+        o_base = dp.row_begin * (dp.row_begin + 1) / 2;
+        o_end = dp.row_end * (dp.row_end + 1) / 2;
+    } else {
+        o_base = (dp.row_begin - dp.out_row0) * dp.n_qry;
+        o_end = (dp.row_end - dp.out_row0) * dp.n_qry;
+    }
+    const uint64_t cells = o_end - o_base;
+    const uint64_t bytes = cells * 4ull * ml_scratch_words(dp.p);
+    if (cells == 0 || bytes > max_bytes) return;
+    if (ctx->d_ml.reserve(bytes) != cudaSuccess) {
+        cudaGetLastError();  // clear the sticky allocation error: the fused kernel needs no scratch
+        return;
+    }
+    dp.ml_scratch = (uint32_t*)ctx->d_ml.p;
+    dp.ml_cells = cells;
+    dp.ml_o_base = o_base;
+}
+
 extern "C" int lash_cardinality_dev(lash_ctx* ctx, int algo, int p, int estimator, const void* regs_dev, uint64_t n,
                                     double* card_dev, void* stream) {
     if (!ctx) return fail(LASH_E_INVALID, "lash_cardinality_dev: NULL ctx");
@@ -681,6 +714,7 @@ extern "C" int lash_dist_dev(lash_ctx* ctx, int algo, int p, int k, int estimato
     dp.flags = flags_dev;
     rc = prepare_regmin(ctx, dp, lash_sketch_reg_bytes(algo, p), stream ? (cudaStream_t)stream : ctx->stream);
     if (rc) return rc;
+    setup_ml_scratch(ctx, dp);
     uint32_t nl = 0;
     CU(launch_dist(dp, stream ? (cudaStream_t)stream : ctx->stream, &nl));
     ctx->dist_launches += nl;
@@ -767,6 +801,7 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
         CUC(cudaEventCreate(&k1));
         done[1] = k1;
         CUC(cudaEventRecord(k0, st));
+        setup_ml_scratch(ctx, dp);
         uint32_t nl = 0;
         CUC(launch_dist(dp, st, &nl));
         ctx->dist_launches += nl;
@@ -802,6 +837,7 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
             if (nblocks >= 2) CUC(cudaEventSynchronize(copied[buf]));  // device buffer free again (its D2H finished)
             dp.row_begin = r0; dp.row_end = r1; dp.out = d_out[buf].p; dp.packed_tri = 0; dp.out_row0 = r0;
             CUC(cudaEventRecord(kstart, st));
+            setup_ml_scratch(ctx, dp);
             uint32_t nl = 0;
             CUC(launch_dist(dp, st, &nl));
             ctx->dist_launches += nl;

@@ -788,12 +788,65 @@ constexpr int kMlTabTR = 16, kMlTabTQ = 64;
 constexpr int kMlTabChunk = 128;
 
 template <int NPL>
+__device__ __forceinline__ void ml_pair_epilogue(const DistParams& dp, MlAccT<NPL>& acc, uint64_t i, uint64_t j, uint64_t o, uint32_t cell_bytes) {
+    const unsigned char* gref = reinterpret_cast<const unsigned char*>(dp.ref);
+    const unsigned char* gqry = reinterpret_cast<const unsigned char*>(dp.qry);
+    bool bias;
+    const double U = finish_union(acc, dp.p, gref + i * cell_bytes, gqry + j * cell_bytes, &bias);
+    const double ca = dp.card_ref[i], cb = dp.card_qry[j];
+    const double sim = (ca + cb - U) / U;
+    const double s = sim < 0.0 ? 0.0 : sim;  // utils.rs:274: NaN propagates
+    const double frac = 2.0 * s / (1.0 + s);
+    if (dp.fp32)
+        reinterpret_cast<float*>(dp.out)[o] = mash_distance_f32((float)frac, dp.k, dp.model);
+    else
+        reinterpret_cast<double*>(dp.out)[o] = mash_distance_f64(frac, dp.k, dp.model);
+}
+
+// K4c, second kernel: one thread per output cell reads the statistics dist_ml_tab_kernel<NPL, true> stored and runs
+// finish_union (count extraction + Ertl's solver) and the distance epilogue -- the same code as the fused form, but with
+// 64 resident warps per SM to cover the divide chains.
+template <int NPL>
+__global__ void __launch_bounds__(256, 4) ml_finish_kernel(DistParams dp, uint32_t cell_bytes) {
+    const uint64_t n = dp.ml_cells;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t o = c + dp.ml_o_base;
+        uint64_t i, j;
+        if (dp.packed_tri) {
+            i = (uint64_t)((sqrt(8.0 * (double)o + 1.0) - 1.0) * 0.5);
+            while ((i + 1) * (i + 2) / 2 <= o) ++i;
+            while (i * (i + 1) / 2 > o) --i;
+            j = o - i * (i + 1) / 2;
+        } else {
+            i = o / dp.n_qry + dp.out_row0;
+            j = o % dp.n_qry;
+        }
+        if (i < dp.row_begin || i >= dp.row_end || j >= dp.n_qry) continue;
+        if (dp.triangular && j > i) continue;
+        const uint32_t* sc = dp.ml_scratch + c;
+        MlAccT<NPL> acc;
+        acc.S = ((uint64_t)sc[n] << 32) | sc[0];
+        acc.mmax = sc[2 * n];
+#pragma unroll
+        for (int l = 0; l < NPL; ++l) acc.pl[l] = sc[(3 + l) * n];
+        ml_pair_epilogue(dp, acc, i, j, o, cell_bytes);
+    }
+}
+
+// SPLIT: store the pair statistics for ml_finish_kernel instead of running the solver here.  The fused epilogue is 35 %
+// of the instructions but 40 % of the time of the fused kernel: one CTA of 16 warps per SM (the tables fill its shared
+// memory) cannot cover the dependent FP64 divide chains of the secant solver, and the main loop cannot overlap them.
+template <int NPL, bool SPLIT>
 __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk,
                                                                        uint32_t tiles_x, uint32_t tiles_y) {
     __shared__ uint32_t s_tile;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* R = reinterpret_cast<uint64_t*>(smem_raw);
-    uint32_t* W = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTabN * kTabN * 8);
+    // three planes of 32-bit words (R low, R high, W), all indexed by the same (row, column) byte offset and read with
+    // LDS.32: a warp reads one table row, so the bank is the query code mod 32 -- no conflicts (see K4b; with R as one
+    // plane of 64-bit words 36 % of this kernel's shared-memory wavefronts were bank conflicts on unrelated sketches)
+    uint32_t* R = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* W = R + 2 * kTabN * kTabN;
+    constexpr uint32_t kPlane = (uint32_t)kTabN * kTabN * 4u;
     const uint32_t a_stride = chunk + 4;   // u32 per reference row
     const uint32_t b_stride = chunk + 8;   // u16 per query row
     uint32_t* sa = W + kTabN * kTabN;
@@ -806,14 +859,16 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
         const uint32_t ca = e >> 7, cb = e & 127u;
         const uint32_t ra = (ca && ca != 127u) ? ca + base - 1u : 0u, rb = (cb && cb != 127u) ? cb + base - 1u : 0u;
         const uint32_t m = ull_merge1(ra, rb);
-        R[e] = ml_ret_of(m, p);
+        const uint64_t ret = ml_ret_of(m, p);
+        R[e] = (uint32_t)ret;
+        R[e + kTabN * kTabN] = (uint32_t)(ret >> 32);
         W[e] = (uint32_t)ml_w_of(m, p);
     }
     const uint32_t ty = threadIdx.x >> 5, tx = threadIdx.x & 31u;  // ty: the warp's reference row
     const unsigned char* gref = reinterpret_cast<const unsigned char*>(dp.ref);
     const unsigned char* gqry = reinterpret_cast<const unsigned char*>(dp.qry);
     const uint32_t chunk_words = chunk / 4;
-    const uint32_t rbase = (uint32_t)__cvta_generic_to_shared(R), wbase = (uint32_t)__cvta_generic_to_shared(W);
+    const uint32_t rbase = (uint32_t)__cvta_generic_to_shared(R);
     const uint64_t n_tiles = (uint64_t)tiles_x * tiles_y;
 
     uint64_t tile;
@@ -829,7 +884,7 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
 
     for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk) {
         __syncthreads();
-        // stage + recode: reference side code << 9, query side code << 2 (W offsets; R offsets are twice that)
+        // stage + recode: reference side code << 9 (byte offset of the 128-word table row), query side code << 2
         for (uint32_t e = threadIdx.x; e < (uint32_t)kMlTabTR * chunk_words; e += kMlTabThreads) {
             const uint32_t r = e / chunk_words, w = e % chunk_words;
             const uint64_t gi = row0 + r;
@@ -864,14 +919,16 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
             for (int i = 0; i < 8; ++i) {
                 const uint32_t q0 = (i & 1) ? (b0w[i >> 1] >> 16) : (b0w[i >> 1] & 0xffffu);
                 const uint32_t q1 = (i & 1) ? (b1w[i >> 1] >> 16) : (b1w[i >> 1] & 0xffffu);
-                const uint32_t aw = wbase + a[i], ar = rbase + 2u * a[i];
-                uint64_t r0v, r1v;
-                asm("ld.shared.u64 %0, [%1];" : "=l"(r0v) : "r"(ar + 2u * q0));
-                asm("ld.shared.u64 %0, [%1];" : "=l"(r1v) : "r"(ar + 2u * q1));
-                asm("ld.shared.u32 %0, [%1];" : "=r"(w0[i]) : "r"(aw + q0));
-                asm("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"(aw + q1));
-                acc[0].S += r0v;
-                acc[1].S += r1v;
+                const uint32_t ar = rbase + a[i];
+                uint32_t l0, h0, l1, h1;
+                asm("ld.shared.u32 %0, [%1];" : "=r"(l0) : "r"(ar + q0));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(h0) : "r"(ar + q0 + kPlane));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(w0[i]) : "r"(ar + q0 + 2u * kPlane));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(l1) : "r"(ar + q1));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(h1) : "r"(ar + q1 + kPlane));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"(ar + q1 + 2u * kPlane));
+                acc[0].S += ((uint64_t)h0 << 32) | l0;
+                acc[1].S += ((uint64_t)h1 << 32) | l1;
             }
             c0 = acc[0].csa8(w0);
             c1 = acc[1].csa8(w1);
@@ -903,17 +960,18 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
         if (i >= dp.row_end || j >= dp.n_qry) continue;
         if (dp.triangular && j > i) continue;
         if (sflag[ty] | sflag[kMlTabTR + tx + 32 * b]) acc[b].mmax = 255u;  // -> exact per-pair path in finish_union
-        bool bias;
-        const double U = finish_union(acc[b], dp.p, gref + i * cell_bytes, gqry + j * cell_bytes, &bias);
-        const double ca = dp.card_ref[i], cb = dp.card_qry[j];
-        const double sim = (ca + cb - U) / U;
-        const double s = sim < 0.0 ? 0.0 : sim;  // utils.rs:274: NaN propagates
-        const double frac = 2.0 * s / (1.0 + s);
         const uint64_t o = dp.packed_tri ? (i * (i + 1) / 2 + j) : ((i - dp.out_row0) * dp.n_qry + j);
-        if (dp.fp32)
-            reinterpret_cast<float*>(dp.out)[o] = mash_distance_f32((float)frac, dp.k, dp.model);
-        else
-            reinterpret_cast<double*>(dp.out)[o] = mash_distance_f64(frac, dp.k, dp.model);
+        if (SPLIT) {
+            uint32_t* sc = dp.ml_scratch + (o - dp.ml_o_base);  // consecutive lanes -> consecutive cells: coalesced per word
+            const uint64_t n = dp.ml_cells;
+            sc[0] = (uint32_t)acc[b].S;
+            sc[n] = (uint32_t)(acc[b].S >> 32);
+            sc[2 * n] = acc[b].mmax;
+#pragma unroll
+            for (int l = 0; l < NPL; ++l) sc[(3 + l) * n] = acc[b].pl[l];
+        } else {
+            ml_pair_epilogue(dp, acc[b], i, j, o, cell_bytes);
+        }
     }
     }  // tiles
 }
@@ -1027,6 +1085,7 @@ cudaError_t ensure_tables() {
 }
 
 static uint32_t cell_bytes_of(int algo, int p) { return algo == HMH ? 32768u : (1u << p); }
+uint32_t ml_scratch_words(int p) { return 3u + (p <= 11 ? 12u : p <= 15 ? 16u : (uint32_t)kMlPlanes); }
 
 template <class ACC, int G>
 static cudaError_t launch_dist_t(const DistParams& dp, cudaStream_t st) {
@@ -1126,7 +1185,12 @@ static cudaError_t launch_dist_ml_tab(const DistParams& dp, cudaStream_t st) {
     const uint32_t chunk = cb < (uint32_t)kMlTabChunk ? cb : (uint32_t)kMlTabChunk;
     const size_t smem = (size_t)kTabN * kTabN * 12 + (size_t)kMlTabTR * (chunk + 4) * 4 + (size_t)kMlTabTQ * (chunk + 8) * 2 +
                         (size_t)(kMlTabTR + kMlTabTQ) * 4;
-    auto kern = dp.p <= 11 ? dist_ml_tab_kernel<12> : dp.p <= 15 ? dist_ml_tab_kernel<16> : dist_ml_tab_kernel<kMlPlanes>;
+    const bool split = dp.ml_scratch != nullptr;
+    const int npl = dp.p <= 11 ? 12 : dp.p <= 15 ? 16 : kMlPlanes;
+    using Kern = void (*)(DistParams, uint32_t, uint32_t, uint32_t, uint32_t);
+    Kern kern = npl == 12 ? (split ? dist_ml_tab_kernel<12, true> : dist_ml_tab_kernel<12, false>)
+              : npl == 16 ? (split ? dist_ml_tab_kernel<16, true> : dist_ml_tab_kernel<16, false>)
+                          : (split ? dist_ml_tab_kernel<kMlPlanes, true> : dist_ml_tab_kernel<kMlPlanes, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint64_t rows = dp.row_end - dp.row_begin;
@@ -1141,6 +1205,12 @@ static cudaError_t launch_dist_ml_tab(const DistParams& dp, cudaStream_t st) {
     }
     const unsigned grid = (unsigned)std::min<uint64_t>(gx * gy, (uint64_t)dp.n_sm);
     kern<<<grid, kMlTabThreads, smem, st>>>(dp, cb, chunk, (uint32_t)gx, (uint32_t)gy);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || !split) return e;
+    const unsigned fgrid = (unsigned)std::min<uint64_t>((dp.ml_cells + 255) / 256, (uint64_t)dp.n_sm * 32);
+    if (npl == 12) ml_finish_kernel<12><<<fgrid, 256, 0, st>>>(dp, cb);
+    else if (npl == 16) ml_finish_kernel<16><<<fgrid, 256, 0, st>>>(dp, cb);
+    else ml_finish_kernel<kMlPlanes><<<fgrid, 256, 0, st>>>(dp, cb);
     return cudaGetLastError();
 }
 
@@ -1153,7 +1223,10 @@ cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launc
         return v && std::string(v) == "merge";
     }();
     if (dp.algo == ULL && dp.estimator == 0 && !fgra_merge) return launch_dist_fgra_tab(dp, st);
-    if (dp.algo == ULL && dp.estimator == 1 && !fgra_merge) return launch_dist_ml_tab(dp, st);
+    if (dp.algo == ULL && dp.estimator == 1 && !fgra_merge) {
+        if (n_launches && dp.ml_scratch) *n_launches += 1;  // tile kernel + ml_finish_kernel
+        return launch_dist_ml_tab(dp, st);
+    }
     // LASH_HLL_KERNEL=table selects K4 (LDS.64 table of 2^-r + per-register zero test) for A/B measurements; default K4h
     static const bool hll_table = [] {
         const char* v = getenv("LASH_HLL_KERNEL");

@@ -72,7 +72,15 @@ struct DistParams {
     // nullptr: static round-robin over the grid
     uint32_t* tile_counter = nullptr;
     int n_sm = 148;
+    // optional (ULL ML pair-table kernel): scratch for the two-kernel form -- the tile kernel stores each pair's integer
+    // statistics (S, exact-path flag, bit planes of b[]) and ml_finish_kernel runs the per-pair solver at full occupancy.
+    // Word w of cell c lives at ml_scratch[w * ml_cells + c], c = output index - ml_o_base.  nullptr: fused epilogue.
+    uint32_t* ml_scratch = nullptr;
+    uint64_t ml_cells = 0;
+    uint64_t ml_o_base = 0;
 };
+// 32-bit words of ML scratch per pair for sketches of precision p (S lo/hi, flag, bit planes)
+uint32_t ml_scratch_words(int p);
 // atomicMin of the smallest non-zero register byte into *out_dev (preset to 0xffffffff by the caller)
 cudaError_t launch_regmin(const void* regs, uint64_t n_bytes, uint32_t* out_dev, int n_sm, cudaStream_t st);
 cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launches);
