@@ -84,6 +84,15 @@ __device__ __forceinline__ uint64_t xxh3_rrmxmx8_tail(uint32_t lo, uint32_t hi) 
     lo ^= add32_opaque(hi >> 3, 8u);  // h ^= (h >> 35) + len, no carry into the high word
     return mk64(lo, hi) * kPrimeMX2;   // caller applies the final h ^= h >> 28 (or only the part it needs)
 }
+// high word only of the same product chain: the second multiply then needs umulhi(lo, M.lo) + lo*M.hi + hi*M.lo
+__device__ __forceinline__ uint32_t xxh3_rrmxmx8_tail_hi(uint32_t lo, uint32_t hi) {
+    uint64_t h = mk64(lo, hi) * kPrimeMX2;
+    lo = (uint32_t)h;
+    hi = (uint32_t)(h >> 32);
+    lo ^= add32_opaque(hi >> 3, 8u);
+    constexpr uint32_t m_lo = (uint32_t)kPrimeMX2, m_hi = (uint32_t)(kPrimeMX2 >> 32);
+    return __umulhi(lo, m_lo) + lo * m_hi + hi * m_lo;
+}
 // pre-xorshift hash (h before `h ^= h >> 28`) of a k-mer that fits 32 bits; see HashConsts::nar_*
 __device__ __forceinline__ uint64_t xxh3_64_narrow_pre(uint32_t kmer, const HashConsts& c) {
     const uint32_t t2 = __funnelshift_r(kmer, c.nar_ch >> 17, 15);      // (kmer >> 15) | (nar_ch & 0xfffe0000)
@@ -91,6 +100,21 @@ __device__ __forceinline__ uint64_t xxh3_64_narrow_pre(uint32_t kmer, const Hash
     const uint32_t hi = kmer ^ t2 ^ t3;
     const uint32_t lo = (kmer * (1u << 17)) ^ (kmer >> 8) ^ c.nar_cl;
     return xxh3_rrmxmx8_tail(lo, hi);
+}
+__device__ __forceinline__ uint32_t xxh3_64_narrow_pre_hi(uint32_t kmer, const HashConsts& c) {
+    const uint32_t t2 = __funnelshift_r(kmer, c.nar_ch >> 17, 15);
+    const uint32_t t3 = kmer * (1u << 24) + (c.nar_ch & 0x1ffffu);
+    const uint32_t hi = kmer ^ t2 ^ t3;
+    const uint32_t lo = (kmer * (1u << 17)) ^ (kmer >> 8) ^ c.nar_cl;
+    return xxh3_rrmxmx8_tail_hi(lo, hi);
+}
+__device__ __forceinline__ uint32_t xxh3_64_wide_pre_hi(uint32_t v_lo, uint32_t v_hi, const HashConsts& c) {
+    uint32_t lo = v_hi ^ c.bf64_lo, hi = v_lo ^ c.bf64_hi;
+    const uint32_t r49_lo = __funnelshift_r(lo, hi, 15), r49_hi = __funnelshift_r(hi, lo, 15);
+    const uint32_t r24_lo = __funnelshift_l(hi, lo, 24), r24_hi = __funnelshift_l(lo, hi, 24);
+    lo ^= r49_lo ^ r24_lo;
+    hi ^= r49_hi ^ r24_hi;
+    return xxh3_rrmxmx8_tail_hi(lo, hi);
 }
 // pre-xorshift hash of a general 64-bit k-mer value
 __device__ __forceinline__ uint64_t xxh3_64_wide_pre(uint32_t v_lo, uint32_t v_hi, const HashConsts& c) {

@@ -181,6 +181,11 @@ def test_adversarial_hashes_with_32_or_more_leading_zeros(oracle, gpu_ctx, algo,
             tail_bits = 64 - p - 32
             tail = int(rng.integers(0, 1 << tail_bits)) >> int(rng.integers(0, tail_bits + 1))
             targets.append((idx << (64 - p)) | tail)
+            # the fast path looks at the 32-p bits after the index only: hashes with 32-p .. 31 zeros there (the first
+            # one lands in the p bits the fast path ignores) must take the exact path too
+            z = int(rng.integers(32 - p, 32)) if p < 32 else 31
+            below = 63 - p - z
+            targets.append((idx << (64 - p)) | (1 << below) | int(rng.integers(0, 1 << below)))
         else:                      # hi word zero; low p bits = index
             lo = int(rng.integers(0, 1 << 32)) >> int(rng.integers(0, 33 - p))
             targets.append((lo << p | int(rng.integers(0, 1 << p))) & 0xFFFFFFFF)
