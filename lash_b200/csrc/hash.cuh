@@ -76,22 +76,35 @@ __device__ __forceinline__ uint32_t add32_opaque(uint32_t a, uint32_t b) {
     return r;
 }
 
+// mad.lo.u32 the optimiser cannot re-associate: a 64x64->64 multiply is IMAD.WIDE (lo*M.lo) and two IMADs that add the
+// cross terms ON TOP of the wide product's high word -- 3 instructions.  Written in C the cross terms are summed first
+// and added to the high word afterwards (4 instructions: the extra IADD is pure issue-slot cost in this kernel).
+__device__ __forceinline__ uint32_t mad32_opaque(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// (lo, hi) * kPrimeMX2 mod 2^64 in three instructions
+__device__ __forceinline__ void mul_mx2(uint32_t& lo, uint32_t& hi) {
+    constexpr uint32_t m_lo = (uint32_t)kPrimeMX2, m_hi = (uint32_t)(kPrimeMX2 >> 32);
+    const uint64_t w = (uint64_t)lo * m_lo;
+    hi = mad32_opaque(hi, m_lo, mad32_opaque(lo, m_hi, (uint32_t)(w >> 32)));
+    lo = (uint32_t)w;
+}
 // tail of XXH3_rrmxmx after the rotate-xor stage, on halves
 __device__ __forceinline__ uint64_t xxh3_rrmxmx8_tail(uint32_t lo, uint32_t hi) {
-    uint64_t h = mk64(lo, hi) * kPrimeMX2;
-    lo = (uint32_t)h;
-    hi = (uint32_t)(h >> 32);
+    mul_mx2(lo, hi);
     lo ^= add32_opaque(hi >> 3, 8u);  // h ^= (h >> 35) + len, no carry into the high word
-    return mk64(lo, hi) * kPrimeMX2;   // caller applies the final h ^= h >> 28 (or only the part it needs)
+    mul_mx2(lo, hi);
+    return mk64(lo, hi);               // caller applies the final h ^= h >> 28 (or only the part it needs)
 }
-// high word only of the same product chain: the second multiply then needs umulhi(lo, M.lo) + lo*M.hi + hi*M.lo
 __device__ __forceinline__ uint32_t xxh3_rrmxmx8_tail_hi(uint32_t lo, uint32_t hi) {
-    uint64_t h = mk64(lo, hi) * kPrimeMX2;
-    lo = (uint32_t)h;
-    hi = (uint32_t)(h >> 32);
-    lo ^= add32_opaque(hi >> 3, 8u);
     constexpr uint32_t m_lo = (uint32_t)kPrimeMX2, m_hi = (uint32_t)(kPrimeMX2 >> 32);
-    return __umulhi(lo, m_lo) + lo * m_hi + hi * m_lo;
+    const uint64_t w = (uint64_t)lo * m_lo;                                   // IMAD.WIDE
+    uint32_t h1 = mad32_opaque(lo, m_hi, (uint32_t)(w >> 32));                // + lo * M.hi
+    h1 = mad32_opaque(hi, m_lo, h1);                                          // + hi * M.lo
+    const uint32_t l1 = (uint32_t)w ^ add32_opaque(h1 >> 3, 8u);              // h ^= (h >> 35) + 8
+    return mad32_opaque(h1, m_lo, mad32_opaque(l1, m_hi, __umulhi(l1, m_lo)));  // high word of the second product
 }
 // pre-xorshift hash (h before `h ^= h >> 28`) of a k-mer that fits 32 bits; see HashConsts::nar_*
 __device__ __forceinline__ uint64_t xxh3_64_narrow_pre(uint32_t kmer, const HashConsts& c) {

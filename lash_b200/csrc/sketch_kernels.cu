@@ -68,19 +68,19 @@ struct SmemAcc<ULL> {
     static constexpr uint32_t kWordsPerCell = 2;
     // fast: (address of word 0, bit to set [0 if the hash is a rare one], rare indicator word)
     // g = hash BEFORE its last step h = g ^ (g >> 28).  Because p <= 26 that xorshift cannot reach the index bits
-    // (idx = g.hi >> (32-p)).  The fast path looks only at the HIGH word of g: the top 32-p bits of h << p are
-    //     ((g.hi << p) ^ (g.hi >> (28-p))) >> p << p
-    // (g.lo only reaches the low p bits), so the second 64-bit multiply of the hash needs no low word (IMAD.HI + 2 IMAD
-    // instead of IMAD.WIDE + 3).  A hash whose 32-p bits after the index are all zero (2^-(32-p) of them; 2^-22 at
-    // p = 10) is "rare": it sets no bit here and sends its 16-k-mer group through the exact path.
+    // (idx = g.hi >> (32-p)).  The fast path looks only at the HIGH word of g: the 32-p hash bits after the index are
+    //     t = (g.hi ^ (g.hi >> 28)) & (2^(32-p) - 1)            (g.lo only reaches bits further down),
+    // so the second 64-bit multiply of the hash needs no low word (IMAD.HI + 2 IMAD) and nlz = 31 - p - bfind(t):
+    // the bit to set is (1 << p) << bfind(t), in the cell layout described above.  A hash with t == 0 (2^-(32-p) of
+    // them; 2^-22 at p = 10) is "rare": it sets no bit here and sends its 16-k-mer group through the exact path.
     template <bool NARROW>
     __device__ static __forceinline__ void prep(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t sbase,
                                                 uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
         const uint32_t hi = NARROW ? xxh3_64_narrow_pre_hi(klo, hc) : xxh3_64_wide_pre_hi(klo, khi, hc);
-        const uint32_t yh = ((hi << p) ^ (hi >> (28 - p))) & (0xffffffffu << p);  // top 32-p bits of h << p, low p bits cleared
+        const uint32_t t = (hi ^ (hi >> 28)) & (0xffffffffu >> p);  // SHF + one LOP3
         saddr = sbase + __umulhi(hi, 1u << p) * 8u;       // (hi >> (32-p)) * 8 on the FMA pipe
-        v = shl_clamp(1u, bfind32(yh));                  // yh == 0 -> bfind = 0xffffffff -> v = 0
-        rare_word = yh;
+        v = shl_clamp(1u << p, bfind32(t));              // t == 0 -> bfind = 0xffffffff -> v = 0
+        rare_word = t;
     }
     __device__ static __forceinline__ uint32_t need(uint32_t cur, uint32_t v) { return ~cur & v; }
     __device__ static __forceinline__ void apply(uint32_t saddr, uint32_t needv) { red_or(saddr, needv); }
