@@ -71,13 +71,18 @@ struct SmemAcc<ULL> {
     // (idx = g.hi >> (32-p)).  The fast path looks only at the HIGH word of g: the 32-p hash bits after the index are
     //     t = (g.hi ^ (g.hi >> 28)) & (2^(32-p) - 1)            (g.lo only reaches bits further down),
     // so the second 64-bit multiply of the hash needs no low word (IMAD.HI + 2 IMAD) and nlz = 31 - p - bfind(t):
-    // the bit to set is (1 << p) << bfind(t), in the cell layout described above.  A hash with t == 0 (2^-(32-p) of
-    // them; 2^-22 at p = 10) is "rare": it sets no bit here and sends its 16-k-mer group through the exact path.
-    template <bool NARROW>
+    // the bit to set is (1 << p) << bfind(t), in the cell layout described above.  The xorshift term only reaches the
+    // low 4 bits of t, so for small p the fast path drops it AND those 4 bits: t' = g.hi & (2^(32-p) - 16) is one LOP3
+    // and has the same highest set bit as t whenever it is non-zero.  A hash with t' == 0 (2^-(28-p) of them; 2^-18 at
+    // p = 10) is "rare": it sets no bit here and sends its 16-k-mer group through the exact path (~2 instructions per
+    // 512 k-mers at p = 10).
+    // DROP4 is set for the small-accumulator instantiation (p <= 11); at p = 14 one group in 30 would hold a "rare"
+    // hash (measured: -3 %), so larger precisions keep the exact t (one more SHF).
+    template <bool NARROW, bool DROP4>
     __device__ static __forceinline__ void prep(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t sbase,
                                                 uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
         const uint32_t hi = NARROW ? xxh3_64_narrow_pre_hi(klo, hc) : xxh3_64_wide_pre_hi(klo, khi, hc);
-        const uint32_t t = (hi ^ (hi >> 28)) & (0xffffffffu >> p);  // SHF + one LOP3
+        const uint32_t t = DROP4 ? hi & ((0xffffffffu >> p) & ~15u) : (hi ^ (hi >> 28)) & (0xffffffffu >> p);
         saddr = sbase + __umulhi(hi, 1u << p) * 8u;       // (hi >> (32-p)) * 8 on the FMA pipe
         v = shl_clamp(1u << p, bfind32(t));              // t == 0 -> bfind = 0xffffffff -> v = 0
         rare_word = t;
@@ -103,7 +108,7 @@ struct SmemAcc<ULL> {
 template <>
 struct SmemAcc<HLL> {
     static constexpr uint32_t kWordsPerCell = 1;
-    template <bool NARROW>
+    template <bool NARROW, bool DROP4>
     __device__ static __forceinline__ void prep(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t sbase,
                                                 uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
         const uint64_t g = NARROW ? xxh3_64_narrow_pre(klo, hc) : xxh3_64_wide_pre(klo, khi, hc);
@@ -126,7 +131,7 @@ struct SmemAcc<HLL> {
 template <>
 struct SmemAcc<HMH> {
     static constexpr uint32_t kWordsPerCell = 1;
-    template <bool NARROW>
+    template <bool NARROW, bool DROP4>
     __device__ static __forceinline__ void prep(uint32_t klo, uint32_t /*khi*/, const HashConsts& hc, int /*p*/, uint32_t sbase,
                                                 uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
         uint64_t hlo, hhi;
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
                     for (int i = 0; i < kGroup; ++i) {
                         uint32_t klo, khi, v, rw;
                         kmer(2 * i, klo, khi);
-                        A::template prep<!WIDE>(klo, khi, hc, p, sbase, addr[i], v, rw);
+                        A::template prep<!WIDE, TB == kTbSmall>(klo, khi, hc, p, sbase, addr[i], v, rw);
                         need[i] = A::need(lds_u32(addr[i]), v);
                         if (CHECKED) need[i] = (mask16 & (1u << i)) ? need[i] : 0u;
                         any |= need[i];

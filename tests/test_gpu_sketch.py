@@ -183,9 +183,11 @@ def test_adversarial_hashes_with_32_or_more_leading_zeros(oracle, gpu_ctx, algo,
             targets.append((idx << (64 - p)) | tail)
             # the fast path looks at the 32-p bits after the index only: hashes with 32-p .. 31 zeros there (the first
             # one lands in the p bits the fast path ignores) must take the exact path too
-            z = int(rng.integers(32 - p, 32)) if p < 32 else 31
-            below = 63 - p - z
-            targets.append((idx << (64 - p)) | (1 << below) | int(rng.integers(0, 1 << below)))
+            # ... and so must those whose first one is among the last 4 of those 32-p bits (the fast path drops them
+            # together with the xorshift term that reaches them)
+            for z in (int(rng.integers(32 - p, 32)), int(rng.integers(max(28 - p, 0), 32 - p))):
+                below = 63 - p - z
+                targets.append((idx << (64 - p)) | (1 << below) | int(rng.integers(0, 1 << below)))
         else:                      # hi word zero; low p bits = index
             lo = int(rng.integers(0, 1 << 32)) >> int(rng.integers(0, 33 - p))
             targets.append((lo << p | int(rng.integers(0, 1 << p))) & 0xFFFFFFFF)
