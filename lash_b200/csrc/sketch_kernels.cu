@@ -112,11 +112,13 @@ struct SmemAcc<HLL> {
     __device__ static __forceinline__ void prep(uint32_t klo, uint32_t khi, const HashConsts& hc, int p, uint32_t sbase,
                                                 uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
         const uint64_t g = NARROW ? xxh3_64_narrow_pre(klo, hc) : xxh3_64_wide_pre(klo, khi, hc);
-        const uint64_t h = g ^ (g >> 28);
-        const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
-        saddr = sbase + (lo & ((1u << p) - 1u)) * 4u;
-        v = 32u - bfind32(hi);  // rho = clz(hi) + 1 when hi != 0; hi == 0 -> 33 <= true rho (p <= 18)
-        rare_word = hi;
+        const uint32_t glo = (uint32_t)g, ghi = (uint32_t)(g >> 32);
+        // h = g ^ (g >> 28): the index needs the low p bits of h.lo.  rho = clz(h.hi) + 1 = clz(g.hi) + 1: the xorshift
+        // folds the top 4 bits of g.hi into its low 4 bits, which moves the highest set bit of neither a g.hi >= 2^28
+        // nor (g.hi >> 28 == 0) a smaller one -- so h.hi is never materialised.
+        saddr = sbase + ((glo ^ __funnelshift_r(glo, ghi, 28)) & ((1u << p) - 1u)) * 4u;
+        v = 32u - bfind32(ghi);  // rho when g.hi != 0; g.hi == 0 (<=> h.hi == 0) -> 33 <= true rho (p <= 18)
+        rare_word = ghi;
     }
     __device__ static __forceinline__ uint32_t need(uint32_t cur, uint32_t v) { return cur < v ? v : 0u; }
     __device__ static __forceinline__ void apply(uint32_t saddr, uint32_t needv) { red_max(saddr, needv); }
