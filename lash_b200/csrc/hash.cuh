@@ -118,7 +118,11 @@ __device__ __forceinline__ uint32_t xxh3_64_narrow_pre_hi(uint32_t kmer, const H
     const uint32_t t2 = __funnelshift_r(kmer, c.nar_ch >> 17, 15);
     const uint32_t t3 = kmer * (1u << 24) + (c.nar_ch & 0x1ffffu);
     const uint32_t hi = kmer ^ t2 ^ t3;
+#ifdef LASH_SHR8_IMAD  // tuning switch: kmer >> 8 as IMAD.HI on the FMA pipe -- measured 1.7 % SLOWER (826 -> 812 Gbp/s)
+    const uint32_t lo = (kmer * (1u << 17)) ^ __umulhi(kmer, 1u << 24) ^ c.nar_cl;
+#else
     const uint32_t lo = (kmer * (1u << 17)) ^ (kmer >> 8) ^ c.nar_cl;
+#endif
     return xxh3_rrmxmx8_tail_hi(lo, hi);
 }
 __device__ __forceinline__ uint32_t xxh3_64_wide_pre_hi(uint32_t v_lo, uint32_t v_hi, const HashConsts& c) {

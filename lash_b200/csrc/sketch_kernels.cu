@@ -83,7 +83,11 @@ struct SmemAcc<ULL> {
                                                 uint32_t& saddr, uint32_t& v, uint32_t& rare_word) {
         const uint32_t hi = NARROW ? xxh3_64_narrow_pre_hi(klo, hc) : xxh3_64_wide_pre_hi(klo, khi, hc);
         const uint32_t t = DROP4 ? hi & ((0xffffffffu >> p) & ~15u) : (hi ^ (hi >> 28)) & (0xffffffffu >> p);
+#ifdef LASH_SADDR_IMAD  // tuning switch (tools/variant_sweep): no difference measured, ptxas picks LEA or IMAD itself
+        saddr = mad32_opaque(__umulhi(hi, 1u << p), 8u, sbase);
+#else
         saddr = sbase + __umulhi(hi, 1u << p) * 8u;       // (hi >> (32-p)) * 8 on the FMA pipe
+#endif
         v = shl_clamp(1u << p, bfind32(t));              // t == 0 -> bfind = 0xffffffff -> v = 0
         rare_word = t;
     }
