@@ -295,3 +295,51 @@ def test_hll_recoded_kernel_ragged_tiles_and_mixed_empties(oracle, gpu_ctx, p, n
     dense, _ = ops.dist(gpu_ctx, ALGO_HLL, p, 21, 0, MODEL_POISSON, False, sq, sq)
     tri, _ = ops.dist(gpu_ctx, ALGO_HLL, p, 21, 0, MODEL_POISSON, False, sq, sq, triangular=True)
     np.testing.assert_array_equal(tri, dense[np.tril_indices(len(sq))])
+
+
+def test_ml_two_kernel_form_matches_fused_in_every_output_layout(oracle, gpu_ctx, tmp_path):
+    """ULL ML runs as a tile kernel that stores the pair statistics + ml_finish_kernel.  The scratch is
+    addressed by output cell, so every output layout is its own case: dense, packed triangle, streamed dense blocks
+    (out_row0 != 0, triangular or not).  All must equal the fused single-kernel form (LASH_ML_KERNEL=fused, read once
+    per process -> a child process) bit for bit, and the oracle within tolerance."""
+    import subprocess
+    import sys
+    regs = _sketches(oracle, ALGO_ULL, 10, 16, 75, 60_000)
+    regs[7] = 0                                                   # an empty sketch (S == 0 branch)
+    regs[9, 5] = 251                                              # outside the pair table: exact per-pair path
+    np.save(tmp_path / "regs.npy", regs)
+    child = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from lash_b200 import ALGO_ULL, EST_ML, MODEL_POISSON, ops\n"
+        "regs = np.load(%r)\n"
+        "with ops.Context(0) as ctx:\n"
+        "    d, _ = ops.dist(ctx, ALGO_ULL, 10, 16, EST_ML, MODEL_POISSON, False, regs, regs)\n"
+        "np.save(%r, d)\n" % (str(__import__('os').path.dirname(__import__('os').path.dirname(__file__))), str(tmp_path / "regs.npy"),
+                             str(tmp_path / "fused.npy")))
+    env = dict(__import__('os').environ, LASH_ML_KERNEL="fused")
+    subprocess.run([sys.executable, "-c", child], check=True, env=env)
+    fused = np.load(tmp_path / "fused.npy")
+    dense, _ = ops.dist(gpu_ctx, ALGO_ULL, 10, 16, EST_ML, MODEL_POISSON, False, regs, regs)
+    np.testing.assert_array_equal(dense, fused)
+    exp = oracle.dist(ALGO_ULL, 10, 16, EST_ML, MODEL_POISSON, False, regs, regs)
+    frac = oracle.dist(ALGO_ULL, 10, 16, EST_ML, 2, False, regs, regs)
+    both_nan = np.isnan(dense) & np.isnan(exp)
+    _assert_close_f64(np.where(both_nan, 0, dense), np.where(both_nan, 0, exp), np.nan_to_num(frac), 16, "ml two-kernel")
+    tri, _ = ops.dist(gpu_ctx, ALGO_ULL, 10, 16, EST_ML, MODEL_POISSON, False, regs, regs, triangular=True)
+    np.testing.assert_array_equal(tri, dense[np.tril_indices(len(regs))])
+    for triangular in (False, True):
+        got = np.full_like(dense, np.nan)
+
+        def on_block(row0, block):
+            got[row0: row0 + block.shape[0]] = block
+
+        ops.dist_stream(gpu_ctx, ALGO_ULL, 10, 16, EST_ML, MODEL_POISSON, False, regs, regs, triangular, 7, on_block)
+        if triangular:
+            il = np.tril_indices(len(regs))
+            np.testing.assert_array_equal(got[il], dense[il])
+        else:
+            np.testing.assert_array_equal(got, dense)
+    # a rectangular problem with different sets on the two sides, fp32 output
+    d32, _ = ops.dist(gpu_ctx, ALGO_ULL, 10, 16, EST_ML, MODEL_BINOMIAL, True, regs[:20], regs[30:])
+    e32 = oracle.dist(ALGO_ULL, 10, 16, EST_ML, MODEL_BINOMIAL, True, regs[:20], regs[30:])
+    np.testing.assert_allclose(d32, e32, rtol=1e-6, atol=2e-7)
