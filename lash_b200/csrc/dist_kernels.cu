@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kHllThreads, 3) dist_hll_fast_kernel(DistParam
     const unsigned char* gref = reinterpret_cast<const unsigned char*>(dp.ref);
     const unsigned char* gqry = reinterpret_cast<const unsigned char*>(dp.qry);
     const uint32_t chunk_words = chunk / 4;                                                // powers of two, both
-    const uint32_t cw_shift = 31u - __clz(chunk_words), cell_shift = 31u - __clz(cell_bytes);
+    const uint32_t g_shift = 31u - __clz(chunk_words) - 2u, cell_shift = 31u - __clz(cell_bytes);  // 16-register groups per row
 
     double sum[kHllRM][kHllQM];
     uint32_t zero[kHllRM][kHllQM];
@@ -550,20 +550,31 @@ __global__ void __launch_bounds__(kHllThreads, 3) dist_hll_fast_kernel(DistParam
         __syncthreads();  // previous chunk consumed; s_zero[par] was cleared during the previous staging pass (or above)
         if (threadIdx.x < 2) s_zero[par ^ 1u][threadIdx.x] = 0u;
         bool za = false, zb = false;
-        for (uint32_t e = threadIdx.x; e < ((uint32_t)kHllTR << cw_shift); e += kHllThreads) {
-            const uint32_t r = e >> cw_shift, w = e & (chunk_words - 1u);
+        // 16 registers per step: one LDG.128, four recoded STS.128 (register arrays are 16-byte aligned: the launcher checks)
+        for (uint32_t e = threadIdx.x; e < ((uint32_t)kHllTR << g_shift); e += kHllThreads) {
+            const uint32_t r = e >> g_shift, g = e & ((1u << g_shift) - 1u);
             const uint64_t gi = row0 + r;
             // rows past the end are staged as "register 255" (never empty, never read back)
-            const uint32_t v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint32_t*>(gref + (gi << cell_shift) + c0) + w) : 0xffffffffu;
-            za |= has_zero_byte(v);
-            *reinterpret_cast<uint4*>(sa + r * stride + 4 * w) = hll_recode(v);
+            const uint4 v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint4*>(gref + (gi << cell_shift) + c0) + g)
+                                            : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            za |= has_zero_byte(v.x) | has_zero_byte(v.y) | has_zero_byte(v.z) | has_zero_byte(v.w);
+            uint4* dst = reinterpret_cast<uint4*>(sa + r * stride + 16 * g);
+            dst[0] = hll_recode(v.x);
+            dst[1] = hll_recode(v.y);
+            dst[2] = hll_recode(v.z);
+            dst[3] = hll_recode(v.w);
         }
-        for (uint32_t e = threadIdx.x; e < ((uint32_t)kHllTQ << cw_shift); e += kHllThreads) {
-            const uint32_t r = e >> cw_shift, w = e & (chunk_words - 1u);
+        for (uint32_t e = threadIdx.x; e < ((uint32_t)kHllTQ << g_shift); e += kHllThreads) {
+            const uint32_t r = e >> g_shift, g = e & ((1u << g_shift) - 1u);
             const uint64_t gj = col0 + r;
-            const uint32_t v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint32_t*>(gqry + (gj << cell_shift) + c0) + w) : 0xffffffffu;
-            zb |= has_zero_byte(v);
-            *reinterpret_cast<uint4*>(sb + r * stride + 4 * w) = hll_recode(v);
+            const uint4 v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint4*>(gqry + (gj << cell_shift) + c0) + g)
+                                          : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            zb |= has_zero_byte(v.x) | has_zero_byte(v.y) | has_zero_byte(v.z) | has_zero_byte(v.w);
+            uint4* dst = reinterpret_cast<uint4*>(sb + r * stride + 16 * g);
+            dst[0] = hll_recode(v.x);
+            dst[1] = hll_recode(v.y);
+            dst[2] = hll_recode(v.z);
+            dst[3] = hll_recode(v.w);
         }
         if (za) s_zero[par][0] = 1u;
         if (zb) s_zero[par][1] = 1u;
@@ -1232,7 +1243,9 @@ cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launc
         const char* v = getenv("LASH_HLL_KERNEL");
         return v && std::string(v) == "table";
     }();
-    if (dp.algo == HLL) return hll_table ? launch_dist_t<HllAcc, 16>(dp, st) : launch_dist_hll_fast(dp, st);
+    // K4h stages with 16-byte loads: register arrays that are not 16-byte aligned (a caller's odd device pointer) use K4
+    const bool hll_aligned = (((uintptr_t)dp.ref | (uintptr_t)dp.qry) & 15u) == 0;
+    if (dp.algo == HLL) return (hll_table || !hll_aligned) ? launch_dist_t<HllAcc, 16>(dp, st) : launch_dist_hll_fast(dp, st);
     if (dp.algo == HMH) return launch_dist_t<HmhAcc, 16>(dp, st);
     const bool tiny = dp.p == 3;  // 8 registers per sketch
     if (dp.estimator == 0) return tiny ? launch_dist_t<FgraAcc, 8>(dp, st) : launch_dist_t<FgraAcc, 16>(dp, st);
