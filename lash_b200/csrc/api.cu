@@ -414,11 +414,16 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
         if (tiles_bytes) memcpy(mh, tiles.data(), tiles_bytes);
         if (mspans_bytes) memcpy(mh + off_mspans, mspans.data(), mspans_bytes);
         if (recs_bytes) memcpy(mh + off_recs, rec_start, recs_bytes);
-        // the slot's previous kernels (two pushes ago) may still be reading sl.meta
-        if (sl.used) CU(cudaStreamWaitEvent(s->meta_stream, sl.k_stop, 0));
-        CU(cudaMemcpyAsync(sl.meta.p, mh, meta_bytes, cudaMemcpyHostToDevice, s->meta_stream));
-        CU(cudaEventRecord(sl.meta_ready, s->meta_stream));
-        CU(cudaStreamWaitEvent(stream, sl.meta_ready, 0));
+        static const bool meta_inline = getenv("LASH_META_SAME_STREAM") != nullptr;  // A/B switch
+        if (meta_inline) {
+            CU(cudaMemcpyAsync(sl.meta.p, mh, meta_bytes, cudaMemcpyHostToDevice, stream));
+        } else {
+            // the slot's previous kernels (two pushes ago) may still be reading sl.meta
+            if (sl.used) CU(cudaStreamWaitEvent(s->meta_stream, sl.k_stop, 0));
+            CU(cudaMemcpyAsync(sl.meta.p, mh, meta_bytes, cudaMemcpyHostToDevice, s->meta_stream));
+            CU(cudaEventRecord(sl.meta_ready, s->meta_stream));
+            CU(cudaStreamWaitEvent(stream, sl.meta_ready, 0));
+        }
     }
     const uint32_t* packed_dev = nullptr;
     if (packed_on_device) {
