@@ -200,3 +200,59 @@ def test_shard_functions_edge_cases():
                 assert rows[0][0] == 0 and rows[-1][1] == n
                 assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
                 assert sum(shard.pair_count(rw, n, tri) for rw in rows) == (n * (n + 1) // 2 if tri else n * n)
+
+
+def test_bench_reference_arm_prints_the_contract_line(monkeypatch, capsys):
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the base contract's
+    keys, `impl`, a `cpu_baseline` describing the run and an `e2e` that repeats the line's own value.  Run here on a
+    shrunken genome length; ranks other than 0 must print nothing."""
+    import argparse
+    import json
+
+    import bench
+    monkeypatch.setattr(bench, "GENOME_LEN", 40_000)
+    args = argparse.Namespace(gpus=1, steps=1, warmup=0)
+    bench.run_reference(args)
+    out = capsys.readouterr().out.strip().splitlines()
+    assert len(out) == 1
+    line = json.loads(out[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "kmer_sketch_gbp_per_s" and line["unit"] == "Gbp/s"
+    assert line["value"] > 0 and line["vs_baseline"] is None and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
+    monkeypatch.setenv("RANK", "1")
+    bench.run_reference(args)
+    assert capsys.readouterr().out == ""
+
+
+def test_bench_clock_sampler_parses_nvidia_smi_lines():
+    """clocks / throttle reasons: only samples after mark() count; median of the busy samples; reasons by column."""
+    import bench
+    s = bench.ClockSampler(0)
+    s.lines = ["0, 210, 1965, 140.2, 0x0, Not Active, Not Active, Not Active, Not Active",      # idle, before the timed region
+               "0, 1965, 1965, 820.0, 0x4, Not Active, Not Active, Not Active, Active",
+               "0, 1950, 1965, 900.0, 0x4, Not Active, Not Active, Not Active, Active",
+               "0, 1965, 1965, 880.0, 0x0, Not Active, Not Active, Not Active, Not Active",
+               "garbage line"]
+    s.mark_at = 1
+    s.proc = type("P", (), {"terminate": lambda self: None, "wait": lambda self, timeout=None: 0, "kill": lambda self: None})()
+    c = s.stop()
+    assert c["sm_mhz"] == 1965.0 and c["sm_max_mhz"] == 1965.0 and c["reasons"] == ["sw_power_cap"] and c["samples"] == 3
+
+
+def test_pin_parity_table_readers(tmp_path):
+    """tools/pin_parity.py compares the reference's and our `dist` outputs as unordered pairs (the reference emits one
+    orientation of each pair, chosen by HashMap order)."""
+    from tools import pin_parity as P
+    a, b = tmp_path / "a.tsv", tmp_path / "b.dm"
+    a.write_text("Reference\tQuery\tDistance\nx\ty\t0.100000\ny\ty\t0.000000\nx\tx\t0.000000\n")
+    b.write_text("\tx\ty\nx\t0.000000\ny\t0.100000\t0.000000\n")
+    n, bad = P.same_pairs(P.read_table(str(a)), P.read_table(str(b)))
+    assert n == 3 and bad == []
+    b.write_text("\tx\ty\nx\t0.000000\ny\t0.100001\t0.000000\n")
+    n, bad = P.same_pairs(P.read_table(str(a)), P.read_table(str(b)))
+    assert len(bad) == 1 and bad[0][0] == ("x", "y")
