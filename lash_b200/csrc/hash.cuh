@@ -70,19 +70,29 @@ __device__ __forceinline__ uint64_t xxh3_rrmxmx8(uint64_t h) {
 // 32-bit add the optimiser cannot widen: written in C, `lo ^ ((hi >> 3) + 8u)` next to mk64() is re-fused by
 // the front end into a 64-bit add and lowered with a carry into the high word (LEA.HI.P + IMAD.X + LOP3:
 // two wasted instructions per hash) although (h >> 35) + 8 < 2^30 can never carry.
+// (LASH_HOST_SHIM: tests/host_shim compiles these headers with g++ to check the device arithmetic on a CPU; it is never
+// defined in a product build, where the PTX forms below are the code.)
 __device__ __forceinline__ uint32_t add32_opaque(uint32_t a, uint32_t b) {
+#ifdef LASH_HOST_SHIM
+    return a + b;
+#else
     uint32_t r;
     asm("add.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
+#endif
 }
 
 // mad.lo.u32 the optimiser cannot re-associate: a 64x64->64 multiply is IMAD.WIDE (lo*M.lo) and two IMADs that add the
 // cross terms ON TOP of the wide product's high word -- 3 instructions.  Written in C the cross terms are summed first
 // and added to the high word afterwards (4 instructions: the extra IADD is pure issue-slot cost in this kernel).
 __device__ __forceinline__ uint32_t mad32_opaque(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef LASH_HOST_SHIM
+    return a * b + c;
+#else
     uint32_t r;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
+#endif
 }
 // (lo, hi) * kPrimeMX2 mod 2^64 in three instructions
 __device__ __forceinline__ void mul_mx2(uint32_t& lo, uint32_t& hi) {
@@ -169,15 +179,23 @@ __device__ __forceinline__ void xxh3_128_le32(uint32_t w, const HashConsts& c, u
 
 // bfind.u32: bit position of the most significant 1, 0xffffffff for 0 (SASS FLO, XU pipe)
 __device__ __forceinline__ uint32_t bfind32(uint32_t x) {
+#ifdef LASH_HOST_SHIM
+    return x ? 31u - (uint32_t)__builtin_clz(x) : 0xffffffffu;
+#else
     uint32_t r;
     asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
     return r;
+#endif
 }
 // shl.b32 clamps: shift amounts >= 32 give 0 (C's << would be undefined)
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t n) {
+#ifdef LASH_HOST_SHIM
+    return n >= 32u ? 0u : x << n;
+#else
     uint32_t r;
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
     return r;
+#endif
 }
 __device__ __forceinline__ int clz64_parts(uint32_t lo, uint32_t hi) {
     return hi ? __clz(hi) : 32 + __clz(lo);  // __clz(0) == 32

@@ -1,0 +1,96 @@
+// Test infrastructure: compiles the DEVICE arithmetic headers (lash_b200/csrc/hash.cuh, registers.cuh) with g++ so that the
+// hash paths and register algebra the kernels use can be checked on a machine without a GPU (tests/test_device_math.py).
+// The shim below stands in for the CUDA intrinsics those headers call; LASH_HOST_SHIM swaps their four inline-PTX helpers
+// for plain C.  Nothing here is part of the product.
+#include <algorithm>
+#include <cstdint>
+
+#define LASH_HOST_SHIM 1
+#define __CUDACC__ 1
+#define __device__
+#define __host__
+#define __forceinline__ inline
+
+using std::max;
+using std::min;
+
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) {  // high word of (hi:lo) << (s & 31)
+    s &= 31u;
+    return s ? (hi << s) | (lo >> (32u - s)) : hi;
+}
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {  // low word of (hi:lo) >> (s & 31)
+    s &= 31u;
+    return s ? (lo >> s) | (hi << (32u - s)) : lo;
+}
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
+static inline uint32_t bytewise(uint32_t a, uint32_t b, uint32_t (*f)(uint32_t, uint32_t)) {
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (f((a >> (8 * i)) & 0xffu, (b >> (8 * i)) & 0xffu) & 0xffu) << (8 * i);
+    return r;
+}
+static inline uint32_t __vmaxu4(uint32_t a, uint32_t b) { return bytewise(a, b, [](uint32_t x, uint32_t y) { return x > y ? x : y; }); }
+static inline uint32_t __vminu4(uint32_t a, uint32_t b) { return bytewise(a, b, [](uint32_t x, uint32_t y) { return x < y ? x : y; }); }
+static inline uint32_t __vcmpne4(uint32_t a, uint32_t b) { return bytewise(a, b, [](uint32_t x, uint32_t y) { return x != y ? 0xffu : 0u; }); }
+static inline uint32_t __vmaxu2(uint32_t a, uint32_t b) {
+    const uint32_t lo = std::max(a & 0xffffu, b & 0xffffu), hi = std::max(a >> 16, b >> 16);
+    return (hi << 16) | lo;
+}
+
+#include "../../lash_b200/csrc/registers.cuh"
+
+using namespace lash;
+
+extern "C" {
+
+// ---- hashes (arrays in, arrays out) -----------------------------------------------------------------------------
+void dm_xxh3_64(const uint64_t* v, uint64_t n, uint64_t seed, uint64_t* out) {
+    const HashConsts hc = make_hash_consts(seed);
+    for (uint64_t i = 0; i < n; ++i) out[i] = xxh3_64_le64((uint32_t)v[i], (uint32_t)(v[i] >> 32), hc);
+}
+// pre-xorshift forms used by the kernels' fast paths: out[0] = narrow/wide_pre (64 bit), out_hi = the *_hi variant
+void dm_pre(const uint64_t* v, uint64_t n, uint64_t seed, int narrow, uint64_t* out, uint32_t* out_hi) {
+    const HashConsts hc = make_hash_consts(seed);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t lo = (uint32_t)v[i], hi = (uint32_t)(v[i] >> 32);
+        out[i] = narrow ? xxh3_64_narrow_pre(lo, hc) : xxh3_64_wide_pre(lo, hi, hc);
+        out_hi[i] = narrow ? xxh3_64_narrow_pre_hi(lo, hc) : xxh3_64_wide_pre_hi(lo, hi, hc);
+    }
+}
+void dm_xxh3_128(const uint32_t* w, uint64_t n, uint64_t seed, uint64_t* out_lo, uint64_t* out_hi) {
+    const HashConsts hc = make_hash_consts(seed);
+    for (uint64_t i = 0; i < n; ++i) xxh3_128_le32(w[i], hc, out_lo[i], out_hi[i]);
+}
+
+// ---- (index, value) a k-mer contributes, in the register domain (Cell<ALGO>::from_kmer) -------------------------------
+void dm_cell(int algo, const uint64_t* v, uint64_t n, uint64_t seed, int p, uint32_t* idx, uint32_t* val) {
+    const HashConsts hc = make_hash_consts(seed);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t lo = (uint32_t)v[i], hi = (uint32_t)(v[i] >> 32);
+        if (algo == HLL) Cell<HLL>::from_kmer(lo, hi, hc, p, idx[i], val[i]);
+        else if (algo == ULL) Cell<ULL>::from_kmer(lo, hi, hc, p, idx[i], val[i]);
+        else Cell<HMH>::from_kmer(lo, hi, hc, p, idx[i], val[i]);
+    }
+}
+
+// ---- what the ULL / HLL fast paths of sketch_kernels.cu derive from the pre-xorshift high word -------------------------
+// (restated from SmemAcc<ULL>::prep / SmemAcc<HLL>::prep: index, the word whose highest set bit gives nlz / rho, and whether
+// the group would be sent to the exact path)
+void dm_ull_fast(const uint32_t* ghi, uint64_t n, int p, int drop4, uint32_t* idx, uint32_t* nlz, uint32_t* rare) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t hi = ghi[i];
+        const uint32_t t = drop4 ? hi & ((0xffffffffu >> p) & ~15u) : (hi ^ (hi >> 28)) & (0xffffffffu >> p);
+        idx[i] = __umulhi(hi, 1u << p);
+        const uint32_t v = shl_clamp(1u << p, bfind32(t));  // bit j of cell word 0 <=> nlz = 31 - j
+        rare[i] = t == 0u;
+        nlz[i] = v ? 31u - bfind32(v) : 0xffffffffu;
+    }
+}
+
+// ---- register algebra -----------------------------------------------------------------------------------------------
+uint32_t dm_ull_update(uint32_t r, uint32_t u) { return ull_update(r, u); }
+uint32_t dm_ull_merge1(uint32_t a, uint32_t b) { return ull_merge1(a, b); }
+uint32_t dm_ull_merge4(uint32_t a, uint32_t b) { return ull_merge4(a, b); }
+}
