@@ -1068,27 +1068,6 @@ __global__ void __launch_bounds__(kCardWarps * 32) card_hmh_kernel(const uint32_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static UllConsts make_ull_consts() {
-    UllConsts c;
-    c.pow2tau = std::pow(2.0, kUllTau);
-    c.pow2mtau = std::pow(2.0, -kUllTau);
-    c.pow4mtau = std::pow(4.0, -kUllTau);
-    c.etaX = kUllEta0 - kUllEta1 - kUllEta2 + kUllEta3;
-    c.eta23X = (kUllEta2 - kUllEta3) / c.etaX;
-    c.eta13X = (kUllEta1 - kUllEta3) / c.etaX;
-    c.eta3012XX = (kUllEta3 * kUllEta0 - kUllEta1 * kUllEta2) / (c.etaX * c.etaX);
-    c.phi1 = kUllEta0 / (c.pow2tau * (2.0 * c.pow2tau - 1.0));
-    c.pinit = c.etaX * (c.pow4mtau / (2.0 - c.pow2mtau));
-    c.minus_inv_tau = -1.0 / kUllTau;
-    const double eta[4] = {kUllEta0, kUllEta1, kUllEta2, kUllEta3};
-    for (int i = 0; i < 256; ++i) c.reg[i] = eta[i & 3] * std::pow(2.0, -kUllTau * (double)(3 + (i >> 2)));
-    for (int p = 0; p < 27; ++p) {
-        double m = (double)(1ull << p);
-        c.factor[p] = m * std::pow(m, 1.0 / kUllTau) / (1.0 + kUllV * (1.0 + kUllTau) / (2.0 * m));
-    }
-    return c;
-}
-
 cudaError_t ensure_tables() {
     // constant memory is per device (per context); upload is cheap, so do it whenever asked
     static const UllConsts host = make_ull_consts();

@@ -9,6 +9,7 @@
 //   HMH   hyperminhash 0.1.4 cardinality()/similarity()         (utils.rs:164)
 //   Mash  main.rs:415-423 compute_distance<F>
 #pragma once
+#include <cmath>
 #include <cstdint>
 
 namespace lash {
@@ -27,6 +28,28 @@ constexpr double kUllEta2 = 2.781144650979996;
 constexpr double kUllEta3 = 0.9824082545153715;
 constexpr double kUllInvSqrtFisher = 0.7608621002725182;
 constexpr double kUllMlBias = 0.48147376527720065;
+
+// host side: the table of constants uploaded into c_ull (and used by the CPU-side check of these epilogues, tests/host_shim)
+inline UllConsts make_ull_consts() {
+    UllConsts c;
+    c.pow2tau = std::pow(2.0, kUllTau);
+    c.pow2mtau = std::pow(2.0, -kUllTau);
+    c.pow4mtau = std::pow(4.0, -kUllTau);
+    c.etaX = kUllEta0 - kUllEta1 - kUllEta2 + kUllEta3;
+    c.eta23X = (kUllEta2 - kUllEta3) / c.etaX;
+    c.eta13X = (kUllEta1 - kUllEta3) / c.etaX;
+    c.eta3012XX = (kUllEta3 * kUllEta0 - kUllEta1 * kUllEta2) / (c.etaX * c.etaX);
+    c.phi1 = kUllEta0 / (c.pow2tau * (2.0 * c.pow2tau - 1.0));
+    c.pinit = c.etaX * (c.pow4mtau / (2.0 - c.pow2mtau));
+    c.minus_inv_tau = -1.0 / kUllTau;
+    const double eta[4] = {kUllEta0, kUllEta1, kUllEta2, kUllEta3};
+    for (int i = 0; i < 256; ++i) c.reg[i] = eta[i & 3] * std::pow(2.0, -kUllTau * (double)(3 + (i >> 2)));
+    for (int p = 0; p < 27; ++p) {
+        double m = (double)(1ull << p);
+        c.factor[p] = m * std::pow(m, 1.0 / kUllTau) / (1.0 + kUllV * (1.0 + kUllTau) / (2.0 * m));
+    }
+    return c;
+}
 
 #ifdef __CUDACC__
 __constant__ UllConsts c_ull;  // this header belongs to exactly one translation unit (dist_kernels.cu)

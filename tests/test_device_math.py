@@ -172,3 +172,131 @@ def test_shim_sources_are_the_product_headers():
     for h in HDRS:
         assert os.path.exists(h)
     assert "LASH_HOST_SHIM" not in open(os.path.join(ROOT, "lash_b200", "csrc", "Makefile")).read()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# estimator epilogues (lash_b200/csrc/estimators.cuh) on the CPU
+# ------------------------------------------------------------------------------------------------------------------
+EST_SRC = os.path.join(ROOT, "tests", "host_shim", "estimators.cpp")
+EPS = np.finfo(np.float64).eps
+
+
+@pytest.fixture(scope="module")
+def est(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("est") / "libestimators.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, EST_SRC])
+    L = C.CDLL(out)
+    d, i32, u32, u64, vp = C.c_double, C.c_int, C.c_uint32, C.c_uint64, C.c_void_p
+    L.dm_ull_reg.argtypes, L.dm_ull_reg.restype = [i32], d
+    L.dm_hll_len.argtypes, L.dm_hll_len.restype = [d, u32, i32, vp], d
+    L.dm_fgra.argtypes, L.dm_fgra.restype = [d, vp, i32], d
+    L.dm_ml.argtypes, L.dm_ml.restype = [u64, vp, i32, u32], d
+    L.dm_hmh_card.argtypes, L.dm_hmh_card.restype = [d, d], d
+    L.dm_hmh_similarity.argtypes, L.dm_hmh_similarity.restype = [u32, u32, d, d], d
+    L.dm_mash64.argtypes, L.dm_mash64.restype = [d, i32, i32], d
+    L.dm_mash32.argtypes, L.dm_mash32.restype = [C.c_float, i32, i32], C.c_float
+    return L
+
+
+def _simulated(algo, p, log2_per_reg, rng):
+    """Registers of a sketch that saw about 2^log2_per_reg hashes per register (negative: mostly empty)."""
+    m = 1 << p
+    if log2_per_reg < 0:
+        hit = rng.random(m) < 2.0 ** log2_per_reg
+        lvl = np.clip(rng.geometric(0.5, size=m) - 1, 0, 60 - p)
+    else:
+        hit = np.ones(m, dtype=bool)
+        lvl = np.clip(np.floor(log2_per_reg - np.log2(-np.log(rng.random(m)))), 0, 60 - p).astype(np.int64)
+    if algo == 1:
+        return (hit * (lvl + 1)).astype(np.uint8)
+    # ULL: register of the OR of a few bits around the top one
+    return (hit * (4 * (lvl + p - 1) + rng.integers(0, 4, size=m))).astype(np.uint8)
+
+
+def _close(a, b, ulps=8):
+    return (np.isnan(a) and np.isnan(b)) or a == b or abs(a - b) <= ulps * EPS * abs(b)
+
+
+@pytest.mark.parametrize("p", [4, 10, 14])
+def test_hll_len_epilogue(est, oracle, p):
+    rng = np.random.default_rng(p)
+    for lg in (-6.0, -2.0, 0.5, 3.0, 9.0, 20.0):
+        regs = _simulated(1, p, lg, rng)
+        s = 0.0
+        for r in regs:                              # register order, exact powers of two (what the kernels add)
+            s += 2.0 ** -int(r)
+        bias = C.c_int(0)
+        got = est.dm_hll_len(s, int((regs == 0).sum()), p, C.byref(bias))
+        exp = oracle.cardinality(1, p, 0, regs)
+        assert _close(got, exp), (p, lg, got, exp)
+        assert bool(bias.value) == bool(np.isnan(exp))
+
+
+@pytest.mark.parametrize("p", [3, 4, 10, 14])
+def test_ull_fgra_and_ml_epilogues(est, oracle, p):
+    """ull_fgra_finalize from (sum, counts) and ull_ml_finalize from (S, b[]) -- the statistics the tile kernels hand
+    to the epilogue -- against the oracle's estimate from the registers, across small-range, normal and saturated
+    sketches.  The ML solver's exact power-of-two / exponent constructions must leave every iteration unchanged."""
+    rng = np.random.default_rng(100 + p)
+    off = 4 * p + 4
+    reg_tab = [est.dm_ull_reg(i) for i in range(256)]
+    cases = [_simulated(2, p, lg, rng) for lg in (-5.0, -1.5, 0.0, 2.0, 7.0, 12.0, 25.0)]
+    sat = _simulated(2, p, 12.0, rng)
+    sat[:: 5] = rng.integers(252, 256, size=len(sat[:: 5]))          # saturated registers: FGRA large-range term
+    cases.append(sat)
+    small = np.zeros(1 << p, dtype=np.uint8)
+    small[:: 3] = rng.choice([4 * p - 4, 4 * p, 4 * p + 2], size=len(small[:: 3]))   # only small-range registers
+    cases.append(small)
+    cases.append(np.zeros(1 << p, dtype=np.uint8))                   # empty sketch
+    for regs in cases:
+        s, cnt = 0.0, np.zeros(8, dtype=np.uint32)
+        for r in regs:
+            r = int(r)
+            r2 = r - off
+            if r2 < 0:
+                cnt[0] += r2 < -8
+                cnt[1] += r2 == -8
+                cnt[2] += r2 == -4
+                cnt[3] += r2 == -2
+            elif r < 252:
+                s += reg_tab[r2]
+            else:
+                cnt[4 + r - 252] += 1
+        got = est.dm_fgra(s, _p(cnt), p)
+        exp = oracle.cardinality(2, p, 0, regs)
+        assert _close(got, exp), ("fgra", p, got, exp)
+        S, b = oracle.ull_ml_stats(regs, p)
+        got = est.dm_ml(S, _p(np.ascontiguousarray(b, dtype=np.int32)), p, int(regs[0]))
+        exp = oracle.cardinality(2, p, 1, regs)
+        assert _close(got, exp) or (np.isinf(got) and np.isinf(exp)), ("ml", p, got, exp)
+
+
+def test_hmh_and_mash_epilogues(est, oracle):
+    rng = np.random.default_rng(5)
+    m = 16384
+    lvl = np.clip(np.floor(7.0 - np.log2(-np.log(rng.random((2, m))))), 0, 40).astype(np.int64)
+    regs = ((lvl + 1) << 10 | rng.integers(0, 1024, size=(2, m))).astype(np.uint16)
+    regs[1, ::3] = regs[0, ::3]                                      # shared registers -> collisions
+    cards = []
+    for r in regs:
+        s, ez = 0.0, 0.0
+        for v in r:
+            lz = int(v) >> 10
+            ez += lz == 0
+            s += 2.0 ** -lz
+        got = est.dm_hmh_card(s, ez)
+        exp = oracle.cardinality(0, 14, 0, r)
+        assert _close(got, exp), (got, exp)
+        cards.append(exp)
+    c, n = oracle.hmh_counts(regs[0], regs[1])
+    sim = est.dm_hmh_similarity(c, n, cards[0], cards[1])
+    frac_exp = oracle.dist(0, 14, 16, 0, 2, False, regs[:1], regs[1:])[0, 0]
+    s = max(sim, 0.0)
+    assert _close(2.0 * s / (1.0 + s), frac_exp), (sim, frac_exp)
+    for frac in (1.0, 0.5, 1e-3, 1e-9, 0.0):
+        for k in (16, 21, 31):
+            assert _close(est.dm_mash64(frac, k, 1), min(-np.log(frac) / k, 1.0) if frac > 0 else 1.0, ulps=4)
+            assert _close(est.dm_mash64(frac, k, 0), 1.0 - frac ** (1.0 / k), ulps=4)
+            assert est.dm_mash64(frac, k, 2) == frac
+            f32 = np.float32(frac)
+            assert abs(float(est.dm_mash32(f32, k, 0)) - float(np.float32(1) - np.power(f32, np.float32(1) / np.float32(k)))) <= 2e-7
