@@ -52,6 +52,7 @@ extern "C" int lash_fastx_close(lash_fastx* r) {
     return 0;
 }
 
+extern "C" int lash_host_pack_isa(void) { return lashhost::pack_has_avx512() ? 2 : lashhost::pack_has_simd() ? 1 : 0; }
 extern "C" int lash_host_pack_has_simd(void) { return lashhost::pack_has_simd() ? 1 : 0; }
 
 extern "C" int lash_host_filter_pack(const uint8_t* seq, size_t n, uint8_t* packed, uint64_t* n_bases, int use_simd) {
@@ -64,7 +65,7 @@ extern "C" int lash_host_filter_pack(const uint8_t* seq, size_t n, uint8_t* pack
     lashhost::BaseStream bs;
     bs.attach(tmp.data(), tmp.size());
     for (uint64_t i = 0; i < have; ++i) bs.push_base((unsigned)(packed[i >> 2] >> (6 - 2 * (i & 3))) & 3u);
-    bs.append_filtered(seq, n, use_simd != 0);
+    bs.append_filtered(seq, n, use_simd);
     const uint64_t total = bs.size();
     bs.finalize();
     memcpy(packed, tmp.data(), (total + 3) / 4);

@@ -48,7 +48,8 @@ class BaseStream {
         if (bit) w_[n >> 5] &= (1ull << bit) - 1ull;
     }
     // filter + code + pack; the caller guarantees room() >= n.  Returns the number of bases kept.
-    uint64_t append_filtered(const uint8_t* s, size_t n, bool use_simd = true);
+    // use_simd: 0 scalar table, 1 best available (AVX-512 VBMI2, else AVX2+BMI2, else scalar), 2 AVX2+BMI2 at most
+    uint64_t append_filtered(const uint8_t* s, size_t n, int use_simd = 1);
     // LSB-first words -> ABI bytes, zero padding up to padded_bytes(); returns padded_bytes(size())
     uint64_t finalize();
 
@@ -64,5 +65,6 @@ class BaseStream {
 };
 
 bool pack_has_simd();
+bool pack_has_avx512();  // AVX-512 F/BW/VL/VBMI2: the 64-byte path
 
 }  // namespace lashhost

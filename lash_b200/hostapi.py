@@ -34,6 +34,7 @@ PROTOTYPES = {
     "lash_fastx_close": (i32, [vp]),
     "lash_host_filter_pack": (i32, [vp, sz, vp, C.POINTER(u64), i32]),
     "lash_host_pack_has_simd": (i32, []),
+    "lash_host_pack_isa": (i32, []),
     "lash_host_sketch_files_regs": (i32, [vp, i32, i32, i32, u64, C.POINTER(cp), u64, i32, u64, vp, C.POINTER(SketchFilesStats)]),
     "lash_host_sketch_files": (i32, [vp, i32, i32, i32, u64, C.POINTER(cp), u64, cp, i32, C.POINTER(SketchFilesStats)]),
     "lash_host_pack_files_dry": (i32, [C.POINTER(cp), u64, i32, i32, u64, C.POINTER(SketchFilesStats)]),
@@ -98,8 +99,9 @@ def read_fastx(path: str) -> Iterator[tuple[bytes, bytes]]:
         lib().lash_fastx_close(h)
 
 
-def filter_pack(seq: bytes, packed: np.ndarray | None = None, n_bases: int = 0, simd: bool = True) -> tuple[np.ndarray, int]:
-    """filter_out_n + 2-bit pack; appends to an existing packed stream when given."""
+def filter_pack(seq: bytes, packed: np.ndarray | None = None, n_bases: int = 0, simd: bool | int = True) -> tuple[np.ndarray, int]:
+    """filter_out_n + 2-bit pack; appends to an existing packed stream when given.
+    simd: False/0 scalar table, True/1 the best path of this CPU, 2 the AVX2+BMI2 path at most."""
     need = (n_bases + len(seq) + 3) // 4 + 16
     buf = np.zeros(need, dtype=np.uint8)
     if packed is not None:

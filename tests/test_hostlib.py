@@ -38,10 +38,11 @@ def _dirty(rng, n):
     return bytes(rng.choice(alphabet) for _ in range(n))
 
 
-@pytest.mark.parametrize("simd", [False, True])
+@pytest.mark.parametrize("simd", [0, 2, 1], ids=["scalar", "avx2", "best"])
 def test_filter_pack_matches_reference_front_end(oracle, simd):
     """filter_out_n (utils.rs:33-41) + KSeq 2-bit codes: C++ packer == oracle filter + numpy packing,
-    on clean and dirty input, at every length / alignment around the 32-byte SIMD block."""
+    on clean and dirty input, at every length / alignment around the 32- and 64-byte SIMD blocks.  "best" is the
+    AVX-512 VBMI2 path where the CPU has it (lash_host_pack_isa() == 2), else the same as "avx2"."""
     if simd and not hostapi.lib().lash_host_pack_has_simd():
         pytest.skip("no AVX2+BMI2 on this CPU")
     rng = random.Random(5)
@@ -55,14 +56,15 @@ def test_filter_pack_matches_reference_front_end(oracle, simd):
             assert np.array_equal(got, want), (n, simd)
 
 
-def test_filter_pack_appends_at_any_base_offset(oracle):
+@pytest.mark.parametrize("simd", [0, 2, 1], ids=["scalar", "avx2", "best"])
+def test_filter_pack_appends_at_any_base_offset(oracle, simd):
     rng = random.Random(6)
     whole = b""
     packed, nb = None, 0
-    for _ in range(60):
-        piece = _dirty(rng, rng.randrange(0, 90))
+    for _ in range(80):
+        piece = _dirty(rng, rng.randrange(0, 200))       # pieces on both sides of the 64-byte block, every bit offset
         whole += piece
-        packed, nb = hostapi.filter_pack(piece, packed, nb)
+        packed, nb = hostapi.filter_pack(piece, packed, nb, simd=simd)
         kept = oracle.filter_out_n(whole)
         assert nb == len(kept)
         assert np.array_equal(packed, pack_codes(encode_record(kept)))
@@ -72,7 +74,8 @@ def test_all_256_byte_values_classified_like_filter_out_n(oracle):
     s = bytes(range(256)) * 3
     got, nb = hostapi.filter_pack(s, simd=True)
     got2, nb2 = hostapi.filter_pack(s, simd=False)
-    assert nb == nb2 == 12 and np.array_equal(got, got2)
+    got3, nb3 = hostapi.filter_pack(s, simd=2)
+    assert nb == nb2 == nb3 == 12 and np.array_equal(got, got2) and np.array_equal(got, got3)
     assert np.array_equal(got, pack_codes(encode_record(b"ACGT" * 3)))
 
 
@@ -216,3 +219,26 @@ def test_parameters_json_is_what_serde_json_writes(tmp_path):
         '{\n  "algorithm": "ull",\n  "k": "16",\n  "molecule": "nucleotide",\n  "precision": "10",\n  "seed": "42"\n}')
     hostapi.check(hostapi.lib().lash_host_write_parameters(out.encode(), ALGO_HMH, 14, 21, 7))
     assert json.load(open(out + "_parameters.json")) == {"algorithm": "hmh", "k": "21", "molecule": "nucleotide", "seed": "7"}
+
+
+def test_filter_pack_simd_paths_agree_with_scalar_on_long_dirty_input():
+    """Differential check of the 32- and 64-byte SIMD packers against the scalar table on long inputs: FASTA-like text
+    (80-column lines), runs of N / lower case, and uniformly random bytes, appended in pieces of random size."""
+    rng = np.random.default_rng(11)
+    text = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=300_000)
+    text[80::81] = 10                                                     # newlines
+    for o in rng.integers(0, len(text) - 500, size=40):
+        text[o:o + int(rng.integers(1, 400))] = rng.choice(np.frombuffer(b"Nacgtn", dtype=np.uint8))
+    noise = rng.integers(0, 256, size=100_000, dtype=np.uint8)
+    data = np.concatenate([text, noise, text[::-1]]).tobytes()
+    cuts = sorted(set([0, len(data)] + [int(x) for x in rng.integers(0, len(data), size=25)]))
+    ref = None
+    for simd in (0, 2, 1):
+        packed, nb = None, 0
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            packed, nb = hostapi.filter_pack(data[a:b], packed, nb, simd=simd)
+        if ref is None:
+            ref = (packed, nb)
+            assert nb > 500_000
+        else:
+            assert nb == ref[1] and np.array_equal(packed, ref[0]), simd
