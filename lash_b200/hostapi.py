@@ -101,7 +101,7 @@ def read_fastx(path: str) -> Iterator[tuple[bytes, bytes]]:
 
 def filter_pack(seq: bytes, packed: np.ndarray | None = None, n_bases: int = 0, simd: bool | int = True) -> tuple[np.ndarray, int]:
     """filter_out_n + 2-bit pack; appends to an existing packed stream when given.
-    simd: False/0 scalar table, True/1 the best path of this CPU, 2 the AVX2+BMI2 path at most."""
+    simd: False/0 scalar table, True/1 the default SIMD path, 2 AVX2+BMI2, 3 AVX-512 VBMI2 (where the CPU has it)."""
     need = (n_bases + len(seq) + 3) // 4 + 16
     buf = np.zeros(need, dtype=np.uint8)
     if packed is not None:

@@ -38,13 +38,18 @@ def _dirty(rng, n):
     return bytes(rng.choice(alphabet) for _ in range(n))
 
 
-@pytest.mark.parametrize("simd", [0, 2, 1], ids=["scalar", "avx2", "best"])
+def _need_isa(simd):
+    if simd in (1, 2) and not hostapi.lib().lash_host_pack_has_simd():
+        pytest.skip("no AVX2+BMI2 on this CPU")
+    if simd == 3 and hostapi.lib().lash_host_pack_isa() < 2:
+        pytest.skip("no AVX-512 VBMI2 on this CPU")
+
+
+@pytest.mark.parametrize("simd", [0, 2, 3, 1], ids=["scalar", "avx2", "avx512", "default"])
 def test_filter_pack_matches_reference_front_end(oracle, simd):
     """filter_out_n (utils.rs:33-41) + KSeq 2-bit codes: C++ packer == oracle filter + numpy packing,
-    on clean and dirty input, at every length / alignment around the 32- and 64-byte SIMD blocks.  "best" is the
-    AVX-512 VBMI2 path where the CPU has it (lash_host_pack_isa() == 2), else the same as "avx2"."""
-    if simd and not hostapi.lib().lash_host_pack_has_simd():
-        pytest.skip("no AVX2+BMI2 on this CPU")
+    on clean and dirty input, at every length / alignment around the 32- and 64-byte SIMD blocks."""
+    _need_isa(simd)
     rng = random.Random(5)
     for n in list(range(0, 100)) + [127, 128, 129, 1000, 4097, 65536 + 31]:
         for maker in (lambda m: bytes(rng.choice(b"ACGT") for _ in range(m)), lambda m: _dirty(rng, m)):
@@ -56,8 +61,9 @@ def test_filter_pack_matches_reference_front_end(oracle, simd):
             assert np.array_equal(got, want), (n, simd)
 
 
-@pytest.mark.parametrize("simd", [0, 2, 1], ids=["scalar", "avx2", "best"])
+@pytest.mark.parametrize("simd", [0, 2, 3, 1], ids=["scalar", "avx2", "avx512", "default"])
 def test_filter_pack_appends_at_any_base_offset(oracle, simd):
+    _need_isa(simd)
     rng = random.Random(6)
     whole = b""
     packed, nb = None, 0
@@ -75,7 +81,8 @@ def test_all_256_byte_values_classified_like_filter_out_n(oracle):
     got, nb = hostapi.filter_pack(s, simd=True)
     got2, nb2 = hostapi.filter_pack(s, simd=False)
     got3, nb3 = hostapi.filter_pack(s, simd=2)
-    assert nb == nb2 == nb3 == 12 and np.array_equal(got, got2) and np.array_equal(got, got3)
+    got4, nb4 = hostapi.filter_pack(s, simd=3)       # falls back to AVX2 / scalar where there is no AVX-512
+    assert nb == nb2 == nb3 == nb4 == 12 and np.array_equal(got, got2) and np.array_equal(got, got3) and np.array_equal(got, got4)
     assert np.array_equal(got, pack_codes(encode_record(b"ACGT" * 3)))
 
 
@@ -233,7 +240,7 @@ def test_filter_pack_simd_paths_agree_with_scalar_on_long_dirty_input():
     data = np.concatenate([text, noise, text[::-1]]).tobytes()
     cuts = sorted(set([0, len(data)] + [int(x) for x in rng.integers(0, len(data), size=25)]))
     ref = None
-    for simd in (0, 2, 1):
+    for simd in (0, 2, 3, 1):
         packed, nb = None, 0
         for a, b in zip(cuts[:-1], cuts[1:]):
             packed, nb = hostapi.filter_pack(data[a:b], packed, nb, simd=simd)
