@@ -20,6 +20,7 @@
 #include <type_traits>
 
 #include "estimators.cuh"
+#include "dist_tables.cuh"
 #include "kernels.h"
 #include "registers.cuh"
 
@@ -28,51 +29,6 @@ namespace lash {
 
 constexpr int kDistThreads = 256;
 constexpr int kChunkBytes = 1024;  // bytes of registers per sketch per stage
-
-// sentinel contribution of a register outside FGRA's table range [4p+4, 252): makes the running sum
-// explode (>= 2^600) so the pair is re-done by the exact path; normal sums are <= 2^26 * 0.85
-#define LASH_FGRA_SENTINEL 0x1p600
-#define LASH_FGRA_SENTINEL_TEST 0x1p500
-
-// ------------------------------------------------------------------------------------------------
-// register-pair primitives (plain 32-bit integer ops; the byte-SIMD "video" intrinsics are emulated
-// with ~10 instructions each on sm_100 and were the bottleneck of the first version)
-// ------------------------------------------------------------------------------------------------
-// ULL union of two register bytes == pack(unpack(a) | unpack(b))  (ultraloglog merge, utils.rs:260-262)
-__device__ __forceinline__ uint32_t ull_merge_fast(uint32_t a, uint32_t b) {
-    const uint32_t hi = max(a, b), lo = min(a, b);
-    const uint32_t d = min((hi >> 2) - (lo >> 2), 3u);
-    // 3-bit window (1,w1,w0) of the smaller register, 0 if it is empty (valid non-empty registers are >= 8)
-    const uint32_t x = (lo & 3u) | (min(lo, 4u) & 4u);
-    return hi | ((x >> d) & 3u);
-}
-
-// hash4j contribute(): alpha contribution (scaled by 2^64) of one register byte, and the bit pattern
-// W it adds to the b[] statistics: b[j] += bit j of W  (W = unpack(r) >> (p-1) for valid registers)
-__device__ __forceinline__ uint64_t ml_ret_of(uint32_t r, int p) {
-    const int r2 = (int)r - 4 * p - 4;
-    if (r2 < 0) {
-        uint64_t ret = 4;
-        if (r2 == -2 || r2 == -8) ret -= 2;
-        if (r2 == -2 || r2 == -4) ret -= 1;
-        return ret << (62 - p);
-    }
-    const int k = r2 >> 2;
-    uint64_t ret = 0xE000000000000000ULL;
-    ret -= (uint64_t)(r & 1u) << 63;
-    ret -= (uint64_t)((r >> 1) & 1u) << 62;
-    return ret >> (k + p);
-}
-__device__ __forceinline__ uint64_t ml_w_of(uint32_t r, int p) {
-    const int r2 = (int)r - 4 * p - 4;
-    if (r2 < 0) {
-        uint64_t w = 0;
-        if (r2 == -2 || r2 == -8) w |= 1;
-        if (r2 == -2 || r2 == -4) w |= 2;
-        return w;
-    }
-    return (uint64_t)(4u | (r & 3u)) << (r2 >> 2);  // b[k] += y0, b[k+1] += y1, b[k+2] += 1
-}
 
 struct SharedTables {
     const double* fgra_tab;    // [256] contribution of a merged register byte (sentinel outside [4p+4, 252))
@@ -629,10 +585,6 @@ constexpr int kTabThreads = 512;
 constexpr int kTabTR = 32, kTabTQ = 64;   // pairs tile of a CTA
 constexpr int kTabChunk = 256;            // registers per sketch per stage
 
-__device__ __forceinline__ uint32_t fgra_code(uint32_t r, uint32_t base) {
-    const uint32_t c = min(r - base + 1u, 127u);  // r < base wraps to a huge value -> 127
-    return r ? c : 0u;
-}
 
 // one table entry: low word from the first plane, high word from the second (two conflict-free LDS.32)
 __device__ __forceinline__ double tab_lookup(uint32_t saddr, uint32_t plane_bytes) {
@@ -680,13 +632,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParam
         if (mn != 0xffffffffu) base = max(base, mn & ~3u);
     }
     for (uint32_t e = threadIdx.x; e < (uint32_t)(kTabN * kTabN); e += kTabThreads) {
-        const uint32_t ca = e >> 7, cb = e & 127u;
-        double v = LASH_FGRA_SENTINEL;
-        if (ca != 127u && cb != 127u) {
-            const uint32_t ra = ca ? ca + base - 1u : 0u, rb = cb ? cb + base - 1u : 0u;
-            const uint32_t m = ull_merge1(ra, rb);
-            if (m >= off && m < 252u) v = c_ull.reg[m - off];
-        }
+        const double v = fgra_tab_entry(e >> 7, e & 127u, base, off, c_ull.reg);
         T[e] = (uint32_t)__double2loint(v);
         T[e + kTabN * kTabN] = (uint32_t)__double2hiint(v);
     }
@@ -867,9 +813,7 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
     const int p = dp.p;
     const uint32_t base = (uint32_t)(4 * p - 4);
     for (uint32_t e = threadIdx.x; e < (uint32_t)(kTabN * kTabN); e += kMlTabThreads) {
-        const uint32_t ca = e >> 7, cb = e & 127u;
-        const uint32_t ra = (ca && ca != 127u) ? ca + base - 1u : 0u, rb = (cb && cb != 127u) ? cb + base - 1u : 0u;
-        const uint32_t m = ull_merge1(ra, rb);
+        const uint32_t m = ml_tab_merged(e >> 7, e & 127u, base);
         const uint64_t ret = ml_ret_of(m, p);
         R[e] = (uint32_t)ret;
         R[e + kTabN * kTabN] = (uint32_t)(ret >> 32);

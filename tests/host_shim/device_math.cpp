@@ -40,6 +40,7 @@ static inline uint32_t __vmaxu2(uint32_t a, uint32_t b) {
 }
 
 #include "../../lash_b200/csrc/registers.cuh"
+#include "../../lash_b200/csrc/dist_tables.cuh"
 
 using namespace lash;
 
@@ -93,4 +94,22 @@ void dm_ull_fast(const uint32_t* ghi, uint64_t n, int p, int drop4, uint32_t* id
 uint32_t dm_ull_update(uint32_t r, uint32_t u) { return ull_update(r, u); }
 uint32_t dm_ull_merge1(uint32_t a, uint32_t b) { return ull_merge1(a, b); }
 uint32_t dm_ull_merge4(uint32_t a, uint32_t b) { return ull_merge4(a, b); }
+uint32_t dm_ull_merge_fast(uint32_t a, uint32_t b) { return ull_merge_fast(a, b); }
+
+// ---- pair tables of the distance kernels (dist_tables.cuh) ----------------------------------------------------------------
+uint32_t dm_fgra_code(uint32_t r, uint32_t base) { return fgra_code(r, base); }
+// the whole 128 x 128 FGRA table exactly as dist_fgra_tab_kernel builds it; returns the sentinel value
+double dm_fgra_table(uint32_t base, int p, const double* reg, double* out) {
+    for (uint32_t e = 0; e < 128u * 128u; ++e) out[e] = fgra_tab_entry(e >> 7, e & 127u, base, (uint32_t)(4 * p + 4), reg);
+    return LASH_FGRA_SENTINEL;
+}
+// the ML tables exactly as dist_ml_tab_kernel builds them (R = contribution to S, W = bit pattern added to b[])
+void dm_ml_tables(int p, uint64_t* R, uint32_t* W) {
+    const uint32_t base = (uint32_t)(4 * p - 4);
+    for (uint32_t e = 0; e < 128u * 128u; ++e) {
+        const uint32_t m = ml_tab_merged(e >> 7, e & 127u, base);
+        R[e] = ml_ret_of(m, p);
+        W[e] = (uint32_t)ml_w_of(m, p);
+    }
+}
 }

@@ -300,3 +300,82 @@ def test_hmh_and_mash_epilogues(est, oracle):
             assert est.dm_mash64(frac, k, 2) == frac
             f32 = np.float32(frac)
             assert abs(float(est.dm_mash32(f32, k, 0)) - float(np.float32(1) - np.power(f32, np.float32(1) / np.float32(k)))) <= 2e-7
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# pair tables of the distance kernels (lash_b200/csrc/dist_tables.cuh) on the CPU
+# ------------------------------------------------------------------------------------------------------------------
+def _valid_registers(p):
+    return np.array([0, 4 * p - 4, 4 * p, 4 * p + 2] + list(range(4 * p + 4, 256)), dtype=np.uint8)
+
+
+def _merge_pairs(oracle, a, b, p):
+    m = 1 << p
+    pad = (-len(a)) % m
+    a2, b2 = np.concatenate([a, np.zeros(pad, np.uint8)]), np.concatenate([b, np.zeros(pad, np.uint8)])
+    out = np.concatenate([oracle.ull_merge(a2[o:o + m], b2[o:o + m], p) for o in range(0, len(a2), m)])
+    return out[: len(a)]
+
+
+@pytest.mark.parametrize("p,base_shift", [(10, 0), (10, 24), (14, 0), (14, 60), (4, 0)])
+def test_fgra_pair_table_reproduces_the_merge_and_its_contribution(dm, est, oracle, p, base_shift):
+    """Every entry of the 128 x 128 table dist_fgra_tab_kernel builds (for a window anchored at `base`) equals
+    REGISTER_CONTRIBUTIONS[merge(ra, rb) - (4p+4)] of the two registers the codes stand for, or the sentinel exactly
+    when a register is outside the window or the merged register needs the small- / large-range treatment."""
+    dm.dm_fgra_code.argtypes, dm.dm_fgra_code.restype = [C.c_uint32, C.c_uint32], C.c_uint32
+    dm.dm_fgra_table.argtypes, dm.dm_fgra_table.restype = [C.c_uint32, C.c_int, C.c_void_p, C.c_void_p], C.c_double
+    dm.dm_ull_merge_fast.argtypes, dm.dm_ull_merge_fast.restype = [C.c_uint32, C.c_uint32], C.c_uint32
+    reg = np.array([est.dm_ull_reg(i) for i in range(256)], dtype=np.float64)
+    off, base = 4 * p + 4, 4 * p - 4 + base_shift
+    table = np.empty(128 * 128, dtype=np.float64)
+    sentinel = dm.dm_fgra_table(base, p, _p(reg), _p(table))
+    table = table.reshape(128, 128)
+    # the kernel's contract: base <= every non-empty register present (base = 4p-4, or the sets' smallest register
+    # rounded down to a multiple of 4), so the registers a table can meet are 0 and the valid ones >= base
+    valid = _valid_registers(p)
+    valid = valid[(valid == 0) | (valid >= base)]
+    codes = np.array([dm.dm_fgra_code(int(r), base) for r in valid])
+    inside = codes != 127
+    # recoding: 0 <-> empty, 1..126 <-> base .. base+125, everything above 127; injective inside the window
+    assert codes[0] == 0
+    for r, c in zip(valid[1:], codes[1:]):
+        assert c == (int(r) - base + 1 if int(r) <= base + 125 else 127)
+    assert dm.dm_fgra_code(max(base - 2, 1), base) == 127                 # far below the window (cannot happen): flagged
+    a = np.repeat(valid[inside], inside.sum())
+    b = np.tile(valid[inside], inside.sum())
+    merged = _merge_pairs(oracle, a, b, p).astype(np.int64)
+    fast = np.array([dm.dm_ull_merge_fast(int(x), int(y)) for x, y in zip(a, b)])
+    assert np.array_equal(fast, merged)                                   # the ALU merge of K4 agrees too
+    ca, cb = np.repeat(codes[inside], inside.sum()), np.tile(codes[inside], inside.sum())
+    got = table[ca, cb]
+    in_range = (merged >= off) & (merged < 252)
+    assert np.array_equal(got[in_range], reg[merged[in_range] - off])
+    assert np.all(got[~in_range] == sentinel)
+    assert np.all(table[127, :] == sentinel) and np.all(table[:, 127] == sentinel)
+
+
+@pytest.mark.parametrize("p", [4, 10, 14])
+def test_ml_pair_tables_sum_to_the_ml_statistics(dm, oracle, p):
+    """R / W tables of dist_ml_tab_kernel: summing R (mod 2^64) and counting the bits of W over the registers of two
+    sketches gives exactly the (S, b[]) hash4j's contribute() produces on the merged sketch."""
+    dm.dm_fgra_code.argtypes, dm.dm_fgra_code.restype = [C.c_uint32, C.c_uint32], C.c_uint32
+    dm.dm_ml_tables.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    R, W = np.empty(128 * 128, dtype=np.uint64), np.empty(128 * 128, dtype=np.uint32)
+    dm.dm_ml_tables(p, _p(R), _p(W))
+    rng = np.random.default_rng(p)
+    m, base = 1 << p, 4 * p - 4
+    for lg in (-3.0, 0.0, 3.0, 10.0, 20.0):
+        a, b = _simulated(2, p, lg, rng), _simulated(2, p, lg + 1.0, rng)
+        a[a > base + 125] = base + 125
+        b[b > base + 125] = base + 125                                    # keep every register inside the table window
+        ca = np.array([dm.dm_fgra_code(int(r), base) for r in a])
+        cb = np.array([dm.dm_fgra_code(int(r), base) for r in b])
+        assert ca.max() < 127 and cb.max() < 127
+        e = ca * 128 + cb
+        S = int(np.sum(R[e].astype(object)) % (1 << 64))
+        bits = np.zeros(66, dtype=np.int64)
+        for j in range(32):
+            bits[j] = int(((W[e] >> np.uint32(j)) & np.uint32(1)).sum())
+        S_exp, b_exp = oracle.ull_ml_stats(oracle.ull_merge(a, b, p), p)
+        assert S == S_exp
+        assert np.array_equal(bits, b_exp.astype(np.int64))
