@@ -21,15 +21,9 @@
 
 #include "kernels.h"
 #include "registers.cuh"
+#include "kmer_windows.cuh"
 
 namespace lash {
-
-__device__ __forceinline__ uint32_t rc16(uint32_t f) {
-    // reverse-complement of 16 bases held big-endian (first base in the top 2 bits)
-    uint32_t y = __brev(f);
-    y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
-    return ~y;
-}
 
 // ------------------------------------------------------------------------------------------------
 // Private (shared-memory) accumulators.  They are NOT kept in the byte/halfword register domain:
@@ -189,7 +183,6 @@ __device__ __forceinline__ void global_update(uint32_t* gacc, uint32_t idx, uint
 // k-mer width classes: the reference's own dispatch is k<=14 / 16 / else (utils.rs:466-502); here the
 // split is by what fits one 32-bit word, with k == 16 (lash's default) special-cased because the
 // window IS the word (no shift, no mask).
-enum KMode : int { K16 = 0, KNARROW = 1, KWIDE = 2 };
 constexpr int kGroup = 16;  // k-mers whose atomics are deferred together (one 32-bit word of bases)
 
 // CTA size is a template parameter so that the register budget follows it.  Measured on B200 (tools/variant_sweep):
@@ -316,25 +309,7 @@ __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
                 // canonical masked k-mer starting at base i of this word (sh = 2*i): funnel-shift windows
                 // of the forward stream and of the reverse-complemented stream, then min
                 auto kmer = [&](const int sh, uint32_t& klo, uint32_t& khi) {
-                    if (KM == K16) {
-                        klo = min(__funnelshift_l(B0, A0, sh), __funnelshift_r(Ar, Br, sh));
-                        khi = 0u;
-                    } else if (KM == KNARROW) {
-                        const uint32_t fw = __funnelshift_l(B0, A0, sh) >> narrow_shr;
-                        const uint32_t rc = __funnelshift_r(Ar, Br, sh) & narrow_mask;
-                        klo = min(fw, rc);
-                        khi = 0u;
-                    } else {
-                        uint32_t fhi = __funnelshift_l(B0, A0, sh), flo = __funnelshift_l(C0, B0, sh);
-                        flo = __funnelshift_r(flo, fhi, wide_shr);
-                        fhi >>= wide_shr;
-                        const uint32_t rlo = __funnelshift_r(Ar, Br, sh);
-                        const uint32_t rhi = __funnelshift_r(Br, Cr, sh) & wide_mask_hi;
-                        const uint64_t f64 = mk64(flo, fhi), r64 = mk64(rlo, rhi);
-                        const uint64_t c64 = f64 < r64 ? f64 : r64;
-                        klo = (uint32_t)c64;
-                        khi = (uint32_t)(c64 >> 32);
-                    }
+                    canonical_kmer<KM>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, klo, khi);
                 };
                 // exact, checked, rolled path: partial validity, rare hashes, global accumulators
                 auto exact_block = [&](const uint32_t mask16) {

@@ -22,6 +22,12 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {  
     s &= 31u;
     return s ? (lo >> s) | (hi << (32u - s)) : lo;
 }
+static inline uint32_t __brev(uint32_t x) {
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    return __builtin_bswap32(x);
+}
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
@@ -41,6 +47,7 @@ static inline uint32_t __vmaxu2(uint32_t a, uint32_t b) {
 
 #include "../../lash_b200/csrc/registers.cuh"
 #include "../../lash_b200/csrc/dist_tables.cuh"
+#include "../../lash_b200/csrc/kmer_windows.cuh"
 
 using namespace lash;
 
@@ -87,6 +94,32 @@ void dm_ull_fast(const uint32_t* ghi, uint64_t n, int p, int drop4, uint32_t* id
         const uint32_t v = shl_clamp(1u << p, bfind32(t));  // bit j of cell word 0 <=> nlz = 31 - j
         rare[i] = t == 0u;
         nlz[i] = v ? 31u - bfind32(v) : 0xffffffffu;
+    }
+}
+
+// ---- canonical k-mers as the sketch kernel extracts them (kmer_windows.cuh) --------------------------------------------
+// packed: 2-bit bases, first base in the high bits of byte 0 (the ABI layout); out[s] = canonical k-mer starting at base s
+void dm_kmers(const uint8_t* packed, uint64_t n_bytes, uint64_t n_bases, int k, uint64_t* out) {
+    auto word = [&](uint64_t j) -> uint32_t {  // 16 bases, first base in the top bits (what the kernel holds after its byte swap)
+        uint32_t w = 0;
+        for (int b = 0; b < 4; ++b) w = (w << 8) | (4 * j + b < n_bytes ? packed[4 * j + b] : 0u);
+        return w;
+    };
+    const bool wide = k > 16;
+    const uint32_t narrow_shr = wide ? 0u : (uint32_t)(32 - 2 * k);
+    const uint32_t narrow_mask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+    const uint32_t wide_shr = wide ? (uint32_t)(64 - 2 * k) : 0u;
+    const uint32_t wide_mask_hi = (k >= 32) ? 0xffffffffu : ((1u << ((2 * k - 32) & 31)) - 1u);
+    for (uint64_t s0 = 0; s0 + (uint64_t)k <= n_bases; ++s0) {
+        const uint64_t j = s0 >> 4;
+        const int sh = 2 * (int)(s0 & 15);
+        const uint32_t A0 = word(j), B0 = word(j + 1), C0 = word(j + 2);
+        const uint32_t Ar = rc16(A0), Br = rc16(B0), Cr = rc16(C0);
+        uint32_t klo, khi;
+        if (k == 16) canonical_kmer<K16>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, klo, khi);
+        else if (!wide) canonical_kmer<KNARROW>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, klo, khi);
+        else canonical_kmer<KWIDE>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, klo, khi);
+        out[s0] = ((uint64_t)khi << 32) | klo;
     }
 }
 

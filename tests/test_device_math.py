@@ -379,3 +379,25 @@ def test_ml_pair_tables_sum_to_the_ml_statistics(dm, oracle, p):
         S_exp, b_exp = oracle.ull_ml_stats(oracle.ull_merge(a, b, p), p)
         assert S == S_exp
         assert np.array_equal(bits, b_exp.astype(np.int64))
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 12, 14, 15, 16, 17, 21, 24, 31, 32])
+def test_funnel_shift_kmer_windows_equal_string_level_canonical_kmers(dm, oracle, k):
+    """kmer_windows.cuh (the sketch kernel's k-mer extraction: funnel-shift windows of the packed stream and of its per-word
+    reverse complement, min, mask) against the oracle's k-mers for every start position, on random sequence plus
+    homopolymers and reverse-complement palindromes."""
+    from lash_b200 import hostapi
+    dm.dm_kmers.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(k)
+    seqs = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n)) for n in (k, k + 1, 63, 64, 65, 500)]
+    seqs += [b"A" * 70, b"T" * 70, b"ACGT" * 20, b"AATT" * 18 + b"GC"]
+    for seq in seqs:
+        if len(seq) < k:
+            continue
+        packed, nb = hostapi.filter_pack(seq, simd=0)
+        assert nb == len(seq)
+        buf = np.concatenate([packed, np.zeros(16, dtype=np.uint8)])
+        out = np.zeros(len(seq) - k + 1, dtype=np.uint64)
+        dm.dm_kmers(_p(buf), len(packed), len(seq), k, _p(out))
+        exp = oracle.canonical_kmers(seq, k)
+        assert np.array_equal(out, np.asarray(exp, dtype=np.uint64)), (k, len(seq))
