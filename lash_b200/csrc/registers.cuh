@@ -54,6 +54,16 @@ __device__ __forceinline__ uint32_t ull_merge4(uint32_t a, uint32_t b) {
     return hi | (x & 0x03030303u);
 }
 
+// Shared-memory ULL cell of the sketch kernel -> register.  The cell is two words of "seen nlz" bits: word 0 bit j <=>
+// nlz = 31-j was seen, word 1 bit j <=> nlz = 63-j.  nlz-mask M = brev(w0) | brev(w1) << 32, unpacked hash prefix =
+// M << (p-1), register = ultraloglog pack(prefix) -- exact because sequential add()s equal pack(OR of 1 << u).
+__device__ __forceinline__ uint32_t ull_cell_to_reg(uint32_t w0, uint32_t w1, int p) {
+    if ((w0 | w1) == 0u) return 0u;
+    const uint64_t m = mk64(__brev(w0), __brev(w1)) << (p - 1);  // unpacked hash prefix
+    const uint32_t u = 63u - (uint32_t)__clzll((long long)m);   // u >= p-1 >= 2
+    return (u << 2) | ((uint32_t)(m >> (u - 2u)) & 3u);          // ultraloglog pack()
+}
+
 template <int ALGO>
 struct Cell;
 

@@ -96,11 +96,7 @@ struct SmemAcc<ULL> {
         if (~lds_u32(saddr) & bit) red_or(saddr, bit);
     }
     __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int p) {
-        const uint32_t w0 = acc[2u * cell], w1 = acc[2u * cell + 1u];
-        if ((w0 | w1) == 0u) return 0u;
-        const uint64_t m = mk64(__brev(w0), __brev(w1)) << (p - 1);  // unpacked hash prefix
-        const uint32_t u = 63u - (uint32_t)__clzll((long long)m);   // u >= p-1 >= 2
-        return (u << 2) | ((uint32_t)(m >> (u - 2u)) & 3u);          // ultraloglog pack()
+        return ull_cell_to_reg(acc[2u * cell], acc[2u * cell + 1u], p);
     }
 };
 template <>

@@ -123,6 +123,22 @@ void dm_kmers(const uint8_t* packed, uint64_t n_bytes, uint64_t n_bases, int k, 
     }
 }
 
+// ---- shared-memory ULL cell (two words of seen-nlz bits) and its conversion at flush ---------------------------------------
+// adds the hashes h[0..n) to an empty cell with the EXACT path's rule (SmemAcc<ULL>::exact: word 0 takes nlz < 32, word 1
+// the rest, bit index = raw bfind result) and converts the cell with ull_cell_to_reg; idx_out = the register index of h[0]
+uint32_t dm_ull_cell(const uint64_t* h, uint64_t n, int p, uint32_t* idx_out, uint32_t* w_out) {
+    uint32_t w[2] = {0u, 0u};
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t lo = (uint32_t)h[i], hi = (uint32_t)(h[i] >> 32);
+        const uint32_t yh = __funnelshift_l(lo, hi, p), yl = (lo << p) | ((1u << p) - 1u);
+        w[yh ? 0 : 1] |= 1u << bfind32(yh ? yh : yl);
+    }
+    *idx_out = (uint32_t)(h[0] >> (64 - p));
+    w_out[0] = w[0];
+    w_out[1] = w[1];
+    return ull_cell_to_reg(w[0], w[1], p);
+}
+
 // ---- register algebra -----------------------------------------------------------------------------------------------
 uint32_t dm_ull_update(uint32_t r, uint32_t u) { return ull_update(r, u); }
 uint32_t dm_ull_merge1(uint32_t a, uint32_t b) { return ull_merge1(a, b); }

@@ -401,3 +401,32 @@ def test_funnel_shift_kmer_windows_equal_string_level_canonical_kmers(dm, oracle
         dm.dm_kmers(_p(buf), len(packed), len(seq), k, _p(out))
         exp = oracle.canonical_kmers(seq, k)
         assert np.array_equal(out, np.asarray(exp, dtype=np.uint64)), (k, len(seq))
+
+
+@pytest.mark.parametrize("p", [3, 10, 14, 20, 26])
+def test_ull_smem_cell_flush_equals_sequential_updates(dm, oracle, p):
+    """The sketch kernel keeps, per register, two words of "seen nlz" bits and converts them once at flush
+    (ull_cell_to_reg).  For sets of hashes that fall into one register -- a few, many, with very long zero runs -- the
+    converted cell must equal the register ultraloglog reaches by sequential add()s (ull_update from the empty register)."""
+    dm.dm_ull_cell.argtypes, dm.dm_ull_cell.restype = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p], C.c_uint32
+    dm.dm_ull_update.argtypes, dm.dm_ull_update.restype = [C.c_uint32, C.c_uint32], C.c_uint32
+    rng = np.random.default_rng(p)
+    for n in (1, 2, 3, 7, 50, 400):
+        for zmax in (4, 20, 64 - p):
+            idx = int(rng.integers(0, 1 << p))
+            hs = []
+            for _ in range(n):
+                z = int(rng.integers(0, zmax + 1))                        # leading zeros after the index
+                below = 63 - p - z
+                tail = ((1 << below) | int(rng.integers(0, 1 << below))) if below >= 0 else 0
+                hs.append((idx << (64 - p)) | tail)
+            h = np.array(hs, dtype=np.uint64)
+            out_idx, w = C.c_uint32(), np.zeros(2, dtype=np.uint32)
+            reg = dm.dm_ull_cell(_p(h), n, p, C.byref(out_idx), _p(w))
+            assert out_idx.value == idx
+            exp = 0
+            for x in hs:
+                body = ((x << p) & ((1 << 64) - 1)) | ((1 << p) - 1)          # nlz = clz(~(~h << p))
+                nlz = 64 - body.bit_length()
+                exp = dm.dm_ull_update(exp, nlz + p - 1)
+            assert reg == exp, (p, n, zmax)
