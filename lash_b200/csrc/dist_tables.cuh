@@ -80,4 +80,147 @@ __device__ __forceinline__ uint32_t ml_tab_merged(uint32_t ca, uint32_t cb, uint
     return ull_merge1(ra, rb);
 }
 
+// ---- K4 / K4c: tables in shared memory and the ML accumulator -------------------------------------------------------------
+struct SharedTables {
+    const double* fgra_tab;    // [256] contribution of a merged register byte (sentinel outside [4p+4, 252))
+    const uint64_t* ml_ret;    // [256]
+    const uint32_t* ml_wlo;    // [256] low 32 bits of W
+    const double* hll_pow;     // [256] 2^-r
+};
+
+// carry-save adder on 32-bit bit-planes: (a + b + c) -> sum (weight 1) and carry (weight 2); 2 LOP3
+__device__ __forceinline__ void csa(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t u = a ^ b;
+    carry = (a & b) | (u & c);
+    sum = u ^ c;
+}
+
+
+constexpr int kMlPlanes = 27;  // counts up to 2^26 registers
+// NPL = bit planes of the vertical counters: a count never exceeds the 2^p registers of a sketch, so p + 1 planes are
+// enough; the pair-table kernel is instantiated for 12 / 16 / 27 planes (15 fewer planes = 30 fewer live registers and
+// 30 fewer LOP3 per ripple for the two accumulators of a thread at p <= 11).
+template <int NPL>
+struct MlAccT {
+    using CT = uint8_t;
+    static constexpr int RM = 1, QM = 2;
+    static constexpr int kTableBytes = 256 * 8 + 256 * 4;
+    uint64_t S;
+    uint32_t mmax;                 // largest merged register seen (decides whether W fits 32 bits)
+    uint32_t pl[NPL];              // vertical (bit-sliced) counters of the low 32 bits of W
+    __device__ __forceinline__ void init() {
+        S = 0;
+        mmax = 0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) pl[i] = 0u;
+    }
+    // add a bit-plane of weight 2^L into the vertical counter (ripple carry, nplanes is CTA-uniform)
+    template <int L>
+    __device__ __forceinline__ void ripple(uint32_t x, int nplanes) {
+#pragma unroll
+        for (int l = L; l < NPL; ++l) {
+            if (l < nplanes) {
+                const uint32_t c = pl[l] & x;
+                pl[l] ^= x;
+                x = c;
+            }
+        }
+    }
+    template <int N>
+    __device__ __forceinline__ void add_group(const uint32_t* a, const uint32_t* b, const SharedTables& t, int nplanes) {
+        uint32_t w[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const uint32_t m = ull_merge_fast(a[i], b[i]);
+            mmax = max(mmax, m);
+            S += t.ml_ret[m];
+            w[i] = t.ml_wlo[m];
+        }
+        add_w<N>(w, nplanes);
+    }
+    // unconditional ripple through every plane from L up (no per-plane range test: 2 LOP3 per plane)
+    template <int L>
+    __device__ __forceinline__ void ripple_all(uint32_t x) {
+#pragma unroll
+        for (int l = L; l < NPL; ++l) {
+            const uint32_t c = pl[l] & x;
+            pl[l] ^= x;
+            x = c;
+        }
+    }
+    // Harley-Seal step over 8 patterns: planes 0..2 absorb them, the weight-8 carry is returned
+    __device__ __forceinline__ uint32_t csa8(const uint32_t* w) {
+        uint32_t t2a, t2b, t4a, t4b, t8;
+        csa(t2a, pl[0], pl[0], w[0], w[1]);
+        csa(t2b, pl[0], pl[0], w[2], w[3]);
+        csa(t4a, pl[1], pl[1], t2a, t2b);
+        csa(t2a, pl[0], pl[0], w[4], w[5]);
+        csa(t2b, pl[0], pl[0], w[6], w[7]);
+        csa(t4b, pl[1], pl[1], t2a, t2b);
+        csa(t8, pl[2], pl[2], t4a, t4b);
+        return t8;
+    }
+    // eight weight-8 carries (64 patterns) -> planes 3..5, then ONE ripple from plane 6: the ripple, which costs
+    // 2 ops per plane, runs once per 64 registers instead of once per 8 or 16
+    __device__ __forceinline__ void fold64(const uint32_t* t8) {
+        uint32_t t16a, t16b, t32a, t32b, t64;
+        csa(t16a, pl[3], pl[3], t8[0], t8[1]);
+        csa(t16b, pl[3], pl[3], t8[2], t8[3]);
+        csa(t32a, pl[4], pl[4], t16a, t16b);
+        csa(t16a, pl[3], pl[3], t8[4], t8[5]);
+        csa(t16b, pl[3], pl[3], t8[6], t8[7]);
+        csa(t32b, pl[4], pl[4], t16a, t16b);
+        csa(t64, pl[5], pl[5], t32a, t32b);
+        ripple_all<6>(t64);
+    }
+    // fold N bit patterns W (b[j] += bit j of W) into the vertical counters
+    template <int N>
+    __device__ __forceinline__ void add_w(const uint32_t* w, int nplanes) {
+        // Harley-Seal: N one-bit words -> weights 1,2,4,(8) planes, then one ripple of the top carry
+        uint32_t t2a, t2b, t4a, t4b;
+        csa(t2a, pl[0], pl[0], w[0], w[1]);
+        csa(t2b, pl[0], pl[0], w[2], w[3]);
+        csa(t4a, pl[1], pl[1], t2a, t2b);
+        csa(t2a, pl[0], pl[0], w[4], w[5]);
+        csa(t2b, pl[0], pl[0], w[6], w[7]);
+        csa(t4b, pl[1], pl[1], t2a, t2b);
+        uint32_t t8a;
+        csa(t8a, pl[2], pl[2], t4a, t4b);
+        if (N == 8) {
+            ripple<3>(t8a, nplanes);
+        } else {
+            csa(t2a, pl[0], pl[0], w[8 % N], w[9 % N]);
+            csa(t2b, pl[0], pl[0], w[10 % N], w[11 % N]);
+            csa(t4a, pl[1], pl[1], t2a, t2b);
+            csa(t2a, pl[0], pl[0], w[12 % N], w[13 % N]);
+            csa(t2b, pl[0], pl[0], w[14 % N], w[15 % N]);
+            csa(t4b, pl[1], pl[1], t2a, t2b);
+            uint32_t t8b, t16;
+            csa(t8b, pl[2], pl[2], t4a, t4b);
+            csa(t16, pl[3], pl[3], t8a, t8b);
+            ripple<4>(t16, nplanes);
+        }
+    }
+};
+using MlAcc = MlAccT<kMlPlanes>;
+
+// counts b[j] (j = 0..65) out of the vertical counters: bit l of b[j] = bit j of plane l
+template <int NPL>
+__device__ __forceinline__ void ml_counts_from_planes(const MlAccT<NPL>& a, int* bb) {
+#pragma unroll 1
+    for (int j = 0; j < 66; ++j) bb[j] = 0;
+    uint32_t any = 0;
+#pragma unroll
+    for (int l = 0; l < NPL; ++l) any |= a.pl[l];
+    if (any) {
+        const int jlo = __ffs((int)any) - 1, jhi = 31 - __clz((int)any);
+        for (int j = jlo; j <= jhi; ++j) {
+            uint32_t c = 0;
+#pragma unroll
+            for (int l = 0; l < NPL; ++l) c |= ((a.pl[l] >> j) & 1u) << l;
+            bb[j] = (int)c;
+        }
+    }
+}
+
 }  // namespace lash

@@ -30,6 +30,7 @@ static inline uint32_t __brev(uint32_t x) {
 }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline uint32_t bytewise(uint32_t a, uint32_t b, uint32_t (*f)(uint32_t, uint32_t)) {
@@ -50,6 +51,27 @@ static inline uint32_t __vmaxu2(uint32_t a, uint32_t b) {
 #include "../../lash_b200/csrc/kmer_windows.cuh"
 
 using namespace lash;
+
+// ---- ML bit-sliced counters (MlAccT in dist_tables.cuh) ---------------------------------------------------------------
+// feeds n patterns W (b[j] += bit j of W) through the accumulator exactly as dist_ml_tab_kernel does -- 8 at a time through
+// csa8, eight carries through fold64 (or ripple_all<3> per 8 when fewer than 64 are left in a "chunk") -- and extracts b[]
+template <int NPL>
+static void run_ml_counters(const uint32_t* w, uint64_t n, uint64_t chunk, int* bb) {
+    MlAccT<NPL> acc;
+    acc.init();
+    for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
+        if (chunk >= 64) {
+            for (uint64_t e = c0; e < c0 + chunk; e += 64) {
+                uint32_t carry[8];
+                for (int g = 0; g < 8; ++g) carry[g] = acc.csa8(w + e + 8 * g);
+                acc.fold64(carry);
+            }
+        } else {
+            for (uint64_t e = c0; e < c0 + chunk; e += 8) acc.template ripple_all<3>(acc.csa8(w + e));
+        }
+    }
+    ml_counts_from_planes(acc, bb);
+}
 
 extern "C" {
 
@@ -137,6 +159,23 @@ uint32_t dm_ull_cell(const uint64_t* h, uint64_t n, int p, uint32_t* idx_out, ui
     w_out[0] = w[0];
     w_out[1] = w[1];
     return ull_cell_to_reg(w[0], w[1], p);
+}
+
+// ---- ML bit-sliced counters (run_ml_counters above) ---------------------------------------------------------------------
+void dm_ml_counters(int npl, const uint32_t* w, uint64_t n, uint64_t chunk, int* bb) {
+    if (npl == 12) run_ml_counters<12>(w, n, chunk, bb);
+    else if (npl == 16) run_ml_counters<16>(w, n, chunk, bb);
+    else run_ml_counters<kMlPlanes>(w, n, chunk, bb);
+}
+// the generic kernels' path: add_w<16> / add_w<8> with the run-time plane limit
+void dm_ml_counters_generic(const uint32_t* w, uint64_t n, int group, int nplanes, int* bb) {
+    MlAcc acc;
+    acc.init();
+    for (uint64_t e = 0; e < n; e += (uint64_t)group) {
+        if (group == 16) acc.add_w<16>(w + e, nplanes);
+        else acc.add_w<8>(w + e, nplanes);
+    }
+    ml_counts_from_planes(acc, bb);
 }
 
 // ---- register algebra -----------------------------------------------------------------------------------------------

@@ -430,3 +430,35 @@ def test_ull_smem_cell_flush_equals_sequential_updates(dm, oracle, p):
                 nlz = 64 - body.bit_length()
                 exp = dm.dm_ull_update(exp, nlz + p - 1)
             assert reg == exp, (p, n, zmax)
+
+
+@pytest.mark.parametrize("npl,p", [(12, 10), (12, 11), (16, 14), (27, 16), (12, 4)])
+def test_ml_bit_sliced_counters_count_exactly(dm, npl, p):
+    """MlAccT: b[j] += bit j of W over all 2^p registers, kept as vertical (bit-sliced) counters -- Harley-Seal steps
+    of 8 patterns, eight carries folded per 64 registers, one ripple through the upper planes.  The extracted counts
+    must equal plain popcounts for sparse, dense and all-ones patterns (counts up to 2^p need p+1 planes)."""
+    dm.dm_ml_counters.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+    dm.dm_ml_counters_generic.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(npl * 100 + p)
+    n = 1 << p
+    chunk = min(n, 128)
+    for kind in ("sparse", "dense", "ones", "levels"):
+        if kind == "sparse":
+            w = (rng.random((n, 32)) < 0.03)
+        elif kind == "dense":
+            w = (rng.random((n, 32)) < 0.6)
+        elif kind == "ones":
+            w = np.ones((n, 32), dtype=bool)
+        else:                                                             # what ULL registers produce: (4 | y) << k
+            k = np.clip(rng.geometric(0.3, size=n), 0, 29)
+            pat = ((4 | rng.integers(0, 4, size=n)).astype(np.uint64) << k.astype(np.uint64)) & np.uint64(0xFFFFFFFF)
+            w = ((pat[:, None] >> np.arange(32, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool)
+        words = (w.astype(np.uint64) << np.arange(32, dtype=np.uint64)[None, :]).sum(axis=1).astype(np.uint32)
+        exp = w.sum(axis=0).astype(np.int32)
+        bb = np.zeros(66, dtype=np.int32)
+        dm.dm_ml_counters(npl, _p(words), n, chunk, _p(bb))
+        assert np.array_equal(bb[:32], exp), (kind, "tab kernel path")
+        assert not bb[32:].any()
+        bb[:] = 0
+        dm.dm_ml_counters_generic(_p(words), n, 16 if n >= 16 else 8, p + 1, _p(bb))
+        assert np.array_equal(bb[:32], exp), (kind, "generic path")
