@@ -305,14 +305,6 @@ constexpr int kHllThreads = 256;
 constexpr int kHllRM = 4, kHllQM = 2;
 constexpr int kHllTR = (kHllThreads / 32) * kHllRM, kHllTQ = 32 * kHllQM;  // 32 x 64 pairs per CTA
 constexpr int kHllChunk = 128;                                            // registers per sketch per stage
-constexpr uint32_t kHllOne = 0x3FF00000u;                                 // high word of 2^-0
-
-__device__ __forceinline__ uint4 hll_recode(uint32_t w) {
-    return make_uint4(kHllOne - (w & 0xffu) * 0x100000u, kHllOne - ((w >> 8) & 0xffu) * 0x100000u,
-                      kHllOne - ((w >> 16) & 0xffu) * 0x100000u, kHllOne - (w >> 24) * 0x100000u);
-}
-// any zero byte in w?  (exact for all byte values)
-__device__ __forceinline__ bool has_zero_byte(uint32_t w) { return ((w - 0x01010101u) & ~w & 0x80808080u) != 0u; }
 
 template <bool COUNT_ZERO>
 __device__ __forceinline__ void hll_chunk(double (&sum)[kHllRM][kHllQM], uint32_t (&zero)[kHllRM][kHllQM], const uint32_t* pa,

@@ -223,4 +223,14 @@ __device__ __forceinline__ void ml_counts_from_planes(const MlAccT<NPL>& a, int*
     }
 }
 
+// ---- K4h: HLL registers recoded to the high word of the double 2^-r ---------------------------------------------------
+// (the low word of a power of two is 0, so 2^-max(ra, rb) = hiloint2double(min(va, vb), 0) with va = kHllOne - (ra << 20))
+constexpr uint32_t kHllOne = 0x3FF00000u;                                 // high word of 2^-0
+__device__ __forceinline__ uint4 hll_recode(uint32_t w) {
+    return make_uint4(kHllOne - (w & 0xffu) * 0x100000u, kHllOne - ((w >> 8) & 0xffu) * 0x100000u,
+                      kHllOne - ((w >> 16) & 0xffu) * 0x100000u, kHllOne - (w >> 24) * 0x100000u);
+}
+// any zero byte in w?  (exact for all byte values)
+__device__ __forceinline__ bool has_zero_byte(uint32_t w) { return ((w - 0x01010101u) & ~w & 0x80808080u) != 0u; }
+
 }  // namespace lash

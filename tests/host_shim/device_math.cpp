@@ -14,6 +14,9 @@
 using std::max;
 using std::min;
 
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+
 static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) {  // high word of (hi:lo) << (s & 31)
     s &= 31u;
     return s ? (hi << s) | (lo >> (32u - s)) : hi;
@@ -176,6 +179,13 @@ void dm_ml_counters_generic(const uint32_t* w, uint64_t n, int group, int nplane
         else acc.add_w<8>(w + e, nplanes);
     }
     ml_counts_from_planes(acc, bb);
+}
+
+// ---- K4h: HLL registers as high words of 2^-r ---------------------------------------------------------------------------
+void dm_hll_recode(uint32_t w, uint32_t* out4, int* zero_byte) {
+    const uint4 v = hll_recode(w);
+    out4[0] = v.x; out4[1] = v.y; out4[2] = v.z; out4[3] = v.w;
+    *zero_byte = has_zero_byte(w) ? 1 : 0;
 }
 
 // ---- register algebra -----------------------------------------------------------------------------------------------

@@ -462,3 +462,25 @@ def test_ml_bit_sliced_counters_count_exactly(dm, npl, p):
         bb[:] = 0
         dm.dm_ml_counters_generic(_p(words), n, 16 if n >= 16 else 8, p + 1, _p(bb))
         assert np.array_equal(bb[:32], exp), (kind, "generic path")
+
+
+def test_hll_recoded_registers_are_high_words_of_powers_of_two(dm):
+    """K4h: v = 0x3FF00000 - (r << 20) is the high word of the double 2^-r (low word 0), so for every pair of register
+    bytes hiloint2double(min(va, vb), 0) == 2^-max(ra, rb); has_zero_byte is exact on every kind of word."""
+    dm.dm_hll_recode.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+    out, z = np.zeros(4, dtype=np.uint32), C.c_int(0)
+    v = np.zeros(256, dtype=np.uint32)
+    for r in range(0, 256, 4):
+        w = r | ((r + 1) << 8) | ((r + 2) << 16) | ((r + 3) << 24)
+        dm.dm_hll_recode(w, _p(out), C.byref(z))
+        v[r:r + 4] = out
+        assert bool(z.value) == (r == 0)
+    as_double = (v.astype(np.uint64) << np.uint64(32)).view(np.float64)
+    assert np.array_equal(as_double, 2.0 ** -np.arange(256, dtype=np.float64))
+    a, b = np.meshgrid(np.arange(256), np.arange(256))
+    m = np.minimum(v[a], v[b])
+    assert np.array_equal((m.astype(np.uint64) << np.uint64(32)).view(np.float64), 2.0 ** -np.maximum(a, b).astype(np.float64))
+    rng = np.random.default_rng(0)
+    for w in list(rng.integers(0, 1 << 32, size=2000)) + [0, 0x01010101, 0x80808080, 0x00ffffff, 0xff00ffff, 0x7f7f7f00, 0x01000101]:
+        dm.dm_hll_recode(int(w), _p(out), C.byref(z))
+        assert bool(z.value) == any(((int(w) >> (8 * i)) & 0xff) == 0 for i in range(4)), hex(int(w))
