@@ -148,6 +148,16 @@ void dm_kmers(const uint8_t* packed, uint64_t n_bytes, uint64_t n_bases, int k, 
     }
 }
 
+// HLL fast path (SmemAcc<HLL>::prep): index from the low p bits of h.lo, rho from the pre-xorshift high word
+void dm_hll_fast(const uint64_t* g, uint64_t n, int p, uint32_t* idx, uint32_t* rho, uint32_t* rare) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t glo = (uint32_t)g[i], ghi = (uint32_t)(g[i] >> 32);
+        idx[i] = (glo ^ __funnelshift_r(glo, ghi, 28)) & ((1u << p) - 1u);
+        rho[i] = 32u - bfind32(ghi);
+        rare[i] = ghi == 0u;
+    }
+}
+
 // ---- shared-memory ULL cell (two words of seen-nlz bits) and its conversion at flush ---------------------------------------
 // adds the hashes h[0..n) to an empty cell with the EXACT path's rule (SmemAcc<ULL>::exact: word 0 takes nlz < 32, word 1
 // the rest, bit index = raw bfind result) and converts the cell with ull_cell_to_reg; idx_out = the register index of h[0]
@@ -187,6 +197,8 @@ void dm_hll_recode(uint32_t w, uint32_t* out4, int* zero_byte) {
     out4[0] = v.x; out4[1] = v.y; out4[2] = v.z; out4[3] = v.w;
     *zero_byte = has_zero_byte(w) ? 1 : 0;
 }
+
+uint32_t dm_ull_cell_to_reg(uint32_t w0, uint32_t w1, int p) { return ull_cell_to_reg(w0, w1, p); }
 
 // ---- register algebra -----------------------------------------------------------------------------------------------
 uint32_t dm_ull_update(uint32_t r, uint32_t u) { return ull_update(r, u); }

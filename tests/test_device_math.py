@@ -484,3 +484,75 @@ def test_hll_recoded_registers_are_high_words_of_powers_of_two(dm):
     for w in list(rng.integers(0, 1 << 32, size=2000)) + [0, 0x01010101, 0x80808080, 0x00ffffff, 0xff00ffff, 0x7f7f7f00, 0x01000101]:
         dm.dm_hll_recode(int(w), _p(out), C.byref(z))
         assert bool(z.value) == any(((int(w) >> (8 * i)) & 0xff) == 0 for i in range(4)), hex(int(w))
+
+
+@pytest.mark.parametrize("p,k,drop4", [(10, 16, 1), (10, 12, 1), (14, 21, 0), (8, 31, 1), (12, 16, 0)])
+def test_cpu_emulation_of_the_ull_sketch_path_end_to_end(dm, oracle, p, k, drop4):
+    """The arithmetic of the sketch kernel's ULL path chained on the CPU, piece by piece as the kernel does it:
+    funnel-shift canonical k-mers -> pre-xorshift hash, high word only -> fast (index, bit) or "rare" -> exact rule ->
+    OR into the two-word cell -> conversion at flush.  The registers must equal the oracle's sketch of the same genome
+    (the GPU tests check the same end to end on the device; this one runs without one)."""
+    from lash_b200 import hostapi
+    from tools import synth
+    dm.dm_kmers.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    dm.dm_ull_cell_to_reg.argtypes, dm.dm_ull_cell_to_reg.restype = [C.c_uint32, C.c_uint32, C.c_int], C.c_uint32
+    seq = synth.genomes(1, 120_000, seed=p * 100 + k)[0][0]
+    packed, nb = hostapi.filter_pack(seq, simd=0)
+    buf = np.concatenate([packed, np.zeros(16, dtype=np.uint8)])
+    kmers = np.zeros(len(seq) - k + 1, dtype=np.uint64)
+    dm.dm_kmers(_p(buf), len(packed), len(seq), k, _p(kmers))
+    narrow = 1 if k <= 16 else 0
+    g = np.empty_like(kmers)
+    ghi = np.empty(len(kmers), dtype=np.uint32)
+    dm.dm_pre(_p(kmers), len(kmers), SEED, narrow, _p(g), _p(ghi))
+    idx, nlz, rare = (np.empty(len(kmers), dtype=np.uint32) for _ in range(3))
+    dm.dm_ull_fast(_p(ghi), len(kmers), p, drop4, _p(idx), _p(nlz), _p(rare))
+    # rare hashes go through the exact rule on the finished hash
+    h = np.empty_like(kmers)
+    dm.dm_xxh3_64(_p(kmers), len(kmers), SEED, _p(h))
+    for i in np.flatnonzero(rare):
+        body = ((int(h[i]) << p) & ((1 << 64) - 1)) | ((1 << p) - 1)
+        nlz[i] = 64 - body.bit_length()
+        idx[i] = int(h[i]) >> (64 - p)
+    # the cell: word 0 bit j <=> nlz = 31 - j, word 1 bit j <=> nlz = 63 - j
+    w = np.zeros((1 << p, 2), dtype=np.uint32)
+    word = (nlz >= 32).astype(np.int64)
+    bit = np.where(nlz >= 32, 63 - nlz.astype(np.int64), 31 - nlz.astype(np.int64))
+    np.bitwise_or.at(w, (idx.astype(np.int64), word), (np.uint32(1) << bit.astype(np.uint32)))
+    regs = np.array([dm.dm_ull_cell_to_reg(int(a), int(b), p) for a, b in w], dtype=np.uint8)
+    exp = oracle.sketch_genomes(2, p, k, SEED, [[seq]])[0]
+    assert np.array_equal(regs, exp)
+    assert (regs != 0).mean() > 0.9
+
+
+@pytest.mark.parametrize("p,k", [(14, 21), (10, 16), (4, 12), (16, 31)])
+def test_cpu_emulation_of_the_hll_sketch_path_end_to_end(dm, oracle, p, k):
+    """Same for HLL: index from the low p bits of the finished hash's low word, rho from the PRE-xorshift high word
+    (the xorshift never moves its highest set bit), max into the register."""
+    from lash_b200 import hostapi
+    from tools import synth
+    dm.dm_kmers.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    dm.dm_hll_fast.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    seq = synth.genomes(1, 100_000, seed=p * 100 + k)[0][0]
+    packed, nb = hostapi.filter_pack(seq, simd=0)
+    buf = np.concatenate([packed, np.zeros(16, dtype=np.uint8)])
+    kmers = np.zeros(len(seq) - k + 1, dtype=np.uint64)
+    dm.dm_kmers(_p(buf), len(packed), len(seq), k, _p(kmers))
+    g = np.empty_like(kmers)
+    ghi = np.empty(len(kmers), dtype=np.uint32)
+    dm.dm_pre(_p(kmers), len(kmers), SEED, 1 if k <= 16 else 0, _p(g), _p(ghi))
+    # adversarial additions: pre-xorshift words with a zero / tiny high word
+    g = np.concatenate([g, np.array([0x00000000_12345678, 0x00000007_9abcdef0, 0x0000000f_00000000, 0xf0000000_00000001], dtype=np.uint64)])
+    idx, rho, rare = (np.empty(len(g), dtype=np.uint32) for _ in range(3))
+    dm.dm_hll_fast(_p(g), len(g), p, _p(idx), _p(rho), _p(rare))
+    h = g ^ (g >> U64(28))
+    exp_idx = (h & U64((1 << p) - 1)).astype(np.uint32)
+    wv = h >> U64(p)                                                      # streaming_algorithms: rho = clz64(w) - p + 1
+    exp_rho = np.array([(64 - int(x).bit_length()) - p + 1 for x in wv], dtype=np.uint32)
+    assert np.array_equal(idx, exp_idx)
+    assert np.array_equal(rare == 1, (h >> U64(32)) == 0)
+    assert np.array_equal(rho[rare == 0], exp_rho[rare == 0])
+    n = len(kmers)
+    regs = np.zeros(1 << p, dtype=np.uint32)
+    np.maximum.at(regs, exp_idx[:n].astype(np.int64), np.where(rare[:n] == 1, exp_rho[:n], rho[:n]))
+    assert np.array_equal(regs.astype(np.uint8), oracle.sketch_genomes(1, p, k, SEED, [[seq]])[0])
