@@ -556,3 +556,47 @@ def test_cpu_emulation_of_the_hll_sketch_path_end_to_end(dm, oracle, p, k):
     regs = np.zeros(1 << p, dtype=np.uint32)
     np.maximum.at(regs, exp_idx[:n].astype(np.int64), np.where(rare[:n] == 1, exp_rho[:n], rho[:n]))
     assert np.array_equal(regs.astype(np.uint8), oracle.sketch_genomes(1, p, k, SEED, [[seq]])[0])
+
+
+def test_cpu_emulation_of_the_pair_table_distance_paths(dm, est, oracle):
+    """K4b / K4c chained on the CPU: registers -> codes relative to the smallest register present -> table lookups in
+    register order (FGRA: running f64 sum; ML: wrapping S and bit counts) -> estimator epilogue -> Jaccard -> frac.
+    With the host libm on both sides the result is the oracle's to the last bit."""
+    from tools import synth
+    dm.dm_fgra_code.argtypes, dm.dm_fgra_code.restype = [C.c_uint32, C.c_uint32], C.c_uint32
+    dm.dm_fgra_table.argtypes, dm.dm_fgra_table.restype = [C.c_uint32, C.c_int, C.c_void_p, C.c_void_p], C.c_double
+    dm.dm_ml_tables.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    p, k = 10, 16
+    regs = oracle.sketch_genomes(2, p, k, SEED, synth.genomes(5, 150_000, seed=3))
+    reg_tab = np.array([est.dm_ull_reg(i) for i in range(256)], dtype=np.float64)
+    off = 4 * p + 4
+    base = max(4 * p - 4, int(regs[regs != 0].min()) & ~3)               # regmin_kernel + the kernel's anchoring
+    T = np.empty(128 * 128, dtype=np.float64)
+    sentinel = dm.dm_fgra_table(base, p, _p(reg_tab), _p(T))
+    R, W = np.empty(128 * 128, dtype=np.uint64), np.empty(128 * 128, dtype=np.uint32)
+    dm.dm_ml_tables(p, _p(R), _p(W))
+    code = np.vectorize(lambda r: dm.dm_fgra_code(int(r), base))(regs)
+    code_ml = np.vectorize(lambda r: dm.dm_fgra_code(int(r), 4 * p - 4))(regs)
+    assert code.max() < 127 and code_ml.max() < 127
+    zeros8 = np.zeros(8, dtype=np.uint32)
+    card_f = [oracle.cardinality(2, p, 0, r) for r in regs]
+    card_m = [oracle.cardinality(2, p, 1, r) for r in regs]
+    frac_f = oracle.dist(2, p, k, 0, 2, False, regs, regs)
+    frac_m = oracle.dist(2, p, k, 1, 2, False, regs, regs)
+    for i in range(len(regs)):
+        for j in range(len(regs)):
+            vals = T[code[i].astype(np.int64) * 128 + code[j]]
+            assert vals.max() < sentinel
+            total = float(np.cumsum(vals)[-1])                              # register order, one running sum
+            U = est.dm_fgra(total, _p(zeros8), p)
+            s = max((card_f[i] + card_f[j] - U) / U, 0.0)
+            assert 2.0 * s / (1.0 + s) == frac_f[i, j], ("fgra", i, j)
+            e = code_ml[i].astype(np.int64) * 128 + code_ml[j]
+            S = int(np.sum(R[e].astype(object)) % (1 << 64))
+            b = np.zeros(66, dtype=np.int32)
+            for bit in range(32):
+                b[bit] = int(((W[e] >> np.uint32(bit)) & np.uint32(1)).sum())
+            merged0 = int(oracle.ull_merge(regs[i], regs[j], p)[0])
+            U = est.dm_ml(S, _p(b), p, merged0)
+            s = max((card_m[i] + card_m[j] - U) / U, 0.0)
+            assert 2.0 * s / (1.0 + s) == frac_m[i, j], ("ml", i, j)
