@@ -88,6 +88,44 @@ int usage() {
     return 2;
 }
 
+// per-command help: the reference's own text (clap output quoted in its README), plus this binary's extras
+int help_sketch() {
+    printf("Sketches genomes and serializes them, sketches are compressed\n\n"
+           "Usage: lash-b200 sketch [OPTIONS] --file <file>\n\nOptions:\n"
+           "  -f, --file <file>            One file containing list of FASTA/FASTQ files (.gz/.bz2/.zstd supported), one per line. File must be UTF-8.\n"
+           "  -o, --output <output>        Input a prefix/name for your output files [default: sketch]\n"
+           "  -k, --kmer <kmer_length>     Length of the kmer [default: 16]\n"
+           "  -t, --threads <threads>      Number of threads to use, default to all logical cores\n"
+           "  -a, --algorithm <algorithm>  Which algorithm to use: HyperMinHash (hmh), UltraLogLog (ull), or HyperLogLog (hll) [default: hmh]\n"
+           "  -p, --precision <precision>  Specifiy precision, for ull and hll only. [default: 10]\n"
+           "  -s, --seed <seed>            Random seed [default: 42]\n"
+           "      --device <device>        GPU index [default: 0]  (lash-b200 only)\n"
+           "  -h, --help                   Print help\n");
+    return 0;
+}
+int help_dist() {
+    printf("Computes distance between sketches\n\n"
+           "Usage: lash-b200 dist [OPTIONS] --query <query> --reference <reference>\n\nOptions:\n"
+           "  -q, --query <query>              Prefix to search for query genome files\n"
+           "  -r, --reference <reference>      Prefix to search for reference genome files\n"
+           "  -o, --output_file <output_file>  Name of output file to write results [default: dist]\n"
+           "  -t, --threads <threads>          Number of threads to use, default to all logical cores\n"
+           "  -e, --estimator <estimator>      Specify estimator (fgra or ml), for ull only [default: fgra]\n"
+           "  -m, --model <model>              Equation used to calculate distance: 1 for poisson model or 0 for binomial model [default: 1]\n"
+           "      --fp32                       Distance output in float 32 instead of 64\n"
+           "      --dm                         Prints distance matrix\n"
+           "      --device <device>            GPU index [default: 0]  (lash-b200 only)\n"
+           "      --mirror                     frac from the GPU, compute_distance + print_dist on the host as main.rs does  (lash-b200 only)\n"
+           "      --rank <r> --world <w>       one process per GPU: write this rank's row range to <output_file>.partRRRR  (lash-b200 only)\n"
+           "  -h, --help                       Print help\n");
+    return 0;
+}
+bool wants_help(int argc, char** argv) {
+    for (int i = 2; i < argc; ++i)
+        if (!strcmp(argv[i], "-h") || !strcmp(argv[i], "--help")) return true;
+    return false;
+}
+
 int fail(const std::string& m) {
     fprintf(stderr, "%s\n", m.c_str());
     return 1;
@@ -180,8 +218,14 @@ int run_dist(int argc, char** argv) {
 int main(int argc, char** argv) {
     if (argc < 2) return usage();
     const std::string cmd = argv[1];
-    if (cmd == "sketch") return run_sketch(argc, argv);
-    if (cmd == "dist") return run_dist(argc, argv);
+    if (cmd == "sketch") return wants_help(argc, argv) ? help_sketch() : run_sketch(argc, argv);
+    if (cmd == "dist") return wants_help(argc, argv) ? help_dist() : run_dist(argc, argv);
+    if (cmd == "help" || cmd == "-h" || cmd == "--help") {
+        if (argc > 2 && !strcmp(argv[2], "sketch")) return help_sketch();
+        if (argc > 2 && !strcmp(argv[2], "dist")) return help_dist();
+        usage();
+        return 0;
+    }
     if (cmd == "-V" || cmd == "--version") {
         printf("lash-b200 0.1.4 (B200 hot paths; reference jianshu93/lash 0.1.4)\n");
         return 0;

@@ -249,3 +249,32 @@ def test_filter_pack_simd_paths_agree_with_scalar_on_long_dirty_input():
             assert nb > 500_000
         else:
             assert nb == ref[1] and np.array_equal(packed, ref[0]), simd
+
+
+def test_cli_surface_without_a_gpu():
+    """`lash-b200`: the reference's command surface (main.rs:26-177) -- help, per-command help with every flag and
+    default of the reference, version, and clap-style errors for unknown / missing arguments, all before any GPU is
+    touched.  (With sketches in hand and no GPU the commands must fail loudly: there is no CPU fallback.)"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(hostapi.lib_path()), "lash-b200")
+    run = lambda *a: subprocess.run([exe, *a], capture_output=True, text=True)  # noqa: E731
+    r = run("-V")
+    assert r.returncode == 0 and r.stdout.startswith("lash-b200 ")
+    r = run("sketch", "-h")
+    assert r.returncode == 0
+    for flag in ("-f, --file", "-o, --output", "-k, --kmer", "-t, --threads", "-a, --algorithm", "-p, --precision", "-s, --seed",
+                 "[default: sketch]", "[default: 16]", "[default: hmh]", "[default: 10]", "[default: 42]"):
+        assert flag in r.stdout, flag
+    r = run("help", "dist")
+    assert r.returncode == 0
+    for flag in ("-q, --query", "-r, --reference", "-o, --output_file", "-e, --estimator", "-m, --model", "--fp32", "--dm",
+                 "[default: fgra]", "[default: 1]"):
+        assert flag in r.stdout, flag
+    assert run("dist", "--help").stdout == r.stdout
+    r = run("dist", "--bogus")
+    assert r.returncode != 0 and "unexpected argument '--bogus'" in r.stderr
+    r = run("sketch")
+    assert r.returncode != 0 and "--file <file>" in r.stderr
+    r = run("dist", "-q", "a")
+    assert r.returncode != 0 and "--reference <reference>" in r.stderr
+    assert run().returncode != 0 and "Usage: lash-b200 <COMMAND>" in run().stderr
