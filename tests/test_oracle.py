@@ -6,6 +6,7 @@ The reference holds no tests, fixtures or golden vectors, 
   * canonical k-mers against brute-force string code (tests/golden/kmers.json) -- exact;
   * register updates against an independent pure-Python restatement (tests/golden/sketch_py.json);
   * ULL constants against hash4j's literal table entries (tests/golden/ull_constants.json);
+  * every estimator against a second pure-Python restatement (tests/golden/estimators.json, tools/estimators_py.py);
   * estimator unbiasedness by simulation, merge/union algebra, quirks of the reference front end.
 """
 import ctypes as C
@@ -182,3 +183,69 @@ def test_distance_formula_and_dist_driver(oracle):
     # threads do not change results
     regs = oracle.sketch_genomes(oracle.ULL, 10, 16, 42, gs, threads=1)
     assert np.array_equal(regs, oracle.sketch_genomes(oracle.ULL, 10, 16, 42, gs, threads=5))
+
+
+def test_estimators_match_the_independent_python_restatement(oracle):
+    """tests/golden/estimators.json: registers -> cardinalities, union estimate, frac and distances computed by
+    tools/estimators_py.py, a pure-Python restatement written from the published algorithms, not
+    from the oracle: ULL FGRA incl. small-range and saturated registers, ULL ML (Ertl's solver), ULL merge, HLL++ len()
+    incl. linear counting and the flagged bias regime, HyperMinHash cardinality / similarity (the n <= 2^19 double loop),
+    Jaccard -> frac -> Mash distance.  Same libm on both sides: agreement to a few ulp."""
+    eps = np.finfo(np.float64).eps
+
+    def close(got, exp_repr, ulps=16):
+        exp = float(exp_repr)
+        if np.isnan(exp):
+            return bool(np.isnan(got))
+        if np.isinf(exp) or exp == 0.0:
+            return got == exp
+        return abs(got - exp) <= ulps * eps * abs(exp)
+
+    cases = _gold("estimators.json")
+    assert len(cases) >= 30
+    seen = set()
+    for c in cases:
+        p = c["p"]
+        if c["algo"] == "ull":
+            est = 0 if c["estimator"] == "fgra" else 1
+            a, b = np.array(c["a"], dtype=np.uint8), np.array(c["b"], dtype=np.uint8)
+            assert list(oracle.ull_merge(a, b, p)) == c["merged"]
+            assert close(oracle.cardinality(oracle.ULL, p, est, a), c["card_a"]), (c["estimator"], p, "card_a")
+            assert close(oracle.cardinality(oracle.ULL, p, est, b), c["card_b"])
+            assert close(oracle.cardinality(oracle.ULL, p, est, np.array(c["merged"], dtype=np.uint8)), c["union"])
+            fr = oracle.dist(oracle.ULL, p, 16, est, 2, False, a[None, :], b[None, :])[0, 0]
+            # frac = 2s/(1+s) with s = (a+b-U)/U: the subtraction amplifies the few-ulp differences of the estimates
+            exp_fr = float(c["frac"])
+            assert (np.isnan(fr) and np.isnan(exp_fr)) or abs(fr - exp_fr) <= 1e-12 * max(abs(exp_fr), 1e-3), (p, fr, exp_fr)
+            d1 = oracle.dist(oracle.ULL, p, 16, est, 1, False, a[None, :], b[None, :])[0, 0]
+            d0 = oracle.dist(oracle.ULL, p, 21, est, 0, False, a[None, :], b[None, :])[0, 0]
+            for got, key in ((d1, "d_poisson_k16"), (d0, "d_binomial_k21")):
+                exp = float(c[key])
+                assert (np.isnan(got) and np.isnan(exp)) or abs(got - exp) <= 1e-11, (key, got, exp)
+            seen.add(("ull", c["estimator"], any(r >= 252 for r in c["a"]), any(0 < r < 4 * p + 4 for r in c["a"])))
+        elif c["algo"] == "hll":
+            a, b = np.array(c["a"], dtype=np.uint8), np.array(c["b"], dtype=np.uint8)
+            assert close(oracle.cardinality(oracle.HLL, p, 0, a), c["card_a"])
+            assert close(oracle.cardinality(oracle.HLL, p, 0, b), c["card_b"])
+            fr, flags = oracle.dist(oracle.HLL, p, 16, 0, 2, False, a[None, :], b[None, :], return_flags=True)
+            assert bool(flags[0, 0]) == bool(c["bias_regime"][2])
+            if not any(c["bias_regime"]):
+                exp_fr = float(c["frac"])
+                assert abs(fr[0, 0] - exp_fr) <= 1e-12 * max(abs(exp_fr), 1e-3)
+            seen.add(("hll", any(c["bias_regime"]), 0 in c["a"]))
+        else:
+            a, b = np.zeros(16384, dtype=np.uint16), np.zeros(16384, dtype=np.uint16)
+            for i, v in c["a"].items():
+                a[int(i)] = v
+            for i, v in c["b"].items():
+                b[int(i)] = v
+            assert close(oracle.cardinality(oracle.HMH, 14, 0, a), c["card_a"])
+            assert close(oracle.cardinality(oracle.HMH, 14, 0, b), c["card_b"])
+            fr = oracle.dist(oracle.HMH, 14, 16, 0, 2, False, a[None, :], b[None, :])[0, 0]
+            assert abs(fr - float(c["frac"])) <= 1e-12 and fr > 0.1
+            seen.add(("hmh",))
+    # the fixture exercises every branch it is meant to
+    assert ("ull", "fgra", True, False) in seen or ("ull", "fgra", True, True) in seen       # saturated registers
+    assert any(s[0] == "ull" and s[3] for s in seen)                                         # small-range registers
+    assert ("hll", True, True) in seen or ("hll", True, False) in seen                       # bias regime flagged
+    assert any(s[0] == "hll" and not s[1] and s[2] for s in seen)                            # linear counting

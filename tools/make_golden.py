@@ -116,6 +116,71 @@ def main():
         nz = {str(i): v for i, v in enumerate(regs) if v}
         sk.append({"algo": algo, "p": p, "k": k, "seed": seed, "records": recs, "n_regs": len(regs), "nonzero": nz})
     json.dump(sk, open(os.path.join(OUT, "sketch_py.json"), "w"))
+
+    # estimators: registers -> cardinalities, union estimate, frac, distances, by the pure-Python restatement of
+    # tools/estimators_py.py (written from SURVEY.md Appendix A, not from the oracle)
+    from tools import estimators_py as E
+    est = []
+
+    def valid_ull(p, n_hashes_log2):
+        regs = []
+        for _ in range(1 << p):
+            if n_hashes_log2 < 0 and rnd.random() > 2.0 ** n_hashes_log2:
+                regs.append(0)
+                continue
+            lvl = 0
+            for _ in range(max(1, int(2 ** max(n_hashes_log2, 0)))):
+                z = 0
+                while rnd.random() < 0.5 and z < 60 - p:
+                    z += 1
+                lvl = max(lvl, z)
+            regs.append(4 * (lvl + p - 1) + rnd.randrange(4) if lvl + p - 1 >= p + 1 else rnd.choice([4 * p - 4, 4 * p, 4 * p + 2]))
+        return regs
+
+    def hll_regs(p, n_hashes_log2):
+        regs = []
+        for _ in range(1 << p):
+            if n_hashes_log2 < 0 and rnd.random() > 2.0 ** n_hashes_log2:
+                regs.append(0)
+                continue
+            rho = 1
+            for _ in range(max(1, int(2 ** max(n_hashes_log2, 0)))):
+                z = 1
+                while rnd.random() < 0.5 and z < 64 - p + 1:
+                    z += 1
+                rho = max(rho, z)
+            regs.append(rho)
+        return regs
+
+    for p in (3, 6, 8):
+        for lg in (-2.0, 0.0, 3.0, 7.0):
+            a, b = valid_ull(p, lg), valid_ull(p, lg + 0.7)
+            if lg == 7.0:
+                a[1], b[2] = 253, 255                                   # saturated registers: FGRA large-range branch
+            u = E.ull_merge(a, b)
+            for name, fn in (("fgra", E.ull_fgra), ("ml", E.ull_ml)):
+                ca, cb, cu = fn(a, p), fn(b, p), fn(u, p)
+                fr = E.frac_from(ca, cb, cu, hll=False)
+                est.append({"algo": "ull", "estimator": name, "p": p, "a": a, "b": b, "merged": u, "card_a": repr(ca), "card_b": repr(cb),
+                            "union": repr(cu), "frac": repr(fr), "d_poisson_k16": repr(E.mash(fr, 16, 1)), "d_binomial_k21": repr(E.mash(fr, 21, 0))})
+    for p in (4, 6, 8):
+        for lg in (-2.0, 1.0, 4.0, 8.0):
+            a, b = hll_regs(p, lg), hll_regs(p, lg + 0.5)
+            u = [max(x, y) for x, y in zip(a, b)]
+            (ca, fa), (cb, fb), (cu, fu) = E.hll_len(a, p), E.hll_len(b, p), E.hll_len(u, p)
+            fr = E.frac_from(ca, cb, cu, hll=True)
+            est.append({"algo": "hll", "p": p, "a": a, "b": b, "card_a": repr(ca), "card_b": repr(cb), "union": repr(cu),
+                        "bias_regime": [fa, fb, fu], "frac": repr(fr), "d_poisson_k16": repr(E.mash(fr, 16, 1))})
+    # HyperMinHash: two real sketches of overlapping sequences (sparse: stored as index -> value)
+    base = "".join(rnd.choice("ACGT") for _ in range(6000))
+    other = base[:3500] + "".join(rnd.choice("ACGT") for _ in range(2500))
+    ha = sketch_py("hmh", 14, 16, 42, [base.encode()])
+    hb = sketch_py("hmh", 14, 16, 42, [other.encode()])
+    sim = E.hmh_similarity(ha, hb)
+    est.append({"algo": "hmh", "p": 14, "a": {str(i): v for i, v in enumerate(ha) if v}, "b": {str(i): v for i, v in enumerate(hb) if v},
+                "card_a": repr(E.hmh_cardinality(ha)), "card_b": repr(E.hmh_cardinality(hb)), "similarity": repr(sim),
+                "frac": repr(2.0 * max(sim, 0.0) / (1.0 + max(sim, 0.0)))})
+    json.dump(est, open(os.path.join(OUT, "estimators.json"), "w"))
     print("golden fixtures written to", OUT)
 
 
