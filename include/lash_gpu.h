@@ -175,7 +175,10 @@ int lash_dist(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, i
  * NOT synchronised.  Computes reference rows [row_begin, row_end) only (output tiling across GPUs:
  * each rank takes a row range); out_dev is indexed like `out` above (full-matrix indexing).
  * card_ref_dev / card_qry_dev: per-sketch cardinalities from lash_cardinality_dev (ignored for HMH).
- * flags_dev: optional uint32 counter incremented for each pair in the HLL bias regime. */
+ * flags_dev: optional uint32 counter incremented for each pair in the HLL bias regime.
+ * Register arrays should be 16-byte aligned (anything cudaMalloc returns is): the HLL tile kernel stages with 16-byte loads and
+ * falls back to the slower generic kernel for unaligned pointers.  ULL ML allocates a per-context scratch (60 B per output cell
+ * at p <= 11) for its two-kernel form and falls back to the fused kernel above LASH_ML_SCRATCH_MAX_MB (default 16 GiB). */
 int lash_dist_dev(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_dev,
                   uint64_t n_ref, const void* qry_dev, uint64_t n_qry, const double* card_ref_dev,
                   const double* card_qry_dev, int triangular, uint64_t row_begin, uint64_t row_end, void* out_dev,
