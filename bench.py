@@ -45,6 +45,31 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def source_sha() -> str:
+    """Hash of the CUDA sources liblash_gpu.so is built from: ties profiles/kernel_costs.json (instructions per unit and
+    DRAM bytes per unit from ncu captures) to the build it was measured on."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "lash_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(ROOT, "lash_b200", "csrc", "*.h"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_costs():
+    """(kernels dict, status).  The roofline fractions are only printed when the committed capture belongs to this build."""
+    p = os.path.join(ROOT, "profiles", "kernel_costs.json")
+    try:
+        d = json.load(open(p))
+    except Exception:
+        return {}, "profiles/kernel_costs.json missing"
+    sha = source_sha()
+    if d.get("source_sha") != sha:
+        return {}, f"stale: captured on source {d.get('source_sha')}, this build is {sha} (re-run tools/profile_round.sh)"
+    return d.get("kernels", {}), f"ncu captures of source {sha}"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -103,17 +128,24 @@ class ClockSampler:
 # synthetic genomes directly in HBM (torch is plumbing: RNG + byte packing, not the measured path)
 # --------------------------------------------------------------------------------------------------
 def make_packed_genomes(torch, device, n_genomes: int, length: int, seed: int, rank: int):
-    """Returns (uint8 device tensor holding all spans, span byte offsets, span stride)."""
+    """Genomes [rank * n_genomes, (rank + 1) * n_genomes) of the synthetic set; see make_packed_genomes_ids."""
+    return make_packed_genomes_ids(torch, device, range(rank * n_genomes, (rank + 1) * n_genomes), length, seed)
+
+
+def make_packed_genomes_ids(torch, device, gids, length: int, seed: int):
+    """The genomes with global ids `gids`, 2-bit packed in HBM: a shared random ancestor with substitutions at a
+    per-genome rate; genome g is a function of (seed, g) only, whichever rank builds it.
+    Returns (uint8 device tensor holding all spans, span stride in bytes)."""
     from lash_b200.pack import padded_bytes
     from tools import synth
+    gids = list(gids)
     stride = padded_bytes(length)
-    buf = torch.zeros(n_genomes * stride + 64, dtype=torch.uint8, device=device)
+    buf = torch.zeros(len(gids) * stride + 64, dtype=torch.uint8, device=device)
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     anc = torch.randint(0, 4, (length,), dtype=torch.uint8, device=device, generator=g)   # shared ancestor
     pad = (-length) % 4
-    for i in range(n_genomes):
-        gid = rank * n_genomes + i
+    for i, gid in enumerate(gids):
         mu = synth.mutation_rate(gid, seed)
         g.manual_seed(seed * 7919 + gid + 1)
         hit = torch.rand(length, device=device, generator=g) < mu
@@ -209,6 +241,7 @@ def run_graft(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     hbm_peak, peak_src, sm_max = load_peaks()
+    costs, costs_status = load_costs()
     L = lib()
     ctx = ops.Context(local)
     # a real (non-default) stream: the C ABI treats a NULL stream as "use the library's own streams"
@@ -329,21 +362,19 @@ def run_graft(args):
     int_peak = 148 * 64 * sm_mhz * 1e6
     # issue-slot bound: 4 schedulers/SM x 1 warp-instruction/clk x 32 lanes; instructions per k-mer come from the
     # committed ncu capture of this kernel (smsp__inst_executed x 32 / k-mers), traffic from its dram__bytes
-    kname = "lash::sketch_kernel<ULL,narrow,smem>"
-    cap = {}
-    try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kname, {})
-    except Exception:
-        pass
-    traffic = cap.get("dram_bytes_per_base")
-    ipk = cap.get("warp_inst_x32_per_kmer")
+    kname = "sketch_kernel<ULL,k16,smem>"
+    cap = costs.get(kname, {})
+    traffic = cap.get("dram_bytes_per_unit")       # per k-mer start == per base (every base is streamed once)
+    ipk = cap.get("warp_inst_x32_per_unit")
     issue_peak = 148 * 4 * 32 * sm_mhz * 1e6
     kps = kmers / (sk_kernel_ms * 1e-3)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic * bases_rank if traffic else None, "traffic_source": cap.get("capture"),
+                "traffic": traffic * kmers if traffic else None, "traffic_source": cap.get("capture"),
                 "peak_source": peak_src, "kernel": kname,
                 "kernel_ms": sk_kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
-                "note": "0.25 B/base streamed once; the kernel is integer-pipe bound, not HBM bound (see int_pipe)",
+                "note": "0.25 B/base streamed once; the kernel is integer-issue bound, not HBM bound (see binding_frac); SURVEY 8d's "
+                        "64-lane integer peak is wrong for sm_100 (ALU and FMA-heavy pipes both take integer work): the denominator is "
+                        "issue slots, 148 SMs x 4 schedulers x 32 lanes x f",
                 # the resource that actually binds this kernel (SM integer pipe) and the fraction of it in use
                 "binding": "sm_integer_issue", "binding_frac": (kps * ipk / issue_peak) if ipk else None,
                 "int_pipe": {"kmers_per_s": kps, "alu_lane_ops_peak_per_s": int_peak,
@@ -351,6 +382,15 @@ def run_graft(args):
                              "alu_instr_per_kmer_at_peak": int_peak / kps,
                              "issue_lane_ops_peak_per_s": issue_peak, "instr_per_kmer_ncu": ipk,
                              "issue_frac": (kps * ipk / issue_peak) if ipk else None}}
+    # dist half of the metric: dist_fgra_tab_kernel is bound by shared-memory bandwidth (two LDS.32 = 8 B per register pair)
+    rp_s = n_pairs_rank * rb / (di_ms * 1e-3)          # this rank's register pairs per second (card + regmin + tiles)
+    dcap = costs.get("dist_fgra_tab_kernel", {})
+    smem_peak = 148 * 128 * sm_mhz * 1e6               # bytes per second, all SMs
+    roofline_dist = {"kernel": "dist_fgra_tab_kernel", "bound": "shared_memory_bandwidth", "register_pairs_per_s": rp_s,
+                     "achieved": rp_s * 8 / 1e9, "peak": smem_peak / 1e9, "unit": "GB/s", "frac": rp_s * 8 / smem_peak,
+                     "issue_frac": (rp_s * dcap["warp_inst_x32_per_unit"] / issue_peak) if dcap.get("warp_inst_x32_per_unit") else None,
+                     "capture": dcap.get("capture"), "ms": di_ms,
+                     "note": "time includes card_kernel + regmin_kernel + the tile kernel of the last step on the slowest rank"}
 
     # ---- parity spot check against the oracle (checker only) -------------------------------------
     parity = None
@@ -473,6 +513,33 @@ def run_graft(args):
     if rank == 0 and world == 1 and not args.no_ingest:
         ingest = fasta_ingest_leg(ctx, buf, stride, min(n_g, 64))
 
+    # ---- BASELINE configs[2..4] as strong-scaled legs (tools/config_legs.py) -----------------------------
+    configs = None
+    if args.legs:
+        from tools import config_legs
+        sk.close()
+        del buf, out, regs_all
+        torch.cuda.empty_cache()
+        sm_mhz_all = float(torch.tensor([sm_mhz], device=device).item())
+        if world > 1:   # every rank uses rank 0's sampled clock for the roofline denominators
+            tclk = torch.tensor([sm_mhz if rank == 0 else 0.0], dtype=torch.float64, device=device)
+            dist.all_reduce(tclk, op=dist.ReduceOp.MAX)
+            sm_mhz_all = float(tclk.item())
+        env = config_legs.Env(torch, dist, rank, world, local, device, ctx, stream, sm_mhz_all, costs)
+        configs = {}
+        for name in args.legs:
+            t_leg = time.perf_counter()
+            try:
+                configs[name] = getattr(config_legs, "leg_" + name)(env)
+                configs[name]["leg_wall_s"] = round(time.perf_counter() - t_leg, 2)
+            except Exception as exc:   # a failed leg must not take the headline line with it
+                import traceback
+                traceback.print_exc()
+                configs[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                torch.cuda.empty_cache()
+        configs["equal_across_n_keys"] = config_legs.EQUAL_ACROSS_N
+        configs["parity"] = all(bool((configs[n].get("parity") or {}).get("ok")) for n in args.legs) if rank == 0 else None
+
     if rank == 0:
         line = {
             "metric": "kmer_sketch_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
@@ -486,11 +553,13 @@ def run_graft(args):
             "phases_ms_last_step": {"sketch": sk_ms, "gather": ga_ms, "cardinality+dist": di_ms},
             "dist": {"metric": "all_vs_all_pairs_per_s", "value": n_pairs_all / (di_ms * 1e-3), "unit": "pairs/s", "pairs": n_pairs_all,
                      "register_merges_per_s": n_pairs_all * rb / (di_ms * 1e-3)},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "fasta_ingest": ingest, "clocks": clocks,
+            "roofline": roofline, "roofline_dist": roofline_dist, "cpu_baseline": cpu_baseline, "e2e": e2e, "fasta_ingest": ingest, "clocks": clocks,
             "gpu_launches": gpu_launches, "parity_spot_check": parity, "hll_bias_flags": int(flags.item()),
+            "configs": configs, "kernel_costs": costs_status,
         }
         print(json.dumps(line), flush=True)
-    sk.close()
+    if not args.legs:
+        sk.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -553,8 +622,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--no-ingest", action="store_true", help="skip the FASTA -> C++ host -> GPU leg")
+    ap.add_argument("--legs", default="c3,c4,c5", help="BASELINE configs[2..4] legs to run after the headline (comma list, '' = none)")
     ap.add_argument("--genomes", type=int, default=N_GENOMES, help="genomes per GPU (default = the BASELINE config; other values are for profiling)")
     args = ap.parse_args()
+    args.legs = [x for x in args.legs.split(",") if x]
     if args.impl == "reference":
         run_reference(args)
     else:

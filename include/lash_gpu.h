@@ -206,6 +206,18 @@ int lash_dist_stream_rows(lash_ctx* ctx, int algo, int p, int k, int estimator, 
                           uint64_t n_ref, const void* qry_regs, uint64_t n_qry, int triangular, uint64_t row_begin,
                           uint64_t row_end, uint64_t rows_per_block, lash_dist_block_cb cb, void* user);
 
+/* Size-independent check of a distance run ("checksum of checksums"): when enabled, every lash_dist / lash_dist_stream*
+ * call also sums, on the device, the bit patterns of the cells it defines (f64 as u64, f32 zero-extended; wrapping) and
+ * counts them.  The sum is order-free: the totals of a matrix computed in row blocks, or in row ranges on several GPUs
+ * (added up by the caller), equal those of one lash_dist call -- the multi-GPU equality test of the path (every pair is
+ * computed by the same arithmetic whatever tile, block or rank it lands in). */
+int lash_dist_set_checksum(lash_ctx* ctx, int enable);
+int lash_dist_checksum(lash_ctx* ctx, uint64_t* sum_bits, uint64_t* n_cells);
+/* Device-resident variant for outputs of lash_dist_dev (full-matrix indexing, packed lower triangle when triangular):
+ * sums_dev[0] += sum of bit patterns, sums_dev[1] += cells over reference rows [row_begin, row_end); enqueued on `stream`. */
+int lash_dist_checksum_dev(lash_ctx* ctx, int fp32, const void* out_dev, uint64_t n_qry, int triangular, uint64_t row_begin,
+                           uint64_t row_end, uint64_t* sums_dev, void* stream);
+
 /* Kernel time (ms) and kernel launches (cardinality, register minimum, distance tiles) of the last lash_dist /
  * lash_dist_stream call on this ctx; the launch count also accumulates over lash_cardinality_dev / lash_dist_dev calls
  * (those are not timed by the library: the caller owns the stream). */

@@ -62,6 +62,9 @@ PROTOTYPES = {
     "lash_dist_stream": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, u64, vp, u64, i32, u64, DIST_BLOCK_CB, vp]),
     "lash_dist_stream_rows": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, u64, vp, u64, i32, u64, u64, u64, DIST_BLOCK_CB, vp]),
     "lash_dist_stats": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
+    "lash_dist_set_checksum": (i32, [vp, i32]),
+    "lash_dist_checksum": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
+    "lash_dist_checksum_dev": (i32, [vp, i32, vp, u64, i32, u64, u64, vp, vp]),
 }
 
 _lib = None

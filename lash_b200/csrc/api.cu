@@ -97,9 +97,12 @@ struct lash_ctx {
     cudaStream_t stream = nullptr;
     double dist_ms = 0.0;
     uint64_t dist_launches = 0;
+    // optional wrapping sum of the output bit patterns of the last lash_dist* call (lash_dist_set_checksum)
+    bool want_checksum = false;
+    uint64_t checksum = 0, checksum_cells = 0;
     // scratch of lash_dist / lash_dist_stream, kept across calls (cudaMalloc/cudaFree per call cost
     // milliseconds of jitter on a 2.5 ms operation)
-    DevBuf d_ref, d_qry, d_card, d_out[2], d_flags, d_regmin, d_ml;
+    DevBuf d_ref, d_qry, d_card, d_out[2], d_flags, d_regmin, d_ml, d_sum;
     PinBuf h_out[2];
 };
 
@@ -128,7 +131,7 @@ extern "C" int lash_ctx_destroy(lash_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_ref.release(); c->d_qry.release(); c->d_card.release(); c->d_out[0].release(); c->d_out[1].release();
-    c->d_flags.release(); c->d_regmin.release(); c->d_ml.release(); c->h_out[0].release(); c->h_out[1].release();
+    c->d_flags.release(); c->d_regmin.release(); c->d_ml.release(); c->d_sum.release(); c->h_out[0].release(); c->h_out[1].release();
     delete c;
     return LASH_OK;
 }
@@ -747,30 +750,50 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
     DevBuf &d_ref = ctx->d_ref, &d_qry = ctx->d_qry, &d_card = ctx->d_card, &d_flags = ctx->d_flags;
     DevBuf* d_out = ctx->d_out;
     PinBuf* h_out = ctx->h_out;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done[2] = {nullptr, nullptr};
-    auto cleanup = [&]() {
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
-        for (int i = 0; i < 2; ++i) if (done[i]) cudaEventDestroy(done[i]);
-    };
+    // Every per-call event and stream lives in this guard: whichever way the function leaves, both streams are drained
+    // first (kernels and D2H copies may still target ctx->d_out / h_out, which the next call may reserve() = free) and
+    // then everything is destroyed.
+    struct Guard {
+        cudaStream_t st, st2 = nullptr;
+        std::vector<cudaEvent_t> evs;
+        explicit Guard(cudaStream_t s) : st(s) {}
+        cudaError_t event(cudaEvent_t* e, unsigned flags = cudaEventDefault) {
+            cudaError_t rc = cudaEventCreateWithFlags(e, flags);
+            if (rc == cudaSuccess) evs.push_back(*e);
+            return rc;
+        }
+        ~Guard() {
+            if (st2) cudaStreamSynchronize(st2);
+            cudaStreamSynchronize(st);
+            for (cudaEvent_t e : evs) cudaEventDestroy(e);
+            if (st2) cudaStreamDestroy(st2);
+        }
+    } guard(st);
 #define CUC(call)                                                                     \
     do {                                                                              \
         cudaError_t e__ = (call);                                                     \
         if (e__ != cudaSuccess) {                                                     \
-            cleanup();                                                                \
             return fail(e__ == cudaErrorMemoryAllocation ? LASH_E_NOMEM : LASH_E_CUDA, \
                         std::string(#call) + ": " + cudaGetErrorString(e__));         \
         }                                                                             \
     } while (0)
+    cudaEvent_t ev0, ev1;
     CUC(d_ref.reserve(rb * n_ref));
     if (!same) CUC(d_qry.reserve(rb * n_qry));
     CUC(d_card.reserve(8 * (n_ref + n_qry)));
     CUC(d_flags.reserve(4));
-    CUC(cudaEventCreate(&ev0));
-    CUC(cudaEventCreate(&ev1));
+    CUC(guard.event(&ev0));
+    CUC(guard.event(&ev1));
     CUC(cudaMemcpyAsync(d_ref.p, ref_regs, rb * n_ref, cudaMemcpyHostToDevice, st));
     if (!same) CUC(cudaMemcpyAsync(d_qry.p, qry_regs, rb * n_qry, cudaMemcpyHostToDevice, st));
     CUC(cudaMemsetAsync(d_flags.p, 0, 4, st));
+    unsigned long long* d_sum = nullptr;
+    ctx->checksum = ctx->checksum_cells = 0;
+    if (ctx->want_checksum) {
+        CUC(ctx->d_sum.reserve(16));
+        d_sum = (unsigned long long*)ctx->d_sum.p;
+        CUC(cudaMemsetAsync(d_sum, 0, 16, st));
+    }
     const void* qdev = same ? d_ref.p : d_qry.p;
     double* card_r = (double*)d_card.p;
     double* card_q = same ? card_r : card_r + n_ref;
@@ -790,10 +813,7 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
     dp.ref = d_ref.p; dp.qry = qdev; dp.n_ref = n_ref; dp.n_qry = n_qry;
     dp.card_ref = card_r; dp.card_qry = card_q; dp.flags = (uint32_t*)d_flags.p;
     rc = prepare_regmin(ctx, dp, rb, st);
-    if (rc) {
-        cleanup();
-        return rc;
-    }
+    if (rc) return rc;
 
     if (!cb) {
         // whole result on device, one D2H
@@ -801,16 +821,18 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
         CUC(d_out[0].reserve(cells * esz));
         dp.row_begin = 0; dp.row_end = n_ref; dp.out = d_out[0].p; dp.packed_tri = triangular ? 1 : 0; dp.out_row0 = 0;
         cudaEvent_t k0, k1;
-        CUC(cudaEventCreate(&k0));
-        done[0] = k0;
-        CUC(cudaEventCreate(&k1));
-        done[1] = k1;
+        CUC(guard.event(&k0));
+        CUC(guard.event(&k1));
         CUC(cudaEventRecord(k0, st));
         setup_ml_scratch(ctx, dp);
         uint32_t nl = 0;
         CUC(launch_dist(dp, st, &nl));
         ctx->dist_launches += nl;
         CUC(cudaEventRecord(k1, st));
+        if (d_sum) {
+            CUC(launch_out_checksum(dp, d_sum, st));
+            ctx->dist_launches += 1;
+        }
         CUC(cudaMemcpyAsync(out, d_out[0].p, cells * esz, cudaMemcpyDeviceToHost, st));
         CUC(cudaStreamSynchronize(st));
         float ms = 0.f;
@@ -820,19 +842,19 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
         if (rows_per_block == 0) rows_per_block = std::max<uint64_t>(1, ((uint64_t)256 << 20) / (n_qry * esz));
         rows_per_block = std::min(rows_per_block, n_ref);
         const size_t blk_bytes = rows_per_block * n_qry * esz;
-        cudaStream_t st2;
-        CUC(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
-        cudaEvent_t kdone[2], copied[2];
+        CUC(cudaStreamCreateWithFlags(&guard.st2, cudaStreamNonBlocking));
+        const cudaStream_t st2 = guard.st2;
+        cudaEvent_t kstart, kdone[2], csum[2], copied[2];
         for (int i = 0; i < 2; ++i) {
             CUC(d_out[i].reserve(blk_bytes));
             CUC(h_out[i].reserve(blk_bytes));
-            CUC(cudaEventCreate(&kdone[i]));
-            CUC(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+            CUC(guard.event(&kdone[i]));
+            CUC(guard.event(&csum[i], cudaEventDisableTiming));
+            CUC(guard.event(&copied[i], cudaEventDisableTiming));
         }
+        CUC(guard.event(&kstart));
         // kernels on st, copies on st2; callback for block b-1 runs on the host while block b computes
         struct Pending { uint64_t row0, nrows; int buf; bool valid; } pend = {0, 0, 0, false};
-        cudaEvent_t kstart;
-        CUC(cudaEventCreate(&kstart));
         int buf = 0;
         int cb_rc = 0;
         uint64_t nblocks = 0;
@@ -847,6 +869,11 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
             CUC(launch_dist(dp, st, &nl));
             ctx->dist_launches += nl;
             CUC(cudaEventRecord(kdone[buf], st));
+            if (d_sum) {
+                CUC(launch_out_checksum(dp, d_sum, st));
+                ctx->dist_launches += 1;
+                CUC(cudaEventRecord(csum[buf], st));
+            }
             // deliver the previous block while this one computes
             if (pend.valid) {
                 CUC(cudaEventSynchronize(copied[pend.buf]));
@@ -858,6 +885,8 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
             // (same pitch on both sides, so the block keeps its dense [n_rows][n_qry] addressing)
             const uint64_t ncols = triangular ? std::min<uint64_t>(n_qry, r1) : n_qry;
             CUC(cudaMemcpy2DAsync(h_out[buf].p, n_qry * esz, d_out[buf].p, n_qry * esz, ncols * esz, r1 - r0, cudaMemcpyDeviceToHost, st2));
+            // the next kernel into this buffer (two blocks on) is ordered after `copied` by the host wait above; the checksum
+            // kernel only reads, so it may overlap the copy
             CUC(cudaEventRecord(copied[buf], st2));
             CUC(cudaEventSynchronize(kdone[buf]));
             float ms = 0.f;
@@ -869,22 +898,21 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
             CUC(cudaEventSynchronize(copied[pend.buf]));
             cb_rc = cb(user, pend.row0, pend.nrows, h_out[pend.buf].p);
         }
-        cudaStreamSynchronize(st2);
-        cudaStreamSynchronize(st);
-        cudaStreamDestroy(st2);
-        cudaEventDestroy(kstart);
-        for (int i = 0; i < 2; ++i) { cudaEventDestroy(kdone[i]); cudaEventDestroy(copied[i]); }
-        if (cb_rc != 0) {
-            cleanup();
-            return fail(LASH_E_STATE, "lash_dist_stream: callback returned non-zero");
-        }
+        CUC(cudaStreamSynchronize(st2));
+        CUC(cudaStreamSynchronize(st));
+        if (cb_rc != 0) return fail(LASH_E_STATE, "lash_dist_stream: callback returned non-zero");
     }
     float ms_card = 0.f;
     CUC(cudaEventElapsedTime(&ms_card, ev0, ev1));
     ctx->dist_ms = ms_total + ms_card;
     uint32_t flags = 0;
     CUC(cudaMemcpy(&flags, d_flags.p, 4, cudaMemcpyDeviceToHost));
-    cleanup();
+    if (d_sum) {
+        unsigned long long hs[2] = {0, 0};
+        CUC(cudaMemcpy(hs, d_sum, 16, cudaMemcpyDeviceToHost));
+        ctx->checksum = hs[0];
+        ctx->checksum_cells = hs[1];
+    }
 #undef CUC
     return flags ? LASH_W_HLL_BIAS_REGIME : LASH_OK;
 }
@@ -908,6 +936,33 @@ extern "C" int lash_dist_stream_rows(lash_ctx* ctx, int algo, int p, int k, int 
     if (row_begin == row_end) return LASH_OK;
     return dist_host(ctx, algo, p, k, estimator, model, fp32, ref_regs, n_ref, qry_regs, n_qry, triangular, nullptr, rows_per_block, cb,
                      user, row_begin, row_end);
+}
+extern "C" int lash_dist_set_checksum(lash_ctx* ctx, int enable) {
+    if (!ctx) return fail(LASH_E_INVALID, "lash_dist_set_checksum: NULL ctx");
+    ctx->want_checksum = enable != 0;
+    return LASH_OK;
+}
+extern "C" int lash_dist_checksum(lash_ctx* ctx, uint64_t* sum_bits, uint64_t* n_cells) {
+    if (!ctx) return fail(LASH_E_INVALID, "lash_dist_checksum: NULL ctx");
+    if (sum_bits) *sum_bits = ctx->checksum;
+    if (n_cells) *n_cells = ctx->checksum_cells;
+    return LASH_OK;
+}
+extern "C" int lash_dist_checksum_dev(lash_ctx* ctx, int fp32, const void* out_dev, uint64_t n_qry, int triangular,
+                                      uint64_t row_begin, uint64_t row_end, uint64_t* sums_dev, void* stream) {
+    if (!ctx || !out_dev || !sums_dev) return fail(LASH_E_INVALID, "lash_dist_checksum_dev: NULL argument");
+    if (row_begin > row_end) return fail(LASH_E_INVALID, "lash_dist_checksum_dev: bad row range");
+    CU(cudaSetDevice(ctx->device));
+    DistParams dp;
+    dp.algo = 0; dp.p = 0; dp.k = 0; dp.estimator = 0; dp.model = 0;
+    dp.fp32 = fp32 ? 1 : 0;
+    dp.triangular = triangular ? 1 : 0;
+    dp.ref = dp.qry = nullptr; dp.n_ref = row_end; dp.n_qry = n_qry; dp.card_ref = dp.card_qry = nullptr;
+    dp.row_begin = row_begin; dp.row_end = row_end; dp.out = const_cast<void*>(out_dev);
+    dp.packed_tri = triangular ? 1 : 0; dp.out_row0 = 0; dp.flags = nullptr; dp.n_sm = ctx->n_sm;
+    CU(launch_out_checksum(dp, (unsigned long long*)sums_dev, stream ? (cudaStream_t)stream : ctx->stream));
+    ctx->dist_launches += 1;
+    return LASH_OK;
 }
 extern "C" int lash_dist_stats(lash_ctx* ctx, double* kernel_ms, uint64_t* launches) {
     if (!ctx) return fail(LASH_E_INVALID, "lash_dist_stats: NULL ctx");

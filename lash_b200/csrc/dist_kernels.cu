@@ -930,6 +930,41 @@ cudaError_t launch_regmin(const void* regs, uint64_t n_bytes, uint32_t* out_dev,
     return cudaGetLastError();
 }
 
+// Wrapping sum of the output bit patterns (f64 -> u64, f32 -> zero-extended u32) of the cells rows [row_begin, row_end)
+// define, plus their count: sums[0] += sum, sums[1] += cells.  Order-free, so it is independent of how the rows were cut
+// into blocks / ranks: the checksum of checksums of a tiled or sharded run equals the one of a single call.
+// Addressing as DistParams: packed_tri ? out[i*(i+1)/2 + j] : out[(i - out_row0) * n_qry + j]; triangular: only j <= i.
+__global__ void __launch_bounds__(256) out_checksum_kernel(DistParams dp, unsigned long long* sums) {
+    unsigned long long acc = 0ull, cnt = 0ull;
+    for (uint64_t i = dp.row_begin + blockIdx.x; i < dp.row_end; i += gridDim.x) {
+        const uint64_t ncol = dp.triangular ? min(dp.n_qry, i + 1) : dp.n_qry;
+        const uint64_t o0 = dp.packed_tri ? i * (i + 1) / 2 : (i - dp.out_row0) * dp.n_qry;
+        if (dp.fp32) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(dp.out) + o0;
+            for (uint64_t j = threadIdx.x; j < ncol; j += blockDim.x) acc += q[j];
+        } else {
+            const unsigned long long* q = reinterpret_cast<const unsigned long long*>(dp.out) + o0;
+            for (uint64_t j = threadIdx.x; j < ncol; j += blockDim.x) acc += q[j];
+        }
+        if (threadIdx.x == 0) cnt += ncol;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        if (acc) atomicAdd(sums, acc);
+        if (cnt) atomicAdd(sums + 1, cnt);
+    }
+}
+cudaError_t launch_out_checksum(const DistParams& dp, unsigned long long* sums_dev, cudaStream_t st) {
+    if (dp.row_end <= dp.row_begin) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>(dp.row_end - dp.row_begin, (uint64_t)dp.n_sm * 8);
+    out_checksum_kernel<<<grid, 256, 0, st>>>(dp, sums_dev);
+    return cudaGetLastError();
+}
+
 static cudaError_t launch_dist_fgra_tab(const DistParams& dp, cudaStream_t st) {
     const uint32_t cb = cell_bytes_of(dp.algo, dp.p);
     const uint32_t chunk = cb < (uint32_t)kTabChunk ? cb : (uint32_t)kTabChunk;

@@ -84,6 +84,8 @@ uint32_t ml_scratch_words(int p);
 // atomicMin of the smallest non-zero register byte into *out_dev (preset to 0xffffffff by the caller)
 cudaError_t launch_regmin(const void* regs, uint64_t n_bytes, uint32_t* out_dev, int n_sm, cudaStream_t st);
 cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launches);
+// sums_dev[0] += wrapping sum of the output cells' bit patterns over rows [row_begin, row_end), sums_dev[1] += their count
+cudaError_t launch_out_checksum(const DistParams& dp, unsigned long long* sums_dev, cudaStream_t st);
 cudaError_t launch_cardinality(int algo, int p, int estimator, const void* regs, uint64_t n, double* card,
                                uint32_t* flags, cudaStream_t st);
 // host-side one-time upload of estimator tables into constant memory (idempotent, per device)

@@ -1,0 +1,256 @@
+// K0: filter_out_n + 2-bit packing on the device (sm_100a, HBM-bound byte work).
+//
+// Replaces, for hosts that ship raw sequence text, the reference's per-record front end
+//   src/utils.rs:33-41   filter_out_n: keep bytes that are exactly one of "ACGT", delete everything else, join the flanks
+//   src/utils.rs:464     KSeq::new(&seq, 2): A0 C1 G2 T3, four bases per byte, first base in the high bits
+// and the "k-mers never span records" rule (utils.rs:457-464), which the sketch kernel gets as an invalid-start bitmask.
+//
+// Input: a span of raw sequence bytes of ONE genome (line breaks, N, lowercase, IUPAC codes ... anything), records
+// separated IN BAND by the byte LASH_TEXT_RECORD_SEP.  Output: exactly the packed span + invalid-start mask that
+// lash_sketch_push takes from a host packer, so K1 (sketch_kernel) runs unchanged on it.
+//
+// Three small kernels per push (all streaming; the text is read twice = 2 B/base of HBM traffic against the 1 B/base
+// that crossed PCIe at 1/100 of the bandwidth to get here):
+//   text_count_kernel     kept bases per 32 KiB block of text
+//   text_scan_kernel      exclusive prefix of the block counts inside each span (one CTA), kept bases per span
+//   text_compact_kernel   re-reads the block: classify, CTA-wide prefix, append the 2-bit codes to a shared-memory bit
+//                         stream aligned with the output words, flush (first / last word with atomicOr: neighbouring
+//                         blocks share them), and turn every separator into invalid-start bits [e-k+1, e)
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace lash {
+
+constexpr int kTextThreads = 256;
+constexpr uint32_t kTextIterBytes = kTextThreads * 16;   // one 16-byte load per thread per iteration
+static_assert(kTextBlockBytes % kTextIterBytes == 0, "a text block is a whole number of CTA iterations");
+
+// byte -> (is one of "ACGT", 2-bit code).  (c >> 1) & 3 separates the four letters (A 0, C 1, T 2, G 3); the byte is a
+// base iff it equals the letter its own index selects; code = idx ^ (idx >> 1) gives A0 C1 G2 T3.
+__device__ __forceinline__ bool base_code(uint32_t c, uint32_t& code) {
+    const uint32_t idx = (c >> 1) & 3u;
+    code = idx ^ (idx >> 1);
+    return c == ((0x47544341u >> (8u * idx)) & 0xffu);
+}
+
+// the 16 bytes a thread owns: number of bases kept and their codes MSB-first (first kept base in the top two bits)
+__device__ __forceinline__ void classify16(const uint4& q, uint32_t n_live, uint32_t& cnt, uint32_t& bits, uint32_t& seps) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    cnt = 0;
+    bits = 0;
+    seps = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+        uint32_t code;
+        const bool live = (uint32_t)i < n_live;
+        const bool ok = base_code(c, code) && live;
+        bits = ok ? ((bits << 2) | code) : bits;
+        cnt += ok ? 1u : 0u;
+        seps |= (live && c == (uint32_t)kTextRecordSep) ? (1u << i) : 0u;
+    }
+    bits = cnt ? (bits << (32u - 2u * cnt)) : 0u;
+}
+
+__global__ void __launch_bounds__(kTextThreads) text_count_kernel(const uint8_t* __restrict__ text, const TextBlock* __restrict__ blocks,
+                                                                  uint32_t n_blocks, uint64_t* __restrict__ block_cnt) {
+    __shared__ uint32_t s_sum[kTextThreads / 32];
+    for (uint32_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const TextBlock tb = blocks[b];
+        uint32_t mine = 0;
+        for (uint32_t off = threadIdx.x * 16u; off < tb.n_bytes; off += kTextIterBytes) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(text + tb.byte_begin + off));
+            uint32_t cnt, bits, seps;
+            classify16(q, min(16u, tb.n_bytes - off), cnt, bits, seps);
+            mine += cnt;
+        }
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31u) == 0) s_sum[threadIdx.x >> 5] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int i = 0; i < kTextThreads / 32; ++i) t += s_sum[i];
+            block_cnt[b] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// In place: block_cnt[b] -> kept bases of the SAME span before block b; span_kept[s] = kept bases of span s.
+// One CTA; the global exclusive prefix G is built chunk by chunk, then every block subtracts G at its span's first block.
+__global__ void __launch_bounds__(1024) text_scan_kernel(uint64_t* __restrict__ block_cnt, uint32_t n_blocks, const TextBlock* __restrict__ blocks,
+                                                         const TextSpanDev* __restrict__ spans, uint32_t n_spans, uint64_t* __restrict__ span_kept) {
+    __shared__ uint64_t s_warp[32];
+    __shared__ uint64_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_blocks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = i < n_blocks ? block_cnt[i] : 0ull;
+        uint64_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if ((threadIdx.x & 31u) >= (uint32_t)d) x += y;
+        }
+        if ((threadIdx.x & 31u) == 31u) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint64_t w = s_warp[threadIdx.x], xw = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t y = __shfl_up_sync(0xffffffffu, xw, d);
+                if (threadIdx.x >= (uint32_t)d) xw += y;
+            }
+            s_warp[threadIdx.x] = xw - w;  // exclusive over warps
+        }
+        __syncthreads();
+        const uint64_t excl = s_carry + s_warp[threadIdx.x >> 5] + (x - v);
+        if (i < n_blocks) block_cnt[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_cnt[n_blocks] = s_carry;  // G[n_blocks]
+    __syncthreads();
+    __threadfence_block();
+    // span totals first (they read G at span starts), then the per-block rebase -- both from an unmodified G: stage the
+    // span starts' G values before anything is overwritten
+    for (uint32_t s = threadIdx.x; s < n_spans; s += 1024) {
+        const TextSpanDev sp = spans[s];
+        span_kept[s] = block_cnt[sp.first_block + sp.n_blocks] - block_cnt[sp.first_block];
+    }
+    __syncthreads();
+    // rebase: walk the spans; a span's first block keeps G (needed by its later blocks) until the span is done, so the
+    // subtraction runs over blocks in DESCENDING order within each chunk of threads: simpler -- read G[first] per block
+    // into a register, sync the whole CTA, then write.
+    for (uint32_t base = 0; base < n_blocks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        uint64_t mine = 0, first = 0;
+        uint32_t fb = 0;
+        if (i < n_blocks) {
+            fb = spans[blocks[i].span].first_block;
+            mine = block_cnt[i];
+            first = block_cnt[fb];
+        }
+        __syncthreads();
+        // G[fb] is only overwritten by the thread that owns block fb, in the chunk that contains fb; blocks of later
+        // chunks that belong to the same span still need it -> keep G[fb] intact and store the rebased values of span
+        // starts (always 0) last, after all chunks: here only non-first blocks are written
+        if (i < n_blocks && i != fb) block_cnt[i] = mine - first;
+        __syncthreads();
+    }
+    for (uint32_t s = threadIdx.x; s < n_spans; s += 1024)
+        if (spans[s].n_blocks) block_cnt[spans[s].first_block] = 0;
+}
+
+// big-endian base order inside a 32-bit word <-> the little-endian bytes of the lash_gpu.h format
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+__global__ void __launch_bounds__(kTextThreads) text_compact_kernel(const uint8_t* __restrict__ text, const TextBlock* __restrict__ blocks,
+                                                                    uint32_t n_blocks, const uint64_t* __restrict__ block_prefix,
+                                                                    const TextSpanDev* __restrict__ spans, const uint64_t* __restrict__ span_kept,
+                                                                    uint32_t* __restrict__ packed_out, uint32_t* __restrict__ inv_mask, int k) {
+    constexpr uint32_t kStageWords = kTextIterBytes / 16 + 2;
+    __shared__ uint32_t s_stage[kStageWords];
+    __shared__ uint32_t s_warp[kTextThreads / 32];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < kStageWords; i += kTextThreads) s_stage[i] = 0u;
+    __syncthreads();
+    // starts [e-k+1, e) cannot begin a k-mer when a record ends at kept position e
+    auto mark_boundary = [&](uint32_t* mask, uint64_t e) {
+        uint64_t lo = e >= (uint64_t)(k - 1) ? e - (uint64_t)(k - 1) : 0;
+        for (uint64_t x = lo; x < e;) {
+            const uint32_t bit = (uint32_t)(x & 31);
+            const uint64_t n = min((uint64_t)(32 - bit), e - x);
+            const uint32_t m = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << bit;
+            atomicOr(mask + (x >> 5), m);
+            x += n;
+        }
+    };
+    for (uint32_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const TextBlock tb = blocks[b];
+        const TextSpanDev sp = spans[tb.span];
+        uint32_t* out = packed_out + sp.out_word_off;
+        uint32_t* mask = sp.mask_word_off != ~0ull ? inv_mask + sp.mask_word_off : nullptr;
+        uint64_t P = block_prefix[b];  // kept bases of this span before the block
+        for (uint32_t off0 = 0; off0 < tb.n_bytes; off0 += kTextIterBytes) {
+            const uint32_t off = off0 + threadIdx.x * 16u;
+            uint32_t cnt = 0, bits = 0, seps = 0;
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (off < tb.n_bytes) {
+                q = __ldg(reinterpret_cast<const uint4*>(text + tb.byte_begin + off));
+                classify16(q, min(16u, tb.n_bytes - off), cnt, bits, seps);
+            }
+            // CTA-wide exclusive prefix of cnt
+            uint32_t x = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (uint32_t)d) x += y;
+            }
+            if (lane == 31u) s_warp[warp] = x;
+            __syncthreads();
+            uint32_t wbase = 0, total = 0;
+#pragma unroll
+            for (int i = 0; i < kTextThreads / 32; ++i) {
+                const uint32_t v = s_warp[i];
+                wbase += (uint32_t)i < warp ? v : 0u;
+                total += v;
+            }
+            const uint32_t excl = wbase + x - cnt;
+            // append this thread's codes to the staged bit stream, aligned with the output words
+            const uint32_t lead = (uint32_t)(P & 15u);
+            if (cnt) {
+                const uint32_t o = 2u * (lead + excl);
+                const uint32_t w = o >> 5, sh = o & 31u;
+                atomicOr(&s_stage[w], bits >> sh);
+                if (sh && ((bits << (32u - sh)) != 0u)) atomicOr(&s_stage[w + 1], bits << (32u - sh));
+            }
+            // record separators (rare: one per record): invalid-start bits relative to the span
+            if (seps && mask) {
+                const uint32_t wq[4] = {q.x, q.y, q.z, q.w};
+                uint32_t before = 0;
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t c = (wq[i >> 2] >> (8 * (i & 3))) & 0xffu;
+                    if ((seps >> i) & 1u) mark_boundary(mask, P + excl + before);
+                    uint32_t code;
+                    before += base_code(c, code) ? 1u : 0u;
+                }
+            }
+            __syncthreads();
+            // flush: the words this iteration touched; the first and the last are shared with the neighbours
+            const uint32_t n_words = (lead + total + 15u) >> 4;
+            const uint64_t w0 = P >> 4;
+            for (uint32_t w = threadIdx.x; w < n_words; w += kTextThreads) {
+                const uint32_t v = s_stage[w];
+                s_stage[w] = 0u;
+                if (w == 0 || w + 1 == n_words) {
+                    if (v) atomicOr(out + w0 + w, bswap32(v));
+                } else {
+                    out[w0 + w] = bswap32(v);
+                }
+            }
+            P += total;
+            __syncthreads();
+        }
+        // the end of the span ends its last record
+        if (mask && threadIdx.x == 0 && b + 1 == sp.first_block + sp.n_blocks) mark_boundary(mask, span_kept[tb.span]);
+    }
+}
+
+cudaError_t launch_text_pack(const uint8_t* text_dev, const TextBlock* blocks_dev, uint32_t n_blocks, const TextSpanDev* spans_dev,
+                             uint32_t n_spans, uint64_t* block_cnt_dev, uint64_t* span_kept_dev, uint32_t* packed_out_dev,
+                             uint32_t* mask_dev, int k, int n_sm, cudaStream_t st) {
+    if (n_blocks == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)n_sm * 8);
+    text_count_kernel<<<grid, kTextThreads, 0, st>>>(text_dev, blocks_dev, n_blocks, block_cnt_dev);
+    text_scan_kernel<<<1, 1024, 0, st>>>(block_cnt_dev, n_blocks, blocks_dev, spans_dev, n_spans, span_kept_dev);
+    text_compact_kernel<<<grid, kTextThreads, 0, st>>>(text_dev, blocks_dev, n_blocks, block_cnt_dev, spans_dev, span_kept_dev,
+                                                       packed_out_dev, mask_dev, k);
+    return cudaGetLastError();
+}
+
+}  // namespace lash

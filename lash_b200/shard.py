@@ -8,20 +8,43 @@ The only exchange step is one broadcast of the sketch set, done by the caller wi
 """
 from __future__ import annotations
 
+import heapq
 import math
 from typing import Sequence
 
 
-def genome_shard(sizes: Sequence[int], rank: int, world: int) -> list[int]:
-    """Indices of the genomes rank `rank` sketches (LPT greedy, deterministic on every rank)."""
-    loads = [0] * world
-    mine: list[int] = []
+def genome_shards(sizes: Sequence[int], world: int) -> list[list[int]]:
+    """Every rank's genome indices at once (LPT greedy: largest genome first onto the least loaded rank, ties to the
+    lower rank; deterministic, so every rank computes the same partition).  O(n log n)."""
+    heap = [(0, r) for r in range(world)]
+    out: list[list[int]] = [[] for _ in range(world)]
     for g in sorted(range(len(sizes)), key=lambda i: (-sizes[i], i)):
-        r = min(range(world), key=lambda j: (loads[j], j))
-        loads[r] += sizes[g]
-        if r == rank:
-            mine.append(g)
-    return sorted(mine)
+        load, r = heapq.heappop(heap)
+        out[r].append(g)
+        heapq.heappush(heap, (load + sizes[g], r))
+    return [sorted(s) for s in out]
+
+
+def genome_shard(sizes: Sequence[int], rank: int, world: int) -> list[int]:
+    """Indices of the genomes rank `rank` sketches."""
+    return genome_shards(sizes, world)[rank]
+
+
+def gather_permutation(shards: Sequence[Sequence[int]], pad_to: int | None = None) -> list[int]:
+    """Sketches come back from an all-gather rank after rank, each rank's block padded to `pad_to` rows (default: the
+    largest shard).  perm[g] = row of global genome g in that rank-concatenated array, so
+    `gathered.index_select(0, perm)` is the register array in list order (what the reference's Vec<S> is, utils.rs:507)."""
+    pad = max((len(s) for s in shards), default=0) if pad_to is None else pad_to
+    n = sum(len(s) for s in shards)
+    perm = [-1] * n
+    for r, s in enumerate(shards):
+        if len(s) > pad:
+            raise ValueError("shard larger than the padded block")
+        for t, g in enumerate(s):
+            if not 0 <= g < n or perm[g] != -1:
+                raise ValueError("shards must partition range(n)")
+            perm[g] = r * pad + t
+    return perm
 
 
 def row_shard(n_rows: int, rank: int, world: int, triangular: bool) -> tuple[int, int]:

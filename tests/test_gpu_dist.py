@@ -122,6 +122,51 @@ def test_stream_blocks_equal_dense(oracle, gpu_ctx):
     assert np.array_equal(got, dense)
 
 
+def _checksum_of(cells: np.ndarray) -> tuple[int, int]:
+    bits = cells.view(np.uint64 if cells.dtype == np.float64 else np.uint32).astype(np.uint64)
+    return int(bits.sum(dtype=np.uint64)), int(cells.size)
+
+
+@pytest.mark.parametrize("fp32", [False, True])
+def test_checksum_of_checksums_is_tiling_independent(oracle, gpu_ctx, fp32):
+    """lash_dist_set_checksum: the device-side wrapping sum of the output bit patterns equals the host sum of the same
+    cells, for one call, for row blocks, for row ranges (the multi-GPU tiling) and for the packed triangle."""
+    import ctypes as C
+
+    from lash_b200 import capi
+    L = capi.lib()
+    regs = _sketches(oracle, ALGO_ULL, 10, 16, 75, 60_000)
+    n = len(regs)
+
+    def read():
+        s, c = C.c_uint64(), C.c_uint64()
+        capi.check(L.lash_dist_checksum(gpu_ctx.handle, C.byref(s), C.byref(c)))
+        return s.value, c.value
+
+    capi.check(L.lash_dist_set_checksum(gpu_ctx.handle, 1))
+    try:
+        dense, _ = ops.dist(gpu_ctx, ALGO_ULL, 10, 16, EST_ML, MODEL_POISSON, fp32, regs, regs)
+        assert read() == _checksum_of(dense)
+        tri, _ = ops.dist(gpu_ctx, ALGO_ULL, 10, 16, EST_ML, MODEL_POISSON, fp32, regs, regs, triangular=True)
+        want_tri = _checksum_of(tri)
+        assert read() == want_tri and want_tri[1] == n * (n + 1) // 2
+        ops.dist_stream(gpu_ctx, ALGO_ULL, 10, 16, EST_ML, MODEL_POISSON, fp32, regs, regs, True, 16, lambda r0, b: None)
+        assert read() == want_tri
+        # row ranges, as two ranks would compute them: the sums add up (mod 2^64)
+        rp = regs.ctypes.data_as(C.c_void_p)
+        cb = capi.DIST_BLOCK_CB(lambda u, r0, nr, ptr: 0)
+        total = [0, 0]
+        for b, e in ((0, 31), (31, n)):
+            capi.check(L.lash_dist_stream_rows(gpu_ctx.handle, ALGO_ULL, 10, 16, EST_ML, MODEL_POISSON, int(fp32), rp, n, rp, n, 1, b, e, 7, cb, None))
+            s, c = read()
+            total = [(total[0] + s) % 2**64, total[1] + c]
+        assert tuple(total) == want_tri
+    finally:
+        capi.check(L.lash_dist_set_checksum(gpu_ctx.handle, 0))
+    ops.dist(gpu_ctx, ALGO_ULL, 10, 16, EST_ML, MODEL_POISSON, fp32, regs[:5], regs[:5])
+    assert read() == (0, 0)   # switched off again
+
+
 def test_small_sketches_hit_small_range_paths(oracle, gpu_ctx):
     """Tiny inputs: most registers empty -> ULL FGRA small-range correction (c0..c10, sigma),
     ULL ML with b[0], b[1] contributions, HLL linear counting, HMH with few collisions."""

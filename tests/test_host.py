@@ -187,12 +187,58 @@ def test_single_sample_in_shares_world_size_2():
     assert out == {"ull": True, "hll": True, "hmh": True}
 
 
+def _perm_worker(rank, world, port, q):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from lash_b200 import shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sizes = [5] * 11 + [9, 1, 7]                        # 14 genomes, uneven: the shards differ in length
+    shards = shard.genome_shards(sizes, world)
+    n_max = max(len(s) for s in shards)
+    mine = torch.zeros((n_max, 4), dtype=torch.int64)    # "registers" of genome g = [g, g, g, g]; padding rows stay 0
+    for t, g in enumerate(shards[rank]):
+        mine[t] = g + 1
+    gath = torch.empty((world * n_max, 4), dtype=torch.int64)
+    dist.all_gather_into_tensor(gath, mine)             # what bench.py's legs do over NCCL
+    perm = torch.tensor(shard.gather_permutation(shards), dtype=torch.int64)
+    ordered = gath.index_select(0, perm)
+    if rank == 0:
+        q.put(ordered[:, 0].tolist())
+    dist.destroy_process_group()
+
+
+def test_gathered_sketches_return_to_list_order_world_size_2():
+    """bench.py configs[2] / configs[4] legs: every rank sketches its genome shard, the all-gather returns the blocks rank
+    after rank (padded), and shard.gather_permutation puts them back into list order (utils.rs:507: Vec<S> in file order)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_perm_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == list(range(1, 15))
+
+
 def test_shard_functions_edge_cases():
     from lash_b200 import shard
     for world in (1, 2, 3, 4, 8):
         for n in (0, 1, 5, 8, 1000):
             got = sorted(g for r in range(world) for g in shard.genome_shard([10] * n, r, world))
             assert got == list(range(n))
+            shards = shard.genome_shards([10] * n, world)
+            assert shards == [list(range(r, n, world)) for r in range(world)]     # equal sizes: round robin
+            perm = shard.gather_permutation(shards)
+            pad = max(len(s) for s in shards)
+            assert sorted(perm) == sorted(r * pad + t for r, s in enumerate(shards) for t in range(len(s)))
             cuts = [shard.read_shard(n, r, world) for r in range(world)]
             assert cuts[0][0] == 0 and cuts[-1][1] == n and all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             for tri in (False, True):
