@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LASH_GPU_ABI_VERSION 1
+#define LASH_GPU_ABI_VERSION 2
 
 /* algorithm ids (main.rs:210-246: "hmh" | "hll" | "ull") */
 #define LASH_ALGO_HMH 0
@@ -126,6 +126,29 @@ int lash_sketch_push(lash_sketcher* s, const uint8_t* packed, uint64_t n_bytes, 
 /* Same, but `packed` already lives in device memory of the context's GPU (no copy). */
 int lash_sketch_push_dev(lash_sketcher* s, const void* packed_dev, uint64_t n_bytes, const lash_span* spans,
                          uint32_t n_spans, const uint64_t* rec_start, uint64_t n_rec_entries, uint64_t* ticket);
+/* ---- raw sequence text in: filter_out_n (utils.rs:33-41) + 2-bit packing (utils.rs:464) on the device -------------------
+ * For hosts with few cores per GPU: the host only finds the records and copies their sequence bytes into a pinned chunk
+ * (1 B/base over PCIe instead of 0.25, but no per-base CPU work); the device deletes every byte that is not one of "ACGT"
+ * (line breaks, N, lowercase, IUPAC codes, anything -- flanks are joined, exactly filter_out_n), packs, and sketches.
+ * A text span = the sequence bytes of the records of ONE genome, back to back; records are separated IN BAND by one
+ * LASH_TEXT_RECORD_SEP byte (k-mers never cross it, utils.rs:457-464; a record that keeps fewer than k bases yields
+ * nothing, utils.rs:460-462).  The separator may appear before the first or after the last record and repeatedly.  A host
+ * must not pass a sequence byte equal to the separator (replace it by any other non-ACGT byte: the filter deletes both).
+ * byte_off: multiple of 16; the buffer must be readable up to the next multiple of 16 past each span.
+ * n_rec: 0 or 1 = the span holds no separator (whole genomes: saves the boundary bitmask), otherwise any value > 1. */
+#define LASH_TEXT_RECORD_SEP 0x01
+typedef struct lash_text_span {
+    uint64_t genome;   /* accumulator slot in [0, n_genomes) */
+    uint64_t byte_off; /* offset of the span's first byte in the push buffer, multiple of 16 */
+    uint64_t n_bytes;  /* raw bytes in the span */
+    uint32_t n_rec;    /* see above */
+    uint32_t reserved; /* 0 */
+} lash_text_span;
+int lash_sketch_push_ascii(lash_sketcher* s, const uint8_t* text, uint64_t n_bytes, const lash_text_span* spans,
+                           uint32_t n_spans, uint64_t* ticket);
+/* Same, `text` already in device memory of the context's GPU (16-byte aligned). */
+int lash_sketch_push_ascii_dev(lash_sketcher* s, const void* text_dev, uint64_t n_bytes, const lash_text_span* spans,
+                               uint32_t n_spans, uint64_t* ticket);
 /* Block until the H2D copy of push `ticket` has completed (its host buffer may be reused). */
 int lash_sketch_wait_copied(lash_sketcher* s, uint64_t ticket);
 /* Block until every enqueued push has been folded into the accumulators. */

@@ -26,6 +26,12 @@ class Span(C.Structure):
                 ("n_rec", C.c_uint32), ("rec_len", C.c_uint32)]
 
 
+class TextSpan(C.Structure):
+    """struct lash_text_span"""
+    _fields_ = [("genome", C.c_uint64), ("byte_off", C.c_uint64), ("n_bytes", C.c_uint64), ("n_rec", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+TEXT_RECORD_SEP = 0x01
 DIST_BLOCK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p)
 
 u64, i32, vp, sz = C.c_uint64, C.c_int, C.c_void_p, C.c_size_t
@@ -45,6 +51,8 @@ PROTOTYPES = {
     "lash_sketch_open": (i32, [vp, i32, i32, i32, u64, u64, C.POINTER(vp)]),
     "lash_sketch_push": (i32, [vp, vp, u64, C.POINTER(Span), C.c_uint32, vp, u64, C.POINTER(u64)]),
     "lash_sketch_push_dev": (i32, [vp, vp, u64, C.POINTER(Span), C.c_uint32, vp, u64, C.POINTER(u64)]),
+    "lash_sketch_push_ascii": (i32, [vp, vp, u64, C.POINTER(TextSpan), C.c_uint32, C.POINTER(u64)]),
+    "lash_sketch_push_ascii_dev": (i32, [vp, vp, u64, C.POINTER(TextSpan), C.c_uint32, C.POINTER(u64)]),
     "lash_sketch_wait_copied": (i32, [vp, u64]),
     "lash_sketch_sync": (i32, [vp]),
     "lash_sketch_fetch": (i32, [vp, u64, u64, vp]),

@@ -224,6 +224,7 @@ struct Slot {
     cudaEvent_t k_start = nullptr, k_stop = nullptr;
     bool timing_pending = false;
     DevBuf packed, meta, mask;
+    DevBuf text, aux;  // lash_sketch_push_ascii: raw text (H2D target) and the block counts / prefixes / kept bases per span
     PinBuf meta_host;
     uint64_t ticket = 0;
     bool used = false;
@@ -246,6 +247,8 @@ struct lash_sketcher {
     uint64_t per_iter = 0;  // k-mer starts one CTA iteration covers
     std::vector<SketchTile> plan_tiles;  // host-side tile plan of the current push (capacity reused across pushes)
     std::vector<SpanRecs> plan_mspans;
+    std::vector<TextBlock> plan_tblocks;
+    std::vector<TextSpanDev> plan_tspans;
     cudaStream_t ext_stream = nullptr;  // caller-provided stream (lash_sketch_set_stream)
 };
 
@@ -387,7 +390,7 @@ static int push_impl(lash_sketcher* s, const void* packed, bool packed_on_device
             t.begin = b;
             t.end = std::min(starts, b + per);
             t.genome = (uint32_t)sp.genome;
-            t.pad = 0;
+            t.clip = 0xffffffffu;
             tiles.push_back(t);
         }
     }
@@ -477,6 +480,161 @@ extern "C" int lash_sketch_push_dev(lash_sketcher* s, const void* packed_dev, ui
     if (((uintptr_t)packed_dev) % 16) return fail(LASH_E_INVALID, "lash_sketch_push_dev: device buffer must be 16-byte aligned");
     return push_impl(s, packed_dev, true, n_bytes, spans, n_spans, rec_start, n_rec_entries, ticket);
 }
+// ------------------------------------------------------------------------------------------------
+// lash_sketch_push_ascii: raw sequence text in, filter_out_n + 2-bit pack on the device (text_kernels.cu), then the same
+// sketch kernel.  The host plans the tiles on the raw byte count (an upper bound of the bases a span keeps); the kernel
+// clips every tile to the kept count the pack kernels leave in span_kept[].
+// ------------------------------------------------------------------------------------------------
+static int push_text_impl(lash_sketcher* s, const void* text, bool text_on_device, uint64_t n_bytes, const lash_text_span* spans,
+                          uint32_t n_spans, uint64_t* ticket_out) {
+    if (!s) return fail(LASH_E_INVALID, "lash_sketch_push_ascii: NULL sketcher");
+    if (n_spans && (!spans || !text)) return fail(LASH_E_INVALID, "lash_sketch_push_ascii: NULL buffer");
+    CU(cudaSetDevice(s->ctx->device));
+    const int k = s->sp.k;
+    uint64_t total_starts = 0, out_bytes = 0, mask_words = 0, n_blocks64 = 0;
+    for (uint32_t i = 0; i < n_spans; ++i) {
+        const lash_text_span& sp = spans[i];
+        if (sp.genome >= s->n_genomes) return fail(LASH_E_INVALID, "lash_sketch_push_ascii: span.genome out of range");
+        if (sp.byte_off % 16) return fail(LASH_E_INVALID, "lash_sketch_push_ascii: span.byte_off must be a multiple of 16");
+        if (sp.byte_off + sp.n_bytes > n_bytes) return fail(LASH_E_INVALID, "lash_sketch_push_ascii: span exceeds buffer");
+        if (sp.n_bytes >= (uint64_t)k) total_starts += sp.n_bytes - k + 1;
+        out_bytes += lash_sketch_padded_bytes(sp.n_bytes);
+        if (sp.n_rec > 1) mask_words += ((sp.n_bytes + 63) / 64) * 2 + 2;
+        n_blocks64 += (sp.n_bytes + kTextBlockBytes - 1) / kTextBlockBytes;
+    }
+    if (n_blocks64 > 0x7fffffffull) return fail(LASH_E_INVALID, "lash_sketch_push_ascii: push too large");
+    const uint64_t target_tiles = (uint64_t)s->ctx->n_sm * 8 * 32;
+    uint64_t chunk = (total_starts + target_tiles - 1) / target_tiles;
+    chunk = std::max(chunk, s->per_iter);
+    chunk = ((chunk + s->per_iter - 1) / s->per_iter) * s->per_iter;
+
+    std::vector<SketchTile>& tiles = s->plan_tiles;
+    std::vector<TextBlock>& tblocks = s->plan_tblocks;
+    std::vector<TextSpanDev>& tspans = s->plan_tspans;
+    tiles.clear();
+    tblocks.clear();
+    tspans.clear();
+    tiles.reserve(total_starts / chunk + 2 * (size_t)n_spans + 16);
+    tblocks.reserve(n_blocks64);
+    tspans.reserve(n_spans);
+    uint64_t out_off = 0, mask_off = 0;
+    for (uint32_t i = 0; i < n_spans; ++i) {
+        const lash_text_span& sp = spans[i];
+        TextSpanDev td;
+        td.out_word_off = out_off / 4;
+        td.mask_word_off = ~0ull;
+        if (sp.n_rec > 1) {
+            td.mask_word_off = mask_off;
+            mask_off += ((sp.n_bytes + 63) / 64) * 2 + 2;
+        }
+        td.first_block = (uint32_t)tblocks.size();
+        for (uint64_t b = 0; b < sp.n_bytes; b += kTextBlockBytes) {
+            TextBlock tb;
+            tb.byte_begin = sp.byte_off + b;
+            tb.n_bytes = (uint32_t)std::min<uint64_t>(kTextBlockBytes, sp.n_bytes - b);
+            tb.span = i;
+            tblocks.push_back(tb);
+        }
+        td.n_blocks = (uint32_t)tblocks.size() - td.first_block;
+        tspans.push_back(td);
+        if (sp.n_bytes >= (uint64_t)k) {
+            const uint64_t starts = sp.n_bytes - k + 1;
+            const uint64_t n_t = (starts + chunk - 1) / chunk;
+            uint64_t per = (starts + n_t - 1) / n_t;
+            per = ((per + s->per_iter - 1) / s->per_iter) * s->per_iter;
+            for (uint64_t b = 0; b < starts; b += per) {
+                SketchTile t;
+                t.word_off = out_off / 4;
+                t.mask_word_off = td.mask_word_off;
+                t.begin = b;
+                t.end = std::min(starts, b + per);
+                t.genome = (uint32_t)sp.genome;
+                t.clip = i;
+                tiles.push_back(t);
+            }
+        }
+        out_off += lash_sketch_padded_bytes(sp.n_bytes);
+    }
+    if (tiles.size() > 0x7fffffffull) return fail(LASH_E_INVALID, "lash_sketch_push_ascii: too many tiles in one push");
+
+    const uint64_t ticket = s->next_ticket++;
+    Slot& sl = s->slot[ticket % kSlots];
+    const cudaStream_t stream = s->ext_stream ? s->ext_stream : sl.stream;
+    if (sl.used) {
+        CU(cudaEventSynchronize(sl.copied));
+        int rc = harvest_timing(s, sl);
+        if (rc) return rc;
+    }
+    const size_t tiles_bytes = tiles.size() * sizeof(SketchTile);
+    const size_t off_blocks = (tiles_bytes + 15) / 16 * 16;
+    const size_t off_spans = off_blocks + (tblocks.size() * sizeof(TextBlock) + 15) / 16 * 16;
+    const size_t meta_bytes = off_spans + tspans.size() * sizeof(TextSpanDev);
+    if (meta_bytes) {
+        CU(sl.meta_host.reserve(meta_bytes));
+        CU(sl.meta.reserve(meta_bytes));
+        char* mh = (char*)sl.meta_host.p;
+        if (tiles_bytes) memcpy(mh, tiles.data(), tiles_bytes);
+        if (!tblocks.empty()) memcpy(mh + off_blocks, tblocks.data(), tblocks.size() * sizeof(TextBlock));
+        if (!tspans.empty()) memcpy(mh + off_spans, tspans.data(), tspans.size() * sizeof(TextSpanDev));
+        if (sl.used) CU(cudaStreamWaitEvent(s->meta_stream, sl.k_stop, 0));
+        CU(cudaMemcpyAsync(sl.meta.p, mh, meta_bytes, cudaMemcpyHostToDevice, s->meta_stream));
+        CU(cudaEventRecord(sl.meta_ready, s->meta_stream));
+        CU(cudaStreamWaitEvent(stream, sl.meta_ready, 0));
+    }
+    const uint8_t* text_dev = nullptr;
+    if (text_on_device) {
+        text_dev = (const uint8_t*)text;
+    } else if (n_bytes) {
+        CU(sl.text.reserve(n_bytes + 64));
+        CU(cudaMemcpyAsync(sl.text.p, text, n_bytes, cudaMemcpyHostToDevice, stream));
+        text_dev = (const uint8_t*)sl.text.p;
+    }
+    CU(cudaEventRecord(sl.copied, stream));
+    const uint32_t n_blocks = (uint32_t)tblocks.size();
+    uint32_t* mask_dev = nullptr;
+    uint64_t* aux = nullptr;
+    if (n_blocks) {
+        CU(sl.packed.reserve(out_off + 64));
+        CU(cudaMemsetAsync(sl.packed.p, 0, out_off + 64, stream));
+        if (mask_off) {
+            CU(sl.mask.reserve(mask_off * 4));
+            mask_dev = (uint32_t*)sl.mask.p;
+            CU(cudaMemsetAsync(mask_dev, 0, mask_off * 4, stream));
+        }
+        CU(sl.aux.reserve(((size_t)2 * n_blocks + 1 + n_spans) * 8));
+        aux = (uint64_t*)sl.aux.p;
+    }
+    CU(cudaEventRecord(sl.k_start, stream));
+    if (n_blocks) {
+        uint64_t* block_cnt = aux;
+        uint64_t* block_prefix = aux + n_blocks + 1;
+        uint64_t* span_kept = block_prefix + n_blocks;
+        CU(launch_text_pack(text_dev, (const TextBlock*)((char*)sl.meta.p + off_blocks), n_blocks,
+                            (const TextSpanDev*)((char*)sl.meta.p + off_spans), n_spans, block_cnt, block_prefix, span_kept,
+                            (uint32_t*)sl.packed.p, mask_dev, k, s->ctx->n_sm, stream));
+        s->launches += 3;
+        if (!tiles.empty()) {
+            CU(launch_sketch(s->sp, (const uint32_t*)sl.packed.p, mask_dev, (const SketchTile*)sl.meta.p, (uint32_t)tiles.size(), s->acc,
+                             stream, span_kept));
+            s->launches += 1;
+        }
+    }
+    CU(cudaEventRecord(sl.k_stop, stream));
+    sl.timing_pending = true;
+    sl.used = true;
+    sl.ticket = ticket;
+    if (ticket_out) *ticket_out = ticket;
+    return LASH_OK;
+}
+extern "C" int lash_sketch_push_ascii(lash_sketcher* s, const uint8_t* text, uint64_t n_bytes, const lash_text_span* spans,
+                                      uint32_t n_spans, uint64_t* ticket) {
+    return push_text_impl(s, text, false, n_bytes, spans, n_spans, ticket);
+}
+extern "C" int lash_sketch_push_ascii_dev(lash_sketcher* s, const void* text_dev, uint64_t n_bytes, const lash_text_span* spans,
+                                          uint32_t n_spans, uint64_t* ticket) {
+    if (((uintptr_t)text_dev) % 16) return fail(LASH_E_INVALID, "lash_sketch_push_ascii_dev: device buffer must be 16-byte aligned");
+    return push_text_impl(s, text_dev, true, n_bytes, spans, n_spans, ticket);
+}
 extern "C" int lash_sketch_wait_copied(lash_sketcher* s, uint64_t ticket) {
     if (!s) return fail(LASH_E_INVALID, "lash_sketch_wait_copied: NULL sketcher");
     if (ticket == 0 || ticket >= s->next_ticket) return fail(LASH_E_INVALID, "lash_sketch_wait_copied: unknown ticket");
@@ -543,6 +701,8 @@ extern "C" int lash_sketch_close(lash_sketcher* s) {
         Slot& sl = s->slot[i];
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         sl.packed.release();
+        sl.text.release();
+        sl.aux.release();
         sl.meta.release();
         sl.mask.release();
         sl.meta_host.release();

@@ -15,7 +15,8 @@ struct SketchTile {
     uint64_t mask_word_off; // offset (32-bit words) of the span's invalid-start bitmask, or ~0ull
     uint64_t begin, end;    // k-mer start range inside the span
     uint32_t genome;
-    uint32_t pad;
+    uint32_t clip;          // 0xffffffff, or index into span_kept[]: the span holds only that many bases (device-side
+                            // filter: the host planned the tiles on the raw byte count), so `end` is clipped to kept - k + 1
 };
 
 // A multi-record span, for the boundary-mask builder.
@@ -26,6 +27,26 @@ struct SpanRecs {
     uint32_t n_rec;
     uint32_t uniform_len;    // != 0: every record has this many bases (the last may be shorter)
 };
+
+// ---- device-side filter + 2-bit pack (text_kernels.cu) ----------------------------------------------------------
+constexpr uint8_t kTextRecordSep = 0x01;            // == LASH_TEXT_RECORD_SEP
+constexpr uint32_t kTextBlockBytes = 32u * 1024u;    // text one CTA compacts at a time
+struct TextBlock {
+    uint64_t byte_begin;  // offset of the block in the staged text (span start + multiple of kTextBlockBytes)
+    uint32_t n_bytes;     // <= kTextBlockBytes
+    uint32_t span;        // index into TextSpanDev[]
+};
+struct TextSpanDev {
+    uint64_t out_word_off;   // packed output of the span, in 32-bit words (multiple of 4)
+    uint64_t mask_word_off;  // invalid-start bitmask of the span (32-bit words), or ~0ull: single record
+    uint32_t first_block, n_blocks;
+};
+// count -> scan -> compact: text spans -> packed spans (+ invalid-start bits at record separators), kept bases per span.
+// block_cnt_dev: n_blocks + 1 words, block_prefix_dev: n_blocks, span_kept_dev: n_spans (all uint64); packed_out_dev and
+// mask_dev must be zeroed by the caller.
+cudaError_t launch_text_pack(const uint8_t* text_dev, const TextBlock* blocks_dev, uint32_t n_blocks, const TextSpanDev* spans_dev,
+                             uint32_t n_spans, uint64_t* block_cnt_dev, uint64_t* block_prefix_dev, uint64_t* span_kept_dev,
+                             uint32_t* packed_out_dev, uint32_t* mask_dev, int k, int n_sm, cudaStream_t st);
 
 constexpr int kStartsPerThread = 64;  // one 16-byte load of packed bases per thread per iteration
 
@@ -48,7 +69,8 @@ void plan_sketch(SketchParams& sp);
 cudaError_t launch_build_invalid_mask(const SpanRecs* spans_dev, uint32_t n_spans, uint64_t n_rec_total,
                                       const uint64_t* rec_start_dev, uint32_t* mask_dev, int k, int n_sm, cudaStream_t st);
 cudaError_t launch_sketch(const SketchParams& sp, const uint32_t* packed_dev, const uint32_t* mask_dev,
-                          const SketchTile* tiles_dev, uint32_t n_tiles, uint32_t* acc_dev, cudaStream_t st);
+                          const SketchTile* tiles_dev, uint32_t n_tiles, uint32_t* acc_dev, cudaStream_t st,
+                          const uint64_t* span_kept_dev = nullptr);
 
 // dst[i] = merge(dst[i], src[i]) over 32-bit words of register arrays
 cudaError_t launch_merge(int algo, uint32_t* dst, const uint32_t* src, uint64_t n_words, int n_sm, cudaStream_t st);

@@ -205,7 +205,7 @@ template <int ALGO, int KM, bool GLOBAL, int TB>
 __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
     sketch_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ inv_mask,
                   const SketchTile* __restrict__ tiles, uint32_t n_tiles, uint32_t* __restrict__ acc_global, int p, int k,
-                  HashConsts hc, uint32_t cell_words, uint32_t n_cells) {
+                  HashConsts hc, uint32_t cell_words, uint32_t n_cells, const uint64_t* __restrict__ span_kept) {
     using C = Cell<ALGO>;
     using A = SmemAcc<ALGO>;
     constexpr bool WIDE = KM == KWIDE;
@@ -260,7 +260,14 @@ __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
     const uint32_t t_end = (uint32_t)(((uint64_t)(blockIdx.x + 1) * n_tiles) / gridDim.x);
     uint32_t cur_genome = 0xffffffffu;
     for (uint32_t ti = t_begin; ti < t_end; ++ti) {
-        const SketchTile t = tiles[ti];
+        SketchTile t = tiles[ti];
+        if (t.clip != 0xffffffffu) {
+            // span packed on the device (text_kernels.cu): the tile plan used the raw byte count as the base count
+            const uint64_t kept = span_kept[t.clip];
+            const uint64_t starts = kept >= (uint64_t)k ? kept - (uint64_t)k + 1 : 0;
+            t.end = min(t.end, starts);
+            if (t.begin >= t.end) continue;   // CTA-uniform
+        }
         if (t.genome != cur_genome) {
             if (!GLOBAL && cur_genome != 0xffffffffu) flush(cur_genome);
             cur_genome = t.genome;
@@ -448,7 +455,7 @@ void plan_sketch(SketchParams& sp) {
 
 template <int ALGO, int KM, bool GLOBAL, int TB>
 static cudaError_t launch_tb(const SketchParams& sp, const uint32_t* packed, const uint32_t* mask,
-                             const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st) {
+                             const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st, const uint64_t* span_kept) {
     auto kern = sketch_kernel<ALGO, KM, GLOBAL, TB>;
     size_t smem = GLOBAL ? 0 : (size_t)sp.smem_bytes;
     if (smem > 48 * 1024) {
@@ -460,35 +467,36 @@ static cudaError_t launch_tb(const SketchParams& sp, const uint32_t* packed, con
     if (e != cudaSuccess) return e;
     const uint32_t resident = (uint32_t)std::max(occ, 1) * (uint32_t)sp.n_sm;
     const uint32_t grid = n_tiles < resident ? n_tiles : resident;  // one persistent CTA per resident slot
-    kern<<<grid, sp.threads, smem, st>>>(packed, mask, tiles, n_tiles, acc, sp.p, sp.k, sp.hc, sp.cell_words, sp.n_cells);
+    kern<<<grid, sp.threads, smem, st>>>(packed, mask, tiles, n_tiles, acc, sp.p, sp.k, sp.hc, sp.cell_words, sp.n_cells, span_kept);
     return cudaGetLastError();
 }
 template <int ALGO, int KM, bool GLOBAL>
 static cudaError_t launch_one(const SketchParams& sp, const uint32_t* packed, const uint32_t* mask,
-                              const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st) {
-    if (GLOBAL || sp.threads == (uint32_t)kTbSmall) return launch_tb<ALGO, KM, GLOBAL, kTbSmall>(sp, packed, mask, tiles, n_tiles, acc, st);
-    return launch_tb<ALGO, KM, false, kTbBig>(sp, packed, mask, tiles, n_tiles, acc, st);
+                              const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st, const uint64_t* span_kept) {
+    if (GLOBAL || sp.threads == (uint32_t)kTbSmall) return launch_tb<ALGO, KM, GLOBAL, kTbSmall>(sp, packed, mask, tiles, n_tiles, acc, st, span_kept);
+    return launch_tb<ALGO, KM, false, kTbBig>(sp, packed, mask, tiles, n_tiles, acc, st, span_kept);
 }
 
 template <int ALGO>
 static cudaError_t launch_algo(const SketchParams& sp, const uint32_t* packed, const uint32_t* mask,
-                               const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st) {
+                               const SketchTile* tiles, uint32_t n_tiles, uint32_t* acc, cudaStream_t st, const uint64_t* span_kept) {
     if (sp.global_acc) {
-        return sp.k > 16 ? launch_one<ALGO, KWIDE, true>(sp, packed, mask, tiles, n_tiles, acc, st)
-                         : launch_one<ALGO, KNARROW, true>(sp, packed, mask, tiles, n_tiles, acc, st);
+        return sp.k > 16 ? launch_one<ALGO, KWIDE, true>(sp, packed, mask, tiles, n_tiles, acc, st, span_kept)
+                         : launch_one<ALGO, KNARROW, true>(sp, packed, mask, tiles, n_tiles, acc, st, span_kept);
     }
-    if (sp.k > 16) return launch_one<ALGO, KWIDE, false>(sp, packed, mask, tiles, n_tiles, acc, st);
-    if (sp.k == 16) return launch_one<ALGO, K16, false>(sp, packed, mask, tiles, n_tiles, acc, st);
-    return launch_one<ALGO, KNARROW, false>(sp, packed, mask, tiles, n_tiles, acc, st);
+    if (sp.k > 16) return launch_one<ALGO, KWIDE, false>(sp, packed, mask, tiles, n_tiles, acc, st, span_kept);
+    if (sp.k == 16) return launch_one<ALGO, K16, false>(sp, packed, mask, tiles, n_tiles, acc, st, span_kept);
+    return launch_one<ALGO, KNARROW, false>(sp, packed, mask, tiles, n_tiles, acc, st, span_kept);
 }
 
 cudaError_t launch_sketch(const SketchParams& sp, const uint32_t* packed_dev, const uint32_t* mask_dev,
-                          const SketchTile* tiles_dev, uint32_t n_tiles, uint32_t* acc_dev, cudaStream_t st) {
+                          const SketchTile* tiles_dev, uint32_t n_tiles, uint32_t* acc_dev, cudaStream_t st,
+                          const uint64_t* span_kept_dev) {
     if (n_tiles == 0) return cudaSuccess;
     switch (sp.algo) {
-        case HMH: return launch_algo<HMH>(sp, packed_dev, mask_dev, tiles_dev, n_tiles, acc_dev, st);
-        case HLL: return launch_algo<HLL>(sp, packed_dev, mask_dev, tiles_dev, n_tiles, acc_dev, st);
-        case ULL: return launch_algo<ULL>(sp, packed_dev, mask_dev, tiles_dev, n_tiles, acc_dev, st);
+        case HMH: return launch_algo<HMH>(sp, packed_dev, mask_dev, tiles_dev, n_tiles, acc_dev, st, span_kept_dev);
+        case HLL: return launch_algo<HLL>(sp, packed_dev, mask_dev, tiles_dev, n_tiles, acc_dev, st, span_kept_dev);
+        case ULL: return launch_algo<ULL>(sp, packed_dev, mask_dev, tiles_dev, n_tiles, acc_dev, st, span_kept_dev);
     }
     return cudaErrorInvalidValue;
 }

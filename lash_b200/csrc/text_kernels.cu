@@ -78,10 +78,11 @@ __global__ void __launch_bounds__(kTextThreads) text_count_kernel(const uint8_t*
     }
 }
 
-// In place: block_cnt[b] -> kept bases of the SAME span before block b; span_kept[s] = kept bases of span s.
-// One CTA; the global exclusive prefix G is built chunk by chunk, then every block subtracts G at its span's first block.
-__global__ void __launch_bounds__(1024) text_scan_kernel(uint64_t* __restrict__ block_cnt, uint32_t n_blocks, const TextBlock* __restrict__ blocks,
-                                                         const TextSpanDev* __restrict__ spans, uint32_t n_spans, uint64_t* __restrict__ span_kept) {
+// block_cnt[0..n) -> G (in place, n+1 entries: exclusive prefix over ALL blocks); block_prefix[b] = kept bases of the
+// SAME span before block b = G[b] - G[first block of the span]; span_kept[s] = kept bases of span s.  One CTA.
+__global__ void __launch_bounds__(1024) text_scan_kernel(uint64_t* __restrict__ block_cnt, uint64_t* __restrict__ block_prefix, uint32_t n_blocks,
+                                                         const TextBlock* __restrict__ blocks, const TextSpanDev* __restrict__ spans,
+                                                         uint32_t n_spans, uint64_t* __restrict__ span_kept) {
     __shared__ uint64_t s_warp[32];
     __shared__ uint64_t s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(1024) text_scan_kernel(uint64_t* __restrict__ 
         if ((threadIdx.x & 31u) == 31u) s_warp[threadIdx.x >> 5] = x;
         __syncthreads();
         if (threadIdx.x < 32) {
-            uint64_t w = s_warp[threadIdx.x], xw = w;
+            const uint64_t w = s_warp[threadIdx.x];
+            uint64_t xw = w;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint64_t y = __shfl_up_sync(0xffffffffu, xw, d);
@@ -113,37 +115,13 @@ __global__ void __launch_bounds__(1024) text_scan_kernel(uint64_t* __restrict__ 
         if (threadIdx.x == 1023) s_carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) block_cnt[n_blocks] = s_carry;  // G[n_blocks]
+    if (threadIdx.x == 0) block_cnt[n_blocks] = s_carry;
     __syncthreads();
-    __threadfence_block();
-    // span totals first (they read G at span starts), then the per-block rebase -- both from an unmodified G: stage the
-    // span starts' G values before anything is overwritten
+    for (uint32_t i = threadIdx.x; i < n_blocks; i += 1024) block_prefix[i] = block_cnt[i] - block_cnt[spans[blocks[i].span].first_block];
     for (uint32_t s = threadIdx.x; s < n_spans; s += 1024) {
         const TextSpanDev sp = spans[s];
         span_kept[s] = block_cnt[sp.first_block + sp.n_blocks] - block_cnt[sp.first_block];
     }
-    __syncthreads();
-    // rebase: walk the spans; a span's first block keeps G (needed by its later blocks) until the span is done, so the
-    // subtraction runs over blocks in DESCENDING order within each chunk of threads: simpler -- read G[first] per block
-    // into a register, sync the whole CTA, then write.
-    for (uint32_t base = 0; base < n_blocks; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        uint64_t mine = 0, first = 0;
-        uint32_t fb = 0;
-        if (i < n_blocks) {
-            fb = spans[blocks[i].span].first_block;
-            mine = block_cnt[i];
-            first = block_cnt[fb];
-        }
-        __syncthreads();
-        // G[fb] is only overwritten by the thread that owns block fb, in the chunk that contains fb; blocks of later
-        // chunks that belong to the same span still need it -> keep G[fb] intact and store the rebased values of span
-        // starts (always 0) last, after all chunks: here only non-first blocks are written
-        if (i < n_blocks && i != fb) block_cnt[i] = mine - first;
-        __syncthreads();
-    }
-    for (uint32_t s = threadIdx.x; s < n_spans; s += 1024)
-        if (spans[s].n_blocks) block_cnt[spans[s].first_block] = 0;
 }
 
 // big-endian base order inside a 32-bit word <-> the little-endian bytes of the lash_gpu.h format
@@ -242,13 +220,13 @@ __global__ void __launch_bounds__(kTextThreads) text_compact_kernel(const uint8_
 }
 
 cudaError_t launch_text_pack(const uint8_t* text_dev, const TextBlock* blocks_dev, uint32_t n_blocks, const TextSpanDev* spans_dev,
-                             uint32_t n_spans, uint64_t* block_cnt_dev, uint64_t* span_kept_dev, uint32_t* packed_out_dev,
-                             uint32_t* mask_dev, int k, int n_sm, cudaStream_t st) {
+                             uint32_t n_spans, uint64_t* block_cnt_dev, uint64_t* block_prefix_dev, uint64_t* span_kept_dev,
+                             uint32_t* packed_out_dev, uint32_t* mask_dev, int k, int n_sm, cudaStream_t st) {
     if (n_blocks == 0) return cudaSuccess;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)n_sm * 8);
     text_count_kernel<<<grid, kTextThreads, 0, st>>>(text_dev, blocks_dev, n_blocks, block_cnt_dev);
-    text_scan_kernel<<<1, 1024, 0, st>>>(block_cnt_dev, n_blocks, blocks_dev, spans_dev, n_spans, span_kept_dev);
-    text_compact_kernel<<<grid, kTextThreads, 0, st>>>(text_dev, blocks_dev, n_blocks, block_cnt_dev, spans_dev, span_kept_dev,
+    text_scan_kernel<<<1, 1024, 0, st>>>(block_cnt_dev, block_prefix_dev, n_blocks, blocks_dev, spans_dev, n_spans, span_kept_dev);
+    text_compact_kernel<<<grid, kTextThreads, 0, st>>>(text_dev, blocks_dev, n_blocks, block_prefix_dev, spans_dev, span_kept_dev,
                                                        packed_out_dev, mask_dev, k);
     return cudaGetLastError();
 }

@@ -15,7 +15,7 @@ from typing import Callable, Sequence
 import numpy as np
 
 from . import capi
-from .capi import ALGO_HLL, ALGO_HMH, ALGO_ULL, Span, check, lib
+from .capi import ALGO_HLL, ALGO_HMH, ALGO_ULL, TEXT_RECORD_SEP, Span, TextSpan, check, lib
 from .pack import PackedBatch
 
 ALGO_BY_NAME = {"hmh": ALGO_HMH, "hll": ALGO_HLL, "ull": ALGO_ULL}  # main.rs:210-246
@@ -86,6 +86,29 @@ class Sketcher:
         check(fn(self._h, C.c_void_p(packed_ptr), n_bytes, spans, n_spans, rec_ptr, n_rec, C.byref(ticket)))
         return ticket.value
 
+    def push_text(self, genomes: Sequence[tuple[int, Sequence[bytes]]]) -> int:
+        """lash_sketch_push_ascii: genomes = [(slot, [raw record bytes, ...])].  Records of a genome are joined with the
+        in-band separator; the device does filter_out_n + 2-bit packing (utils.rs:33-41,464)."""
+        sep = bytes([TEXT_RECORD_SEP])
+        parts, spans, off = [], [], 0
+        for slot, recs in genomes:
+            recs = list(recs)
+            if any(sep in r for r in recs):
+                raise ValueError("a sequence byte equals LASH_TEXT_RECORD_SEP")
+            body = sep.join(recs)
+            spans.append((slot, off, len(body), len(recs)))
+            room = (len(body) + 15) // 16 * 16 + 16
+            parts.append(body + b"\xff" * (room - len(body)))   # padding the device must ignore
+            off += room
+        buf = np.frombuffer(b"".join(parts) or b"\0" * 16, dtype=np.uint8)
+        arr = (TextSpan * max(len(spans), 1))()
+        for i, (slot, o, n, nr) in enumerate(spans):
+            arr[i] = TextSpan(slot, o, n, nr, 0)
+        ticket = C.c_uint64()
+        check(lib().lash_sketch_push_ascii(self._h, buf.ctypes.data_as(C.c_void_p), buf.nbytes, arr, len(spans), C.byref(ticket)))
+        self._keep.append((buf, arr))
+        return ticket.value
+
     def wait_copied(self, ticket: int):
         check(lib().lash_sketch_wait_copied(self._h, ticket))
 
@@ -145,6 +168,16 @@ def sketch_genomes(ctx: Context, algo: int, p: int, k: int, seed: int, genomes: 
             for g in range(g0, min(len(genomes), g0 + genomes_per_push)):
                 b.add_genome(g, list(genomes[g]))
             sk.push_batch(b)
+        regs = sk.fetch()
+    return regs[: len(genomes)]
+
+
+def sketch_genomes_text(ctx: Context, algo: int, p: int, k: int, seed: int, genomes: Sequence[Sequence[bytes]],
+                        genomes_per_push: int = 64) -> np.ndarray:
+    """sketch_genomes through lash_sketch_push_ascii: raw record bytes go to the GPU, which filters and packs them."""
+    with Sketcher(ctx, algo, p, k, seed, max(len(genomes), 1)) as sk:
+        for g0 in range(0, len(genomes), genomes_per_push):
+            sk.push_text([(g, genomes[g]) for g in range(g0, min(len(genomes), g0 + genomes_per_push))])
         regs = sk.fetch()
     return regs[: len(genomes)]
 

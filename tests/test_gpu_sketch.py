@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from lash_b200 import ALGO_HLL, ALGO_HMH, ALGO_ULL, LashError
-from lash_b200.ops import Sketcher, sketch_genomes
+from lash_b200.ops import Sketcher, sketch_genomes, sketch_genomes_text
 from lash_b200.pack import PackedBatch
 from tools import synth
 
@@ -228,3 +228,80 @@ def test_merge_of_shares_equals_sketch_of_the_whole(oracle, gpu_ctx, algo, p):
         assert np.array_equal(merged, np.maximum(ra, rb))
     assert np.array_equal(ops.merge(gpu_ctx, algo, p, merged, merged), merged)      # idempotent
     assert np.array_equal(ops.merge(gpu_ctx, algo, p, rb, ra), merged)              # commutative
+
+
+# ---- lash_sketch_push_ascii: filter_out_n + 2-bit pack on the device (text_kernels.cu) ------------------------------
+def _check_text(oracle, gpu_ctx, algo, p, k, genomes, **kw):
+    got = sketch_genomes_text(gpu_ctx, algo, p, k, SEED, genomes, **kw)
+    exp = oracle.sketch_genomes(algo, p, k, SEED, [list(g) for g in genomes], threads=4)
+    bad = np.argwhere(got != exp)
+    assert bad.size == 0, f"{len(bad)} register mismatches, first at {bad[0]}: gpu={got[tuple(bad[0])]} cpu={exp[tuple(bad[0])]}"
+    return got
+
+
+def _fasta_lines(seq: bytes, width: int = 80) -> bytes:
+    """A FASTA body as it sits in the file: line breaks (and a stray CR) are just bytes the filter deletes."""
+    return b"\r\n".join(seq[o:o + width] for o in range(0, len(seq), width)) + b"\n"
+
+
+@pytest.mark.parametrize("algo,p,k", [(ALGO_ULL, 10, 16), (ALGO_HLL, 12, 21), (ALGO_HMH, 14, 16), (ALGO_ULL, 10, 5), (ALGO_ULL, 14, 32)])
+def test_ascii_push_dirty_multi_record_genomes(oracle, gpu_ctx, algo, p, k):
+    """The same dirty inputs as the host-packed path: lowercase / N / IUPAC deleted with flanks joined (utils.rs:36),
+    k-mers never span records, records shorter than k skipped (:460), empty and all-filtered records."""
+    genomes = [synth.dirty_genome(60_000, k, seed=s) for s in range(4)]
+    genomes.append([b""])
+    genomes.append([])
+    genomes.append([b"ACGT" * 3, b"NNNN", b"acgt"])
+    genomes.append([_fasta_lines(synth.genomes(1, 50_000, seed=5)[0][0])])      # one record with line breaks inside
+    _check_text(oracle, gpu_ctx, algo, p, k, genomes)
+    _check_text(oracle, gpu_ctx, algo, p, k, genomes, genomes_per_push=3)
+
+
+@pytest.mark.parametrize("algo,p,k", [(ALGO_ULL, 10, 16), (ALGO_HLL, 14, 21)])
+def test_ascii_push_spans_many_text_blocks(oracle, gpu_ctx, algo, p, k):
+    """Genomes far larger than one 32 KiB text block, with long deleted runs, so kept positions drift away from byte
+    positions: block prefixes, word sharing between neighbouring blocks and the tile clipping all matter."""
+    rng = np.random.default_rng(11)
+    genomes = []
+    for g in range(3):
+        seq = bytearray(synth.genomes(1, 1_500_000 + 77 * g, seed=20 + g)[0][0])
+        for _ in range(40):
+            a = int(rng.integers(0, len(seq) - 50_000))
+            n = int(rng.integers(1, 40_000))
+            seq[a:a + n] = (b"N" if rng.integers(0, 2) else b"a") * n
+        genomes.append([_fasta_lines(bytes(seq), 60)])
+    genomes.append([b"N" * 200_000])                                               # nothing survives
+    genomes.append([b"N" * 100_000 + b"ACGTTGCAAGGCTTAACCGGTTAAACCCGGGTTTACGT" + b"n" * 70_000])   # one short island
+    _check_text(oracle, gpu_ctx, algo, p, k, genomes)
+
+
+def test_ascii_push_short_reads(oracle, gpu_ctx):
+    """config 4 shape: 150 bp reads, one record each, some with N, some shorter than k after filtering."""
+    rng = np.random.default_rng(4)
+    pool = synth.to_ascii(synth.ancestor_codes(300_000, seed=9))
+    reads = []
+    for i in range(20_000):
+        a = int(rng.integers(0, len(pool) - 150))
+        r = bytearray(pool[a:a + 150])
+        if i % 17 == 0:
+            r[40:45] = b"NNNNN"
+        if i % 501 == 0:
+            r = bytearray(b"N" * 140 + bytes(r[:10]))
+        reads.append(bytes(r))
+    _check_text(oracle, gpu_ctx, ALGO_ULL, 14, 21, [reads, reads[:7], reads[100:5000]])
+
+
+def test_ascii_push_equals_packed_push_and_rejects_bad_spans(oracle, gpu_ctx):
+    import ctypes as C
+
+    from lash_b200 import capi
+    genomes = synth.genomes(3, 200_000, seed=SEED)
+    a = sketch_genomes(gpu_ctx, ALGO_ULL, 10, 16, SEED, genomes)
+    b = sketch_genomes_text(gpu_ctx, ALGO_ULL, 10, 16, SEED, genomes)
+    assert np.array_equal(a, b)
+    with Sketcher(gpu_ctx, ALGO_ULL, 10, 16, SEED, 2) as sk:
+        buf = np.zeros(64, dtype=np.uint8)
+        for span in (capi.TextSpan(2, 0, 16, 1, 0), capi.TextSpan(0, 8, 16, 1, 0), capi.TextSpan(0, 0, 128, 1, 0)):
+            arr = (capi.TextSpan * 1)(span)
+            rc = capi.lib().lash_sketch_push_ascii(sk._h, buf.ctypes.data_as(C.c_void_p), buf.nbytes, arr, 1, None)
+            assert rc == -1

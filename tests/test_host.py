@@ -24,7 +24,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", capi.lib_path()], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (lash_[a-z0-9_]+)", out))
     assert declared <= exported
-    assert L.lash_gpu_abi_version() == 1
+    assert L.lash_gpu_abi_version() == 2
 
 
 def test_library_carries_sm100a_code_only():
