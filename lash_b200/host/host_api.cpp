@@ -108,6 +108,11 @@ extern "C" int lash_host_pack_files_dry(const char* const* files, uint64_t n_fil
     return from_status(lash::pack_files_dry(to_vec(files, n_files), (size_t)k, (uint32_t)std::max(threads, 0), chunk_bytes, stats));
 }
 
+extern "C" int lash_host_set_ingest_mode(int mode) {
+    if (mode < 0 || mode > 2) return fail(LASH_E_INVALID, "lash_host_set_ingest_mode: 0 auto, 1 packed, 2 ascii");
+    lash::set_ingest_mode(mode);
+    return 0;
+}
 extern "C" int lash_host_release_pinned(void) {
     lash::release_pinned();
     return 0;

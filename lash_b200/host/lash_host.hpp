@@ -53,6 +53,8 @@ Status pack_files_dry(const std::vector<std::string>& files, size_t kmer_length,
 
 // return the cached pinned staging blocks of sketch_files to the driver
 void release_pinned();
+// 0 auto, 1 host filter + pack (lash_sketch_push), 2 device filter + pack (lash_sketch_push_ascii)
+void set_ingest_mode(int mode);
 
 template <class S>
 Status sketch_files(lash_ctx* ctx, std::optional<uint32_t> precision, const std::vector<std::string>& files, size_t kmer_length,

@@ -11,6 +11,7 @@
 // across chunks with a (k-1)-base overlap so that every k-mer start is produced exactly once.
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdlib>
@@ -102,6 +103,11 @@ struct Gpu {
 class Chunk {
   public:
     // pinned: staging for lash_sketch_push; !pinned: plain memory for the parse+pack dry run (no GPU involved)
+    // text mode (lash_sketch_push_ascii): the chunk holds the raw sequence bytes of the records, one separator byte after
+    // every record; the device does filter_out_n + the 2-bit packing.  The host work per base is a memcpy.
+    void set_text_mode(bool on) { text_ = on; }
+    bool text_mode() const { return text_; }
+
     bool alloc(uint64_t bytes, bool pinned = true) {
         cap_ = bytes;
         pinned_ = pinned;
@@ -121,15 +127,26 @@ class Chunk {
         else if (buf_) free(buf_);
         buf_ = nullptr;
     }
-    bool empty() const { return spans_.empty() && !span_open_; }
+    bool empty() const { return spans_.empty() && tspans_.empty() && !span_open_; }
     uint64_t used() const { return off_; }
     uint64_t cap() const { return cap_; }
-    // room (in bases) the current span can still take
-    uint64_t room() const { return bs_.room(); }
+    // room (in bases; text mode: bytes) the current span can still take
+    uint64_t room() const {
+        if (!text_) return bs_.room();
+        const uint64_t used = off_ + tw_ + 64;  // separator + 16-byte pad + slack
+        return cap_ > used ? cap_ - used : 0;
+    }
     bool can_begin_span() const { return off_ + 4096 <= cap_; }
 
     void begin_span(uint64_t genome) {
         genome_ = genome;
+        if (text_) {
+            tw_ = 0;
+            n_rec_ = 0;
+            rec_begin_ = 0;
+            span_open_ = true;
+            return;
+        }
         bs_.attach(buf_ + off_, cap_ - off_);
         rec_first_ = rec_start_.size();
         rec_start_.push_back(0);
@@ -139,13 +156,36 @@ class Chunk {
         rec_begin_ = 0;
         span_open_ = true;
     }
-    void begin_record() { rec_begin_ = bs_.size(); }
-    uint64_t append(const uint8_t* s, size_t n) { return bs_.append_filtered(s, n); }
-    void push_base(unsigned c) { bs_.push_base(c); }
+    void begin_record() { rec_begin_ = text_ ? tw_ : bs_.size(); }
+    uint64_t append(const uint8_t* s, size_t n) {
+        if (!text_) return bs_.append_filtered(s, n);
+        uint8_t* dst = buf_ + off_ + tw_;
+        memcpy(dst, s, n);
+        // a sequence byte equal to the separator would split the record: it is not a base, so any other non-base byte
+        // stands for it (filter_out_n deletes both)
+        for (uint8_t* q = static_cast<uint8_t*>(memchr(dst, LASH_TEXT_RECORD_SEP, n)); q;
+             q = static_cast<uint8_t*>(memchr(q + 1, LASH_TEXT_RECORD_SEP, (size_t)(dst + n - (q + 1)))))
+            *q = '\n';
+        tw_ += n;
+        return 0;  // bases kept: only the device knows
+    }
+    // the (k-1)-base overlap of a record that was split across chunks
+    void push_carry(const std::vector<uint8_t>& carry) {
+        if (text_) {
+            if (!carry.empty()) append(carry.data(), carry.size());
+        } else {
+            for (uint8_t c : carry) bs_.push_base(c);
+        }
+    }
     uint64_t record_len() const { return bs_.size() - rec_begin_; }
     unsigned record_base(uint64_t i) const { return bs_.base_at(rec_begin_ + i); }
     // utils.rs:460-462: a (filtered) record shorter than k contributes nothing -- it is dropped here
     void end_record(int k) {
+        if (text_) {  // records shorter than k are dropped by the device (their starts are all invalid)
+            buf_[off_ + tw_++] = LASH_TEXT_RECORD_SEP;
+            ++n_rec_;
+            return;
+        }
         const uint64_t len = record_len();
         if (len < (uint64_t)k) {
             bs_.truncate(rec_begin_);
@@ -155,6 +195,19 @@ class Chunk {
     }
     // first part of a record that continues in the next chunk; returns the bases to carry over
     void split_record(int k, std::vector<uint8_t>& carry) {
+        if (text_) {
+            // carry = the last k-1 BASES of this part (the bytes between them are deleted by the filter anyway)
+            const uint8_t* b = buf_ + off_;
+            carry.clear();
+            for (uint64_t pos = tw_; pos > rec_begin_ && carry.size() < (size_t)(k - 1);) {
+                const uint8_t c = b[--pos];
+                if (c == 'A' || c == 'C' || c == 'G' || c == 'T') carry.push_back(c);
+            }
+            std::reverse(carry.begin(), carry.end());
+            buf_[off_ + tw_++] = LASH_TEXT_RECORD_SEP;
+            ++n_rec_;
+            return;
+        }
         const uint64_t len = record_len();
         const uint64_t c = std::min<uint64_t>(len, (uint64_t)(k - 1));
         carry.resize(c);
@@ -163,6 +216,19 @@ class Chunk {
         else close_record(len);
     }
     void end_span() {
+        if (text_) {
+            span_open_ = false;
+            if (tw_ == 0) return;
+            lash_text_span sp;
+            sp.genome = genome_;
+            sp.byte_off = off_;
+            sp.n_bytes = tw_;
+            sp.n_rec = n_rec_ > 1 ? n_rec_ : 1;
+            sp.reserved = 0;
+            tspans_.push_back(sp);
+            off_ += (tw_ + 15) / 16 * 16 + 16;
+            return;
+        }
         const uint64_t n = bs_.size();
         if (n == 0) {  // nothing kept: no span
             rec_start_.resize(rec_first_);
@@ -192,14 +258,15 @@ class Chunk {
     // hand the chunk to the GPU; returns the ticket (0 = nothing to push)
     bool submit(Gpu& gpu, uint64_t* ticket) {
         *ticket = 0;
-        if (spans_.empty() || !gpu.sk) {  // nothing to push, or dry run
-            if (!spans_.empty()) gpu.pushes.fetch_add(1);
+        if ((spans_.empty() && tspans_.empty()) || !gpu.sk) {  // nothing to push, or dry run
+            if (!spans_.empty() || !tspans_.empty()) gpu.pushes.fetch_add(1);
             reset();
             return true;
         }
         std::lock_guard<std::mutex> g(gpu.mu);
-        const int rc = lash_sketch_push(gpu.sk, buf_, off_, spans_.data(), (uint32_t)spans_.size(),
-                                        rec_start_.empty() ? nullptr : rec_start_.data(), rec_start_.size(), ticket);
+        const int rc = text_ ? lash_sketch_push_ascii(gpu.sk, buf_, off_, tspans_.data(), (uint32_t)tspans_.size(), ticket)
+                             : lash_sketch_push(gpu.sk, buf_, off_, spans_.data(), (uint32_t)spans_.size(),
+                                                rec_start_.empty() ? nullptr : rec_start_.data(), rec_start_.size(), ticket);
         if (rc != LASH_OK) {
             if (!gpu.failed.exchange(true)) gpu.err = lash_gpu_last_error();
             return false;
@@ -209,6 +276,7 @@ class Chunk {
     }
     void reset() {
         spans_.clear();
+        tspans_.clear();
         rec_start_.clear();
         off_ = 0;
         span_open_ = false;
@@ -227,6 +295,9 @@ class Chunk {
     uint64_t cap_ = 0, off_ = 0, block_ = 0;
     BaseStream bs_;
     std::vector<lash_span> spans_;
+    std::vector<lash_text_span> tspans_;
+    uint64_t tw_ = 0;     // text mode: bytes written in the open span
+    bool text_ = false;
     std::vector<uint64_t> rec_start_;
     uint64_t genome_ = 0, rec_first_ = 0, rec_begin_ = 0, uniform_len_ = 0, last_len_ = 0;
     uint32_t n_rec_ = 0;
@@ -243,6 +314,7 @@ struct Worker {
     bool rotate(Gpu& gpu) {
         if (!chunk[cur].submit(gpu, &ticket[cur])) return false;
         cur ^= 1;
+        chunk[cur].set_text_mode(chunk[cur ^ 1].text_mode());
         if (!chunk[cur].allocated() && !chunk[cur].alloc(chunk[cur ^ 1].cap(), gpu.sk != nullptr)) {  // second buffer on first need
             gpu.fail(std::string("pinned staging allocation failed: ") + lash_gpu_last_error());
             return false;
@@ -291,7 +363,7 @@ struct Worker {
                         if (!rotate(gpu)) return false;
                         chunk[cur].begin_span(genome);
                         chunk[cur].begin_record();
-                        for (uint8_t c : carry) chunk[cur].push_base(c);
+                        chunk[cur].push_carry(carry);
                         if (chunk[cur].room() < n) {
                             err = "staging chunk too small";
                             return false;
@@ -324,6 +396,22 @@ uint64_t auto_chunk_bytes(const std::vector<std::string>& files, uint32_t n_work
 }  // namespace
 
 void release_pinned() { pinned_pool().clear(); }
+
+// Who filters and packs: 1 = host (AVX2 packer, 0.25 B/base over PCIe), 2 = device (raw text, 1 B/base over PCIe, the
+// host only copies).  0 = auto: the device while the host workers could not feed the link with packed bases anyway
+// (about 1.3 Gbp/s per worker against ~50 Gbp/s of text through one x16 link).  LASH_INGEST=packed|ascii overrides.
+static std::atomic<int> g_ingest_mode{0};
+void set_ingest_mode(int mode) { g_ingest_mode.store(mode); }
+static bool use_text_ingest(uint32_t n_workers) {
+    int mode = g_ingest_mode.load();
+    if (const char* e = getenv("LASH_INGEST")) {
+        if (!strcmp(e, "ascii") || !strcmp(e, "text")) mode = 2;
+        else if (!strcmp(e, "packed")) mode = 1;
+    }
+    if (mode == 1) return false;
+    if (mode == 2) return true;
+    return n_workers < 40;
+}
 
 // Parse + filter + pack every file exactly as sketch_files does, but drop the chunks instead of pushing
 // them: the host-side ingest ceiling (no GPU, no sketch -- a measurement aid for bench.py).
@@ -405,7 +493,12 @@ Status sketch_files_impl(lash_ctx* ctx, int algo, std::optional<uint32_t> precis
             return Status{LASH_E_CUDA, lash_gpu_last_error()};
         std::vector<Worker> workers(n_workers);
         bool alloc_ok = true;
-        for (auto& w : workers) alloc_ok = alloc_ok && w.chunk[0].alloc(chunk_bytes);  // chunk[1]: on first rotate
+        const bool text = use_text_ingest(n_workers);
+        if (text) chunk_bytes = std::min<uint64_t>(chunk_bytes * 4, kDefaultChunk);  // same bases per chunk, bounded
+        for (auto& w : workers) {
+            w.chunk[0].set_text_mode(text);
+            alloc_ok = alloc_ok && w.chunk[0].alloc(chunk_bytes);  // chunk[1]: on first rotate
+        }
         std::atomic<uint64_t> next_file{0};
         const auto t_open = std::chrono::steady_clock::now();
         st.seconds_open = std::chrono::duration<double>(t_open - t0).count();

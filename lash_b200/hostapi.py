@@ -39,6 +39,7 @@ PROTOTYPES = {
     "lash_host_sketch_files": (i32, [vp, i32, i32, i32, u64, C.POINTER(cp), u64, cp, i32, C.POINTER(SketchFilesStats)]),
     "lash_host_pack_files_dry": (i32, [C.POINTER(cp), u64, i32, i32, u64, C.POINTER(SketchFilesStats)]),
     "lash_host_release_pinned": (i32, []),
+    "lash_host_set_ingest_mode": (i32, [i32]),
     "lash_host_write_parameters": (i32, [cp, i32, i32, i32, u64]),
     "lash_host_write_sketches": (i32, [cp, i32, i32, vp, u64, i32]),
     "lash_host_read_sketches": (i32, [cp, i32, C.POINTER(i32), u64, vp]),

@@ -33,12 +33,20 @@ def _write_fastq(path, records):
             f.write(b"@read%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
 
 
+@pytest.fixture(params=["packed", "ascii"])
+def ingest(request):
+    """sketch_files with the host packer (lash_sketch_push) and with the device-side filter + pack (lash_sketch_push_ascii)."""
+    hostapi.check(hostapi.lib().lash_host_set_ingest_mode({"packed": 1, "ascii": 2}[request.param]))
+    yield request.param
+    hostapi.check(hostapi.lib().lash_host_set_ingest_mode(0))
+
+
 def _oname(algo):
     return {ALGO_HMH: "HMH", ALGO_HLL: "HLL", ALGO_ULL: "ULL"}[algo]
 
 
 @pytest.mark.parametrize("algo,p,k", [(ALGO_ULL, 10, 16), (ALGO_HLL, 12, 21), (ALGO_HMH, 14, 16), (ALGO_ULL, 14, 31), (ALGO_ULL, 8, 5)])
-def test_sketch_files_matches_oracle_on_dirty_fasta(oracle, gpu_ctx, tmp_path, algo, p, k):
+def test_sketch_files_matches_oracle_on_dirty_fasta(oracle, gpu_ctx, tmp_path, algo, p, k, ingest):
     """Per-file record loop of utils.rs:457-503 on multi-record, multi-line, dirty, gzipped and
     short files -- several files per staging chunk."""
     genomes = [synth.dirty_genome(60_000 + 7919 * g, k, seed=g + 1) for g in range(6)]
@@ -58,7 +66,7 @@ def test_sketch_files_matches_oracle_on_dirty_fasta(oracle, gpu_ctx, tmp_path, a
 
 
 @pytest.mark.parametrize("k", [16, 21, 32])
-def test_large_records_split_across_staging_chunks(oracle, gpu_ctx, tmp_path, k):
+def test_large_records_split_across_staging_chunks(oracle, gpu_ctx, tmp_path, k, ingest):
     """A record larger than a staging chunk is cut with a (k-1)-base overlap: every k-mer start
     exactly once (chunk = 1 MiB = 4 Mbp; records of 9 and 5 Mbp, plus small ones around them)."""
     rng = np.random.default_rng(k)
@@ -75,7 +83,7 @@ def test_large_records_split_across_staging_chunks(oracle, gpu_ctx, tmp_path, k)
         assert np.array_equal(regs, exp)
 
 
-def test_fastq_reads_uniform_and_ragged(oracle, gpu_ctx, tmp_path):
+def test_fastq_reads_uniform_and_ragged(oracle, gpu_ctx, tmp_path, ingest):
     """config 4 shape: 150 bp reads of one sample.  Equal-length reads take the table-free
     rec_len path, ragged reads (and reads that lose bases to the filter) the rec_start table."""
     rng = np.random.default_rng(4)
@@ -96,7 +104,7 @@ def test_fastq_reads_uniform_and_ragged(oracle, gpu_ctx, tmp_path):
     assert st.n_records == 3 * len(starts)
 
 
-def test_many_small_files_share_chunks(oracle, gpu_ctx, tmp_path):
+def test_many_small_files_share_chunks(oracle, gpu_ctx, tmp_path, ingest):
     genomes = synth.genomes(300, 20_000, seed=5)
     files = []
     for g, recs in enumerate(genomes):
