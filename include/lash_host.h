@@ -84,9 +84,10 @@ int lash_host_sketch_files(lash_ctx* ctx, int algo, int p, int k, uint64_t seed,
  * (no GPU work, no registers) -- the host ingest ceiling bench.py reports next to the end-to-end rate. */
 int lash_host_pack_files_dry(const char* const* files, uint64_t n_files, int k, int threads, uint64_t chunk_bytes,
                              lash_sketch_files_stats* stats);
-/* Who runs filter_out_n + the 2-bit packing for sketch_files: 0 = auto (the device unless the call has >= 40 host workers),
- * 1 = the host packer (lash_sketch_push: 0.25 B/base over PCIe, ~1.3 Gbp/s per worker), 2 = the device
- * (lash_sketch_push_ascii: the host only copies sequence bytes into pinned chunks, 1 B/base over PCIe).  Process-wide;
+/* Who runs filter_out_n + the 2-bit packing for sketch_files: 0 = auto (the host packer when the CPU has its SIMD path, else
+ * the device), 1 = the host packer (lash_sketch_push: 0.25 B/base over PCIe), 2 = the device (lash_sketch_push_ascii: the
+ * host only moves sequence bytes into pinned chunks -- plain FASTA is read() straight into them -- 1 B/base over PCIe).
+ * Process-wide;
  * the environment variable LASH_INGEST=packed|ascii overrides it.  Registers are identical either way.
  * In device mode lash_sketch_files_stats.n_bases_kept is 0 (the host never looks at the bases). */
 int lash_host_set_ingest_mode(int mode);

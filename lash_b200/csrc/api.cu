@@ -503,6 +503,8 @@ static int push_text_impl(lash_sketcher* s, const void* text, bool text_on_devic
         n_blocks64 += (sp.n_bytes + kTextBlockBytes - 1) / kTextBlockBytes;
     }
     if (n_blocks64 > 0x7fffffffull) return fail(LASH_E_INVALID, "lash_sketch_push_ascii: push too large");
+    static const bool trace = getenv("LASH_TRACE_PUSH") != nullptr;
+    const auto tp0 = std::chrono::steady_clock::now();
     const uint64_t target_tiles = (uint64_t)s->ctx->n_sm * 8 * 32;
     uint64_t chunk = (total_starts + target_tiles - 1) / target_tiles;
     chunk = std::max(chunk, s->per_iter);
@@ -557,6 +559,7 @@ static int push_text_impl(lash_sketcher* s, const void* text, bool text_on_devic
     }
     if (tiles.size() > 0x7fffffffull) return fail(LASH_E_INVALID, "lash_sketch_push_ascii: too many tiles in one push");
 
+    const auto tp1 = std::chrono::steady_clock::now();
     const uint64_t ticket = s->next_ticket++;
     Slot& sl = s->slot[ticket % kSlots];
     const cudaStream_t stream = s->ext_stream ? s->ext_stream : sl.stream;
@@ -565,6 +568,7 @@ static int push_text_impl(lash_sketcher* s, const void* text, bool text_on_devic
         int rc = harvest_timing(s, sl);
         if (rc) return rc;
     }
+    const auto tp2 = std::chrono::steady_clock::now();
     const size_t tiles_bytes = tiles.size() * sizeof(SketchTile);
     const size_t off_blocks = (tiles_bytes + 15) / 16 * 16;
     const size_t off_spans = off_blocks + (tblocks.size() * sizeof(TextBlock) + 15) / 16 * 16;
@@ -590,6 +594,7 @@ static int push_text_impl(lash_sketcher* s, const void* text, bool text_on_devic
         text_dev = (const uint8_t*)sl.text.p;
     }
     CU(cudaEventRecord(sl.copied, stream));
+    const auto tp3 = std::chrono::steady_clock::now();
     const uint32_t n_blocks = (uint32_t)tblocks.size();
     uint32_t* mask_dev = nullptr;
     uint64_t* aux = nullptr;
@@ -620,6 +625,12 @@ static int push_text_impl(lash_sketcher* s, const void* text, bool text_on_devic
         }
     }
     CU(cudaEventRecord(sl.k_stop, stream));
+    if (trace) {
+        const auto tp4 = std::chrono::steady_clock::now();
+        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "[lash push_ascii] %llu bytes, %zu tiles, %u blocks: plan %.0f us, slot wait %.0f us, uploads %.0f us, launches %.0f us\n",
+                (unsigned long long)n_bytes, tiles.size(), n_blocks, us(tp0, tp1), us(tp1, tp2), us(tp2, tp3), us(tp3, tp4));
+    }
     sl.timing_pending = true;
     sl.used = true;
     sl.ticket = ticket;

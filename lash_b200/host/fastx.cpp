@@ -1,5 +1,6 @@
 #include "fastx.hpp"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace lashhost {
@@ -14,7 +15,8 @@ bool FastxReader::open(const std::string& path, size_t buf_bytes) {
     pos_ = end_ = 0;
     eof_ = false;
     // uncompressed regular files are parsed in place (page cache mapped read-only, no copy)
-    if (map_plain_file(path, &map_, &map_len_)) {
+    static const bool use_mmap = getenv("LASH_FASTX_MMAP") != nullptr;
+    if (use_mmap && map_plain_file(path, &map_, &map_len_)) {
         end_ = map_len_;
         eof_ = true;
     } else {
@@ -23,7 +25,7 @@ bool FastxReader::open(const std::string& path, size_t buf_bytes) {
             state_ = kStFailed;
             return false;
         }
-        buf_.resize(buf_bytes < 4096 ? 4096 : buf_bytes);
+        if (buf_.size() < 4096) buf_.resize(buf_bytes < 4096 ? 4096 : buf_bytes);   // kept across open() calls of one reader
     }
     at_line_start_ = true;
     fa_open_ = false;

@@ -27,7 +27,7 @@ class FastxReader {
     ~FastxReader();
     FastxReader(const FastxReader&) = delete;
     FastxReader& operator=(const FastxReader&) = delete;
-    bool open(const std::string& path, size_t buf_bytes = 4u << 20);
+    bool open(const std::string& path, size_t buf_bytes = 1u << 18);
     Ev next();
     // 1 record, 0 end of file, -1 error
     int next_record(std::string& id, std::string& seq);

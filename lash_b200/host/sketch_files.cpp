@@ -9,11 +9,14 @@
 // (pack.cpp) into a pinned chunk and hands full chunks to the GPU (lash_sketch_push) while it fills
 // its second chunk.  Several small files share a chunk (one span each); a large record is split
 // across chunks with a (k-1)-base overlap so that every k-mer start is produced exactly once.
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cerrno>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -142,7 +145,7 @@ class Chunk {
         genome_ = genome;
         if (text_) {
             tw_ = 0;
-            n_rec_ = 0;
+            n_seps_ = 0;
             rec_begin_ = 0;
             span_open_ = true;
             return;
@@ -169,6 +172,49 @@ class Chunk {
         tw_ += n;
         return 0;  // bases kept: only the device knows
     }
+    // ---- text mode, plain FASTA read straight into the pinned chunk (no intermediate buffer, no memcpy) ----------------
+    // The file's bytes land where the GPU will read them; the only host work per byte is the scan below: every header
+    // line is overwritten in place -- its '>' by the record separator, its text by 'N' (never a base) -- and a sequence
+    // byte equal to the separator by a line feed.  State carries across pieces and chunks.
+    struct FastaScan {
+        bool in_header = false;      // the piece starts inside a header line
+        bool at_line_start = true;   // the byte before the piece was '\n' (or the piece starts the file)
+        uint64_t n_headers = 0;
+    };
+    uint8_t* text_ptr() { return buf_ + off_ + tw_; }
+    void text_commit_fasta(size_t n, FastaScan& st) {
+        uint8_t* p = buf_ + off_ + tw_;
+        size_t i = 0;
+        while (i < n) {
+            if (st.in_header) {
+                uint8_t* nl = static_cast<uint8_t*>(memchr(p + i, '\n', n - i));
+                const size_t end = nl ? (size_t)(nl - p) : n;
+                memset(p + i, 'N', end - i);
+                if (!nl) break;
+                st.in_header = false;
+                i = end + 1;
+                continue;
+            }
+            uint8_t* g = static_cast<uint8_t*>(memchr(p + i, '>', n - i));
+            const size_t seq_end = g ? (size_t)(g - p) : n;
+            for (uint8_t* q = static_cast<uint8_t*>(memchr(p + i, LASH_TEXT_RECORD_SEP, seq_end - i)); q;
+                 q = static_cast<uint8_t*>(memchr(q + 1, LASH_TEXT_RECORD_SEP, (size_t)(p + seq_end - (q + 1)))))
+                *q = '\n';
+            if (!g) break;
+            const bool line_start = seq_end > 0 ? p[seq_end - 1] == '\n' : st.at_line_start;
+            if (line_start) {   // a header: the previous record ends here
+                p[seq_end] = LASH_TEXT_RECORD_SEP;
+                ++n_seps_;
+                ++st.n_headers;
+                rec_begin_ = tw_ + seq_end + 1;
+                st.in_header = true;
+            }                   // else: a '>' inside a sequence line is just a byte filter_out_n deletes
+            i = seq_end + 1;
+        }
+        st.at_line_start = n > 0 ? p[n - 1] == '\n' : st.at_line_start;
+        tw_ += n;
+    }
+
     // the (k-1)-base overlap of a record that was split across chunks
     void push_carry(const std::vector<uint8_t>& carry) {
         if (text_) {
@@ -183,7 +229,7 @@ class Chunk {
     void end_record(int k) {
         if (text_) {  // records shorter than k are dropped by the device (their starts are all invalid)
             buf_[off_ + tw_++] = LASH_TEXT_RECORD_SEP;
-            ++n_rec_;
+            ++n_seps_;
             return;
         }
         const uint64_t len = record_len();
@@ -205,7 +251,7 @@ class Chunk {
             }
             std::reverse(carry.begin(), carry.end());
             buf_[off_ + tw_++] = LASH_TEXT_RECORD_SEP;
-            ++n_rec_;
+            ++n_seps_;
             return;
         }
         const uint64_t len = record_len();
@@ -223,7 +269,12 @@ class Chunk {
             sp.genome = genome_;
             sp.byte_off = off_;
             sp.n_bytes = tw_;
-            sp.n_rec = n_rec_ > 1 ? n_rec_ : 1;
+            // records = separators strictly inside the span + 1; one record needs no boundary bitmask on the device
+            const uint8_t* b = buf_ + off_;
+            uint64_t inner = n_seps_;
+            if (inner && b[0] == LASH_TEXT_RECORD_SEP) --inner;
+            if (inner && tw_ > 1 && b[tw_ - 1] == LASH_TEXT_RECORD_SEP) --inner;
+            sp.n_rec = (uint32_t)std::min<uint64_t>(inner + 1, 0xffffffffull);
             sp.reserved = 0;
             tspans_.push_back(sp);
             off_ += (tw_ + 15) / 16 * 16 + 16;
@@ -297,6 +348,7 @@ class Chunk {
     std::vector<lash_span> spans_;
     std::vector<lash_text_span> tspans_;
     uint64_t tw_ = 0;     // text mode: bytes written in the open span
+    uint64_t n_seps_ = 0; // text mode: record separators written in the open span
     bool text_ = false;
     std::vector<uint64_t> rec_start_;
     uint64_t genome_ = 0, rec_first_ = 0, rec_begin_ = 0, uniform_len_ = 0, last_len_ = 0;
@@ -331,8 +383,63 @@ struct Worker {
         return true;
     }
 
+    FastxReader rd;  // one reader per worker: its read buffer is allocated once, not per file
+
+    // plain (uncompressed) FASTA in text mode: read() straight into the pinned chunk.  Returns 0 = not applicable (the
+    // generic reader takes over), 1 = done, -1 = error.
+    int sketch_fasta_direct(Gpu& gpu, const std::string& path, uint64_t genome, int k, std::string& err) {
+        static const bool off = getenv("LASH_FASTA_DIRECT") && !strcmp(getenv("LASH_FASTA_DIRECT"), "0");
+        if (off) return 0;
+        const int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd < 0) return 0;
+        uint8_t m[6] = {0, 0, 0, 0, 0, 0};
+        struct stat sb;
+        const bool plain_fasta = fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && ::pread(fd, m, 6, 0) >= 1 && m[0] == '>';
+        if (!plain_fasta) {   // compressed ('>' is no magic byte of gzip / bzip2 / xz / zstd), FASTQ, empty, a pipe ...
+            ::close(fd);
+            return 0;
+        }
+        constexpr size_t kPiece = 1u << 20;   // read + scan granularity: the scan finds the piece in the core's L2
+        if (!chunk[cur].can_begin_span() && !rotate(gpu)) { ::close(fd); return -1; }
+        chunk[cur].begin_span(genome);
+        chunk[cur].begin_record();
+        Chunk::FastaScan st;
+        std::vector<uint8_t> carry;
+        int rc = 1;
+        for (;;) {
+            if (chunk[cur].room() < 4096) {
+                // chunk full: close this part of the record (a header needs no overlap), continue in the other chunk
+                if (st.in_header) carry.clear();
+                else chunk[cur].split_record(k, carry);
+                chunk[cur].end_span();
+                if (!rotate(gpu)) { rc = -1; break; }
+                chunk[cur].begin_span(genome);
+                chunk[cur].begin_record();
+                chunk[cur].push_carry(carry);
+            }
+            const size_t want = (size_t)std::min<uint64_t>(chunk[cur].room(), kPiece);
+            const ssize_t got = ::read(fd, chunk[cur].text_ptr(), want);
+            if (got < 0) {
+                if (errno == EINTR) continue;
+                err = "Invalid input file " + path + ": read failed: " + strerror(errno);
+                rc = -1;
+                break;
+            }
+            if (got == 0) break;
+            n_in += (uint64_t)got;
+            chunk[cur].text_commit_fasta((size_t)got, st);
+        }
+        ::close(fd);
+        n_records += st.n_headers;
+        if (rc == 1) chunk[cur].end_span();
+        return rc;
+    }
+
     bool sketch_file(Gpu& gpu, const std::string& path, uint64_t genome, int k, std::string& err) {
-        FastxReader rd;
+        if (chunk[cur].text_mode()) {
+            const int rc = sketch_fasta_direct(gpu, path, genome, k, err);
+            if (rc != 0) return rc > 0;
+        }
         if (!rd.open(path)) {
             err = "Invalid input file " + path + ": " + rd.err();  // utils.rs:453 expect("Invalid input file")
             return false;
@@ -397,9 +504,11 @@ uint64_t auto_chunk_bytes(const std::vector<std::string>& files, uint32_t n_work
 
 void release_pinned() { pinned_pool().clear(); }
 
-// Who filters and packs: 1 = host (AVX2 packer, 0.25 B/base over PCIe), 2 = device (raw text, 1 B/base over PCIe, the
-// host only copies).  0 = auto: the device while the host workers could not feed the link with packed bases anyway
-// (about 1.3 Gbp/s per worker against ~50 Gbp/s of text through one x16 link).  LASH_INGEST=packed|ascii overrides.
+// Who filters and packs: 1 = host (SIMD packer, 0.25 B/base over PCIe), 2 = device (raw text, 1 B/base over PCIe, the
+// host only copies).  0 = auto: the host packer when the CPU has the SIMD path (measured on the B200 boxes: 4.3 Gbp/s per
+// worker packed against 4.8-7.3 as text, but the text moves 2 B/base through host DRAM against 1.25 and both are bound by
+// host memory bandwidth from 4 workers on -- packed 41 Gbp/s, text 25 Gbp/s at 16 workers), the device otherwise (the
+// scalar packer does 1 Gbp/s per worker).  LASH_INGEST=packed|ascii overrides.
 static std::atomic<int> g_ingest_mode{0};
 void set_ingest_mode(int mode) { g_ingest_mode.store(mode); }
 static bool use_text_ingest(uint32_t n_workers) {
@@ -410,7 +519,8 @@ static bool use_text_ingest(uint32_t n_workers) {
     }
     if (mode == 1) return false;
     if (mode == 2) return true;
-    return n_workers < 40;
+    (void)n_workers;
+    return !lashhost::pack_has_simd();
 }
 
 // Parse + filter + pack every file exactly as sketch_files does, but drop the chunks instead of pushing
@@ -427,8 +537,11 @@ Status pack_files_dry(const std::vector<std::string>& files, size_t kmer_length,
         n_workers = (uint32_t)std::min<uint64_t>(n_workers, n_files);
         Gpu gpu;  // sk == nullptr: submit() only counts
         std::vector<Worker> workers(n_workers);
-        for (auto& w : workers)
+        const bool text = use_text_ingest(n_workers);
+        for (auto& w : workers) {
+            w.chunk[0].set_text_mode(text);
             if (!w.chunk[0].alloc(chunk_bytes, false)) return Status{LASH_E_NOMEM, "staging allocation failed"};
+        }
         std::atomic<uint64_t> next_file{0};
         auto run = [&](Worker& w) {
             for (;;) {

@@ -83,6 +83,29 @@ def test_large_records_split_across_staging_chunks(oracle, gpu_ctx, tmp_path, k,
         assert np.array_equal(regs, exp)
 
 
+def test_fasta_read_straight_into_pinned_chunks(oracle, gpu_ctx, tmp_path, ingest):
+    """Plain FASTA in device-filter mode is read() directly into the pinned chunk and fixed up in place: headers blanked
+    (even when they are made of base letters), '>' inside a sequence line, CRLF line ends, a separator byte in the data, a
+    header that straddles a chunk boundary (chunk = 4 MiB here), no line end at the end of the file."""
+    rng = np.random.default_rng(31)
+    seq = lambda n: synth.to_ascii(rng.integers(0, 4, size=n, dtype=np.uint8))
+    recs = [seq((4 << 20) - 150_000), seq(300_000), seq(20), seq(2_000_000)]
+    recs[1] = recs[1][:1000] + b">" + recs[1][1000:2000] + b"\x01" + recs[1][2000:]      # '>' and the separator byte inside a line
+    path = str(tmp_path / "odd.fa")
+    with open(path, "wb") as f:
+        f.write(b">first\r\n" + b"\r\n".join(recs[0][o:o + 70] for o in range(0, len(recs[0]), 70)) + b"\r\n")
+        f.write(b">" + b"ACGT" * 75_000 + b" a header made of bases, 300 kB long\n")         # straddles the 4 MiB chunk end
+        f.write(b"\n".join(recs[1][o:o + 61] for o in range(0, len(recs[1]), 61)) + b"\n")
+        f.write(b">tiny\n" + recs[2] + b"\n>last\n" + recs[3])                           # no trailing line end
+    # what needletail hands over: line ends removed, everything else (the in-line '>', the 0x01) is sequence content
+    want = [recs[0], recs[1], recs[2], recs[3]]
+    for algo, p, k in ((ALGO_ULL, 12, 21), (ALGO_HMH, 14, 16)):
+        regs, st = hostapi.sketch_files_regs(gpu_ctx, algo, p, k, 42, [path, path], threads=2, chunk_bytes=1 << 20)
+        exp = oracle.sketch_genomes(getattr(oracle, _oname(algo)), p, k, 42, [want, want], threads=2)
+        assert np.array_equal(regs, exp)
+        assert st.n_records == 8
+
+
 def test_fastq_reads_uniform_and_ragged(oracle, gpu_ctx, tmp_path, ingest):
     """config 4 shape: 150 bp reads of one sample.  Equal-length reads take the table-free
     rec_len path, ragged reads (and reads that lose bases to the filter) the rec_start table."""
