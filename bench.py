@@ -394,6 +394,7 @@ def run_graft(args):
 
     # ---- parity spot check against the oracle (checker only) -------------------------------------
     parity = None
+    dist_parity = None
     e2e = None
     cpu_baseline = None
     if rank == 0:
@@ -401,6 +402,18 @@ def run_graft(args):
         host_regs = regs_view.view(n_g, rb)[:2].cpu().numpy()
         gen = [[unpack_to_ascii(buf[i * stride: i * stride + (GENOME_LEN + 3) // 4].cpu().numpy(), GENOME_LEN)] for i in range(2)]
         parity = bool(np.array_equal(O.sketch_genomes(O.ULL, P, K, SEED, gen, threads=2), host_regs))
+        # the dist half: the leading 256 x 256 triangle of the all-vs-all (rank 0's rows start at 0) against the oracle, every
+        # cell, with the raw error figures (max relative error, fraction within plain 1e-12, bit-identical fraction)
+        from tools import config_legs
+        nb = min(256, rows[1])
+        src_t = regs_all if world > 1 else regs_view
+        lead = src_t.view(-1, rb)[:nb].cpu().numpy()
+        r_idx = torch.arange(nb, device=device)
+        got_blk = out[((r_idx * (r_idx + 1) // 2)[:, None] + r_idx[None, :]).clamp(max=out.numel() - 1)].cpu().numpy()
+        tri_ok = np.tril(np.ones((nb, nb), dtype=bool))
+        exp_blk = O.dist(O.ULL, P, K, O.FGRA, O.POISSON, False, lead, lead, threads=os.cpu_count() or 1)
+        dist_parity = config_legs.error_stats(got_blk[tri_ok], exp_blk[tri_ok], K)
+        parity = parity and dist_parity["ok"]
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------------
     # Two-stage software pipeline over steps: while step i's distance phase runs (registers up, NCCL all-gather, this rank's
@@ -601,7 +614,7 @@ def run_graft(args):
             "dist": {"metric": "all_vs_all_pairs_per_s", "value": n_pairs_all / (di_ms * 1e-3), "unit": "pairs/s", "pairs": n_pairs_all,
                      "register_merges_per_s": n_pairs_all * rb / (di_ms * 1e-3)},
             "roofline": roofline, "roofline_dist": roofline_dist, "cpu_baseline": cpu_baseline, "e2e": e2e, "fasta_ingest": ingest, "clocks": clocks,
-            "gpu_launches": gpu_launches, "parity_spot_check": parity, "hll_bias_flags": int(flags.item()),
+            "gpu_launches": gpu_launches, "parity_spot_check": parity, "dist_parity": dist_parity, "hll_bias_flags": int(flags.item()),
             "configs": configs, "kernel_costs": costs_status,
         }
         print(json.dumps(line), flush=True)

@@ -427,6 +427,156 @@ __global__ void __launch_bounds__(kHllThreads, 3) dist_hll_fast_kernel(DistParam
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4m: HyperMinHash distance tiles (hmh_distance inner loop, utils.rs:150-180; hyperminhash similarity()).
+//
+// Per pair, over the 16384 u16 registers:  C = #{a == b and a != 0},  N = #{a != 0 or b != 0}  -- integers, so any
+// evaluation order is exact.  dist_kernel<HmhAcc> spends ~8 scalar instructions per register on halfword extracts and
+// compares (45 M pairs/s).  Here two registers are handled per 32-bit word, branch-free:
+//     x = a ^ b;  t = (x & 0x7fff7fff) + 0x7fff7fff;  v = (t | x) & 0x80008000      bit 15 / 31 <=> the halfwords differ
+//     nz += v >> 15                                                                   (IMAD.HI by 2^17: both 16-bit lanes count)
+// = 5 instructions per register pair-of-pairs (3 LOP3 + 1 add on the ALU pipe, the accumulate on the FMA pipe), and
+//     C = N - NZ.   N itself only deviates from "all registers" where BOTH sketches hold an empty register at the same
+// index; staging records per chunk whether any reference row and any query column has an empty register at all, and only
+// such chunks run the loop variant that also counts (a | b) != 0 the same way (sketches of >= ~10^5 k-mers never do).
+// A warp owns 4 reference rows (warp-uniform -> broadcast LDS.128) x 64 query columns, two per lane; 3 CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHmhThreads = 256;
+constexpr int kHmhRM = 4, kHmhQM = 2;
+constexpr int kHmhTR = (kHmhThreads / 32) * kHmhRM, kHmhTQ = 32 * kHmhQM;  // 32 x 64 pairs per CTA
+constexpr int kHmhChunkWords = 64;                                        // 128 registers per sketch per stage
+constexpr uint32_t kHmhWords = 8192;                                      // 16384 u16 registers
+
+__device__ __forceinline__ uint32_t halfwords_nonzero(uint32_t x) {  // bit 15 / bit 31 set <=> that halfword of x is non-zero
+    return (((x & 0x7fff7fffu) + 0x7fff7fffu) | x) & 0x80008000u;
+}
+// The same test on x = a ^ b (or a | b) accumulated into two 16-bit lane counters, with the add and the accumulate on the
+// FMA pipe: t = y * one + M and acc += hi32(v * 2^17), where `one` and `two17` are RUN-TIME values (derived from blockDim
+// by the caller).  With literal constants ptxas strength-reduces both back to ALU instructions (VIADD, LEA.HI) and the
+// loop runs 5 ALU instructions per word pair with the FMA pipe idle; this way it is 3 LOP3 + 2 IMAD.
+// The accumulator is 64 bits wide so that the accumulate is ONE IMAD.WIDE (v * 2^17 lands in bits 32.. / 48.. of the
+// pair; as a 32-bit IMAD.HI the addend pair needs a zeroed low register, which ptxas re-materialises every time).
+template <bool XOR>
+__device__ __forceinline__ uint64_t count_halfwords_nonzero(uint32_t a, uint32_t b, uint64_t acc, uint32_t one, uint32_t two17) {
+    const uint32_t x = XOR ? (a ^ b) : (a | b);
+    const uint32_t t = (x & 0x7fff7fffu) * one + 0x7fff7fffu;
+    const uint32_t v = (t | x) & 0x80008000u;
+    return (uint64_t)v * two17 + acc;
+}
+
+template <bool COUNT_N>
+__device__ __forceinline__ void hmh_chunk(uint64_t (&nz)[kHmhRM][kHmhQM], uint64_t (&nn)[kHmhRM][kHmhQM], const uint32_t* pa,
+                                          const uint32_t* pb, uint32_t a_row, uint32_t b_row32, uint32_t one, uint32_t two17) {
+#pragma unroll 2
+    for (uint32_t e = 0; e < (uint32_t)kHmhChunkWords; e += 4) {
+        uint4 a[kHmhRM], b[kHmhQM];
+#pragma unroll
+        for (int r = 0; r < kHmhRM; ++r) a[r] = *reinterpret_cast<const uint4*>(pa + r * a_row + e);
+#pragma unroll
+        for (int c = 0; c < kHmhQM; ++c) b[c] = *reinterpret_cast<const uint4*>(pb + c * b_row32 + e);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int r = 0; r < kHmhRM; ++r) {
+                const uint32_t av = j == 0 ? a[r].x : j == 1 ? a[r].y : j == 2 ? a[r].z : a[r].w;
+#pragma unroll
+                for (int c = 0; c < kHmhQM; ++c) {
+                    const uint32_t bv = j == 0 ? b[c].x : j == 1 ? b[c].y : j == 2 ? b[c].z : b[c].w;
+                    nz[r][c] = count_halfwords_nonzero<true>(av, bv, nz[r][c], one, two17);
+                    if (COUNT_N) nn[r][c] = count_halfwords_nonzero<false>(av, bv, nn[r][c], one, two17);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kHmhThreads, 3) dist_hmh_fast_kernel(DistParams dp) {
+    __shared__ __align__(16) uint32_t sa[kHmhTR * (kHmhChunkWords + 4)];
+    __shared__ __align__(16) uint32_t sb[kHmhTQ * (kHmhChunkWords + 4)];
+    __shared__ uint32_t s_zero[2][2];                    // [chunk parity][ref, qry]: an empty register was staged
+    constexpr uint32_t stride = kHmhChunkWords + 4;      // +16 B pad: conflict-free LDS.128 across the 32 query rows of a warp
+
+    const uint64_t row0 = dp.row_begin + (uint64_t)blockIdx.y * kHmhTR;
+    const uint64_t col0 = (uint64_t)blockIdx.x * kHmhTQ;
+    if (row0 >= dp.row_end) return;
+    const uint64_t row_hi = min(row0 + kHmhTR, dp.row_end);
+    if (dp.triangular && col0 > row_hi - 1) return;      // tile entirely above the diagonal
+
+    const uint32_t wy = threadIdx.x >> 5, tx = threadIdx.x & 31u;
+    const uint32_t* gref = reinterpret_cast<const uint32_t*>(dp.ref);
+    const uint32_t* gqry = reinterpret_cast<const uint32_t*>(dp.qry);
+    const uint32_t one = blockDim.x / kHmhThreads, two17 = blockDim.x << 9;  // 1 and 2^17, opaque to ptxas (see above)
+
+    // per-lane pair counters: two 16-bit lanes per word (low / high halfword of the register words); a lane counts at
+    // most 8192, so neither overflows
+    uint64_t nz[kHmhRM][kHmhQM], nn[kHmhRM][kHmhQM];    // counts sit in the HIGH word (bits 32.. and 48..), the low word stays 0
+    uint32_t full = 0;                                   // registers of chunks where N needed no counting (same for every pair)
+#pragma unroll
+    for (int r = 0; r < kHmhRM; ++r)
+#pragma unroll
+        for (int c = 0; c < kHmhQM; ++c) nz[r][c] = nn[r][c] = 0ull;
+    if (threadIdx.x < 2) s_zero[0][threadIdx.x] = 0u;
+
+    uint32_t par = 0;
+    for (uint32_t c0 = 0; c0 < kHmhWords; c0 += kHmhChunkWords, par ^= 1u) {
+        __syncthreads();  // previous chunk consumed; s_zero[par] was cleared during the previous staging pass (or above)
+        if (threadIdx.x < 2) s_zero[par ^ 1u][threadIdx.x] = 0u;
+        bool za = false, zb = false;
+        // 16-byte loads: 16 per staged row (register arrays are 16-byte aligned: the launcher checks)
+        for (uint32_t e = threadIdx.x; e < (uint32_t)kHmhTR * (kHmhChunkWords / 4); e += kHmhThreads) {
+            const uint32_t r = e / (kHmhChunkWords / 4), g = e % (kHmhChunkWords / 4);
+            const uint64_t gi = row0 + r;
+            // rows past the end are staged as all-ones registers (never empty, never read back)
+            const uint4 v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint4*>(gref + gi * kHmhWords + c0) + g)
+                                            : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            za |= (halfwords_nonzero(v.x) & halfwords_nonzero(v.y) & halfwords_nonzero(v.z) & halfwords_nonzero(v.w)) != 0x80008000u;
+            *reinterpret_cast<uint4*>(sa + r * stride + 4 * g) = v;
+        }
+        for (uint32_t e = threadIdx.x; e < (uint32_t)kHmhTQ * (kHmhChunkWords / 4); e += kHmhThreads) {
+            const uint32_t r = e / (kHmhChunkWords / 4), g = e % (kHmhChunkWords / 4);
+            const uint64_t gj = col0 + r;
+            const uint4 v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint4*>(gqry + gj * kHmhWords + c0) + g)
+                                          : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            zb |= (halfwords_nonzero(v.x) & halfwords_nonzero(v.y) & halfwords_nonzero(v.z) & halfwords_nonzero(v.w)) != 0x80008000u;
+            *reinterpret_cast<uint4*>(sb + r * stride + 4 * g) = v;
+        }
+        if (za) s_zero[par][0] = 1u;
+        if (zb) s_zero[par][1] = 1u;
+        __syncthreads();
+        const uint32_t* pa = sa + (wy * kHmhRM) * stride;
+        const uint32_t* pb = sb + tx * stride;
+        if (s_zero[par][0] & s_zero[par][1]) {  // CTA-uniform
+            hmh_chunk<true>(nz, nn, pa, pb, stride, 32u * stride, one, two17);
+        } else {
+            hmh_chunk<false>(nz, nn, pa, pb, stride, 32u * stride, one, two17);
+            full += 2u * kHmhChunkWords;
+        }
+    }
+
+    // epilogue: identical to dist_kernel<HmhAcc>
+#pragma unroll
+    for (int a = 0; a < kHmhRM; ++a) {
+#pragma unroll
+        for (int b = 0; b < kHmhQM; ++b) {
+            const uint64_t i = row0 + wy * kHmhRM + a, j = col0 + tx + 32 * b;
+            if (i >= dp.row_end || j >= dp.n_qry) continue;
+            if (dp.triangular && j > i) continue;
+            const uint32_t nzh = (uint32_t)(nz[a][b] >> 32), nnh = (uint32_t)(nn[a][b] >> 32);
+            const uint32_t NZ = (nzh & 0xffffu) + (nzh >> 16);
+            const uint32_t N = (nnh & 0xffffu) + (nnh >> 16) + full;
+            const uint32_t Cc = N - NZ;   // equal and non-empty = (equal) - (both empty) = (16384 - NZ) - (16384 - N)
+            const double sim = hmh_similarity_from(Cc, N, dp.card_qry[j], dp.card_ref[i]);
+            const double s = fmax(sim, 0.0);
+            const double frac = 2.0 * s / (1.0 + s);
+            const uint64_t o = dp.packed_tri ? (i * (i + 1) / 2 + j) : ((i - dp.out_row0) * dp.n_qry + j);
+            if (dp.fp32)
+                reinterpret_cast<float*>(dp.out)[o] = mash_distance_f32((float)frac, dp.k, dp.model);
+            else
+                reinterpret_cast<double*>(dp.out)[o] = mash_distance_f64(frac, dp.k, dp.model);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4b: FGRA distance tiles through a PAIR table.
 //
 // dist_kernel<FgraAcc> spends ~12 ALU instructions per register pair on the packed-domain merge
@@ -1008,6 +1158,23 @@ static cudaError_t launch_dist_hll_fast(const DistParams& dp, cudaStream_t st) {
     return cudaSuccess;
 }
 
+static cudaError_t launch_dist_hmh_fast(const DistParams& dp, cudaStream_t st) {
+    const uint64_t rows = dp.row_end - dp.row_begin;
+    const uint64_t gy = (rows + kHmhTR - 1) / kHmhTR;
+    uint64_t ncols = dp.n_qry;
+    if (dp.triangular && dp.row_end < ncols) ncols = dp.row_end;  // nothing right of the diagonal
+    const uint64_t gx = (ncols + kHmhTQ - 1) / kHmhTQ;
+    for (uint64_t y0 = 0; y0 < gy; y0 += 65535) {  // grid.y is limited to 65535: walk row bands
+        DistParams q = dp;
+        q.row_begin = dp.row_begin + y0 * kHmhTR;
+        const uint64_t ny = (gy - y0) < 65535 ? (gy - y0) : 65535;
+        dist_hmh_fast_kernel<<<dim3((unsigned)gx, (unsigned)ny), kHmhThreads, 0, st>>>(q);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 static cudaError_t launch_dist_ml_tab(const DistParams& dp, cudaStream_t st) {
     const uint32_t cb = cell_bytes_of(dp.algo, dp.p);
     const uint32_t chunk = cb < (uint32_t)kMlTabChunk ? cb : (uint32_t)kMlTabChunk;
@@ -1063,7 +1230,12 @@ cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launc
     // K4h stages with 16-byte loads: register arrays that are not 16-byte aligned (a caller's odd device pointer) use K4
     const bool hll_aligned = (((uintptr_t)dp.ref | (uintptr_t)dp.qry) & 15u) == 0;
     if (dp.algo == HLL) return (hll_table || !hll_aligned) ? launch_dist_t<HllAcc, 16>(dp, st) : launch_dist_hll_fast(dp, st);
-    if (dp.algo == HMH) return launch_dist_t<HmhAcc, 16>(dp, st);
+    // LASH_HMH_KERNEL=generic selects K4 for A/B measurements; K4m stages with 16-byte loads like K4h
+    static const bool hmh_generic = [] {
+        const char* v = getenv("LASH_HMH_KERNEL");
+        return v && std::string(v) == "generic";
+    }();
+    if (dp.algo == HMH) return (hmh_generic || !hll_aligned) ? launch_dist_t<HmhAcc, 16>(dp, st) : launch_dist_hmh_fast(dp, st);
     const bool tiny = dp.p == 3;  // 8 registers per sketch
     if (dp.estimator == 0) return tiny ? launch_dist_t<FgraAcc, 8>(dp, st) : launch_dist_t<FgraAcc, 16>(dp, st);
     return tiny ? launch_dist_t<MlAcc, 8>(dp, st) : launch_dist_t<MlAcc, 16>(dp, st);
