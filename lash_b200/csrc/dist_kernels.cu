@@ -431,13 +431,14 @@ __global__ void __launch_bounds__(kHllThreads, 3) dist_hll_fast_kernel(DistParam
 //
 // Per pair, over the 16384 u16 registers:  C = #{a == b and a != 0},  N = #{a != 0 or b != 0}  -- integers, so any
 // evaluation order is exact.  dist_kernel<HmhAcc> spends ~8 scalar instructions per register on halfword extracts and
-// compares (45 M pairs/s).  Here two registers are handled per 32-bit word, branch-free:
-//     x = a ^ b;  t = (x & 0x7fff7fff) + 0x7fff7fff;  v = (t | x) & 0x80008000      bit 15 / 31 <=> the halfwords differ
-//     nz += v >> 15                                                                   (IMAD.HI by 2^17: both 16-bit lanes count)
-// = 5 instructions per register pair-of-pairs (3 LOP3 + 1 add on the ALU pipe, the accumulate on the FMA pipe), and
-//     C = N - NZ.   N itself only deviates from "all registers" where BOTH sketches hold an empty register at the same
-// index; staging records per chunk whether any reference row and any query column has an empty register at all, and only
-// such chunks run the loop variant that also counts (a | b) != 0 the same way (sketches of >= ~10^5 k-mers never do).
+// compares.  Here two registers are handled per 32-bit word with the packed-halfword minimum of sm_90+ (VIMNMX.U16x2):
+//     m = min.u16x2(a ^ b, 0x00010001)          each 16-bit lane: 1 <=> the registers differ
+//     nz = m * one + nz                         both lane counters at once, on the FMA pipe (`one` is a run-time 1:
+//                                               with a literal ptxas turns the IMAD back into an ALU add)
+// = LOP3 + VIMNMX + IMAD per two register pairs, and  C = N - NZ.  N itself only deviates from "all registers" where
+// BOTH sketches hold an empty register at the same index; staging records per chunk whether any reference row and any
+// query column has an empty register at all, and only such chunks run the loop variant that also counts
+// min.u16x2(a | b, 0x00010001) (sketches of >= ~10^5 k-mers never do).
 // A warp owns 4 reference rows (warp-uniform -> broadcast LDS.128) x 64 query columns, two per lane; 3 CTAs per SM.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHmhThreads = 256;
@@ -446,26 +447,11 @@ constexpr int kHmhTR = (kHmhThreads / 32) * kHmhRM, kHmhTQ = 32 * kHmhQM;  // 32
 constexpr int kHmhChunkWords = 64;                                        // 128 registers per sketch per stage
 constexpr uint32_t kHmhWords = 8192;                                      // 16384 u16 registers
 
-__device__ __forceinline__ uint32_t halfwords_nonzero(uint32_t x) {  // bit 15 / bit 31 set <=> that halfword of x is non-zero
-    return (((x & 0x7fff7fffu) + 0x7fff7fffu) | x) & 0x80008000u;
-}
-// The same test on x = a ^ b (or a | b) accumulated into two 16-bit lane counters, with the add and the accumulate on the
-// FMA pipe: t = y * one + M and acc += hi32(v * 2^17), where `one` and `two17` are RUN-TIME values (derived from blockDim
-// by the caller).  With literal constants ptxas strength-reduces both back to ALU instructions (VIADD, LEA.HI) and the
-// loop runs 5 ALU instructions per word pair with the FMA pipe idle; this way it is 3 LOP3 + 2 IMAD.
-// The accumulator is 64 bits wide so that the accumulate is ONE IMAD.WIDE (v * 2^17 lands in bits 32.. / 48.. of the
-// pair; as a 32-bit IMAD.HI the addend pair needs a zeroed low register, which ptxas re-materialises every time).
-template <bool XOR>
-__device__ __forceinline__ uint64_t count_halfwords_nonzero(uint32_t a, uint32_t b, uint64_t acc, uint32_t one, uint32_t two17) {
-    const uint32_t x = XOR ? (a ^ b) : (a | b);
-    const uint32_t t = (x & 0x7fff7fffu) * one + 0x7fff7fffu;
-    const uint32_t v = (t | x) & 0x80008000u;
-    return (uint64_t)v * two17 + acc;
-}
+__device__ __forceinline__ bool has_empty_halfword(uint32_t x) { return __vminu2(x, 0x00010001u) != 0x00010001u; }
 
 template <bool COUNT_N>
-__device__ __forceinline__ void hmh_chunk(uint64_t (&nz)[kHmhRM][kHmhQM], uint64_t (&nn)[kHmhRM][kHmhQM], const uint32_t* pa,
-                                          const uint32_t* pb, uint32_t a_row, uint32_t b_row32, uint32_t one, uint32_t two17) {
+__device__ __forceinline__ void hmh_chunk(uint32_t (&nz)[kHmhRM][kHmhQM], uint32_t (&nn)[kHmhRM][kHmhQM], const uint32_t* pa,
+                                          const uint32_t* pb, uint32_t a_row, uint32_t b_row32, uint32_t one) {
 #pragma unroll 2
     for (uint32_t e = 0; e < (uint32_t)kHmhChunkWords; e += 4) {
         uint4 a[kHmhRM], b[kHmhQM];
@@ -481,8 +467,8 @@ __device__ __forceinline__ void hmh_chunk(uint64_t (&nz)[kHmhRM][kHmhQM], uint64
 #pragma unroll
                 for (int c = 0; c < kHmhQM; ++c) {
                     const uint32_t bv = j == 0 ? b[c].x : j == 1 ? b[c].y : j == 2 ? b[c].z : b[c].w;
-                    nz[r][c] = count_halfwords_nonzero<true>(av, bv, nz[r][c], one, two17);
-                    if (COUNT_N) nn[r][c] = count_halfwords_nonzero<false>(av, bv, nn[r][c], one, two17);
+                    nz[r][c] = __vminu2(av ^ bv, 0x00010001u) * one + nz[r][c];
+                    if (COUNT_N) nn[r][c] = __vminu2(av | bv, 0x00010001u) * one + nn[r][c];
                 }
             }
         }
@@ -504,16 +490,16 @@ __global__ void __launch_bounds__(kHmhThreads, 3) dist_hmh_fast_kernel(DistParam
     const uint32_t wy = threadIdx.x >> 5, tx = threadIdx.x & 31u;
     const uint32_t* gref = reinterpret_cast<const uint32_t*>(dp.ref);
     const uint32_t* gqry = reinterpret_cast<const uint32_t*>(dp.qry);
-    const uint32_t one = blockDim.x / kHmhThreads, two17 = blockDim.x << 9;  // 1 and 2^17, opaque to ptxas (see above)
+    const uint32_t one = blockDim.x / kHmhThreads;       // 1, opaque to ptxas (see above)
 
     // per-lane pair counters: two 16-bit lanes per word (low / high halfword of the register words); a lane counts at
     // most 8192, so neither overflows
-    uint64_t nz[kHmhRM][kHmhQM], nn[kHmhRM][kHmhQM];    // counts sit in the HIGH word (bits 32.. and 48..), the low word stays 0
+    uint32_t nz[kHmhRM][kHmhQM], nn[kHmhRM][kHmhQM];
     uint32_t full = 0;                                   // registers of chunks where N needed no counting (same for every pair)
 #pragma unroll
     for (int r = 0; r < kHmhRM; ++r)
 #pragma unroll
-        for (int c = 0; c < kHmhQM; ++c) nz[r][c] = nn[r][c] = 0ull;
+        for (int c = 0; c < kHmhQM; ++c) nz[r][c] = nn[r][c] = 0u;
     if (threadIdx.x < 2) s_zero[0][threadIdx.x] = 0u;
 
     uint32_t par = 0;
@@ -528,7 +514,7 @@ __global__ void __launch_bounds__(kHmhThreads, 3) dist_hmh_fast_kernel(DistParam
             // rows past the end are staged as all-ones registers (never empty, never read back)
             const uint4 v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint4*>(gref + gi * kHmhWords + c0) + g)
                                             : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-            za |= (halfwords_nonzero(v.x) & halfwords_nonzero(v.y) & halfwords_nonzero(v.z) & halfwords_nonzero(v.w)) != 0x80008000u;
+            za |= has_empty_halfword(v.x) | has_empty_halfword(v.y) | has_empty_halfword(v.z) | has_empty_halfword(v.w);
             *reinterpret_cast<uint4*>(sa + r * stride + 4 * g) = v;
         }
         for (uint32_t e = threadIdx.x; e < (uint32_t)kHmhTQ * (kHmhChunkWords / 4); e += kHmhThreads) {
@@ -536,7 +522,7 @@ __global__ void __launch_bounds__(kHmhThreads, 3) dist_hmh_fast_kernel(DistParam
             const uint64_t gj = col0 + r;
             const uint4 v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint4*>(gqry + gj * kHmhWords + c0) + g)
                                           : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-            zb |= (halfwords_nonzero(v.x) & halfwords_nonzero(v.y) & halfwords_nonzero(v.z) & halfwords_nonzero(v.w)) != 0x80008000u;
+            zb |= has_empty_halfword(v.x) | has_empty_halfword(v.y) | has_empty_halfword(v.z) | has_empty_halfword(v.w);
             *reinterpret_cast<uint4*>(sb + r * stride + 4 * g) = v;
         }
         if (za) s_zero[par][0] = 1u;
@@ -545,9 +531,9 @@ __global__ void __launch_bounds__(kHmhThreads, 3) dist_hmh_fast_kernel(DistParam
         const uint32_t* pa = sa + (wy * kHmhRM) * stride;
         const uint32_t* pb = sb + tx * stride;
         if (s_zero[par][0] & s_zero[par][1]) {  // CTA-uniform
-            hmh_chunk<true>(nz, nn, pa, pb, stride, 32u * stride, one, two17);
+            hmh_chunk<true>(nz, nn, pa, pb, stride, 32u * stride, one);
         } else {
-            hmh_chunk<false>(nz, nn, pa, pb, stride, 32u * stride, one, two17);
+            hmh_chunk<false>(nz, nn, pa, pb, stride, 32u * stride, one);
             full += 2u * kHmhChunkWords;
         }
     }
@@ -560,9 +546,8 @@ __global__ void __launch_bounds__(kHmhThreads, 3) dist_hmh_fast_kernel(DistParam
             const uint64_t i = row0 + wy * kHmhRM + a, j = col0 + tx + 32 * b;
             if (i >= dp.row_end || j >= dp.n_qry) continue;
             if (dp.triangular && j > i) continue;
-            const uint32_t nzh = (uint32_t)(nz[a][b] >> 32), nnh = (uint32_t)(nn[a][b] >> 32);
-            const uint32_t NZ = (nzh & 0xffffu) + (nzh >> 16);
-            const uint32_t N = (nnh & 0xffffu) + (nnh >> 16) + full;
+            const uint32_t NZ = (nz[a][b] & 0xffffu) + (nz[a][b] >> 16);
+            const uint32_t N = (nn[a][b] & 0xffffu) + (nn[a][b] >> 16) + full;
             const uint32_t Cc = N - NZ;   // equal and non-empty = (equal) - (both empty) = (16384 - NZ) - (16384 - N)
             const double sim = hmh_similarity_from(Cc, N, dp.card_qry[j], dp.card_ref[i]);
             const double s = fmax(sim, 0.0);
