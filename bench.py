@@ -419,22 +419,78 @@ def run_graft(args):
     # Two-stage software pipeline over steps: while step i's distance phase runs (registers up, NCCL all-gather, this rank's
     # row blocks down to pinned memory) on a second host thread and its own streams, step i+1's pushes already stream
     # packed bases up -- PCIe is full duplex and the two phases touch different handles (sketcher / ctx).
+    # Link-aware genome shards (N > 1): the step ends when the slowest rank has pushed its bases, and on this box class the
+    # GPUs sit behind links of different speed when all copy at once (measured below, in the same run).  Which rank sketches
+    # which genome is free -- the registers are all-gathered and put back into list order anyway -- so every rank takes a
+    # share of the n_all genomes proportional to its measured H2D rate (shard.weighted_counts) instead of n_all / N.
     e2e_ms = None
     h2d = d2h = 0
     if not args.no_e2e:
         from concurrent.futures import ThreadPoolExecutor
         sk.set_stream(None)
-        pin = C.c_void_p()
-        check(L.lash_host_alloc(n_bytes + 64, C.byref(pin)))
-        host_in = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_uint8)), shape=(n_bytes + 64,))
+
+        def pinned_bytes(nbytes):
+            ptr = C.c_void_p()
+            check(L.lash_host_alloc(nbytes + 64, C.byref(ptr)))
+            return ptr, np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(nbytes + 64,))
+
+        pin, host_in = pinned_bytes(n_bytes)
         host_in[:n_bytes] = buf[:n_bytes].cpu().numpy()
+        # same-run H2D probe (what the push phase is bound by): every rank copies slices of its pinned input buffer for the
+        # SAME wall time, so all links are busy during the whole window -- a fixed-bytes probe lets the fast links finish first
+        # and then overstates the slow ones.  Rate = bytes whose copy completed inside the window.
+        pin_t = torch.from_numpy(host_in[:n_bytes])
+        slice_b = 32 << 20
+        n_slices = n_bytes // slice_b
+        probe = []
+        for _ in range(3):
+            evs = []
+            barrier()
+            w0 = time.perf_counter()
+            i = 0
+            while time.perf_counter() - w0 < 0.12:
+                o = (i % n_slices) * slice_b
+                buf[o:o + slice_b].copy_(pin_t[o:o + slice_b], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(stream)
+                evs.append(e)
+                i += 1
+                while len(evs) > 4 and not evs[len(evs) - 4].query():      # keep a few copies in flight, never a long queue
+                    pass
+            done = sum(1 for e in evs if e.query())
+            wall = time.perf_counter() - w0
+            torch.cuda.synchronize(device)
+            probe.append(done * slice_b / wall / 1e9)
+        my_bw = float(np.median(probe[1:]))
+        bw_t = torch.tensor([my_bw], dtype=torch.float64, device=device)
+        bws = [torch.zeros_like(bw_t) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(bws, bw_t)
+        else:
+            bws = [bw_t]
+        bws = [float(x.item()) for x in bws]
+        link_aware = world > 1 and not args.no_link_aware
+        counts = shard.weighted_counts(n_all, bws) if link_aware else [n_g] * world
+        offs = [sum(counts[:r]) for r in range(world)]
+        e_n, e_off = counts[rank], offs[rank]                    # this rank sketches genomes [e_off, e_off + e_n) of the n_all
+        n_max = max(counts)
+        e_bytes = e_n * stride
+        if link_aware and (e_n != n_g or e_off != rank * n_g):
+            del pin_t
+            check(L.lash_host_free(pin))
+            pin, host_in = pinned_bytes(e_bytes)
+            tmp, _ = make_packed_genomes_ids(torch, device, range(e_off, e_off + e_n), GENOME_LEN, SEED)
+            host_in[:e_bytes] = tmp[:e_bytes].cpu().numpy()
+            del tmp
+            torch.cuda.empty_cache()
         per_push = 50
-        host_regs_t = [torch.empty((n_g, rb), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        host_regs_t = [torch.zeros((n_max, rb), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
         host_regs = [t.numpy() for t in host_regs_t]
         tri_out = np.empty(n_g * (n_g + 1) // 2, dtype=np.float64)
+        e2e_sk = sk if e_n == n_g else ops.Sketcher(ctx, ALGO_ULL, P, K, SEED, e_n)
         pushes = []
-        for g0 in range(0, n_g, per_push):
-            g1 = min(n_g, g0 + per_push)
+        for g0 in range(0, e_n, per_push):
+            g1 = min(e_n, g0 + per_push)
             sp = (Span * (g1 - g0))()
             for i in range(g0, g1):
                 sp[i - g0] = Span(i, (i - g0) * stride, GENOME_LEN, 0, 1, 0)
@@ -442,10 +498,13 @@ def run_graft(args):
         stream2 = torch.cuda.Stream(device)
         blocks = {"n": 0, "bytes": 0, "sum": 0.0}
         if world > 1:
-            t_local = torch.empty(n_g * rb, dtype=torch.uint8, device=device)
-            t_all = torch.empty(n_all * rb, dtype=torch.uint8, device=device)
+            t_local = torch.zeros(n_max * rb, dtype=torch.uint8, device=device)
+            t_gath = torch.empty(world * n_max * rb, dtype=torch.uint8, device=device)
+            perm_t = torch.from_numpy(np.asarray(shard.gather_permutation([range(offs[r], offs[r] + counts[r]) for r in range(world)], pad_to=n_max),
+                                                 dtype=np.int64)).to(device)
             host_all_t = torch.empty(n_all * rb, dtype=torch.uint8, pin_memory=True)
             host_all = host_all_t.numpy()
+            last_all = {}
 
             def _cb(user, row0, nrows, ptr):
                 # the block sits in pinned host memory owned by the library: this IS the device->host read of the result
@@ -459,11 +518,11 @@ def run_graft(args):
 
         def sketch_phase(slot):
             t0 = time.perf_counter()
-            check(L.lash_sketch_reset(sk._h))
+            check(L.lash_sketch_reset(e2e_sk._h))
             for off, nb, sp, ns in pushes:
-                check(L.lash_sketch_push(sk._h, C.c_void_p(pin.value + off), nb, sp, ns, None, 0, None))
+                check(L.lash_sketch_push(e2e_sk._h, C.c_void_p(pin.value + off), nb, sp, ns, None, 0, None))
             t1 = time.perf_counter()
-            check(L.lash_sketch_fetch(sk._h, 0, n_g, host_regs[slot].ctypes.data_as(C.c_void_p)))
+            check(L.lash_sketch_fetch(e2e_sk._h, 0, e_n, host_regs[slot].ctypes.data_as(C.c_void_p)))
             t2 = time.perf_counter()
             return {"push_calls": 1e3 * (t1 - t0), "push+fetch": 1e3 * (t2 - t0)}
 
@@ -477,9 +536,11 @@ def run_graft(args):
                 return {"gather": 0.0, "dist+d2h": 1e3 * (time.perf_counter() - t0)}
             with torch.cuda.stream(stream2):
                 t_local.copy_(host_regs_t[slot].view(-1), non_blocking=True)
-                dist.all_gather_into_tensor(t_all, t_local)
-                host_all_t.copy_(t_all, non_blocking=True)
+                dist.all_gather_into_tensor(t_gath, t_local)
+                t_all = t_gath.view(world * n_max, rb).index_select(0, perm_t)      # back into list order
+                host_all_t.copy_(t_all.view(-1), non_blocking=True)
                 stream2.synchronize()
+            last_all["t"] = t_all
             t1 = time.perf_counter()
             blocks["n"] = blocks["bytes"] = 0
             check(L.lash_dist_stream_rows(ctx.handle, ALGO_ULL, P, K, EST_FGRA, MODEL, 0, host_all.ctypes.data_as(C.c_void_p), n_all,
@@ -514,49 +575,47 @@ def run_graft(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_ms = float(te.item()) * 1e3 / args.steps
         if world == 1:
-            h2d = n_bytes + n_g * rb
+            h2d = e_bytes + n_g * rb
             d2h = n_g * rb + tri_out.nbytes
         else:   # rank 0's bytes: packed bases, local registers up again for the all-gather, all registers up for dist
-            h2d = n_bytes + n_g * rb + n_all * rb
-            d2h = n_g * rb + n_all * rb + blocks["bytes"]
-        # same-run H2D probe: all ranks copy their pinned input buffer at the same time (what the push phase is bound by)
-        pin_t = torch.from_numpy(host_in[:n_bytes])
-        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        probe = []
-        for _ in range(3):
-            barrier()
-            pe0.record(stream)
-            buf[:n_bytes].copy_(pin_t, non_blocking=True)
-            pe1.record(stream)
-            torch.cuda.synchronize(device)
-            probe.append(n_bytes / (pe0.elapsed_time(pe1) * 1e-3) / 1e9)
+            h2d = e_bytes + n_max * rb + n_all * rb
+            d2h = e_n * rb + n_all * rb + blocks["bytes"]
         med = {k_: float(np.median([p_[k_] for p_ in phases])) for k_ in phases[0]}
-        mine = torch.tensor([med["push_calls"], med["push+fetch"], med["gather"], med["dist+d2h"], n_bytes / (med["push+fetch"] * 1e-3) / 1e9,
-                             float(np.median(probe)), float(pin_t.is_pinned())], dtype=torch.float64, device=device)
+        mine = torch.tensor([med["push_calls"], med["push+fetch"], med["gather"], med["dist+d2h"], e_bytes / (med["push+fetch"] * 1e-3) / 1e9,
+                             my_bw, float(torch.from_numpy(host_in[:16]).is_pinned()), float(e_n)], dtype=torch.float64, device=device)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         if world > 1:
             dist.all_gather(allr, mine)
         else:
             allr = [mine]
         allr = torch.stack(allr).cpu().numpy()
+        # registers that came through the host path == the resident run's, for EVERY genome of the job (same genome ids)
+        if world > 1:
+            same = torch.equal(last_all["t"].view(-1), regs_all)
+        else:
+            same = bool(np.array_equal(host_regs[(args.steps - 1) & 1][:n_g], regs_view.view(n_g, rb).cpu().numpy()))
         if rank == 0:
-            e2e_parity = bool(np.array_equal(host_regs[(args.steps - 1) & 1][:2], regs_view.view(n_g, rb)[:2].cpu().numpy()))
-            parity = parity and e2e_parity
+            parity = parity and bool(same)
         check(L.lash_host_free(pin))
-        slow = int(np.argmin(allr[:, 4]))
+        if e2e_sk is not sk:
+            e2e_sk.close()
+        slow = int(np.argmin(allr[:, 4] / allr[:, 5]))
         e2e = {"value": (bases_rank * world) / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
+               "genomes_per_rank": [int(x) for x in allr[:, 7]], "link_aware_shards": bool(link_aware),
+               "all_registers_equal_resident_run": bool(same),
                "phases_ms_per_rank": {"push_calls": allr[:, 0].round(2).tolist(), "push+fetch": allr[:, 1].round(2).tolist(),
                                       "gather(up,nccl,down)": allr[:, 2].round(2).tolist(), "dist+d2h": allr[:, 3].round(2).tolist()},
                "h2d_gbs_per_rank_in_push_phase": allr[:, 4].round(2).tolist(), "h2d_probe_gbs_per_rank_concurrent": allr[:, 5].round(2).tolist(),
+               "aggregate_h2d_gbs_in_push_phase": float(allr[:, 4].sum()), "aggregate_h2d_probe_gbs": float(allr[:, 5].sum()),
                "pinned_probe_source": bool(allr[:, 6].all()),
                "slowest_rank": slow, "slowest_rank_h2d_frac_of_probe": float(allr[slow, 4] / allr[slow, 5]),
                "pipeline": "2 stages: step i's distance phase (second host thread, own streams) overlaps step i+1's pushes",
-               "note": (f"per rank: {n_g} genomes pushed from pinned host memory in {per_push}-genome slices (double-buffered H2D), "
+               "note": (f"{n_all} genomes pushed from pinned host memory in {per_push}-genome slices (double-buffered H2D), "
                         "registers fetched to host, " +
                         ("lash_dist on host registers (packed triangle copied back)" if world == 1 else
-                         f"host registers all-gathered over NCCL (up, gather, down), lash_dist_stream_rows on the {n_all} host "
-                         "sketches for this rank's row range of the triangle (pinned row blocks delivered to a callback)"))}
+                         f"host registers all-gathered over NCCL (up, gather, permute to list order, down), lash_dist_stream_rows on the {n_all} "
+                         "host sketches for this rank's row range of the triangle (pinned row blocks delivered to a callback)"))}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -724,6 +783,7 @@ def main():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--no-link-aware", action="store_true", help="e2e at N>1: equal genome shares instead of shares by measured H2D rate")
     ap.add_argument("--no-ingest", action="store_true", help="skip the FASTA -> C++ host -> GPU leg")
     ap.add_argument("--legs", default="c3,c4,c5", help="BASELINE configs[2..4] legs to run after the headline (comma list, '' = none)")
     ap.add_argument("--genomes", type=int, default=N_GENOMES, help="genomes per GPU (default = the BASELINE config; other values are for profiling)")

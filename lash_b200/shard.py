@@ -30,6 +30,22 @@ def genome_shard(sizes: Sequence[int], rank: int, world: int) -> list[int]:
     return genome_shards(sizes, world)[rank]
 
 
+def weighted_counts(n: int, weights: Sequence[float]) -> list[int]:
+    """n units split over the ranks in proportion to `weights` (largest-remainder rounding, every rank with a positive
+    weight gets at least one unit when n allows): link-aware genome shards -- a rank's weight is the host-to-device rate
+    it measured while all ranks copy at once, so every rank finishes pushing its share at the same time."""
+    w = [max(float(x), 0.0) for x in weights]
+    tot = sum(w)
+    if tot <= 0:
+        w, tot = [1.0] * len(w), float(len(w))
+    exact = [n * x / tot for x in w]
+    counts = [int(e) for e in exact]
+    order = sorted(range(len(w)), key=lambda i: (-(exact[i] - counts[i]), i))
+    for i in order[: n - sum(counts)]:
+        counts[i] += 1
+    return counts
+
+
 def gather_permutation(shards: Sequence[Sequence[int]], pad_to: int | None = None) -> list[int]:
     """Sketches come back from an all-gather rank after rank, each rank's block padded to `pad_to` rows (default: the
     largest shard).  perm[g] = row of global genome g in that rank-concatenated array, so

@@ -230,6 +230,14 @@ def test_gathered_sketches_return_to_list_order_world_size_2():
 
 def test_shard_functions_edge_cases():
     from lash_b200 import shard
+    # link-aware shares: proportional to the measured rates, exact total, deterministic
+    assert shard.weighted_counts(8000, [23.2] * 4 + [35.2] * 4) == [795] * 4 + [1205] * 4
+    for n in (0, 1, 7, 1000):
+        for w in ([1.0], [1, 1, 1], [3, 1], [0, 0], [5.5, 0.0, 2.25]):
+            c = shard.weighted_counts(n, w)
+            assert sum(c) == n and len(c) == len(w) and all(x >= 0 for x in c)
+            if sum(w) > 0:
+                assert all(abs(x - n * wi / sum(w)) < 1 for x, wi in zip(c, w))
     for world in (1, 2, 3, 4, 8):
         for n in (0, 1, 5, 8, 1000):
             got = sorted(g for r in range(world) for g in shard.genome_shard([10] * n, r, world))
