@@ -487,7 +487,14 @@ Status dist_command(lash_ctx* ctx, const std::string& ref_prefix, const std::str
         return Status{LASH_HOST_E_FORMAT, query_files["files"] + ": " + err};
     if (!lashhost::read_file(ref_files["files"], text, err) || !lashhost::json_parse_string_array(text, reference_names, err))
         return Status{LASH_HOST_E_FORMAT, ref_files["files"] + ": " + err};
-    const bool same_files = query_files["files"] == ref_files["files"];  // main.rs:404
+    // main.rs:404 compares the two *_files.json names; the reference only ever looks in the CWD, so equal names there mean
+    // the same file.  Here a prefix may carry a directory, so "sub/a" and "./sub/a" must compare equal too: same inode.
+    bool same_files = query_files["files"] == ref_files["files"];
+    if (!same_files) {
+        struct stat sa, sb;
+        same_files = stat(query_files["files"].c_str(), &sa) == 0 && stat(ref_files["files"].c_str(), &sb) == 0 &&
+                     sa.st_dev == sb.st_dev && sa.st_ino == sb.st_ino;
+    }
 
     OutFile file;
     std::string out_path = output_file;

@@ -117,6 +117,7 @@ int help_dist() {
            "      --device <device>            GPU index [default: 0]  (lash-b200 only)\n"
            "      --mirror                     frac from the GPU, compute_distance + print_dist on the host as main.rs does  (lash-b200 only)\n"
            "      --rank <r> --world <w>       one process per GPU: write this rank's row range to <output_file>.partRRRR  (lash-b200 only)\n"
+           "      --allow-hll-bias-regime      hll: write pairs whose estimate needs the HLL++ bias tables as distance 1 instead of failing  (lash-b200 only)\n"
            "  -h, --help                       Print help\n");
     return 0;
 }
@@ -189,7 +190,7 @@ int run_dist(int argc, char** argv) {
     if (!parse(argc, argv, 2,
                {{'q', "query", true}, {'r', "reference", true}, {'o', "output_file", true}, {'t', "threads", true},
                 {'e', "estimator", true}, {'m', "model", true}, {0, "fp32", false}, {0, "dm", false}, {0, "device", true},
-                {0, "mirror", false}, {0, "rank", true}, {0, "world", true}},
+                {0, "mirror", false}, {0, "rank", true}, {0, "world", true}, {0, "allow-hll-bias-regime", false}},
                a, err))
         return fail(err);
     if (!a.get("query") || !a.get("reference"))
@@ -209,7 +210,23 @@ int run_dist(int argc, char** argv) {
                                                (int)world);
     lash_ctx_destroy(ctx);
     if (!rc.ok()) return fail(rc.message);
-    if (rc.code > 0) fprintf(stderr, "warning: %s\n", rc.message.c_str());
+    if (rc.code > 0) {
+        // LASH_W_HLL_BIAS_REGIME: some pair's HLL estimate lies in (linear-counting threshold, 5m], where the reference's
+        // len() subtracts the HLL++ empirical bias (utils.rs:315,358 -> streaming_algorithms).  Those tables cannot be
+        // reproduced offline; the cells were written as distance 1.  A silently different file is worse than none.
+        if (!a.get("allow-hll-bias-regime")) {
+            std::string out_path = output;
+            if (world > 1) {
+                char suffix[16];
+                snprintf(suffix, sizeof(suffix), ".part%04d", (int)rank);
+                out_path += suffix;
+            }
+            remove(out_path.c_str());
+            return fail("error: " + rc.message + "; no output written.  These sketches are too small for HLL at this precision in this build "
+                        "(use ull or hmh, or a smaller -p); --allow-hll-bias-regime writes such pairs as distance 1.");
+        }
+        fprintf(stderr, "warning: %s\n", rc.message.c_str());
+    }
     return 0;
 }
 

@@ -17,6 +17,7 @@
 #include <atomic>
 #include <chrono>
 #include <cerrno>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -447,17 +448,29 @@ struct Worker {
         if (!chunk[cur].can_begin_span() && !rotate(gpu)) return false;
         chunk[cur].begin_span(genome);
         std::vector<uint8_t> carry;
+        bool seen_record = false, record_open = false;
         for (;;) {
             FastxReader::Ev e = rd.next();
             if (e.type == FastxReader::kEof) break;
             if (e.type == FastxReader::kError) {
-                err = "Invalid input file " + path + ": " + rd.err();
-                return false;
+                // utils.rs:453 `.expect("Invalid input file")` only covers a file that cannot be opened or recognised;
+                // a record that fails to parse later is skipped (`if let Ok(seqrec) = res`, utils.rs:458) and the file
+                // keeps the sketch of what came before.  The same here: warn, keep the records read so far.
+                if (!seen_record) {
+                    err = "Invalid input file " + path + ": " + rd.err();
+                    return false;
+                }
+                fprintf(stderr, "warning: %s: %s -- the rest of the file is ignored (records so far: %llu)\n", path.c_str(), rd.err().c_str(),
+                        (unsigned long long)n_records);
+                if (record_open) chunk[cur].end_record(k);
+                break;
             }
             if (e.type == FastxReader::kBegin) {
                 ++n_records;
+                seen_record = record_open = true;
                 chunk[cur].begin_record();
             } else if (e.type == FastxReader::kEnd) {
+                record_open = false;
                 chunk[cur].end_record(k);
             } else {
                 n_in += e.n;

@@ -327,6 +327,50 @@ def test_cli_binary_mirrors_lash_sketch_and_dist(oracle, tmp_path):
     assert r.returncode != 0 and "There should be 3 files" in r.stderr                         # main.rs:330
 
 
+def test_cli_hll_bias_regime_fails_loudly_and_same_files_by_inode(oracle, tmp_path):
+    """(1) HLL sketches of tiny inputs land in the HLL++ bias-table regime, which this build cannot reproduce: `dist` must fail
+    and write nothing unless --allow-hll-bias-regime is given.  (2) `-r sub/a -q ./sub/a` is the same file set:
+    lower triangle, not the full matrix."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lash_b200", "_lib", "lash-b200")
+    (tmp_path / "sub").mkdir()
+    rng = np.random.default_rng(21)
+    names = []
+    for g in range(3):
+        _write_fasta(str(tmp_path / f"v{g}.fa"), [synth.to_ascii(rng.integers(0, 4, size=30_000, dtype=np.uint8))])   # 30k k-mers < 5 * 2^14
+        names.append(f"v{g}.fa")
+    (tmp_path / "list.txt").write_text("\n".join(names) + "\n")
+    run = lambda *a: subprocess.run([exe, *a], cwd=tmp_path, capture_output=True, text=True)
+    assert run("sketch", "-f", "list.txt", "-o", "sub/h", "-a", "hll", "-p", "14", "-k", "21").returncode == 0
+    r = run("dist", "-q", "sub/h", "-r", "sub/h", "-o", "d.tsv")
+    assert r.returncode != 0 and "bias" in r.stderr and not (tmp_path / "d.tsv").exists()
+    r = run("dist", "-q", "sub/h", "-r", "sub/h", "-o", "d.tsv", "--allow-hll-bias-regime")
+    assert r.returncode == 0 and "warning" in r.stderr
+    rows = _parse_list(str(tmp_path / "d.tsv"))
+    assert len(rows) == 6 and all(d == "1.000000" for a, b, d in rows if a != b)
+    # the same sketches as ULL: no regime, and the two spellings of the prefix are recognised as one file set
+    assert run("sketch", "-f", "list.txt", "-o", "sub/u", "-a", "ull", "-p", "10").returncode == 0
+    r = run("dist", "-q", "./sub/u", "-r", "sub/u", "-o", "u.tsv")
+    assert r.returncode == 0, r.stderr
+    assert len(_parse_list(str(tmp_path / "u.tsv"))) == 6           # 3 * 4 / 2 pairs, not 9
+
+
+def test_damaged_record_keeps_the_sketch_so_far(oracle, gpu_ctx, tmp_path):
+    """utils.rs:458 `if let Ok(seqrec) = res`: a record that fails to parse is skipped and the file keeps its sketch; only a
+    file that cannot be opened / recognised at all is "Invalid input file" (utils.rs:453)."""
+    rng = np.random.default_rng(2)
+    reads = [synth.to_ascii(rng.integers(0, 4, size=150, dtype=np.uint8)) for _ in range(300)]
+    good, bad = str(tmp_path / "good.fq"), str(tmp_path / "bad.fq")
+    _write_fastq(good, reads)
+    body = open(good, "rb").read()
+    cut = body.index(b"@", len(body) // 2)                                     # a record boundary in the middle
+    n_ok = body[:cut].count(b"\n") // 4
+    open(bad, "wb").write(body[:cut] + b"@broken\nACGTACGTACGTACGTACGTACGTAC\n+\nIII\n" + body[cut:])   # seq / qual lengths differ
+    regs, st = hostapi.sketch_files_regs(gpu_ctx, ALGO_ULL, 12, 21, 42, [good, bad, good], threads=2)
+    exp = oracle.sketch_genomes(oracle.ULL, 12, 21, 42, [reads, reads[:n_ok], reads], threads=2)
+    assert np.array_equal(regs, exp)
+
+
 @pytest.mark.parametrize("dm", [False, True])
 @pytest.mark.parametrize("same", [True, False])
 def test_row_sharded_dist_parts_concatenate_to_the_single_file(gpu_ctx, tmp_path, dm, same):

@@ -48,9 +48,10 @@ def reads_case(ctx, key, regex, p, k, n_reads, read_len):
     with ops.Sketcher(ctx, ALGO_ULL, p, k, 42, 1) as sk:
         sk.push_raw(packed.data_ptr(), padded_bytes(n_bases), spans, 1, None, 0, dev=True)
         sk.sync()
+    emit(key="build_invalid_mask_kernel", kernels=["build_invalid_mask_kernel"], units=n_reads, unit="record", launches=1,
+         shape="the boundary-mask launch of the reads push below")
     emit(key=key, kernels=[regex], units=n_reads * (read_len - k + 1), unit="kmer", launches=1,
          shape=f"{n_reads} reads x {read_len} bp of one sample, ULL p={p} k={k}")
-    emit(key="build_invalid_mask_kernel", kernels=["build_invalid_mask_kernel"], units=n_reads, unit="record", launches=1, shape="same push")
 
 
 def text_case(ctx, n_g, length):
