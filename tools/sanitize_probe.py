@@ -1,31 +1,52 @@
-"""Small end-to-end pass over every kernel, for compute-sanitizer (memcheck / racecheck) runs:
-    compute-sanitizer --tool memcheck python tools/sanitize_probe.py
-"""
+"""Small end-to-end pass over every kernel, for compute-sanitizer runs:
+    compute-sanitizer --tool memcheck  python tools/sanitize_probe.py            (every kernel, every output layout)
+    compute-sanitizer --tool racecheck python tools/sanitize_probe.py --small    (reduced: racecheck is ~1000x slower)
+racecheck looks at the shared-memory hazards the design rests on: the sketch kernel's shared `red.*` cells + deferred
+atomics + flush, the staged tiles / pair tables / tile counters of the dist kernels, the bit-stream staging of the text
+pack kernel."""
+import ctypes as C
 import sys
 
 import numpy as np
 
 sys.path.insert(0, ".")
-from lash_b200 import ALGO_HLL, ALGO_HMH, ALGO_ULL, EST_FGRA, EST_ML, ops  # noqa: E402
+from lash_b200 import ALGO_HLL, ALGO_HMH, ALGO_ULL, EST_FGRA, EST_ML, capi, ops  # noqa: E402
 from tools import synth  # noqa: E402
 
+small = "--small" in sys.argv
 rng = np.random.default_rng(0)
 with ops.Context(0) as ctx:
-    genomes = synth.genomes(5, 40_000, seed=1) + [synth.dirty_genome(30_000, 21, seed=2)]
-    for algo, p, k in ((ALGO_ULL, 10, 16), (ALGO_ULL, 14, 21), (ALGO_HLL, 12, 21), (ALGO_HMH, 14, 16), (ALGO_ULL, 16, 31)):
+    if small:
+        genomes = synth.genomes(2, 200_000, seed=1) + [synth.dirty_genome(20_000, 16, seed=2)]
+        cases = ((ALGO_ULL, 10, 16), (ALGO_HLL, 12, 21), (ALGO_HMH, 14, 16))
+    else:
+        genomes = synth.genomes(5, 40_000, seed=1) + [synth.dirty_genome(30_000, 21, seed=2)]
+        cases = ((ALGO_ULL, 10, 16), (ALGO_ULL, 14, 21), (ALGO_HLL, 12, 21), (ALGO_HMH, 14, 16), (ALGO_ULL, 16, 31))
+    for algo, p, k in cases:
         regs = ops.sketch_genomes(ctx, algo, p, k, 42, genomes)
+        regs_t = ops.sketch_genomes_text(ctx, algo, p, k, 42, genomes)          # device-side filter + pack
+        assert np.array_equal(regs, regs_t)
         for est in ((EST_FGRA, EST_ML) if algo == ALGO_ULL else (0,)):
             d, _ = ops.dist(ctx, algo, p, k, est, 1, False, regs, regs)
-            t, _ = ops.dist(ctx, algo, p, k, est, 0, True, regs[:3], regs, triangular=False)
-            tri, _ = ops.dist(ctx, algo, p, k, est, 1, False, regs, regs, triangular=True)
-            ops.dist_stream(ctx, algo, p, k, est, 1, False, regs, regs, True, 2, lambda r0, b: None)
+            if not small:
+                t, _ = ops.dist(ctx, algo, p, k, est, 0, True, regs[:3], regs, triangular=False)
+                tri, _ = ops.dist(ctx, algo, p, k, est, 1, False, regs, regs, triangular=True)
+                ops.dist_stream(ctx, algo, p, k, est, 1, False, regs, regs, True, 2, lambda r0, b: None)
         ops.cardinality(ctx, algo, p, 0, regs)
         ops.merge(ctx, algo, p, regs, regs[::-1].copy())
-    # wider problems: several tiles per kernel, ragged edges
+    # wider problems: several tiles per kernel, ragged edges, the checksum kernel
+    capi.check(capi.lib().lash_dist_set_checksum(ctx.handle, 1))
     m = 1 << 10
-    ull = (4 * (rng.integers(3, 12, size=(150, m)) + 9) + rng.integers(0, 4, size=(150, m))).astype(np.uint8)
+    n = 64 if small else 150
+    ull = (4 * (rng.integers(3, 12, size=(n, m)) + 9) + rng.integers(0, 4, size=(n, m))).astype(np.uint8)
     for est in (EST_FGRA, EST_ML):
-        ops.dist(ctx, ALGO_ULL, 10, 16, est, 1, False, ull[:70], ull)
-    hll = rng.integers(0, 30, size=(100, 1 << 12)).astype(np.uint8)
-    ops.dist(ctx, ALGO_HLL, 12, 21, 0, 1, False, hll[:45], hll)
+        ops.dist(ctx, ALGO_ULL, 10, 16, est, 1, False, ull[: n // 2 + 3], ull)
+    hll = rng.integers(0, 30, size=(n, 1 << 12)).astype(np.uint8)
+    ops.dist(ctx, ALGO_HLL, 12, 21, 0, 1, False, hll[: n // 2 - 3], hll)
+    hmh = ((rng.integers(0, 12, size=(n, 16384)) << 10) | rng.integers(0, 1024, size=(n, 16384))).astype(np.uint16)
+    hmh[0, ::3] = 0
+    ops.dist(ctx, ALGO_HMH, 14, 16, 0, 1, False, hmh[: n // 2 + 1], hmh)
+    s, c = C.c_uint64(), C.c_uint64()
+    capi.check(capi.lib().lash_dist_checksum(ctx.handle, C.byref(s), C.byref(c)))
+    assert c.value == (n // 2 + 1) * n
 print("sanitize probe done")
