@@ -310,3 +310,13 @@ def test_pin_parity_table_readers(tmp_path):
     b.write_text("\tx\ty\nx\t0.000000\ny\t0.100001\t0.000000\n")
     n, bad = P.same_pairs(P.read_table(str(a)), P.read_table(str(b)))
     assert len(bad) == 1 and bad[0][0] == ("x", "y")
+
+
+def test_pin_parity_self_test_names_every_flipped_convention(capsys):
+    """tools/pin_parity.py --self-test: "reference" registers fabricated with each recalled convention flipped (HMH x / y
+    halves, HLL index end) are diagnosed as exactly that switch, the current conventions as "current", a corrupted register
+    as "unknown" -- so the first run against a real lash binary pins parity or says what to flip."""
+    from tools import pin_parity
+    assert pin_parity.self_test() == 0
+    out = capsys.readouterr().out
+    assert "hmh_x_low64" in out and "hll_index_high" in out and "SELF-TEST PASSED" in out
