@@ -57,9 +57,18 @@ __device__ __forceinline__ void red_max(uint32_t saddr, uint32_t v) {
 template <int ALGO>
 struct SmemAcc;
 
+// LASH_ULL_PLANES=1: ULL cells as TWO PLANES (all word-0s, then all word-1s) instead of interleaved pairs.  The fast path only
+// ever loads word 0, and with 8-byte cells those loads touch the even banks only (ncu r01: 4.7 wavefronts per warp-level
+// LDS).  Measured in round 2 (tools/bench_configs.py, B200): the planes are 1-1.7 % SLOWER (C2 836.9 vs 845.9 Gbp/s, k = 12
+// 769.5 vs 782.6, p = 14 542 vs 547) -- the shared-memory pipe is not what binds this kernel -- so the default stays the
+// interleaved cell.
+#ifndef LASH_ULL_PLANES
+#define LASH_ULL_PLANES 0
+#endif
 template <>
 struct SmemAcc<ULL> {
     static constexpr uint32_t kWordsPerCell = 2;
+    static constexpr uint32_t kCellStride = LASH_ULL_PLANES ? 4u : 8u;   // bytes between the word-0s of neighbouring cells
     // fast: (address of word 0, bit to set [0 if the hash is a rare one], rare indicator word)
     // g = hash BEFORE its last step h = g ^ (g >> 28).  Because p <= 26 that xorshift cannot reach the index bits
     // (idx = g.hi >> (32-p)).  The fast path looks only at the HIGH word of g: the 32-p hash bits after the index are
@@ -78,9 +87,9 @@ struct SmemAcc<ULL> {
         const uint32_t hi = NARROW ? xxh3_64_narrow_pre_hi(klo, hc) : xxh3_64_wide_pre_hi(klo, khi, hc);
         const uint32_t t = DROP4 ? hi & ((0xffffffffu >> p) & ~15u) : (hi ^ (hi >> 28)) & (0xffffffffu >> p);
 #ifdef LASH_SADDR_IMAD  // tuning switch (tools/variant_sweep): no difference measured, ptxas picks LEA or IMAD itself
-        saddr = mad32_opaque(__umulhi(hi, 1u << p), 8u, sbase);
+        saddr = mad32_opaque(__umulhi(hi, 1u << p), kCellStride, sbase);
 #else
-        saddr = sbase + __umulhi(hi, 1u << p) * 8u;       // (hi >> (32-p)) * 8 on the FMA pipe
+        saddr = sbase + __umulhi(hi, 1u << p) * kCellStride;       // (hi >> (32-p)) * stride on the FMA pipe
 #endif
         v = shl_clamp(1u << p, bfind32(t));              // t == 0 -> bfind = 0xffffffff -> v = 0
         rare_word = t;
@@ -91,12 +100,17 @@ struct SmemAcc<ULL> {
         const uint64_t h = xxh3_64_le64(klo, khi, hc);
         const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
         const uint32_t yh = __funnelshift_l(lo, hi, p), yl = (lo << p) | ((1u << p) - 1u);
-        const uint32_t saddr = sbase + (hi >> (32 - p)) * 8u + (yh ? 0u : 4u);
+        const uint32_t w1_off = LASH_ULL_PLANES ? (4u << p) : 4u;   // word 1: the second plane, or the next word
+        const uint32_t saddr = sbase + (hi >> (32 - p)) * kCellStride + (yh ? 0u : w1_off);
         const uint32_t bit = 1u << bfind32(yh ? yh : yl);
         if (~lds_u32(saddr) & bit) red_or(saddr, bit);
     }
-    __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int p) {
-        return ull_cell_to_reg(acc[2u * cell], acc[2u * cell + 1u], p);
+    // word index of word z of a cell in the accumulator array
+    __device__ static __forceinline__ uint32_t word_of(uint32_t cell, uint32_t z, uint32_t n_cells) {
+        return LASH_ULL_PLANES ? z * n_cells + cell : 2u * cell + z;
+    }
+    __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int p, uint32_t n_cells) {
+        return ull_cell_to_reg(acc[word_of(cell, 0, n_cells)], acc[word_of(cell, 1, n_cells)], p);
     }
 };
 template <>
@@ -122,7 +136,8 @@ struct SmemAcc<HLL> {
         const uint32_t saddr = sbase + idx * 4u;
         if (lds_u32(saddr) < rho) red_max(saddr, rho);
     }
-    __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int) { return acc[cell]; }
+    __device__ static __forceinline__ uint32_t word_of(uint32_t cell, uint32_t, uint32_t) { return cell; }
+    __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int, uint32_t) { return acc[cell]; }
 };
 template <>
 struct SmemAcc<HMH> {
@@ -151,7 +166,8 @@ struct SmemAcc<HMH> {
         const uint32_t saddr = sbase + idx * 4u;
         if (lds_u32(saddr) < val) red_max(saddr, val);
     }
-    __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int) { return acc[cell]; }
+    __device__ static __forceinline__ uint32_t word_of(uint32_t cell, uint32_t, uint32_t) { return cell; }
+    __device__ static __forceinline__ uint32_t to_reg(const uint32_t* acc, uint32_t cell, int, uint32_t) { return acc[cell]; }
 };
 
 // Global-accumulator fallback (2^p too large for shared memory): byte / halfword cells of the
@@ -227,9 +243,9 @@ __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
             for (uint32_t j = 0; j < per; ++j) {
                 const uint32_t c = i * per + j;
                 if (c < n_cells) {
-                    v |= A::to_reg(sacc, c, p) << (j * 8 * C::kBytes);
+                    v |= A::to_reg(sacc, c, p, n_cells) << (j * 8 * C::kBytes);
 #pragma unroll
-                    for (uint32_t z = 0; z < A::kWordsPerCell; ++z) sacc[c * A::kWordsPerCell + z] = 0u;
+                    for (uint32_t z = 0; z < A::kWordsPerCell; ++z) sacc[A::word_of(c, z, n_cells)] = 0u;
                 }
             }
             if (v == 0u) continue;
