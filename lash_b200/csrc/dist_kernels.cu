@@ -751,7 +751,7 @@ __device__ __forceinline__ void ml_pair_epilogue(const DistParams& dp, MlAccT<NP
     if (dp.fp32)
         reinterpret_cast<float*>(dp.out)[o] = mash_distance_f32((float)frac, dp.k, dp.model);
     else
-        reinterpret_cast<double*>(dp.out)[o] = mash_distance_f64(frac, dp.k, dp.model);
+        reinterpret_cast<double*>(dp.out)[o] = mash_distance_f64<false>(frac, dp.k, dp.model);
 }
 
 // K4c, second kernel: one thread per output cell reads the statistics dist_ml_tab_kernel<NPL, true> stored and runs

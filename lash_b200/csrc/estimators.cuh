@@ -12,6 +12,8 @@
 #include <cmath>
 #include <cstdint>
 
+#include "ddmath.cuh"
+
 namespace lash {
 
 struct UllConsts {
@@ -55,11 +57,16 @@ inline UllConsts make_ull_consts() {
 __constant__ UllConsts c_ull;  // this header belongs to exactly one translation unit (dist_kernels.cu)
 
 // ---------------------------------------------------------------- Mash distance, main.rs:415-423
+// CR: log / pow correctly rounded (ddmath.cuh) -- equal to glibc's except in ~0.01-0.1 % of the arguments, where glibc itself
+// is one ulp off the correctly rounded value.  The ML epilogue passes CR = false: its union estimate comes out of a secant
+// iteration whose path already depends on the last bit of its starting value, so the extra 6 % of kernel time (measured at
+// 100k x 100k) would buy +0.2 % bit-identical cells; everywhere else the cost is noise next to the register loop.
+template <bool CR = true>
 __device__ __forceinline__ double mash_distance_f64(double frac, int k, int model) {
     const double kk = (double)k;
     if (model == 2) return frac;  // LASH_MODEL_FRAC: what the reference's emit() carries (utils.rs:176,277,364)
-    if (model == 1) return fmin(-log(frac) / kk, 1.0);
-    return 1.0 - pow(frac, 1.0 / kk);
+    if (model == 1) return fmin(-(CR ? log_cr(frac) : log(frac)) / kk, 1.0);
+    return 1.0 - (CR ? pow_cr(frac, 1.0 / kk) : pow(frac, 1.0 / kk));
 }
 __device__ __forceinline__ float mash_distance_f32(float frac, int k, int model) {
     const float kk = (float)k;
@@ -91,7 +98,7 @@ __device__ inline double hll_len(double sum, uint32_t zero, int p, bool* bias) {
     const double m = (double)(1ull << p);
     *bias = false;
     if (zero > 0) {
-        double h = m * log(m / (double)zero);
+        double h = m * log_cr(m / (double)zero);
         if (h <= hll_threshold(p)) return h;
     }
     double e = hll_alpha(p) * (m * m) / sum;
@@ -167,9 +174,9 @@ __device__ inline double ull_fgra_finalize(double sum, const uint32_t* cnt, int 
         s += z * (1.0 + rz) * ((double)w0 * kUllEta0 + (double)w1 * kUllEta1 + (double)w2 * kUllEta2 + (double)w3 * kUllEta3);
         s += rz * ((double)(w0 + w1) * (z * (c_ull.pow2mtau * (kUllEta0 - kUllEta2)) + c_ull.pow2mtau * kUllEta2) +
                    (double)(w2 + w3) * (z * (c_ull.pow2mtau * (kUllEta1 - kUllEta3)) + c_ull.pow2mtau * kUllEta3));
-        sum += s * pow(c_ull.pow2mtau, (double)(65 - p)) / ((1.0 + rz) * (1.0 + z));
+        sum += s * pow_cr(c_ull.pow2mtau, (double)(65 - p)) / ((1.0 + rz) * (1.0 + z));
     }
-    return c_ull.factor[p] * pow(sum, c_ull.minus_inv_tau);
+    return c_ull.factor[p] * pow_cr(sum, c_ull.minus_inv_tau);
 }
 
 // ---------------------------------------------------------------- ULL ML (Ertl 2017 Alg. 8 as in hash4j)
@@ -243,10 +250,10 @@ __device__ inline double ull_ml_finalize(uint64_t S, int* b, int p, uint32_t reg
 
 // ---------------------------------------------------------------- HyperMinHash
 __device__ inline double hmh_beta(double ez) {
-    double zl = log(ez + 1.0);
-    return -0.370393911 * ez + 0.070471823 * zl + 0.17393686 * pow(zl, 2.0) + 0.16339839 * pow(zl, 3.0) +
-           -0.09237745 * pow(zl, 4.0) + 0.03738027 * pow(zl, 5.0) + -0.005384159 * pow(zl, 6.0) +
-           0.00042419 * pow(zl, 7.0);
+    double zl = log_cr(ez + 1.0);
+    return -0.370393911 * ez + 0.070471823 * zl + 0.17393686 * pow_cr(zl, 2.0) + 0.16339839 * pow_cr(zl, 3.0) +
+           -0.09237745 * pow_cr(zl, 4.0) + 0.03738027 * pow_cr(zl, 5.0) + -0.005384159 * pow_cr(zl, 6.0) +
+           0.00042419 * pow_cr(zl, 7.0);
 }
 __device__ inline double hmh_cardinality_from(double sum, double ez) {
     const double M = 16384.0;
@@ -258,7 +265,7 @@ __device__ inline double hmh_expected_collisions(double n, double m) {
     if (n > 0x1p74) return 18446744073709551615.0;
     if (n > 524288.0) {
         double r = (1.0 + n) / m;
-        double d = (4.0 * n / m) / pow(r, 2.0);
+        double d = (4.0 * n / m) / pow_cr(r, 2.0);
         return 0.169919487159739093975315012348 * 16.0 * d + 0.5;
     }
     double x = 0.0;

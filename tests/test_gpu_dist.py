@@ -6,12 +6,15 @@ compute_distance (src/main.rs:415-423) would check.
 Tolerance (north_star: 1e-12 relative in f64, 1e-6 with --fp32), written out:
   * per-sketch cardinalities: <= 8 ulp (only pow/log differ between CUDA and glibc; every sum runs
     in register order on both sides and is bit-identical);
-  * distances: |d_gpu - d_cpu| <= 1e-12*|d_cpu| + C(s), where C(s) = 64*eps/(s*k) is the
+  * distances (the per-pair epilogues use correctly rounded pow / log / log1p, csrc/ddmath.cuh, so the union estimate and the
+    cardinalities equal glibc's except where glibc itself is an ulp off: measured max relative error 9e-15 (FGRA),
+    1.7e-13 (ML), 3e-16 (HLL, HMH) on the BASELINE shapes, 99.7-99.95 % of the cells bit-identical);  the asserted bound is
+    |d_gpu - d_cpu| <= 1e-12*|d_cpu| + C(s), where C(s) = 64*eps/(s*k) is the
     first-order effect on d of a 4-ulp change of the union estimate U through
     s = (a+b-U)/U  (d = -ln(2s/(1+s))/k  =>  |dd/dU * U| ~ 1/(s*k)): the Jaccard subtraction
     cancels catastrophically for unrelated genomes, so a pure relative 1e-12 on d is not a
     property of the formula itself (any two libm's differ there).  C(s) is < 1e-12 whenever
-    s > 1e-3/k; the test also asserts that almost all cells meet the plain 1e-12 bound.
+    s > 1e-3/k; the test also asserts that >= 99.9 % of the cells meet the plain 1e-12 bound and prints the achieved figures.
 """
 import numpy as np
 import pytest
@@ -30,7 +33,7 @@ def _sketches(oracle, algo, p, k, n, length, seed=42):
     return oracle.sketch_genomes(algo, p, k, seed, synth.genomes(n, length, seed=seed), threads=8)
 
 
-def _assert_close_f64(got, exp, frac, k, what, strict_frac=0.98):
+def _assert_close_f64(got, exp, frac, k, what, strict_frac=0.999):
     """The stated bound, and the achieved figures on stdout (pytest -s / -rP shows them): worst relative error, fraction of
     cells within plain 1e-12 relative, fraction bit-identical."""
     assert got.shape == exp.shape
