@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -91,6 +92,17 @@ struct PinBuf {
     }
 };
 
+// Staging buffers of one sketcher slot.  They are handed back to the context when a sketcher closes and reused by the next
+// one: cudaFree / cudaFreeHost of tens of MiB per lash_sketch_close showed up as 10-500 ms "drain" outliers in the
+// FASTA ingest runs (a host that sketches batch after batch opens and closes a sketcher per batch).
+struct SlotBufs {
+    DevBuf packed, meta, mask, text, aux;
+    PinBuf meta_host;
+    void release() {
+        packed.release(); meta.release(); mask.release(); text.release(); aux.release(); meta_host.release();
+    }
+};
+
 struct lash_ctx {
     int device = 0;
     int n_sm = 148;
@@ -104,7 +116,10 @@ struct lash_ctx {
     // milliseconds of jitter on a 2.5 ms operation)
     DevBuf d_ref, d_qry, d_card, d_out[2], d_flags, d_regmin, d_ml, d_sum;
     PinBuf h_out[2];
+    std::mutex slot_mu;
+    std::vector<SlotBufs> slot_cache;   // at most kSlotCacheMax sets
 };
+static constexpr size_t kSlotCacheMax = 4;
 
 extern "C" int lash_ctx_create(int device, lash_ctx** out) {
     if (!out) return fail(LASH_E_INVALID, "lash_ctx_create: out is NULL");
@@ -132,6 +147,7 @@ extern "C" int lash_ctx_destroy(lash_ctx* c) {
     if (c->stream) cudaStreamDestroy(c->stream);
     c->d_ref.release(); c->d_qry.release(); c->d_card.release(); c->d_out[0].release(); c->d_out[1].release();
     c->d_flags.release(); c->d_regmin.release(); c->d_ml.release(); c->d_sum.release(); c->h_out[0].release(); c->h_out[1].release();
+    for (auto& b : c->slot_cache) b.release();
     delete c;
     return LASH_OK;
 }
@@ -217,15 +233,14 @@ extern "C" uint64_t lash_sketch_padded_bytes(uint64_t n_bases) {
 // ------------------------------------------------------------------------------------------------
 static constexpr int kSlots = 2;  // double-buffered staging: copy of push n+1 overlaps kernels of push n
 
-struct Slot {
+struct Slot : SlotBufs {
     cudaStream_t stream = nullptr;
     cudaEvent_t copied = nullptr;   // H2D of packed + metadata done
     cudaEvent_t meta_ready = nullptr;  // metadata upload (on the sketcher's meta stream) done
     cudaEvent_t k_start = nullptr, k_stop = nullptr;
     bool timing_pending = false;
-    DevBuf packed, meta, mask;
-    DevBuf text, aux;  // lash_sketch_push_ascii: raw text (H2D target) and the block counts / prefixes / kept bases per span
-    PinBuf meta_host;
+    // SlotBufs: packed / meta / mask, text + aux (lash_sketch_push_ascii: raw text as the H2D target, block counts /
+    // prefixes / kept bases per span), meta_host (pinned)
     uint64_t ticket = 0;
     bool used = false;
 };
@@ -292,6 +307,13 @@ extern "C" int lash_sketch_open(lash_ctx* ctx, int algo, int p, int k, uint64_t 
     }
     CU(cudaMemsetAsync(s->acc, 0, acc_bytes, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    {
+        std::lock_guard<std::mutex> g(ctx->slot_mu);
+        for (int i = 0; i < kSlots && !ctx->slot_cache.empty(); ++i) {
+            static_cast<SlotBufs&>(s->slot[i]) = ctx->slot_cache.back();
+            ctx->slot_cache.pop_back();
+        }
+    }
     for (int i = 0; i < kSlots; ++i) {
         CU(cudaStreamCreateWithFlags(&s->slot[i].stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&s->slot[i].copied, cudaEventDisableTiming));
@@ -711,12 +733,15 @@ extern "C" int lash_sketch_close(lash_sketcher* s) {
     for (int i = 0; i < kSlots; ++i) {
         Slot& sl = s->slot[i];
         if (sl.stream) cudaStreamSynchronize(sl.stream);
-        sl.packed.release();
-        sl.text.release();
-        sl.aux.release();
-        sl.meta.release();
-        sl.mask.release();
-        sl.meta_host.release();
+        if (s->ext_stream) cudaStreamSynchronize(s->ext_stream);
+        {
+            std::lock_guard<std::mutex> g(s->ctx->slot_mu);
+            if (s->ctx->slot_cache.size() < kSlotCacheMax) {
+                s->ctx->slot_cache.push_back(static_cast<SlotBufs&>(sl));
+                static_cast<SlotBufs&>(sl) = SlotBufs();
+            }
+        }
+        sl.release();
         if (sl.copied) cudaEventDestroy(sl.copied);
         if (sl.meta_ready) cudaEventDestroy(sl.meta_ready);
         if (sl.k_start) cudaEventDestroy(sl.k_start);

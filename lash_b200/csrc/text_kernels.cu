@@ -34,23 +34,80 @@ __device__ __forceinline__ bool base_code(uint32_t c, uint32_t& code) {
     return c == ((0x47544341u >> (8u * idx)) & 0xffu);
 }
 
-// the 16 bytes a thread owns: number of bases kept and their codes MSB-first (first kept base in the top two bits)
-__device__ __forceinline__ void classify16(const uint4& q, uint32_t n_live, uint32_t& cnt, uint32_t& bits, uint32_t& seps) {
+// Four bytes at a time (SIMD in a 32-bit word; byte j of the little-endian word is the j-th byte of the text):
+//   idx    = (w >> 1) & 0x03030303                                   per byte: which letter it could be
+//   expect = PRMT("ACTG", nibbles(idx))                              the letter each byte would have to equal
+//   valid  = bit 7 of every byte of  ~(((w ^ expect) & 0x7f..) + 0x7f.. | (w ^ expect))     (zero-byte test, no carries between bytes)
+//   vm     = (valid * 0x00204081) >> 28                              the four bit-7s gathered into a 4-bit mask
+// -- 12 instructions per word instead of ~18 per byte; the first version of these kernels classified byte by byte and was
+// ALU-bound at 37 instructions per text byte over its two passes (0.55 TB/s of text).
+__device__ __forceinline__ uint32_t valid_bits4(uint32_t w, uint32_t& idx) {
+    idx = (w >> 1) & 0x03030303u;
+    const uint32_t t = idx | (idx >> 4);
+    const uint32_t expect = __byte_perm(0x47544341u, 0u, __byte_perm(t, 0u, 0x4420));
+    const uint32_t x = w ^ expect;
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t gather_bit7s(uint32_t v) { return (v * 0x00204081u) >> 28; }   // bit 7 of byte j -> bit j
+// bytes beyond the live part of a thread's 16 (only the last thread of a span's last block): make them a non-base, non-separator
+__device__ __forceinline__ uint32_t live_word(uint32_t w, uint32_t n_live, int wi) {
+    const int lim = (int)n_live - 4 * wi;
+    return lim >= 4 ? w : lim <= 0 ? 0u : (w & ((1u << (8 * lim)) - 1u));
+}
+
+// kept bases among the 16 bytes a thread owns (count pass)
+__device__ __forceinline__ uint32_t count16(const uint4& q, uint32_t n_live) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-    cnt = 0;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t idx;
+        cnt += __popc(valid_bits4(n_live >= 16u ? w[i] : live_word(w[i], n_live, i), idx));
+    }
+    return cnt;
+}
+
+// s_lut[vm] (shared, built by compact_lut_init): low 16 bits = PRMT selector that moves the valid bytes of a word to the
+// front in order (the rest become zero bytes), bits 16.. = 2 * number of valid bytes
+__device__ __forceinline__ void compact_lut_init(uint32_t* s_lut) {
+    if (threadIdx.x < 16) {
+        uint32_t sel = 0, n = 0;
+        for (uint32_t j = 0; j < 4; ++j)
+            if ((threadIdx.x >> j) & 1u) sel |= j << (4 * n++);
+        for (uint32_t k = n; k < 4; ++k) sel |= 4u << (4 * k);   // selector 4 = byte 0 of the second PRMT operand (zero)
+        s_lut[threadIdx.x] = sel | ((2u * n) << 16);
+    }
+}
+
+// the 16 bytes a thread owns (compact pass): number of bases kept, their codes MSB-first (first kept base in the top two
+// bits), and -- only when WANT_SEPS -- which of the 16 bytes are record separators
+template <bool WANT_SEPS>
+__device__ __forceinline__ void classify16(const uint4& q, uint32_t n_live, const uint32_t* s_lut, uint32_t& cnt, uint32_t& bits, uint32_t& seps) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t sh_total = 0;
     bits = 0;
     seps = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
-        uint32_t code;
-        const bool live = (uint32_t)i < n_live;
-        const bool ok = base_code(c, code) && live;
-        bits = ok ? ((bits << 2) | code) : bits;
-        cnt += ok ? 1u : 0u;
-        seps |= (live && c == (uint32_t)kTextRecordSep) ? (1u << i) : 0u;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t wi = n_live >= 16u ? w[i] : live_word(w[i], n_live, i);
+        uint32_t idx;
+        const uint32_t vm = gather_bit7s(valid_bits4(wi, idx));
+        const uint32_t codes = (idx ^ (idx >> 1)) & 0x03030303u;                     // A0 C1 G2 T3 per byte
+        const uint32_t lut = s_lut[vm];
+        const uint32_t front = __byte_perm(codes, 0u, lut);                          // valid codes first, in order
+        // c0 << 30 | c1 << 28 | c2 << 26 | c3 << 24 in the top byte of the product (the lower bits are cross terms); the
+        // funnel shift takes exactly the 2 * n top bits that hold codes
+        const uint32_t sh = lut >> 16;
+        bits = __funnelshift_l(front * 0x40100401u, bits, sh);
+        sh_total += sh;
+        if (WANT_SEPS) {
+            const uint32_t y = wi ^ (0x01010101u * (uint32_t)kTextRecordSep);
+            const uint32_t z = ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u;
+            seps |= gather_bit7s(z) << (4 * i);
+        }
     }
-    bits = cnt ? (bits << (32u - 2u * cnt)) : 0u;
+    cnt = sh_total >> 1;
+    bits = cnt ? (bits << (32u - sh_total)) : 0u;
 }
 
 __global__ void __launch_bounds__(kTextThreads) text_count_kernel(const uint8_t* __restrict__ text, const TextBlock* __restrict__ blocks,
@@ -61,9 +118,7 @@ __global__ void __launch_bounds__(kTextThreads) text_count_kernel(const uint8_t*
         uint32_t mine = 0;
         for (uint32_t off = threadIdx.x * 16u; off < tb.n_bytes; off += kTextIterBytes) {
             const uint4 q = __ldg(reinterpret_cast<const uint4*>(text + tb.byte_begin + off));
-            uint32_t cnt, bits, seps;
-            classify16(q, min(16u, tb.n_bytes - off), cnt, bits, seps);
-            mine += cnt;
+            mine += count16(q, min(16u, tb.n_bytes - off));
         }
         mine = __reduce_add_sync(0xffffffffu, mine);
         if ((threadIdx.x & 31u) == 0) s_sum[threadIdx.x >> 5] = mine;
@@ -134,8 +189,10 @@ __global__ void __launch_bounds__(kTextThreads) text_compact_kernel(const uint8_
     constexpr uint32_t kStageWords = kTextIterBytes / 16 + 2;
     __shared__ uint32_t s_stage[kStageWords];
     __shared__ uint32_t s_warp[kTextThreads / 32];
+    __shared__ uint32_t s_lut[16];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < kStageWords; i += kTextThreads) s_stage[i] = 0u;
+    compact_lut_init(s_lut);
     __syncthreads();
     // starts [e-k+1, e) cannot begin a k-mer when a record ends at kept position e
     auto mark_boundary = [&](uint32_t* mask, uint64_t e) {
@@ -160,7 +217,8 @@ __global__ void __launch_bounds__(kTextThreads) text_compact_kernel(const uint8_
             uint4 q = make_uint4(0u, 0u, 0u, 0u);
             if (off < tb.n_bytes) {
                 q = __ldg(reinterpret_cast<const uint4*>(text + tb.byte_begin + off));
-                classify16(q, min(16u, tb.n_bytes - off), cnt, bits, seps);
+                if (mask) classify16<true>(q, min(16u, tb.n_bytes - off), s_lut, cnt, bits, seps);    // block-uniform
+                else classify16<false>(q, min(16u, tb.n_bytes - off), s_lut, cnt, bits, seps);
             }
             // CTA-wide exclusive prefix of cnt
             uint32_t x = cnt;

@@ -275,6 +275,23 @@ def test_ascii_push_spans_many_text_blocks(oracle, gpu_ctx, algo, p, k):
     _check_text(oracle, gpu_ctx, algo, p, k, genomes)
 
 
+def test_ascii_push_every_byte_value(oracle, gpu_ctx):
+    """The device classifies four bytes per 32-bit word (PRMT-selected expected letter + zero-byte test): every byte value in
+    every position of the word, mixed with bases at random, must be kept / deleted exactly like filter_out_n (utils.rs:33-41)."""
+    rng = np.random.default_rng(12)
+    every = np.array([v for v in range(256) if v != 1], dtype=np.uint8)          # 0x01 is the record separator of the text ABI
+    recs = []
+    for r in range(6):
+        n = 40_000 + 13 * r
+        body = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)].copy()
+        pos = rng.choice(n, size=n // 5, replace=False)
+        body[pos] = every[rng.integers(0, len(every), size=len(pos))]
+        body[r::997] = every[(np.arange(len(body[r::997])) + r) % len(every)]      # each value at every word offset over the records
+        recs.append(body.tobytes())
+    _check_text(oracle, gpu_ctx, ALGO_ULL, 12, 16, [recs, recs[:2], [recs[3][5:]], [recs[4][1:70_001]]])
+    _check_text(oracle, gpu_ctx, ALGO_HLL, 10, 31, [recs[::-1]])
+
+
 def test_ascii_push_short_reads(oracle, gpu_ctx):
     """config 4 shape: 150 bp reads, one record each, some with N, some shorter than k after filtering."""
     rng = np.random.default_rng(4)
