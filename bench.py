@@ -630,7 +630,12 @@ def run_graft(args):
     # ---- from FASTA text through the C++ host layer (rank 0, N=1 only; bounded sample) ----------------
     ingest = None
     if not args.no_ingest:
-        ingest = fasta_ingest_leg(torch, dist, ctx, buf, stride, rank, world, device, n_distinct=min(n_g, 64))
+        try:
+            ingest = fasta_ingest_leg(torch, dist, ctx, buf, stride, rank, world, device, n_distinct=min(n_g, 64))
+        except Exception as exc:   # a full tmpfs must not take the headline line with it
+            import traceback
+            traceback.print_exc()
+            ingest = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- BASELINE configs[2..4] as strong-scaled legs (tools/config_legs.py) -----------------------------
     configs = None
@@ -696,7 +701,15 @@ def fasta_ingest_leg(torch, dist, ctx, buf, stride, rank, world, device, n_disti
     import tempfile
 
     from lash_b200 import ALGO_ULL, hostapi
-    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    need = n_distinct * (GENOME_LEN + GENOME_LEN // 80 + 64) * 2
+    base = None
+    for cand in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if os.path.isdir(cand) and shutil.disk_usage(cand).free > need * max(world, 1):
+                base = cand
+                break
+        except OSError:
+            pass
     d = tempfile.mkdtemp(prefix=f"lash_bench_r{rank}_", dir=base)
     try:
         distinct = []
