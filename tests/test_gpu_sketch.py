@@ -322,3 +322,32 @@ def test_ascii_push_equals_packed_push_and_rejects_bad_spans(oracle, gpu_ctx):
             arr = (capi.TextSpan * 1)(span)
             rc = capi.lib().lash_sketch_push_ascii(sk._h, buf.ctypes.data_as(C.c_void_p), buf.nbytes, arr, 1, None)
             assert rc == -1
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_ascii_push_fuzz_against_packed_push_and_oracle(oracle, gpu_ctx, seed):
+    """Randomised text: record counts and lengths from 0 to beyond a text block, junk runs of every kind at random places
+    (incl. right at 16-byte, 4 KiB-iteration and 32 KiB-block edges), random k / precision / algorithm; the device-side
+    filter + pack, the host packer and the oracle must agree register for register."""
+    rng = np.random.default_rng(1000 + seed)
+    junk = np.array([v for v in range(256) if v not in (1, 65, 67, 71, 84)], dtype=np.uint8)
+    genomes = []
+    for g in range(int(rng.integers(3, 9))):
+        recs = []
+        for r in range(int(rng.integers(0, 7))):
+            n = int(rng.choice([0, 1, 15, 16, 17, 31, 33, 150, 4095, 4096, 4097, 32767, 32768, 32769, 70_000, int(rng.integers(1, 200_000))]))
+            body = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)].copy()
+            for _ in range(int(rng.integers(0, 6))):
+                if n == 0:
+                    break
+                a = int(rng.choice([0, 15, 16, 4095, 4096, 32767, 32768, int(rng.integers(0, n))])) % n
+                m = int(rng.choice([1, 2, 3, 16, 17, 100, 5000]))
+                body[a:a + m] = junk[rng.integers(0, len(junk), size=len(body[a:a + m]))]
+            recs.append(body.tobytes())
+        genomes.append(recs)
+    algo, p = [(ALGO_ULL, 10), (ALGO_ULL, 13), (ALGO_HLL, 11), (ALGO_HMH, 14), (ALGO_ULL, 16), (ALGO_HLL, 14)][seed % 6]
+    k = int(rng.choice([4, 11, 16, 21, 32]))
+    exp = oracle.sketch_genomes(algo, p, k, SEED, genomes, threads=4)
+    per = int(rng.integers(1, 5))
+    assert np.array_equal(sketch_genomes_text(gpu_ctx, algo, p, k, SEED, genomes, genomes_per_push=per), exp)
+    assert np.array_equal(sketch_genomes(gpu_ctx, algo, p, k, SEED, genomes, genomes_per_push=per), exp)
