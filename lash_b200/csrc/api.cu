@@ -115,6 +115,7 @@ struct lash_ctx {
     // scratch of lash_dist / lash_dist_stream, kept across calls (cudaMalloc/cudaFree per call cost
     // milliseconds of jitter on a 2.5 ms operation)
     DevBuf d_ref, d_qry, d_card, d_out[2], d_flags, d_regmin, d_ml, d_sum;
+    DevBuf d_hmh_terms_r, d_hmh_terms_q, d_hmh_ec, d_hmh_idx;   // HMH small-sketch path (setup_hmh_ec)
     PinBuf h_out[2];
     std::mutex slot_mu;
     std::vector<SlotBufs> slot_cache;   // at most kSlotCacheMax sets
@@ -148,6 +149,7 @@ extern "C" int lash_ctx_destroy(lash_ctx* c) {
     c->d_ref.release(); c->d_qry.release(); c->d_card.release(); c->d_out[0].release(); c->d_out[1].release();
     c->d_flags.release(); c->d_regmin.release(); c->d_ml.release(); c->d_sum.release(); c->h_out[0].release(); c->h_out[1].release();
     for (auto& b : c->slot_cache) b.release();
+    c->d_hmh_terms_r.release(); c->d_hmh_terms_q.release(); c->d_hmh_ec.release(); c->d_hmh_idx.release();
     delete c;
     return LASH_OK;
 }
@@ -852,6 +854,64 @@ static void setup_ml_scratch(lash_ctx* ctx, DistParams& dp) {
     dp.ml_o_base = o_base;
 }
 
+// HMH: expected-collision sums of all pairs of SMALL sketches (cardinality <= 2^19), before the tile kernel (dist_kernels.cu,
+// "K4m, small sketches").  Counts the small sketches of the row range and of the query set (one 8-byte D2H + stream sync: the
+// only place where the device-resident API synchronises, and only for HMH), sizes the scratch (41 x 1024 doubles per small
+// sketch, one double per small pair; LASH_HMH_EC_MAX_MB caps it, default 24 GiB -- sketches beyond the cap keep the per-pair
+// loop), and enqueues slots -> term vectors -> tile product on `st`.  LASH_HMH_EC=loop disables the path (A/B measurements).
+static int setup_hmh_ec(lash_ctx* ctx, DistParams& dp, cudaStream_t st) {
+    dp.hmh_ec = nullptr;
+    if (dp.algo != LASH_ALGO_HMH || dp.row_end <= dp.row_begin || dp.n_qry == 0) return LASH_OK;
+    static const bool off = [] { const char* v = getenv("LASH_HMH_EC"); return v && std::string(v) == "loop"; }();
+    if (off) return LASH_OK;
+    static const uint64_t max_bytes = [] {
+        const char* v = getenv("LASH_HMH_EC_MAX_MB");
+        return (uint64_t)(v ? strtoull(v, nullptr, 10) : 24576ull) << 20;
+    }();
+    const uint64_t n_rows = dp.row_end - dp.row_begin;
+    // index scratch: [0] small rows, [1] small queries (counts), then slot_r[n_rows], slot_q[n_qry], src_r[n_rows], src_q[n_qry]
+    const size_t idx_bytes = 16 + 4 * (2 * n_rows + 2 * dp.n_qry);
+    if (ctx->d_hmh_idx.reserve(idx_bytes) != cudaSuccess) { cudaGetLastError(); return LASH_OK; }
+    uint32_t* counts = (uint32_t*)ctx->d_hmh_idx.p;
+    int32_t* slot_r = (int32_t*)(counts + 4);
+    int32_t* slot_q = slot_r + n_rows;
+    uint32_t* src_r = (uint32_t*)(slot_q + dp.n_qry);
+    uint32_t* src_q = src_r + n_rows;
+    CU(cudaMemsetAsync(counts, 0, 16, st));
+    CU(launch_hmh_count_small(dp.card_ref, dp.row_begin, dp.row_end, counts, st));
+    CU(launch_hmh_count_small(dp.card_qry, 0, dp.n_qry, counts + 1, st));
+    uint32_t h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, counts, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->dist_launches += 2;
+    if (h[0] == 0 || h[1] == 0) return LASH_OK;   // no pair of two small sketches: nothing runs the loop
+    // caps: both below the grid limit, scratch within the budget (term vectors dominate; shrink the larger side first)
+    const uint64_t per = (uint64_t)kHmhEcTermsPerSketch * 8;
+    uint64_t cap_r = std::min<uint64_t>(h[0], 65535), cap_q = std::min<uint64_t>(h[1], 65535);
+    while ((cap_r + cap_q) * per + cap_r * cap_q * 8 > max_bytes && (cap_r > 64 || cap_q > 64)) {
+        if (cap_r >= cap_q) cap_r = std::max<uint64_t>(64, cap_r * 3 / 4);
+        else cap_q = std::max<uint64_t>(64, cap_q * 3 / 4);
+    }
+    if (ctx->d_hmh_terms_r.reserve(cap_r * per) != cudaSuccess || ctx->d_hmh_terms_q.reserve(cap_q * per) != cudaSuccess ||
+        ctx->d_hmh_ec.reserve(cap_r * cap_q * 8) != cudaSuccess) {
+        cudaGetLastError();   // no scratch: the per-pair loop computes the same numbers
+        return LASH_OK;
+    }
+    CU(launch_hmh_slots(dp.card_ref, dp.row_begin, dp.row_end, (uint32_t)cap_r, slot_r, src_r, counts + 2, st));
+    CU(launch_hmh_slots(dp.card_qry, 0, dp.n_qry, (uint32_t)cap_q, slot_q, src_q, counts + 3, st));
+    CU(launch_hmh_ec_fill(dp.card_ref, src_r, counts + 2, (uint32_t)cap_r, (double*)ctx->d_hmh_terms_r.p, st));
+    CU(launch_hmh_ec_fill(dp.card_qry, src_q, counts + 3, (uint32_t)cap_q, (double*)ctx->d_hmh_terms_q.p, st));
+    CU(launch_hmh_ec_gemm((const double*)ctx->d_hmh_terms_r.p, src_r, counts + 2, (uint32_t)cap_r, (const double*)ctx->d_hmh_terms_q.p, src_q,
+                          counts + 3, (uint32_t)cap_q, dp.triangular, (double*)ctx->d_hmh_ec.p, (uint32_t)cap_q, st));
+    ctx->dist_launches += 5;
+    dp.hmh_slot_ref = slot_r;
+    dp.hmh_slot_qry = slot_q;
+    dp.hmh_ec = (const double*)ctx->d_hmh_ec.p;
+    dp.hmh_row0 = dp.row_begin;
+    dp.hmh_ec_ld = (uint32_t)cap_q;
+    return LASH_OK;
+}
+
 extern "C" int lash_cardinality_dev(lash_ctx* ctx, int algo, int p, int estimator, const void* regs_dev, uint64_t n,
                                     double* card_dev, void* stream) {
     if (!ctx) return fail(LASH_E_INVALID, "lash_cardinality_dev: NULL ctx");
@@ -919,6 +979,8 @@ extern "C" int lash_dist_dev(lash_ctx* ctx, int algo, int p, int k, int estimato
     rc = prepare_regmin(ctx, dp, lash_sketch_reg_bytes(algo, p), stream ? (cudaStream_t)stream : ctx->stream);
     if (rc) return rc;
     setup_ml_scratch(ctx, dp);
+    rc = setup_hmh_ec(ctx, dp, stream ? (cudaStream_t)stream : ctx->stream);
+    if (rc) return rc;
     uint32_t nl = 0;
     CU(launch_dist(dp, stream ? (cudaStream_t)stream : ctx->stream, &nl));
     ctx->dist_launches += nl;
@@ -1021,6 +1083,8 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
         CUC(guard.event(&k1));
         CUC(cudaEventRecord(k0, st));
         setup_ml_scratch(ctx, dp);
+        rc = setup_hmh_ec(ctx, dp, st);
+        if (rc) return rc;
         uint32_t nl = 0;
         CUC(launch_dist(dp, st, &nl));
         ctx->dist_launches += nl;
@@ -1061,6 +1125,8 @@ static int dist_host(lash_ctx* ctx, int algo, int p, int k, int estimator, int m
             dp.row_begin = r0; dp.row_end = r1; dp.out = d_out[buf].p; dp.packed_tri = 0; dp.out_row0 = r0;
             CUC(cudaEventRecord(kstart, st));
             setup_ml_scratch(ctx, dp);
+            rc = setup_hmh_ec(ctx, dp, st);
+            if (rc) return rc;
             uint32_t nl = 0;
             CUC(launch_dist(dp, st, &nl));
             ctx->dist_launches += nl;

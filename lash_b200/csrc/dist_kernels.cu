@@ -177,6 +177,13 @@ struct IsHmh { static constexpr bool value = false; };
 template <>
 struct IsHmh<HmhAcc> { static constexpr bool value = true; };
 
+// the precomputed expected-collision loop sum of pair (i, j), when both sketches are small and have a stored term vector
+__device__ __forceinline__ const double* hmh_ec_of(const DistParams& dp, uint64_t i, uint64_t j) {
+    if (!dp.hmh_ec) return nullptr;
+    const int32_t sr = dp.hmh_slot_ref[i - dp.hmh_row0], sq = dp.hmh_slot_qry[j];
+    return (sr >= 0 && sq >= 0) ? dp.hmh_ec + (size_t)sr * dp.hmh_ec_ld + (size_t)sq : nullptr;
+}
+
 template <class ACC, int G>
 __device__ __forceinline__ void acc_add(ACC& acc, const uint32_t* a, const uint32_t* b, const SharedTables& t, int nplanes) {
     if constexpr (std::is_same<ACC, MlAcc>::value)
@@ -265,7 +272,7 @@ __global__ void __launch_bounds__(kDistThreads) dist_kernel(DistParams dp, uint3
             if (dp.triangular && j > i) continue;
             double s;
             if constexpr (IsHmh<ACC>::value) {
-                double sim = hmh_similarity_from(acc[a][b].C, acc[a][b].N, dp.card_qry[j], dp.card_ref[i]);
+                double sim = hmh_similarity_from(acc[a][b].C, acc[a][b].N, dp.card_qry[j], dp.card_ref[i], hmh_ec_of(dp, i, j));
                 s = fmax(sim, 0.0);
             } else {
                 bool bias;
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(kHmhThreads, 3) dist_hmh_fast_kernel(DistParam
             const uint32_t NZ = (nz[a][b] & 0xffffu) + (nz[a][b] >> 16);
             const uint32_t N = (nn[a][b] & 0xffffu) + (nn[a][b] >> 16) + full;
             const uint32_t Cc = N - NZ;   // equal and non-empty = (equal) - (both empty) = (16384 - NZ) - (16384 - N)
-            const double sim = hmh_similarity_from(Cc, N, dp.card_qry[j], dp.card_ref[i]);
+            const double sim = hmh_similarity_from(Cc, N, dp.card_qry[j], dp.card_ref[i], hmh_ec_of(dp, i, j));
             const double s = fmax(sim, 0.0);
             const double frac = 2.0 * s / (1.0 + s);
             const uint64_t o = dp.packed_tri ? (i * (i + 1) / 2 + j) : ((i - dp.out_row0) * dp.n_qry + j);
@@ -923,6 +930,150 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
         }
     }
     }  // tiles
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4m, small sketches: expectedCollision's 41 x 1024 loop as per-sketch term vectors and an exact-order tile product
+// (estimators.cuh: hmh_ec_term).  Per pair the loop costs 2 x 41 x 1024 pow calls in the reference; here every small sketch
+// pays them once (hmh_ec_fill_kernel), and a pair costs 41 984 multiply-adds summed in the reference's (i, j) order with one
+// scalar accumulator per pair -- the same doubles in the same order, so the sum is the per-pair loop's bit for bit.
+// ------------------------------------------------------------------------------------------------
+__global__ void hmh_count_small_kernel(const double* __restrict__ card, uint64_t begin, uint64_t end, uint32_t* count) {
+    uint32_t mine = 0;
+    for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (uint64_t)gridDim.x * blockDim.x)
+        mine += hmh_ec_is_small(card[i]) ? 1u : 0u;
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(count, mine);
+}
+cudaError_t launch_hmh_count_small(const double* card, uint64_t begin, uint64_t end, uint32_t* count_dev, cudaStream_t st) {
+    if (end <= begin) return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>((end - begin + 255) / 256, 1024);
+    hmh_count_small_kernel<<<grid, 256, 0, st>>>(card, begin, end, count_dev);
+    return cudaGetLastError();
+}
+
+// one CTA: ranks of the small sketches in index order (so slots ascend with the sketch index)
+__global__ void __launch_bounds__(1024) hmh_slots_kernel(const double* __restrict__ card, uint64_t begin, uint64_t end, uint32_t cap,
+                                                         int32_t* __restrict__ slot, uint32_t* __restrict__ src, uint32_t* count) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint64_t base = begin; base < end; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint32_t v = (i < end && hmh_ec_is_small(card[i])) ? 1u : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if ((threadIdx.x & 31u) >= (uint32_t)d) x += y;
+        }
+        if ((threadIdx.x & 31u) == 31u) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t w = s_warp[threadIdx.x];
+            uint32_t xw = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, xw, d);
+                if (threadIdx.x >= (uint32_t)d) xw += y;
+            }
+            s_warp[threadIdx.x] = xw - w;
+        }
+        __syncthreads();
+        const uint32_t rank = s_carry + s_warp[threadIdx.x >> 5] + (x - v);
+        if (i < end) {
+            const bool take = v && rank < cap;
+            slot[i - begin] = take ? (int32_t)rank : -1;
+            if (take) src[rank] = (uint32_t)i;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = rank + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = min(s_carry, cap);
+}
+cudaError_t launch_hmh_slots(const double* card, uint64_t begin, uint64_t end, uint32_t cap, int32_t* slot, uint32_t* src,
+                             uint32_t* count_dev, cudaStream_t st) {
+    hmh_slots_kernel<<<1, 1024, 0, st>>>(card, begin, end, cap, slot, src, count_dev);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) hmh_ec_fill_kernel(const double* __restrict__ card, const uint32_t* __restrict__ src,
+                                                          const uint32_t* __restrict__ count, double* __restrict__ terms) {
+    const uint32_t s = blockIdx.y;
+    if (s >= *count) return;
+    const double n = card[src[s]];
+    double* out = terms + (size_t)s * kHmhEcLen;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < (uint32_t)kHmhEcLen; e += gridDim.x * blockDim.x)
+        out[e] = hmh_ec_term(1 + (int)(e >> 10), 1 + (int)(e & 1023u), n);
+}
+cudaError_t launch_hmh_ec_fill(const double* card, const uint32_t* src, const uint32_t* count_dev, uint32_t cap, double* terms,
+                               cudaStream_t st) {
+    if (cap == 0) return cudaSuccess;
+    if (cap > 65535) return cudaErrorInvalidValue;   // grid.y limit: the caller caps the slots below it
+    hmh_ec_fill_kernel<<<dim3(41, cap), 256, 0, st>>>(card, src, count_dev, terms);
+    return cudaGetLastError();
+}
+
+constexpr int kEcTile = 64, kEcKC = 16, kEcThreads = 256;
+__global__ void __launch_bounds__(kEcThreads) hmh_ec_gemm_kernel(const double* __restrict__ tr, const uint32_t* __restrict__ src_r,
+                                                                  const uint32_t* __restrict__ count_r, const double* __restrict__ tq,
+                                                                  const uint32_t* __restrict__ src_q, const uint32_t* __restrict__ count_q,
+                                                                  int triangular, double* __restrict__ ec, uint32_t ld) {
+    // k-major tiles: sA[kk][row], sB[kk][col] (+1 pad against the transposing stores)
+    __shared__ double sA[kEcKC][kEcTile + 1];
+    __shared__ double sB[kEcKC][kEcTile + 1];
+    const uint32_t nr = *count_r, nq = *count_q;
+    const uint32_t r0 = blockIdx.y * kEcTile, q0 = blockIdx.x * kEcTile;
+    if (r0 >= nr || q0 >= nq) return;
+    if (triangular && src_r[min(r0 + kEcTile, nr) - 1] < src_q[q0]) return;   // every pair of the tile has j > i
+    const uint32_t ty = threadIdx.x >> 4, tx = threadIdx.x & 15u;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    // loader: thread t brings 4 consecutive k of one row of each operand (rows past the count read row 0: never stored)
+    const uint32_t lrow = threadIdx.x >> 2, lk = (threadIdx.x & 3u) * 4u;
+    const double* ga = tr + (size_t)(r0 + lrow < nr ? r0 + lrow : 0) * kHmhEcLen + lk;
+    const double* gb = tq + (size_t)(q0 + lrow < nq ? q0 + lrow : 0) * kHmhEcLen + lk;
+    for (uint32_t k0 = 0; k0 < (uint32_t)kHmhEcLen; k0 += kEcKC) {
+        const double4 a4 = *reinterpret_cast<const double4*>(ga + k0);
+        const double4 b4 = *reinterpret_cast<const double4*>(gb + k0);
+        __syncthreads();
+        sA[lk + 0][lrow] = a4.x; sA[lk + 1][lrow] = a4.y; sA[lk + 2][lrow] = a4.z; sA[lk + 3][lrow] = a4.w;
+        sB[lk + 0][lrow] = b4.x; sB[lk + 1][lrow] = b4.y; sB[lk + 2][lrow] = b4.z; sB[lk + 3][lrow] = b4.w;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kEcKC; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sB[kk][j * 16 + tx];    // lanes read consecutive doubles: no bank conflicts
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = acc[i][j] + a[i] * b[j];   // -fmad=false: multiply, then add, like the loop
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t r = r0 + ty * 4 + i, q = q0 + j * 16 + tx;
+            if (r < nr && q < nq) ec[(size_t)r * ld + q] = acc[i][j];
+        }
+}
+cudaError_t launch_hmh_ec_gemm(const double* terms_r, const uint32_t* src_r, const uint32_t* count_r, uint32_t cap_r,
+                               const double* terms_q, const uint32_t* src_q, const uint32_t* count_q, uint32_t cap_q, int triangular,
+                               double* ec, uint32_t ld, cudaStream_t st) {
+    if (cap_r == 0 || cap_q == 0) return cudaSuccess;
+    const dim3 grid((cap_q + kEcTile - 1) / kEcTile, (cap_r + kEcTile - 1) / kEcTile);
+    if (grid.y > 65535) return cudaErrorInvalidValue;
+    hmh_ec_gemm_kernel<<<grid, kEcThreads, 0, st>>>(terms_r, src_r, count_r, terms_q, src_q, count_q, triangular, ec, ld);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -260,37 +260,48 @@ __device__ inline double hmh_cardinality_from(double sum, double ez) {
     const double alpha = 0.7213 / (1.0 + 1.079 / M);
     return alpha * M * (M - ez) / (hmh_beta(ez) + sum);
 }
-__device__ inline double hmh_expected_collisions(double n, double m) {
+// expectedCollision(n, m) of hyperminhash for n <= 2^19 is a 64 x 1024 double loop  x += prx(i, j; n) * pry(i, j; m)  with
+//     prx(i, j; n) = (1 - b2)^n - (1 - b1)^n,   b1 = (1024 + j) / 2^(24 + i),  b2 = (1025 + j) / 2^(24 + i)     (i < 64)
+// (row i = 64 uses b1 = j / 2^87, b2 = (j + 1) / 2^87).  The term depends on ONE cardinality, so it is a per-sketch vector;
+// and from i = 42 on b <= 2049 / 2^66 < 2^-54 makes 1 - b == 1.0 in double, the term exactly 0 and the product an exact +0
+// that leaves x untouched -- rows 1..41 are all that can matter (row 41 still holds one non-zero term, j = 1024;
+// tests/test_device_math.py checks the zero rows).  K4m's small-sketch path stores the 41 x 1024 vector of every small
+// sketch once (hmh_ec_fill_kernel) and sums the products of two vectors in the reference's (i, j) order
+// (hmh_ec_gemm_kernel); the per-pair loop below is the same arithmetic for pairs without a stored vector.
+constexpr int kHmhEcRows = 41;
+constexpr int kHmhEcLen = kHmhEcRows * 1024;
+constexpr double kHmhEcSmall = 524288.0;   // 2^(P + 5): above it the closed form applies
+
+__device__ __forceinline__ double hmh_ec_term(int i, int j, double n) {   // i in 1..63, j in 1..1024
+    const double inv_den = __hiloint2double((1023 - (24 + i)) << 20, 0);    // 2^-(24+i), exact; x / 2^k == x * 2^-k exactly
+    const double b1 = (1024.0 + j) * inv_den;
+    const double b2 = (1024.0 + j + 1.0) * inv_den;
+    return pow_cr(1.0 - b2, n) - pow_cr(1.0 - b1, n);
+}
+// which branch expectedCollision takes: true = the double loop
+__device__ __forceinline__ bool hmh_ec_is_small(double card) { return !(card > kHmhEcSmall); }
+
+// x_pre: the loop sum computed elsewhere (both sketches small), or nullptr
+__device__ inline double hmh_expected_collisions(double n, double m, const double* x_pre = nullptr) {
     if (n < m) { double t = n; n = m; m = t; }
     if (n > 0x1p74) return 18446744073709551615.0;
-    if (n > 524288.0) {
+    if (n > kHmhEcSmall) {
         double r = (1.0 + n) / m;
         double d = (4.0 * n / m) / pow_cr(r, 2.0);
         return 0.169919487159739093975315012348 * 16.0 * d + 0.5;
     }
     double x = 0.0;
-    for (int i = 1; i <= 64; ++i) {
-        for (int j = 1; j <= 1024; ++j) {
-            double b1, b2;
-            if (i != 64) {
-                double den = ldexp(1.0, 24 + i);
-                b1 = (1024.0 + j) / den;
-                b2 = (1024.0 + j + 1.0) / den;
-            } else {
-                double den = ldexp(1.0, 24 + i - 1);
-                b1 = j / den;
-                b2 = (j + 1.0) / den;
-            }
-            double prx = pow(1.0 - b2, n) - pow(1.0 - b1, n);
-            double pry = pow(1.0 - b2, m) - pow(1.0 - b1, m);
-            x += prx * pry;
-        }
+    if (x_pre) {
+        x = *x_pre;
+    } else {
+        for (int i = 1; i <= kHmhEcRows; ++i)
+            for (int j = 1; j <= 1024; ++j) x += hmh_ec_term(i, j, n) * hmh_ec_term(i, j, m);
     }
     return (x * 14.0 + 0.5) / 14.0;
 }
-__device__ inline double hmh_similarity_from(uint32_t C, uint32_t N, double card_q, double card_r) {
+__device__ inline double hmh_similarity_from(uint32_t C, uint32_t N, double card_q, double card_r, const double* x_pre = nullptr) {
     if (C == 0) return 0.0;
-    double ec = hmh_expected_collisions(card_q, card_r);
+    double ec = hmh_expected_collisions(card_q, card_r, x_pre);
     if ((double)C < ec) return 0.0;
     return ((double)C - ec) / (double)N;
 }

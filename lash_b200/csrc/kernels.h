@@ -100,7 +100,32 @@ struct DistParams {
     uint32_t* ml_scratch = nullptr;
     uint64_t ml_cells = 0;
     uint64_t ml_o_base = 0;
+    // optional (HMH): expected-collision sums of pairs of SMALL sketches (cardinality <= 2^19), computed before the tile kernel:
+    // hmh_slot_ref[i - hmh_row0] / hmh_slot_qry[j] = slot of the sketch's term vector (or -1), hmh_ec[slot_r * hmh_ec_ld + slot_q]
+    // = the loop sum x of expectedCollision.  nullptr: every such pair runs the 41 x 1024 loop itself.
+    const int32_t* hmh_slot_ref = nullptr;
+    const int32_t* hmh_slot_qry = nullptr;
+    const double* hmh_ec = nullptr;
+    uint64_t hmh_row0 = 0;
+    uint32_t hmh_ec_ld = 0;
 };
+
+// ---- HMH small-sketch path (dist_kernels.cu) ---------------------------------------------------------------------------------
+// number of sketches among card[begin, end) whose expectedCollision runs the double loop (cardinality <= 2^19): *count_dev += n
+cudaError_t launch_hmh_count_small(const double* card, uint64_t begin, uint64_t end, uint32_t* count_dev, cudaStream_t st);
+// slot[i - begin] = rank of sketch i among the small ones of [begin, end) (capped at `cap`: beyond it -1), src[slot] = i,
+// *count_dev = min(number of small sketches, cap)
+cudaError_t launch_hmh_slots(const double* card, uint64_t begin, uint64_t end, uint32_t cap, int32_t* slot, uint32_t* src,
+                             uint32_t* count_dev, cudaStream_t st);
+// terms[slot][41 * 1024] of the first *count_dev slots
+cudaError_t launch_hmh_ec_fill(const double* card, const uint32_t* src, const uint32_t* count_dev, uint32_t cap, double* terms,
+                               cudaStream_t st);
+// ec[r * ld + q] = sum over (i, j) in the reference's order of terms_r[r][ij] * terms_q[q][ij]; triangular: tiles whose largest
+// reference sketch index is below their smallest query sketch index are skipped
+cudaError_t launch_hmh_ec_gemm(const double* terms_r, const uint32_t* src_r, const uint32_t* count_r, uint32_t cap_r,
+                               const double* terms_q, const uint32_t* src_q, const uint32_t* count_q, uint32_t cap_q, int triangular,
+                               double* ec, uint32_t ld, cudaStream_t st);
+constexpr uint32_t kHmhEcTermsPerSketch = 41u * 1024u;
 // 32-bit words of ML scratch per pair for sketches of precision p (S lo/hi, flag, bit planes)
 uint32_t ml_scratch_words(int p);
 // atomicMin of the smallest non-zero register byte into *out_dev (preset to 0xffffffff by the caller)

@@ -55,6 +55,9 @@ double dm_ml(uint64_t S, const int* b_in, int p, uint32_t reg0) {
 }
 double dm_hmh_card(double sum, double ez) { return hmh_cardinality_from(sum, ez); }
 double dm_hmh_similarity(uint32_t C, uint32_t N, double card_q, double card_r) { return hmh_similarity_from(C, N, card_q, card_r); }
+double dm_hmh_ec_term(int i, int j, double n) { return hmh_ec_term(i, j, n); }
+double dm_hmh_ec(double n, double m) { return hmh_expected_collisions(n, m); }
+int dm_hmh_ec_rows(void) { return kHmhEcRows; }
 double dm_mash64(double frac, int k, int model) { return mash_distance_f64(frac, k, model); }
 float dm_mash32(float frac, int k, int model) { return mash_distance_f32(frac, k, model); }
 }

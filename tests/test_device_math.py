@@ -193,6 +193,9 @@ def est(tmp_path_factory):
     L.dm_ml.argtypes, L.dm_ml.restype = [u64, vp, i32, u32], d
     L.dm_hmh_card.argtypes, L.dm_hmh_card.restype = [d, d], d
     L.dm_hmh_similarity.argtypes, L.dm_hmh_similarity.restype = [u32, u32, d, d], d
+    L.dm_hmh_ec_term.argtypes, L.dm_hmh_ec_term.restype = [i32, i32, d], d
+    L.dm_hmh_ec.argtypes, L.dm_hmh_ec.restype = [d, d], d
+    L.dm_hmh_ec_rows.argtypes, L.dm_hmh_ec_rows.restype = [], i32
     L.dm_mash64.argtypes, L.dm_mash64.restype = [d, i32, i32], d
     L.dm_mash32.argtypes, L.dm_mash32.restype = [C.c_float, i32, i32], C.c_float
     return L
@@ -300,6 +303,36 @@ def test_hmh_and_mash_epilogues(est, oracle):
             assert est.dm_mash64(frac, k, 2) == frac
             f32 = np.float32(frac)
             assert abs(float(est.dm_mash32(f32, k, 0)) - float(np.float32(1) - np.power(f32, np.float32(1) / np.float32(k)))) <= 2e-7
+
+
+def test_hmh_expected_collision_terms_and_sum(est, oracle):
+    """K4m's small-sketch path (estimators.cuh: hmh_ec_term, kHmhEcRows): the term of rows beyond kHmhEcRows is exactly +0 for
+    every cardinality that takes the loop (so cutting the 64 x 1024 loop at row 41 changes nothing), row 41 still holds a
+    non-zero term, and the loop sum equals the oracle's expectedCollision (glibc pow there, correctly rounded pow here)."""
+    rows = est.dm_hmh_ec_rows()
+    assert rows == 41
+    for n in (1.0, 17.0, 1234.5, 65536.0, 524288.0):
+        for i in range(rows + 1, 64):
+            for j in (1, 2, 511, 1023, 1024):
+                t = est.dm_hmh_ec_term(i, j, n)
+                assert t == 0.0 and not np.signbit(t), (i, j, n, t)
+    assert est.dm_hmh_ec_term(41, 1024, 524288.0) != 0.0
+    # b = (1024 + j) / 2^(24 + i) as the reference builds it (a division by a power of two) is the product used here
+    for i in (1, 7, 40):
+        for j in (1, 333, 1024):
+            b1 = (1024.0 + j) / 2.0 ** (24 + i)
+            b2 = (1024.0 + j + 1.0) / 2.0 ** (24 + i)
+            n = 70000.0
+            t = est.dm_hmh_ec_term(i, j, n)
+            ref = (1.0 - b2) ** n - (1.0 - b1) ** n
+            assert abs(t - ref) <= 4 * EPS, (i, j, t, ref)
+    L = oracle.lib()
+    for n, m in ((3.0, 2.0), (1000.0, 10.0), (52345.25, 480000.0), (524288.0, 524288.0), (100.0, 100.0)):
+        got = est.dm_hmh_ec(n, m)
+        exp = L.lo_hmh_expected_collisions(n, m)
+        assert abs(got - exp) <= 1e-13 * max(abs(exp), 1.0), (n, m, got, exp)
+    # the closed form above 2^19 is untouched
+    assert _close(est.dm_hmh_ec(3e6, 2e6), L.lo_hmh_expected_collisions(3e6, 2e6), ulps=4)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -201,6 +201,55 @@ def test_small_sketches_hit_small_range_paths(oracle, gpu_ctx):
         assert np.all(np.abs(card_g[fin] - card_c[fin]) <= 8 * EPS * np.abs(card_c[fin]))
 
 
+def test_hmh_small_sketches_precomputed_expected_collisions(oracle, gpu_ctx):
+    """hyperminhash's expectedCollision runs a 64 x 1024 loop of pows when both cardinalities are <= 2^19 (utils.rs:150-180 ->
+    similarity()).  K4m's small-sketch path stores a term vector per small sketch and sums the products in the loop's order
+    (setup_hmh_ec, hmh_ec_fill_kernel, hmh_ec_gemm_kernel): related small genomes (C > 0, so the value matters), large ones
+    mixed in (closed form), an empty sketch, rectangular / triangular / row-ranged calls."""
+    import ctypes as C
+
+    from lash_b200 import capi
+    lengths = [3000, 20_000, 20_000, 90_000, 90_000, 250_000, 250_000, 400_000, 1_500_000, 1_500_000, 60_000, 60_000, 8000]
+    gs = []
+    for g, n in enumerate(lengths):
+        base = synth.ancestor_codes(n, seed=100 + n)          # equal lengths share an ancestor -> collisions
+        gs.append([synth.to_ascii(synth.mutate(base, 0.01 * (1 + g % 3), seed=g))])
+    gs.append([b""])
+    regs = oracle.sketch_genomes(ALGO_HMH, 14, 16, 42, gs, threads=8)
+    n = len(regs)
+    cards = np.array([oracle.cardinality(ALGO_HMH, 14, 0, r) for r in regs])
+    assert (cards[:8] <= 524288).all() and (cards[8:10] > 524288).all()
+    exp = oracle.dist(ALGO_HMH, 14, 16, 0, MODEL_POISSON, False, regs, regs, threads=8)
+    frac = oracle.dist(ALGO_HMH, 14, 16, 0, 2, False, regs, regs, threads=8)
+    assert ((frac > 0) & (frac < 1)).sum() >= 8, "the fixture must hold small pairs with collisions beyond the expected ones"
+    got, w = ops.dist(gpu_ctx, ALGO_HMH, 14, 16, 0, MODEL_POISSON, False, regs, regs)
+    assert w == 0
+    _assert_close_f64(got, exp, frac, 16, "HMH small sketches, dense")
+    # rectangular, reference and query sets with different small subsets
+    ref, qry = regs[2:11], regs[[0, 9, 4, 13, 7, 12]]
+    got_r, _ = ops.dist(gpu_ctx, ALGO_HMH, 14, 16, 0, MODEL_POISSON, False, ref, qry)
+    np.testing.assert_array_equal(got_r, got[2:11][:, [0, 9, 4, 13, 7, 12]])
+    # packed triangle and row ranges (slots relative to the row range)
+    tri, _ = ops.dist(gpu_ctx, ALGO_HMH, 14, 16, 0, MODEL_BINOMIAL, False, regs, regs, triangular=True)
+    full_b, _ = ops.dist(gpu_ctx, ALGO_HMH, 14, 16, 0, MODEL_BINOMIAL, False, regs, regs)
+    np.testing.assert_array_equal(tri, full_b[np.tril_indices(n)])
+    L = capi.lib()
+    rows = {}
+
+    def _cb(user, row0, nrows, ptr):
+        block = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), (nrows * n,)).reshape(nrows, n)
+        for r in range(nrows):
+            rows[row0 + r] = block[r, : row0 + r + 1].copy()    # triangular: cells j > i are unspecified
+        return 0
+
+    cb = capi.DIST_BLOCK_CB(_cb)
+    rp = regs.ctypes.data_as(C.c_void_p)
+    for b, e in ((0, 5), (5, n)):
+        capi.check(L.lash_dist_stream_rows(gpu_ctx.handle, ALGO_HMH, 14, 16, 0, MODEL_BINOMIAL, 0, rp, n, rp, n, 1, b, e, 3, cb, None))
+    for i in range(n):
+        np.testing.assert_array_equal(rows[i], full_b[i, : i + 1])
+
+
 def test_hll_bias_regime_is_flagged_not_silently_different(oracle, gpu_ctx):
     """HLL++ estimates in (threshold, 5m] need Google's empirical bias tables (not reproducible
     offline): both sides must flag those cells instead of inventing a number."""

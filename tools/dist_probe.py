@@ -1,5 +1,6 @@
 """One all-vs-all launch on simulated sketches, for ncu captures and A/B timings of the dist kernels.
-    python tools/dist_probe.py ull-ml|ull-fgra|hll|hmh [n] [p]
+    python tools/dist_probe.py ull-ml|ull-fgra|hll|hmh|hmh-small [n] [p]
+hmh-small: sketches of ~10^5 k-mers, so every pair takes expectedCollision's double-loop branch (LASH_HMH_EC=loop: per pair).
 """
 import json
 import sys
@@ -25,7 +26,8 @@ elif kind == "hll":
     algo, est = ALGO_HLL, 0
 else:
     m = 16384
-    lvl = np.clip(np.floor(7.0 - np.log2(-np.log(rng.random((n, m))))), 0, 40).astype(np.int64)
+    per_reg = 2.6 if kind == "hmh-small" else 7.0
+    lvl = np.clip(np.floor(per_reg - np.log2(-np.log(rng.random((n, m))))), 0, 40).astype(np.int64)
     regs = ((lvl << 10) | rng.integers(0, 1024, size=(n, m))).astype(np.uint16)
     regs[1::2] = np.where(rng.random((n // 2 + n % 2 if False else regs[1::2].shape[0], m)) < 0.3, regs[0::2][: regs[1::2].shape[0]], regs[1::2])
     algo, est, p = ALGO_HMH, 0, 14
