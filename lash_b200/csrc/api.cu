@@ -116,6 +116,7 @@ struct lash_ctx {
     // milliseconds of jitter on a 2.5 ms operation)
     DevBuf d_ref, d_qry, d_card, d_out[2], d_flags, d_regmin, d_ml, d_sum;
     DevBuf d_hmh_terms_r, d_hmh_terms_q, d_hmh_ec, d_hmh_idx;   // HMH small-sketch path (setup_hmh_ec)
+    DevBuf d_hll_mm;                                            // HLL per-sketch register min / max (prepare_regmin)
     PinBuf h_out[2];
     std::mutex slot_mu;
     std::vector<SlotBufs> slot_cache;   // at most kSlotCacheMax sets
@@ -149,6 +150,7 @@ extern "C" int lash_ctx_destroy(lash_ctx* c) {
     c->d_ref.release(); c->d_qry.release(); c->d_card.release(); c->d_out[0].release(); c->d_out[1].release();
     c->d_flags.release(); c->d_regmin.release(); c->d_ml.release(); c->d_sum.release(); c->h_out[0].release(); c->h_out[1].release();
     for (auto& b : c->slot_cache) b.release();
+    c->d_hll_mm.release();
     c->d_hmh_terms_r.release(); c->d_hmh_terms_q.release(); c->d_hmh_ec.release(); c->d_hmh_idx.release();
     delete c;
     return LASH_OK;
@@ -808,6 +810,20 @@ static int check_dist_args(int algo, int p, int k, int estimator, int model, uin
 // smallest non-empty register of both sets, for the FGRA pair-table kernel (dist_kernels.cu)
 static int prepare_regmin(lash_ctx* ctx, DistParams& dp, size_t rb, cudaStream_t st) {
     dp.n_sm = ctx->n_sm;
+    if (dp.algo == LASH_ALGO_HLL) {
+        // K4i's windows: smallest / largest register of every sketch (16-byte staging: p >= 4 always gives 16-register rows)
+        dp.hll_mm_ref = dp.hll_mm_qry = nullptr;
+        if ((((uintptr_t)dp.ref | (uintptr_t)dp.qry) & 15u) != 0 || rb % 16 != 0) return LASH_OK;
+        const bool same = dp.qry == dp.ref && dp.n_qry == dp.n_ref;
+        if (ctx->d_hll_mm.reserve(4 * (dp.n_ref + (same ? 0 : dp.n_qry))) != cudaSuccess) { cudaGetLastError(); return LASH_OK; }
+        uint32_t* mm = (uint32_t*)ctx->d_hll_mm.p;
+        CU(launch_hll_minmax(dp.ref, dp.n_ref, (uint32_t)rb, mm, st));
+        if (!same) CU(launch_hll_minmax(dp.qry, dp.n_qry, (uint32_t)rb, mm + dp.n_ref, st));
+        ctx->dist_launches += same ? 1 : 2;
+        dp.hll_mm_ref = mm;
+        dp.hll_mm_qry = same ? mm : mm + dp.n_ref;
+        return LASH_OK;
+    }
     if (dp.algo != LASH_ALGO_ULL) return LASH_OK;
     CU(ctx->d_regmin.reserve(8));
     uint32_t* w = (uint32_t*)ctx->d_regmin.p;

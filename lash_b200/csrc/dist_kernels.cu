@@ -434,6 +434,251 @@ __global__ void __launch_bounds__(kHllThreads, 3) dist_hll_fast_kernel(DistParam
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4i: HLL distance tiles in 32-bit fixed point (dist_tables.cuh: hll_int_recode).
+//
+// K4h pays a VIMNMX, a DADD and (ptxas) 0.6 MOV per register pair: 3.5 issue slots, 7.3 T register pairs/s.  The sum of a
+// pair whose registers all lie within 29 levels of the tile's smallest register is exact in f64 -- no partial sum of the
+// reference's loop ever rounds -- so it can be formed in ANY arithmetic: here min (VIMNMX, ALU pipe) + a 32-bit
+// multiply-add by a run-time 1 (IMAD, FMA-heavy pipe; with a literal 1 ptxas turns it back into an ALU add), eight terms
+// per 32-bit batch, one IMAD.WIDE per batch into the 64-bit sum: 2.1 issue slots per register pair split evenly over the
+// two integer pipes.  Per tile: lo = min over the tile's sketches of their smallest register (zero registers included:
+// then lo = 0 and an empty register is the term 2^28), sketches whose largest register exceeds lo + 28 are flagged and
+// their pairs are redone by the sequential f64 loop (hll_pair_exact) -- 10^-3 of the sketches of 5 Mbp genomes at p = 14.
+// The zero count is only needed where both sketches hold an empty register, as in K4h.
+// ------------------------------------------------------------------------------------------------
+__global__ void hll_minmax_kernel(const unsigned char* __restrict__ regs, uint64_t n, uint32_t cell_bytes, uint32_t* __restrict__ mm) {
+    const uint64_t s = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= n) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint4* src = reinterpret_cast<const uint4*>(regs + s * cell_bytes);
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    for (uint32_t e = lane; e < cell_bytes / 16; e += 32) {
+        const uint4 v = __ldg(src + e);
+        mn = __vminu4(__vminu4(mn, v.x), __vminu4(__vminu4(v.y, v.z), v.w));
+        mx = __vmaxu4(__vmaxu4(mx, v.x), __vmaxu4(__vmaxu4(v.y, v.z), v.w));
+    }
+    mn = __vminu4(mn, mn >> 16), mn = __vminu4(mn, mn >> 8) & 0xffu;
+    mx = __vmaxu4(mx, mx >> 16), mx = __vmaxu4(mx, mx >> 8) & 0xffu;
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) mm[s] = mn | (mx << 8);
+}
+cudaError_t launch_hll_minmax(const void* regs, uint64_t n, uint32_t cell_bytes, uint32_t* mm, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    hll_minmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(reinterpret_cast<const unsigned char*>(regs), n, cell_bytes, mm);
+    return cudaGetLastError();
+}
+
+// the reference's loop on one pair, straight from global memory (flagged pairs only)
+__device__ __noinline__ void hll_pair_exact(const unsigned char* a, const unsigned char* b, uint32_t cell_bytes, double& sum, uint32_t& zero) {
+    double s = 0.0;
+    uint32_t z = 0;
+    for (uint32_t e = 0; e < cell_bytes; e += 16) {
+        const uint4 va = __ldg(reinterpret_cast<const uint4*>(a + e)), vb = __ldg(reinterpret_cast<const uint4*>(b + e));
+        const uint32_t m4[4] = {__vmaxu4(va.x, vb.x), __vmaxu4(va.y, vb.y), __vmaxu4(va.z, vb.z), __vmaxu4(va.w, vb.w)};
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t r = (m4[w] >> (8 * j)) & 0xffu;
+                z += (r == 0u);
+                s += __hiloint2double((int)(kHllOne - (r << 20)), 0);
+            }
+    }
+    sum = s;
+    zero = z;
+}
+
+__device__ __forceinline__ uint32_t mad_one(uint32_t a, uint32_t one, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c));
+    return d;
+}
+
+// Staged rows are laid out in 16-register groups of kHllIntGroup = 20 words (16 terms + 4 words of padding) and a row stride of
+// groups * 20 + 4 words: a staging thread recodes one LDG.128 (16 registers) into four consecutive STS.128, and with 16-word
+// groups the eight threads of a row hit only two bank quads (ncu: 4-way conflicts, the shared-memory pipe at 79 %); with
+// 20-word groups they cover all eight.  The query rows of a warp's lanes still start 4 banks apart (stride = 4 mod 32).
+// STRIDE: u32 per staged row at compile time (the usual 128-register chunk: every LDS offset is an immediate), 0 = run time
+// Two tile shapes: a thread owns RM reference rows x 2 query columns.  RM = 8 (64 x 64 pairs per CTA, 128 registers, two CTAs per
+// SM) stages 1/32 sketch row per pair instead of 3/64 and reads fewer shared-memory wavefronts per pair: +7 % at n = 6000;
+// RM = 4 (32 x 64, 80 registers, three CTAs per SM) has half-size tiles for grids of only a few waves.
+constexpr int kHiQM = 2;
+constexpr int kHiTQ = 32 * kHiQM;
+constexpr int kHiChunk = 128;                                             // registers per sketch per stage
+template <int RM>
+struct HiShape {
+    static constexpr int kTR = (kHllThreads / 32) * RM;                   // reference rows per CTA
+    static constexpr int kMinBlocks = RM == 8 ? 2 : 3;
+};
+constexpr uint32_t kHllIntGroup = 20;
+__host__ __device__ constexpr uint32_t hll_int_stride(uint32_t chunk) { return chunk / 16 * kHllIntGroup + 4; }
+
+template <bool COUNT_ZERO, int STRIDE, int kHiRM>
+__device__ __forceinline__ void hll_int_chunk(uint64_t (&sum)[kHiRM][kHiQM], uint32_t (&zero)[kHiRM][kHiQM], const uint32_t* pa,
+                                              const uint32_t* pb, uint32_t stride_rt, uint32_t chunk, uint32_t one) {
+    static_assert(kHllIntBatch == 8, "two 4-register steps per 32-bit batch");
+    const uint32_t a_row = STRIDE ? (uint32_t)STRIDE : stride_rt, b_row32 = 32u * a_row;
+    const uint32_t n_groups = chunk / 16;
+#pragma unroll 1
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        const uint32_t* ga = pa + g * kHllIntGroup;
+        const uint32_t* gb = pb + g * kHllIntGroup;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t acc[kHiRM][kHiQM];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint4 a[kHiRM], b[kHiQM];
+#pragma unroll
+                for (int r = 0; r < kHiRM; ++r) a[r] = *reinterpret_cast<const uint4*>(ga + r * a_row + 8 * half + 4 * h);
+#pragma unroll
+                for (int c = 0; c < kHiQM; ++c) b[c] = *reinterpret_cast<const uint4*>(gb + c * b_row32 + 8 * half + 4 * h);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                    for (int r = 0; r < kHiRM; ++r) {
+                        const uint32_t av = j == 0 ? a[r].x : j == 1 ? a[r].y : j == 2 ? a[r].z : a[r].w;
+#pragma unroll
+                        for (int c = 0; c < kHiQM; ++c) {
+                            const uint32_t bv = j == 0 ? b[c].x : j == 1 ? b[c].y : j == 2 ? b[c].z : b[c].w;
+                            const uint32_t m = min(av, bv);
+                            if (COUNT_ZERO) zero[r][c] += m >> kHllIntW;            // lo == 0 here: 2^28 <=> both registers empty
+                            acc[r][c] = (h == 0 && j == 0) ? m : mad_one(m, one, acc[r][c]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kHiRM; ++r)
+#pragma unroll
+                for (int c = 0; c < kHiQM; ++c) {
+                    sum[r][c] += (uint64_t)acc[r][c];
+                }
+        }
+    }
+}
+
+template <int kHiRM>
+__global__ void __launch_bounds__(kHllThreads, HiShape<kHiRM>::kMinBlocks) dist_hll_int_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk, uint32_t one) {
+    constexpr int kHiTR = HiShape<kHiRM>::kTR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_zero[2][2];                    // [chunk parity][ref, qry]: an empty register was staged
+    __shared__ uint32_t s_lo;
+    __shared__ unsigned char s_flag[kHiTR + kHiTQ];    // sketch has a register above the tile's window
+    const uint32_t stride = hll_int_stride(chunk);        // u32 per staged row (20-word groups + 16 B pad)
+    uint32_t* sa = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* sb = sa + (size_t)kHiTR * stride;
+
+    const uint64_t row0 = dp.row_begin + (uint64_t)blockIdx.y * kHiTR;
+    const uint64_t col0 = (uint64_t)blockIdx.x * kHiTQ;
+    if (row0 >= dp.row_end) return;
+    const uint64_t row_hi = min(row0 + kHiTR, dp.row_end);
+    if (dp.triangular && col0 > row_hi - 1) return;      // tile entirely above the diagonal
+
+    const uint32_t wy = threadIdx.x >> 5, tx = threadIdx.x & 31u;
+    const unsigned char* gref = reinterpret_cast<const unsigned char*>(dp.ref);
+    const unsigned char* gqry = reinterpret_cast<const unsigned char*>(dp.qry);
+    const uint32_t chunk_words = chunk / 4;
+    const uint32_t g_shift = 31u - __clz(chunk_words) - 2u, cell_shift = 31u - __clz(cell_bytes);
+
+    // the tile's window: lo = smallest register of its sketches; flag the sketches that reach above lo + 28
+    if (threadIdx.x == 0) s_lo = 0xffu;
+    if (threadIdx.x < 2) s_zero[0][threadIdx.x] = 0u;
+    __syncthreads();
+    uint32_t my_mm = 0xff00ffu;   // min 255, max 0 ... rows past the end: never flagged, never lower the minimum
+    if (threadIdx.x < kHiTR) {
+        if (row0 + threadIdx.x < dp.row_end) my_mm = dp.hll_mm_ref[row0 + threadIdx.x];
+    } else if (threadIdx.x < kHiTR + kHiTQ) {
+        if (col0 + (threadIdx.x - kHiTR) < dp.n_qry) my_mm = dp.hll_mm_qry[col0 + (threadIdx.x - kHiTR)];
+    }
+    if (threadIdx.x < kHiTR + kHiTQ) {
+        const uint32_t wmin = __reduce_min_sync(0xffffffffu, my_mm & 0xffu);
+        if (tx == 0) atomicMin(&s_lo, wmin);
+    }
+    __syncthreads();
+    const uint32_t lo = s_lo;
+    if (threadIdx.x < kHiTR + kHiTQ) s_flag[threadIdx.x] = ((my_mm >> 8) & 0xffu) > lo + (uint32_t)kHllIntW ? 1 : 0;
+
+    uint64_t sum[kHiRM][kHiQM];
+    uint32_t zero[kHiRM][kHiQM];
+#pragma unroll
+    for (int r = 0; r < kHiRM; ++r)
+#pragma unroll
+        for (int c = 0; c < kHiQM; ++c) sum[r][c] = 0ull, zero[r][c] = 0u;
+
+    uint32_t par = 0;
+    for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk, par ^= 1u) {
+        __syncthreads();  // previous chunk consumed; s_zero[par] was cleared during the previous staging pass (or above)
+        if (threadIdx.x < 2) s_zero[par ^ 1u][threadIdx.x] = 0u;
+        bool za = false, zb = false;
+        for (uint32_t e = threadIdx.x; e < ((uint32_t)kHiTR << g_shift); e += kHllThreads) {
+            const uint32_t r = e >> g_shift, g = e & ((1u << g_shift) - 1u);
+            const uint64_t gi = row0 + r;
+            const uint4 v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint4*>(gref + (gi << cell_shift) + c0) + g)
+                                            : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            za |= has_zero_byte(v.x) | has_zero_byte(v.y) | has_zero_byte(v.z) | has_zero_byte(v.w);
+            uint4* dst = reinterpret_cast<uint4*>(sa + r * stride + kHllIntGroup * g);
+            dst[0] = hll_int_recode(v.x, lo);
+            dst[1] = hll_int_recode(v.y, lo);
+            dst[2] = hll_int_recode(v.z, lo);
+            dst[3] = hll_int_recode(v.w, lo);
+        }
+        for (uint32_t e = threadIdx.x; e < ((uint32_t)kHiTQ << g_shift); e += kHllThreads) {
+            const uint32_t r = e >> g_shift, g = e & ((1u << g_shift) - 1u);
+            const uint64_t gj = col0 + r;
+            const uint4 v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint4*>(gqry + (gj << cell_shift) + c0) + g)
+                                          : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            zb |= has_zero_byte(v.x) | has_zero_byte(v.y) | has_zero_byte(v.z) | has_zero_byte(v.w);
+            uint4* dst = reinterpret_cast<uint4*>(sb + r * stride + kHllIntGroup * g);
+            dst[0] = hll_int_recode(v.x, lo);
+            dst[1] = hll_int_recode(v.y, lo);
+            dst[2] = hll_int_recode(v.z, lo);
+            dst[3] = hll_int_recode(v.w, lo);
+        }
+        if (za) s_zero[par][0] = 1u;
+        if (zb) s_zero[par][1] = 1u;
+        __syncthreads();
+        const uint32_t* pa = sa + (wy * kHiRM) * stride;
+        const uint32_t* pb = sb + tx * stride;
+        if (s_zero[par][0] & s_zero[par][1])  // CTA-uniform; an empty register anywhere means lo == 0
+            hll_int_chunk<true, 0, kHiRM>(sum, zero, pa, pb, stride, chunk, one);
+        else if (chunk == (uint32_t)kHiChunk)
+            hll_int_chunk<false, (int)hll_int_stride(kHiChunk), kHiRM>(sum, zero, pa, pb, stride, chunk, one);
+        else
+            hll_int_chunk<false, 0, kHiRM>(sum, zero, pa, pb, stride, chunk, one);
+    }
+
+    // epilogue: identical to dist_kernel<HllAcc> once the sum is back in f64 (exact: < 2^53, times a power of two)
+    const double scale = __hiloint2double((int)((1023u - (uint32_t)kHllIntW - lo) << 20), 0);
+#pragma unroll
+    for (int a = 0; a < kHiRM; ++a) {
+#pragma unroll
+        for (int b = 0; b < kHiQM; ++b) {
+            const uint64_t i = row0 + wy * kHiRM + a, j = col0 + tx + 32 * b;
+            if (i >= dp.row_end || j >= dp.n_qry) continue;
+            if (dp.triangular && j > i) continue;
+            double sm = (double)sum[a][b] * scale;
+            uint32_t zr = zero[a][b];
+            if (s_flag[wy * kHiRM + a] | s_flag[kHiTR + tx + 32 * b])
+                hll_pair_exact(gref + (i << cell_shift), gqry + (j << cell_shift), cell_bytes, sm, zr);
+            bool bias;
+            const double U = hll_len(sm, zr, dp.p, &bias);
+            if (bias && dp.flags) atomicAdd(dp.flags, 1u);
+            const double ca = dp.card_ref[i], cb = dp.card_qry[j];
+            const double sim = (ca + cb - U) / U;
+            const double s = fmax(sim, 0.0);  // f64::max: NaN -> 0 (utils.rs:362)
+            const double frac = 2.0 * s / (1.0 + s);
+            const uint64_t o = dp.packed_tri ? (i * (i + 1) / 2 + j) : ((i - dp.out_row0) * dp.n_qry + j);
+            if (dp.fp32)
+                reinterpret_cast<float*>(dp.out)[o] = mash_distance_f32((float)frac, dp.k, dp.model);
+            else
+                reinterpret_cast<double*>(dp.out)[o] = mash_distance_f64(frac, dp.k, dp.model);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4m: HyperMinHash distance tiles (hmh_distance inner loop, utils.rs:150-180; hyperminhash similarity()).
 //
 // Per pair, over the 16384 u16 registers:  C = #{a == b and a != 0},  N = #{a != 0 or b != 0}  -- integers, so any
@@ -1294,6 +1539,38 @@ static cudaError_t launch_dist_hll_fast(const DistParams& dp, cudaStream_t st) {
     return cudaSuccess;
 }
 
+template <int RM>
+static cudaError_t launch_dist_hll_int_t(const DistParams& dp, uint32_t cb, uint32_t chunk, uint64_t gx, cudaStream_t st) {
+    constexpr int TR = HiShape<RM>::kTR;
+    const size_t smem = (size_t)(TR + kHiTQ) * hll_int_stride(chunk) * 4;
+    cudaError_t e = cudaFuncSetAttribute(dist_hll_int_kernel<RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint64_t gy = (dp.row_end - dp.row_begin + TR - 1) / TR;
+    for (uint64_t y0 = 0; y0 < gy; y0 += 65535) {  // grid.y is limited to 65535: walk row bands
+        DistParams q = dp;
+        q.row_begin = dp.row_begin + y0 * TR;
+        const uint64_t ny = (gy - y0) < 65535 ? (gy - y0) : 65535;
+        dist_hll_int_kernel<RM><<<dim3((unsigned)gx, (unsigned)ny), kHllThreads, smem, st>>>(q, cb, chunk, 1u);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+static cudaError_t launch_dist_hll_int(const DistParams& dp, cudaStream_t st) {
+    const uint32_t cb = cell_bytes_of(dp.algo, dp.p);
+    const uint32_t chunk = cb < (uint32_t)kHiChunk ? cb : (uint32_t)kHiChunk;
+    const uint64_t rows = dp.row_end - dp.row_begin;
+    uint64_t ncols = dp.n_qry;
+    if (dp.triangular && dp.row_end < ncols) ncols = dp.row_end;  // nothing right of the diagonal
+    const uint64_t gx = (ncols + kHiTQ - 1) / kHiTQ;
+    // 64 x 64 tiles once they fill the GPU's 2 x n_sm resident slots about four times over (the triangle keeps half of them)
+    uint64_t tiles8 = gx * ((rows + HiShape<8>::kTR - 1) / HiShape<8>::kTR);
+    if (dp.triangular) tiles8 /= 2;
+    static const int force = [] { const char* v = getenv("LASH_HLL_INT_RM"); return v ? atoi(v) : 0; }();   // A/B measurements
+    const bool big = force ? force == 8 : tiles8 >= 8ull * (uint64_t)dp.n_sm;
+    return big ? launch_dist_hll_int_t<8>(dp, cb, chunk, gx, st) : launch_dist_hll_int_t<4>(dp, cb, chunk, gx, st);
+}
+
 static cudaError_t launch_dist_hmh_fast(const DistParams& dp, cudaStream_t st) {
     const uint64_t rows = dp.row_end - dp.row_begin;
     const uint64_t gy = (rows + kHmhTR - 1) / kHmhTR;
@@ -1365,7 +1642,17 @@ cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launc
     }();
     // K4h stages with 16-byte loads: register arrays that are not 16-byte aligned (a caller's odd device pointer) use K4
     const bool hll_aligned = (((uintptr_t)dp.ref | (uintptr_t)dp.qry) & 15u) == 0;
-    if (dp.algo == HLL) return (hll_table || !hll_aligned) ? launch_dist_t<HllAcc, 16>(dp, st) : launch_dist_hll_fast(dp, st);
+    // LASH_HLL_KERNEL=float selects K4h (f64 adds in register order); default K4i (32-bit fixed point, needs the per-sketch
+    // min / max the API computes before the launch; 16-register rows as the 16-byte staging loads)
+    static const bool hll_float = [] {
+        const char* v = getenv("LASH_HLL_KERNEL");
+        return v && std::string(v) == "float";
+    }();
+    if (dp.algo == HLL) {
+        if (hll_table || !hll_aligned) return launch_dist_t<HllAcc, 16>(dp, st);
+        if (hll_float || !dp.hll_mm_ref || !dp.hll_mm_qry) return launch_dist_hll_fast(dp, st);
+        return launch_dist_hll_int(dp, st);
+    }
     // LASH_HMH_KERNEL=generic selects K4 for A/B measurements; K4m stages with 16-byte loads like K4h
     static const bool hmh_generic = [] {
         const char* v = getenv("LASH_HMH_KERNEL");

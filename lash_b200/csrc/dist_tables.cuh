@@ -233,4 +233,25 @@ __device__ __forceinline__ uint4 hll_recode(uint32_t w) {
 // any zero byte in w?  (exact for all byte values)
 __device__ __forceinline__ bool has_zero_byte(uint32_t w) { return ((w - 0x01010101u) & ~w & 0x80808080u) != 0u; }
 
+// ---- K4i: HLL registers as 32-bit fixed-point terms -------------------------------------------------------------------
+// With `lo` = the smallest register of the sketches a tile touches, register r becomes the INTEGER
+//     v(r) = 2^(kHllIntW - (r - lo))   for lo <= r <= lo + kHllIntW,   0 for larger r   ("out of window"),
+// so min(v(ra), v(rb)) = v(max(ra, rb)) and the pair's  sum 2^-max  is  2^-(lo + kHllIntW) * (sum of the minima), an integer
+// sum.  When no register of either sketch is out of the window, every term of the reference's sequential f64 loop is a
+// multiple of u = 2^-(lo + 28) and every PARTIAL sum is n * u with n <= 2^p * 2^28 <= 2^46 < 2^53: the f64 loop never
+// rounds, so its result IS the exact sum, in any order, and equals the integer sum scaled by a power of two
+// (tests/test_device_math.py checks this against sequential double sums).  Sketches with an out-of-window register are
+// flagged per tile (per-sketch min / max, hll_minmax_kernel) and their pairs take the sequential f64 path.
+// kHllIntBatch minima are added in a 32-bit register before they go into the 64-bit sum: 8 * 2^28 = 2^31 cannot overflow.
+constexpr int kHllIntW = 28;
+constexpr int kHllIntBatch = 8;
+// bytes of w minus lo (no byte of w is below lo, so there is no borrow between the bytes)
+__device__ __forceinline__ uint32_t hll_int_rebase(uint32_t w, uint32_t lo) { return w - lo * 0x01010101u; }
+// one rebased register byte -> v:  2^28 >> min(d, 32)
+__device__ __forceinline__ uint32_t hll_int_term(uint32_t d) { return __funnelshift_rc(1u << kHllIntW, 0u, d); }
+__device__ __forceinline__ uint4 hll_int_recode(uint32_t w, uint32_t lo) {
+    const uint32_t d = hll_int_rebase(w, lo);
+    return make_uint4(hll_int_term(d & 0xffu), hll_int_term((d >> 8) & 0xffu), hll_int_term((d >> 16) & 0xffu), hll_int_term(d >> 24));
+}
+
 }  // namespace lash

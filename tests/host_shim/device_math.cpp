@@ -25,6 +25,10 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {  
     s &= 31u;
     return s ? (lo >> s) | (hi << (32u - s)) : lo;
 }
+static inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t s) {  // low word of (hi:lo) >> min(s, 32)
+    s = s > 32u ? 32u : s;
+    return s == 32u ? hi : s ? (lo >> s) | (hi << (32u - s)) : lo;
+}
 static inline uint32_t __brev(uint32_t x) {
     x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
     x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
@@ -196,6 +200,35 @@ void dm_hll_recode(uint32_t w, uint32_t* out4, int* zero_byte) {
     const uint4 v = hll_recode(w);
     out4[0] = v.x; out4[1] = v.y; out4[2] = v.z; out4[3] = v.w;
     *zero_byte = has_zero_byte(w) ? 1 : 0;
+}
+
+// ---- K4i: HLL registers as 32-bit fixed-point terms; the pair sum as the tile kernel forms it --------------------------
+void dm_hll_int_recode(uint32_t w, uint32_t lo, uint32_t* out4) {
+    const uint4 v = hll_int_recode(w, lo);
+    out4[0] = v.x; out4[1] = v.y; out4[2] = v.z; out4[3] = v.w;
+}
+// sum of 2^-max(a[i], b[i]) over n registers (n a multiple of 8) through recode -> min -> 32-bit batches of kHllIntBatch ->
+// 64-bit sum -> double scaled by 2^-(lo + kHllIntW); *zero = both-empty count the way the COUNT_ZERO loop takes it (lo == 0)
+double dm_hll_int_pair_sum(const uint8_t* a, const uint8_t* b, uint32_t n, uint32_t lo, uint32_t* zero) {
+    uint64_t sum = 0;
+    uint32_t z = 0;
+    for (uint32_t e = 0; e < n; e += kHllIntBatch) {
+        uint32_t acc = 0;
+        for (uint32_t i = 0; i < (uint32_t)kHllIntBatch; i += 4) {
+            uint32_t wa, wb;
+            __builtin_memcpy(&wa, a + e + i, 4);
+            __builtin_memcpy(&wb, b + e + i, 4);
+            const uint4 va = hll_int_recode(wa, lo), vb = hll_int_recode(wb, lo);
+            const uint32_t m[4] = {min(va.x, vb.x), min(va.y, vb.y), min(va.z, vb.z), min(va.w, vb.w)};
+            for (int j = 0; j < 4; ++j) {
+                acc += m[j];   // 32-bit, as the kernel's batch register
+                z += m[j] >> kHllIntW;
+            }
+        }
+        sum += acc;
+    }
+    *zero = z;
+    return (double)sum * __builtin_ldexp(1.0, -(int)(lo + kHllIntW));
 }
 
 uint32_t dm_ull_cell_to_reg(uint32_t w0, uint32_t w1, int p) { return ull_cell_to_reg(w0, w1, p); }

@@ -519,6 +519,53 @@ def test_hll_recoded_registers_are_high_words_of_powers_of_two(dm):
         assert bool(z.value) == any(((int(w) >> (8 * i)) & 0xff) == 0 for i in range(4)), hex(int(w))
 
 
+def test_hll_fixed_point_terms_and_exact_pair_sums(dm):
+    """K4i (dist_tables.cuh: hll_int_recode): v(r) = 2^(28 - (r - lo)) inside the window, 0 above it; min of two terms is the
+    term of the larger register; and for registers inside the window the integer sum, scaled, equals the reference's
+    sequential f64 loop bit for bit (no partial sum of that loop rounds) -- including batches that hold eight copies of the
+    largest term, and the both-empty count when lo = 0."""
+    dm.dm_hll_int_recode.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+    dm.dm_hll_int_pair_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    dm.dm_hll_int_pair_sum.restype = C.c_double
+    out = np.zeros(4, dtype=np.uint32)
+    for lo in (0, 1, 5, 23, 200):
+        v = np.zeros(256, dtype=np.uint64)
+        for r in range(lo - lo % 4, 256, 4):
+            rr = [max(r + i, lo) for i in range(4)]             # bytes below lo never occur (lo is the minimum)
+            w = rr[0] | (rr[1] << 8) | (rr[2] << 16) | (rr[3] << 24)
+            dm.dm_hll_int_recode(w, lo, _p(out))
+            for i in range(4):
+                v[rr[i]] = out[i]
+        for r in range(lo, 256):
+            assert int(v[r]) == ((1 << (28 - (r - lo))) if r - lo <= 28 else 0), (lo, r, int(v[r]))
+        a, b = np.meshgrid(np.arange(lo, 256), np.arange(lo, 256))
+        assert np.array_equal(np.minimum(v[a], v[b]), v[np.maximum(a, b)])
+    rng = np.random.default_rng(11)
+    z = C.c_uint32(0)
+    for p, lo, shape in ((14, 4, "genome"), (14, 0, "small"), (18, 2, "genome"), (10, 7, "flat"), (14, 3, "all-lo")):
+        m = 1 << p
+        for _ in range(3):
+            if shape == "genome":
+                regs = np.clip(np.floor(lo + 4.5 - np.log2(-np.log(rng.random((2, m))))), lo, lo + 28).astype(np.uint8)
+            elif shape == "small":
+                regs = (rng.random((2, m)) < 0.3) * np.clip(rng.geometric(0.5, size=(2, m)), 1, 28).astype(np.uint8)
+            elif shape == "flat":
+                regs = rng.integers(lo, lo + 29, size=(2, m)).astype(np.uint8)
+            else:
+                regs = np.full((2, m), lo, dtype=np.uint8)
+            regs = np.ascontiguousarray(regs, dtype=np.uint8)
+            assert regs.min() >= lo
+            regs[0, 0] = lo                                        # the window is anchored at the smallest register present
+            got = dm.dm_hll_int_pair_sum(_p(regs[0]), _p(regs[1]), m, lo, C.byref(z))
+            mx = np.maximum(regs[0], regs[1])
+            seq = 0.0
+            for t in (2.0 ** -mx.astype(np.float64)):             # the reference's loop: sequential f64 adds in register order
+                seq += t
+            assert got == seq, (p, lo, shape, got, seq)
+            if lo == 0:
+                assert z.value == int((mx == 0).sum())
+
+
 @pytest.mark.parametrize("p,k,drop4", [(10, 16, 1), (10, 12, 1), (14, 21, 0), (8, 31, 1), (12, 16, 0)])
 def test_cpu_emulation_of_the_ull_sketch_path_end_to_end(dm, oracle, p, k, drop4):
     """The arithmetic of the sketch kernel's ULL path chained on the CPU, piece by piece as the kernel does it:

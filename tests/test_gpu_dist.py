@@ -402,6 +402,36 @@ def test_hll_recoded_kernel_ragged_tiles_and_mixed_empties(oracle, gpu_ctx, p, n
     np.testing.assert_array_equal(tri, dense[np.tril_indices(len(sq))])
 
 
+@pytest.mark.parametrize("p,n", [(5, 150), (7, 150), (12, 150), (14, 150), (7, 2300)])
+def test_hll_fixed_point_kernel_is_bit_identical_in_and_out_of_its_window(oracle, gpu_ctx, p, n):
+    """K4i sums min(v(ra), v(rb)) in integers, exact while every register lies within 29 levels of the tile's smallest one;
+    sketches that reach above the window are flagged per tile and their pairs redone by the sequential f64 loop.  Without
+    empty registers the estimate is alpha*m^2/sum -- no libm call -- so `frac` must equal the oracle's BIT FOR BIT on every
+    pair: in-window sketches (several tiles, ragged edges), sketches with a planted register just inside (lo + 28), just
+    outside (lo + 29) and far outside the window, a sketch that lowers the window of its tiles, and all of them again as
+    query columns.  n = 2300 is large enough for the launcher to pick the 64 x 64 tile shape (8 rows per thread)."""
+    rng = np.random.default_rng(p)
+    m = 1 << p
+    regs = np.clip(np.floor(9.0 - np.log2(-np.log(rng.random((n, m))))) + 1, 6, 30).astype(np.uint8)
+    lo = int(regs.min())
+    assert lo == 6
+    regs[:, 0] = lo                          # every sketch touches the minimum: the window of every tile is [6, 34]
+    regs[3, 5] = lo + 28                     # last level inside
+    regs[40, 9] = lo + 29                    # first level outside -> flagged
+    regs[41, m - 1] = 64 - p + 1             # the largest register HLL can hold
+    regs[100, 17] = lo + 33
+    regs[120, :] = np.clip(regs[120].astype(np.int64) - 4, 2, 255).astype(np.uint8)   # lowers lo to 2 in its tiles -> neighbours flagged there
+    regs[n - 1, 3] = lo + 31
+    for ref, qry in ((regs, regs), (regs[30:75], regs[90:])):
+        exp = oracle.dist(ALGO_HLL, p, 21, 0, 2, False, ref, qry, threads=8)
+        got, w = ops.dist(gpu_ctx, ALGO_HLL, p, 21, 0, 2, False, ref, qry)
+        assert w == 0
+        np.testing.assert_array_equal(got, exp)
+    tri, _ = ops.dist(gpu_ctx, ALGO_HLL, p, 21, 0, 2, False, regs, regs, triangular=True)
+    full, _ = ops.dist(gpu_ctx, ALGO_HLL, p, 21, 0, 2, False, regs, regs)
+    np.testing.assert_array_equal(tri, full[np.tril_indices(n)])
+
+
 @pytest.mark.parametrize("n_ref,n_qry", [(5, 9), (37, 101), (70, 33)])
 def test_hmh_word_kernel_ragged_tiles_and_mixed_empties(oracle, gpu_ctx, n_ref, n_qry, monkeypatch):
     """K4m (two u16 registers per 32-bit word, C = N - NZ, N counted only in chunks where both sides hold an empty
