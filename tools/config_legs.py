@@ -1,7 +1,7 @@
 """BASELINE.json configs[2..4] as legs of bench.py (any N; the driver's SCALE run shows them at N = 1, 2, 4, 8).
 
   C3  HLL p=14 k=21 sketch of 10,000 synthetic 5 Mbp genomes sharded across the ranks (shard.genome_shards), then the
-      row-sharded poisson all-vs-all (dist_hll_fast_kernel)                       -- src/utils.rs:449-510, 342-370
+      row-sharded poisson all-vs-all (dist_hll_int_kernel)                        -- src/utils.rs:449-510, 342-370
   C4  ONE sample of 100 Gbp of 150 bp reads split across the ranks (read groups), every rank sketches its share into a
       ULL p=14 accumulator, NCCL all-gather of world x 2^14 B, lash_sketch_merge_dev (UltraLogLog::merge, utils.rs:260)
   C5  100k x 100k ULL p=10, ML estimator, --dm shape: row ranges per rank, lash_dist_stream_rows -> pinned host blocks
@@ -249,7 +249,7 @@ def leg_c3(env: Env, n_total=10_000, length=5_000_000, steps=3):
            "step_ms_rank0": step_ms, "sketch_kernel_ms": sk_kernel, "sketch_kernel_gbp_per_s_per_gpu": sk_gbps,
            "register_merges_per_s": n_pairs * rb / (di_ms * 1e-3),
            "roofline_sketch_kernel": env.issue_frac("sketch_kernel<HLL,wide,smem>", len(mine) * (length - K + 1) / (sk_kernel * 1e-3)),
-           "roofline_dist_hll_fast_kernel": env.issue_frac("dist_hll_fast_kernel", shard.pair_count(rows, n_total, True) * rb / (di_ms * 1e-3)),
+           "roofline_dist_hll_int_kernel": env.issue_frac("dist_hll_int_kernel", shard.pair_count(rows, n_total, True) * rb / (di_ms * 1e-3)),
            "registers_hash": f"{rhash:016x}", "dist_checksum": f"{dsum:016x}", "dist_cells": dcells,
            "hll_bias_flags": int(flags.item()), "parity": parity}
     sk.close()

@@ -98,7 +98,7 @@ def main():
         dist_case(ctx, "dist_fgra_tab_kernel@n=1000", ["dist_fgra_tab_kernel"], ALGO_ULL, 10, 16, EST_FGRA, np.tile(regs_ull, (3, 1))[:1000], 1)
         dist_case(ctx, "dist_fgra_tab_kernel", ["dist_fgra_tab_kernel"], ALGO_ULL, 10, 16, EST_FGRA, regs_small, 1)
         dist_case(ctx, "dist_ml_tab_kernel+ml_finish_kernel", ["dist_ml_tab_kernel", "ml_finish_kernel"], ALGO_ULL, 10, 16, EST_ML, regs_small, 2)
-        dist_case(ctx, "dist_hll_fast_kernel", ["dist_hll_fast_kernel"], ALGO_HLL, 14, 21, 0, np.tile(regs_hll, (5, 1)), 1)
+        dist_case(ctx, "dist_hll_int_kernel", ["dist_hll_int_kernel"], ALGO_HLL, 14, 21, 0, np.tile(regs_hll, (10, 1)), 1)
         dist_case(ctx, "dist_hmh_fast_kernel", ["dist_hmh_fast_kernel"], ALGO_HMH, 14, 16, 0, np.tile(regs_hmh, (5, 1)), 1)
 
 

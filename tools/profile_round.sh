@@ -14,7 +14,7 @@ NCU="ncu --clock-control none"
 B="python bench.py --genomes 400 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ingest --legs ''"
 M="smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,launch__registers_per_thread,launch__grid_size"
 eval $NCU --metrics gpu__time_duration.sum -k regex:"'sketch_kernel|dist_|ml_finish|card_|regmin|build_invalid|merge_kernel|text_|out_checksum|nccl'" -c 400 --csv --log-file $out/${tag}_launches.csv $B > $out/${tag}_launches.log 2>&1
-$NCU --metrics $M -k regex:'sketch_kernel|build_invalid_mask|dist_kernel|dist_fgra_tab|dist_ml_tab|ml_finish|dist_hll_fast|dist_hmh_fast|text_' --csv --page raw --log-file $out/${tag}_kernels_raw.csv python -m tools.profile_kernels $out/${tag}_manifest.jsonl > $out/${tag}_kernels.log 2>&1
+$NCU --metrics $M -k regex:'sketch_kernel|build_invalid_mask|dist_kernel|dist_fgra_tab|dist_ml_tab|ml_finish|dist_hll_fast|dist_hll_int|dist_hmh_fast|text_' --csv --page raw --log-file $out/${tag}_kernels_raw.csv python -m tools.profile_kernels $out/${tag}_manifest.jsonl > $out/${tag}_kernels.log 2>&1
 python -m tools.kernel_costs $out/${tag}_manifest.jsonl $out/${tag}_kernels_raw.csv profiles/${tag}_kernels_raw.csv $out/${tag}_kernel_costs.json >> $out/${tag}_kernels.log 2>&1
 if [ -z "$SKIP_FULL" ]; then
 eval $NCU --set full --import-source on -k regex:sketch_kernel --launch-skip 3 -c 1 -f -o /tmp/${tag}_sketch $B > $out/${tag}_ncu1.log 2>&1
