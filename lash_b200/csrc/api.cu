@@ -810,19 +810,25 @@ static int check_dist_args(int algo, int p, int k, int estimator, int model, uin
 // smallest non-empty register of both sets, for the FGRA pair-table kernel (dist_kernels.cu)
 static int prepare_regmin(lash_ctx* ctx, DistParams& dp, size_t rb, cudaStream_t st) {
     dp.n_sm = ctx->n_sm;
-    if (dp.algo == LASH_ALGO_HLL) {
-        // K4i's windows: smallest / largest register of every sketch (16-byte staging: p >= 4 always gives 16-register rows)
-        dp.hll_mm_ref = dp.hll_mm_qry = nullptr;
-        if ((((uintptr_t)dp.ref | (uintptr_t)dp.qry) & 15u) != 0 || rb % 16 != 0) return LASH_OK;
-        const bool same = dp.qry == dp.ref && dp.n_qry == dp.n_ref;
-        if (ctx->d_hll_mm.reserve(4 * (dp.n_ref + (same ? 0 : dp.n_qry))) != cudaSuccess) { cudaGetLastError(); return LASH_OK; }
-        uint32_t* mm = (uint32_t*)ctx->d_hll_mm.p;
-        CU(launch_hll_minmax(dp.ref, dp.n_ref, (uint32_t)rb, mm, st));
-        if (!same) CU(launch_hll_minmax(dp.qry, dp.n_qry, (uint32_t)rb, mm + dp.n_ref, st));
-        ctx->dist_launches += same ? 1 : 2;
-        dp.hll_mm_ref = mm;
-        dp.hll_mm_qry = same ? mm : mm + dp.n_ref;
-        return LASH_OK;
+    dp.reg_mm_ref = dp.reg_mm_qry = nullptr;
+    static const bool ml_table = [] { const char* v = getenv("LASH_ML_S"); return v && std::string(v) == "table"; }();   // A/B
+    if (dp.algo == LASH_ALGO_HLL || (dp.algo == LASH_ALGO_ULL && dp.estimator == LASH_EST_ML && !ml_table)) {
+        // K4i's windows / K4c's G-sum tiles: smallest and largest register of every sketch (16-byte loads: aligned arrays of
+        // sketches of >= 16 registers)
+        if ((((uintptr_t)dp.ref | (uintptr_t)dp.qry) & 15u) == 0 && rb % 16 == 0) {
+            const bool same = dp.qry == dp.ref && dp.n_qry == dp.n_ref;
+            if (ctx->d_hll_mm.reserve(4 * (dp.n_ref + (same ? 0 : dp.n_qry))) == cudaSuccess) {
+                uint32_t* mm = (uint32_t*)ctx->d_hll_mm.p;
+                CU(launch_hll_minmax(dp.ref, dp.n_ref, (uint32_t)rb, mm, st));
+                if (!same) CU(launch_hll_minmax(dp.qry, dp.n_qry, (uint32_t)rb, mm + dp.n_ref, st));
+                ctx->dist_launches += same ? 1 : 2;
+                dp.reg_mm_ref = mm;
+                dp.reg_mm_qry = same ? mm : mm + dp.n_ref;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (dp.algo == LASH_ALGO_HLL) return LASH_OK;
     }
     if (dp.algo != LASH_ALGO_ULL) return LASH_OK;
     CU(ctx->d_regmin.reserve(8));

@@ -162,14 +162,15 @@ __device__ __forceinline__ double finish_union(FgraAcc& a, int p, const void* ga
 template <int NPL>
 __device__ __forceinline__ double finish_union(MlAccT<NPL>& a, int p, const void* ga, const void* gb, bool* bias) {
     *bias = false;
-    // W = (4|w) << k fits 32 bits iff k <= 29, i.e. merged register < 4p+4 + 4*30
-    if (a.mmax >= (uint32_t)(4 * p + 4 + 120))
+    // W = (4|w) << k fits 32 bits iff k <= 29, i.e. merged register < 4p+4 + 4*30 (mmax >= 256: a G-sum tile's marker)
+    if (a.mmax >= (uint32_t)(4 * p + 4 + 120) && a.mmax < kMlGsMarker)
         return ml_exact_pair(reinterpret_cast<const uint8_t*>(ga), reinterpret_cast<const uint8_t*>(gb), p);
     int bb[66];
     ml_counts_from_planes(a, bb);
     const uint8_t* pa = reinterpret_cast<const uint8_t*>(ga);
     const uint8_t* pb = reinterpret_cast<const uint8_t*>(gb);
-    return ull_ml_finalize(a.S, bb, p, ull_merge1(pa[0], pb[0]));
+    const uint64_t S = a.mmax >= kMlGsMarker ? ml_gs_S(a.S, bb, p, a.mmax & 0xffu) : a.S;   // G-sum tiles of dist_ml_tab_kernel
+    return ull_ml_finalize(S, bb, p, ull_merge1(pa[0], pb[0]));
 }
 
 template <class ACC>
@@ -588,9 +589,9 @@ __global__ void __launch_bounds__(kHllThreads, HiShape<kHiRM>::kMinBlocks) dist_
     __syncthreads();
     uint32_t my_mm = 0xff00ffu;   // min 255, max 0 ... rows past the end: never flagged, never lower the minimum
     if (threadIdx.x < kHiTR) {
-        if (row0 + threadIdx.x < dp.row_end) my_mm = dp.hll_mm_ref[row0 + threadIdx.x];
+        if (row0 + threadIdx.x < dp.row_end) my_mm = dp.reg_mm_ref[row0 + threadIdx.x];
     } else if (threadIdx.x < kHiTR + kHiTQ) {
-        if (col0 + (threadIdx.x - kHiTR) < dp.n_qry) my_mm = dp.hll_mm_qry[col0 + (threadIdx.x - kHiTR)];
+        if (col0 + (threadIdx.x - kHiTR) < dp.n_qry) my_mm = dp.reg_mm_qry[col0 + (threadIdx.x - kHiTR)];
     }
     if (threadIdx.x < kHiTR + kHiTQ) {
         const uint32_t wmin = __reduce_min_sync(0xffffffffu, my_mm & 0xffu);
@@ -1041,7 +1042,7 @@ __global__ void __launch_bounds__(256, 4) ml_finish_kernel(DistParams dp, uint32
 // memory) cannot cover the dependent FP64 divide chains of the secant solver, and the main loop cannot overlap them.
 template <int NPL, bool SPLIT>
 __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk,
-                                                                       uint32_t tiles_x, uint32_t tiles_y) {
+                                                                       uint32_t tiles_x, uint32_t tiles_y, uint32_t one) {
     __shared__ uint32_t s_tile;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // three planes of 32-bit words (R low, R high, W), all indexed by the same (row, column) byte offset and read with
@@ -1053,8 +1054,10 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
     const uint32_t a_stride = chunk + 4;   // u32 per reference row
     const uint32_t b_stride = chunk + 8;   // u16 per query row
     uint32_t* sa = W + kTabN * kTabN;
-    uint16_t* sb = reinterpret_cast<uint16_t*>(sa + (size_t)kMlTabTR * a_stride);
+    uint32_t* sga = sa + (size_t)kMlTabTR * a_stride;                                 // G terms of the reference rows (G-sum tiles)
+    uint16_t* sb = reinterpret_cast<uint16_t*>(sga + (size_t)kMlTabTR * a_stride);
     uint32_t* sflag = reinterpret_cast<uint32_t*>(sb + (size_t)kMlTabTQ * b_stride);  // [TR + TQ] "has a register outside the table"
+    __shared__ uint32_t s_lo;                                                         // smallest register of the tile's sketches
 
     const int p = dp.p;
     const uint32_t base = (uint32_t)(4 * p - 4);
@@ -1078,7 +1081,32 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
     const uint64_t col0 = (tile % tiles_x) * kMlTabTQ;
     const uint64_t row_hi = min(row0 + kMlTabTR, dp.row_end);
     if (dp.triangular && col0 > row_hi - 1) continue;  // tile entirely above the diagonal (CTA-uniform)
-    if (threadIdx.x < kMlTabTR + kMlTabTQ) sflag[threadIdx.x] = 0u;  // ordered before the staging by its first barrier
+    // G-sum tile (dist_tables.cuh): every register of every sketch of the tile has r2 >= 0, i.e. the smallest one is >= 4p + 4;
+    // sketches reaching above k = 27 are flagged like those outside the table
+    bool gs = false;
+    uint32_t k0 = 0;
+    if (dp.reg_mm_ref) {
+        __syncthreads();                      // the previous tile's epilogue has read sflag
+        if (threadIdx.x == 0) s_lo = 0xffu;
+        __syncthreads();
+        uint32_t mm = 0x00ffu;            // past the end (and threads beyond the tile's 80 sketches): min 255, max 0
+        if (threadIdx.x < kMlTabTR) {
+            if (row0 + threadIdx.x < dp.row_end) mm = dp.reg_mm_ref[row0 + threadIdx.x];
+        } else if (threadIdx.x < kMlTabTR + kMlTabTQ) {
+            if (col0 + (threadIdx.x - kMlTabTR) < dp.n_qry) mm = dp.reg_mm_qry[col0 + (threadIdx.x - kMlTabTR)];
+        }
+        if (threadIdx.x < 96) {               // three whole warps cover the 80 sketches
+            const uint32_t wmin = __reduce_min_sync(0xffffffffu, mm & 0xffu);
+            if (tx == 0) atomicMin(&s_lo, wmin);
+        }
+        __syncthreads();
+        const uint32_t lo = s_lo;
+        gs = lo >= (uint32_t)(4 * p + 4) && ml_gs_k(lo, p) + (uint32_t)p <= 36u;
+        k0 = gs ? ml_gs_k(lo, p) : 0u;
+        if (threadIdx.x < kMlTabTR + kMlTabTQ) sflag[threadIdx.x] = (gs && (mm >> 8) > ml_gs_max_reg(p, k0)) ? 1u : 0u;   // table tile: only code 127 flags
+    } else if (threadIdx.x < kMlTabTR + kMlTabTQ) {
+        sflag[threadIdx.x] = 0u;  // ordered before the staging by its first barrier
+    }
     MlAccT<NPL> acc[2];
     acc[0].init();
     acc[1].init();
@@ -1093,7 +1121,12 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
             const uint32_t c0_ = fgra_code(v & 0xffu, base), c1_ = fgra_code((v >> 8) & 0xffu, base);
             const uint32_t c2_ = fgra_code((v >> 16) & 0xffu, base), c3_ = fgra_code(v >> 24, base);
             if (max(max(c0_, c1_), max(c2_, c3_)) == 127u) atomicOr(&sflag[r], 1u);
-            *reinterpret_cast<uint4*>(sa + r * a_stride + 4 * w) = make_uint4(c0_ << 9, c1_ << 9, c2_ << 9, c3_ << 9);
+            // G-sum tiles stage the absolute shared address of the W-plane row (one add per register saved in the loop)
+            const uint32_t a_off = gs ? rbase + 2u * kPlane : 0u;
+            *reinterpret_cast<uint4*>(sa + r * a_stride + 4 * w) = make_uint4((c0_ << 9) + a_off, (c1_ << 9) + a_off, (c2_ << 9) + a_off, (c3_ << 9) + a_off);
+            if (gs)
+                *reinterpret_cast<uint4*>(sga + r * a_stride + 4 * w) = make_uint4(ml_gs_term(ml_gs_n(v & 0xffu, p, k0)), ml_gs_term(ml_gs_n((v >> 8) & 0xffu, p, k0)),
+                                                                                   ml_gs_term(ml_gs_n((v >> 16) & 0xffu, p, k0)), ml_gs_term(ml_gs_n(v >> 24, p, k0)));
         }
         for (uint32_t e = threadIdx.x; e < (uint32_t)kMlTabTQ * chunk_words; e += kMlTabThreads) {
             const uint32_t r = e / chunk_words, w = e % chunk_words;
@@ -1102,7 +1135,9 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
             const uint32_t c0_ = fgra_code(v & 0xffu, base), c1_ = fgra_code((v >> 8) & 0xffu, base);
             const uint32_t c2_ = fgra_code((v >> 16) & 0xffu, base), c3_ = fgra_code(v >> 24, base);
             if (max(max(c0_, c1_), max(c2_, c3_)) == 127u) atomicOr(&sflag[kMlTabTR + r], 1u);
-            *reinterpret_cast<uint2*>(sb + r * b_stride + 4 * w) = make_uint2((c0_ << 2) | (c1_ << 18), (c2_ << 2) | (c3_ << 18));
+            *reinterpret_cast<uint2*>(sb + r * b_stride + 4 * w) =
+                make_uint2(ml_pack_b(c0_, ml_gs_n(v & 0xffu, p, k0), c1_, ml_gs_n((v >> 8) & 0xffu, p, k0)),
+                           ml_pack_b(c2_, ml_gs_n((v >> 16) & 0xffu, p, k0), c3_, ml_gs_n(v >> 24, p, k0)));
         }
         __syncthreads();
         const uint32_t* pa = sa + ty * a_stride;
@@ -1118,8 +1153,8 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
             uint32_t w0[8], w1[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const uint32_t q0 = (i & 1) ? (b0w[i >> 1] >> 16) : (b0w[i >> 1] & 0xffffu);
-                const uint32_t q1 = (i & 1) ? (b1w[i >> 1] >> 16) : (b1w[i >> 1] & 0xffffu);
+                const uint32_t q0 = (i & 1) ? ml_b_q1(b0w[i >> 1]) : ml_b_q0(b0w[i >> 1]);
+                const uint32_t q1 = (i & 1) ? ml_b_q1(b1w[i >> 1]) : ml_b_q0(b1w[i >> 1]);
                 const uint32_t ar = rbase + a[i];
                 uint32_t l0, h0, l1, h1;
                 asm("ld.shared.u32 %0, [%1];" : "=r"(l0) : "r"(ar + q0));
@@ -1134,7 +1169,59 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
             c0 = acc[0].csa8(w0);
             c1 = acc[1].csa8(w1);
         };
-        if (chunk >= 64u) {
+        // the same 8 registers x 2 pairs on a G-sum tile: ONE table lookup (W); S as min of the two staged powers of two,
+        // eight per 32-bit batch
+        const uint32_t* pg = sga + ty * a_stride;
+        // ncu (n = 6000): ALU pipe 80 %, FMA-heavy 29 %, issue 64 % with the 16 resident warps the table leaves room for.
+        // Moving the three field shifts onto the FMA pipe (IMAD.HI by run-time powers of two: ALU 60 %, FMA-heavy 59 %) did
+        // not shorten the kernel (9.0 -> 9.5 ms, dispatch stalls x10): with four warps per scheduler it is the dependent
+        // LDS -> carry-save chains that set the pace, not a pipe.
+        auto step8g = [&](uint32_t e, uint32_t& c0, uint32_t& c1) {
+            const uint4 al = *reinterpret_cast<const uint4*>(pa + e), ah = *reinterpret_cast<const uint4*>(pa + e + 4);
+            const uint4 gl = *reinterpret_cast<const uint4*>(pg + e), gh = *reinterpret_cast<const uint4*>(pg + e + 4);
+            const uint4 b0 = *reinterpret_cast<const uint4*>(pb0 + e);
+            const uint4 b1 = *reinterpret_cast<const uint4*>(pb1 + e);
+            const uint32_t a[8] = {al.x, al.y, al.z, al.w, ah.x, ah.y, ah.z, ah.w};
+            const uint32_t ga[8] = {gl.x, gl.y, gl.z, gl.w, gh.x, gh.y, gh.z, gh.w};
+            const uint32_t b0w[4] = {b0.x, b0.y, b0.z, b0.w}, b1w[4] = {b1.x, b1.y, b1.z, b1.w};
+            uint32_t w0[8], w1[8], s0 = 0u, s1 = 0u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t x0 = b0w[i >> 1], x1 = b1w[i >> 1];
+                const uint32_t q0 = (i & 1) ? ml_b_q1(x0) : ml_b_q0(x0), q1 = (i & 1) ? ml_b_q1(x1) : ml_b_q0(x1);
+                const uint32_t n0 = (i & 1) ? ml_b_n1(x0) : ml_b_n0(x0), n1 = (i & 1) ? ml_b_n1(x1) : ml_b_n0(x1);
+                const uint32_t g0 = min(ga[i], ml_gs_term(n0));
+                const uint32_t g1 = min(ga[i], ml_gs_term(n1));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(w0[i]) : "r"(mad_one(q0, one, a[i])));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"(mad_one(q1, one, a[i])));
+                s0 = i == 0 ? g0 : mad_one(g0, one, s0);
+                s1 = i == 0 ? g1 : mad_one(g1, one, s1);
+            }
+            acc[0].S += (uint64_t)s0;
+            acc[1].S += (uint64_t)s1;
+            c0 = acc[0].csa8(w0);
+            c1 = acc[1].csa8(w1);
+        };
+        if (gs) {   // G-sum tiles only exist for 16-byte-aligned sketches of >= 16 registers: chunk >= 16
+            if (chunk >= 64u) {
+#pragma unroll 1
+                for (uint32_t e = 0; e < chunk; e += 64) {
+                    uint32_t c0[8], c1[8];
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) step8g(e + 8u * g, c0[g], c1[g]);
+                    acc[0].fold64(c0);
+                    acc[1].fold64(c1);
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t e = 0; e < chunk; e += 8) {
+                    uint32_t c0, c1;
+                    step8g(e, c0, c1);
+                    acc[0].template ripple_all<3>(c0);
+                    acc[1].template ripple_all<3>(c1);
+                }
+            }
+        } else if (chunk >= 64u) {
 #pragma unroll 1
             for (uint32_t e = 0; e < chunk; e += 64) {
                 uint32_t c0[8], c1[8];
@@ -1160,6 +1247,7 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
         const uint64_t i = row0 + ty, j = col0 + tx + 32 * b;
         if (i >= dp.row_end || j >= dp.n_qry) continue;
         if (dp.triangular && j > i) continue;
+        if (gs) acc[b].mmax = kMlGsMarker | k0;                             // S holds the G-sum: finish_union rebuilds S
         if (sflag[ty] | sflag[kMlTabTR + tx + 32 * b]) acc[b].mmax = 255u;  // -> exact per-pair path in finish_union
         const uint64_t o = dp.packed_tri ? (i * (i + 1) / 2 + j) : ((i - dp.out_row0) * dp.n_qry + j);
         if (SPLIT) {
@@ -1591,11 +1679,11 @@ static cudaError_t launch_dist_hmh_fast(const DistParams& dp, cudaStream_t st) {
 static cudaError_t launch_dist_ml_tab(const DistParams& dp, cudaStream_t st) {
     const uint32_t cb = cell_bytes_of(dp.algo, dp.p);
     const uint32_t chunk = cb < (uint32_t)kMlTabChunk ? cb : (uint32_t)kMlTabChunk;
-    const size_t smem = (size_t)kTabN * kTabN * 12 + (size_t)kMlTabTR * (chunk + 4) * 4 + (size_t)kMlTabTQ * (chunk + 8) * 2 +
+    const size_t smem = (size_t)kTabN * kTabN * 12 + 2 * (size_t)kMlTabTR * (chunk + 4) * 4 + (size_t)kMlTabTQ * (chunk + 8) * 2 +
                         (size_t)(kMlTabTR + kMlTabTQ) * 4;
     const bool split = dp.ml_scratch != nullptr;
     const int npl = dp.p <= 11 ? 12 : dp.p <= 15 ? 16 : kMlPlanes;
-    using Kern = void (*)(DistParams, uint32_t, uint32_t, uint32_t, uint32_t);
+    using Kern = void (*)(DistParams, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t);
     Kern kern = npl == 12 ? (split ? dist_ml_tab_kernel<12, true> : dist_ml_tab_kernel<12, false>)
               : npl == 16 ? (split ? dist_ml_tab_kernel<16, true> : dist_ml_tab_kernel<16, false>)
                           : (split ? dist_ml_tab_kernel<kMlPlanes, true> : dist_ml_tab_kernel<kMlPlanes, false>);
@@ -1612,7 +1700,7 @@ static cudaError_t launch_dist_ml_tab(const DistParams& dp, cudaStream_t st) {
         if (e != cudaSuccess) return e;
     }
     const unsigned grid = (unsigned)std::min<uint64_t>(gx * gy, (uint64_t)dp.n_sm);
-    kern<<<grid, kMlTabThreads, smem, st>>>(dp, cb, chunk, (uint32_t)gx, (uint32_t)gy);
+    kern<<<grid, kMlTabThreads, smem, st>>>(dp, cb, chunk, (uint32_t)gx, (uint32_t)gy, 1u);
     e = cudaGetLastError();
     if (e != cudaSuccess || !split) return e;
     const unsigned fgrid = (unsigned)std::min<uint64_t>((dp.ml_cells + 255) / 256, (uint64_t)dp.n_sm * 32);
@@ -1650,7 +1738,7 @@ cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launc
     }();
     if (dp.algo == HLL) {
         if (hll_table || !hll_aligned) return launch_dist_t<HllAcc, 16>(dp, st);
-        if (hll_float || !dp.hll_mm_ref || !dp.hll_mm_qry) return launch_dist_hll_fast(dp, st);
+        if (hll_float || !dp.reg_mm_ref || !dp.reg_mm_qry) return launch_dist_hll_fast(dp, st);
         return launch_dist_hll_int(dp, st);
     }
     // LASH_HMH_KERNEL=generic selects K4 for A/B measurements; K4m stages with 16-byte loads like K4h

@@ -80,6 +80,45 @@ __device__ __forceinline__ uint32_t ml_tab_merged(uint32_t ca, uint32_t cb, uint
     return ull_merge1(ra, rb);
 }
 
+// ---- K4c, "G-sum" form of S ------------------------------------------------------------------------------------------------
+// For a register with r2 = r - 4p - 4 >= 0 (top level k = r2 >> 2, sub-bits y1 y0) hash4j's contribute() returns
+//     ret = (7 - 4 y0 - 2 y1) * 2^(61-k-p) = g(k+2) + (1 - y1) g(k+1) + (1 - y0) g(k),      g(j) = 2^(63-j-p),
+// and adds  W = 1 << (k+2) | y1 << (k+1) | y0 << k  to the counts b[].  ret plus the register's share of  sum_j b[j] g(j)
+// is  2 g(k+2) + g(k+1) + g(k) = 2 g(k), so over a whole (merged) sketch, mod 2^64,
+//     S = sum_regs 2^(64-k-p)  -  sum_j b[j] * 2^(63-j-p):
+// the table lookup of the 64-bit contribution (two LDS + a 64-bit add per register pair) becomes a sum of powers of two of
+// the merged TOP LEVEL -- and the top level of a merge is the larger of the two, so with G(r) = 2^(28-(k-k0)), k0 the
+// smallest top level among the tile's sketches, the term is min(G(ra), G(rb)): VIMNMX + IMAD, K4i's arithmetic, and
+//     sum_regs 2^(64-k-p) = (sum of the minima) << (36 - p - k0).
+// Valid while every register of both sketches has r2 >= 0 (no empty or "small-range" registers: the tile's smallest
+// register decides), k - k0 <= 27 (sketches above it are flagged for the tile, as for W's 32-bit limit k <= 29) and
+// 36 - p - k0 >= 0; exact because k + p <= 61 always holds on this path.  Eight terms fit a 32-bit batch (8 * 2^28).
+// n = k - k0 + 4 in 4..31 is what the staged query word carries (5 bits); G = 2^32 >> n.
+__device__ __forceinline__ uint32_t ml_gs_n(uint32_t r, int p, uint32_t k0) { return (((r - 4u * (uint32_t)p + 12u) >> 2) - k0) & 31u; }
+__device__ __forceinline__ uint32_t ml_gs_term(uint32_t n) { return __funnelshift_r(0u, 1u, n); }   // uses n & 31
+constexpr uint32_t kMlGsSpan = 27;
+// top level of a register with r2 >= 0
+__device__ __forceinline__ uint32_t ml_gs_k(uint32_t r, int p) { return (r - 4u * (uint32_t)p - 4u) >> 2; }
+// largest register a sketch may hold on a G-sum tile anchored at k0
+__device__ __forceinline__ uint32_t ml_gs_max_reg(int p, uint32_t k0) { return 4u * (uint32_t)p + 4u + 4u * (k0 + kMlGsSpan) + 3u; }
+// two query registers in one staged word: q = code << 2 (byte offset in a 128-word table row) and n, one instruction each
+//     bits 0..8 q0 | 9..13 n0 | 14..18 n1 | 23..31 q1
+__device__ __forceinline__ uint32_t ml_pack_b(uint32_t c0, uint32_t n0, uint32_t c1, uint32_t n1) {
+    return (c0 << 2) | (n0 << 9) | (n1 << 14) | (c1 << 25);
+}
+__device__ __forceinline__ uint32_t ml_b_q0(uint32_t w) { return w & 0x1fcu; }
+__device__ __forceinline__ uint32_t ml_b_q1(uint32_t w) { return w >> 23; }
+__device__ __forceinline__ uint32_t ml_b_n0(uint32_t w) { return w >> 9; }     // low 5 bits
+__device__ __forceinline__ uint32_t ml_b_n1(uint32_t w) { return w >> 14; }    // low 5 bits
+// S from the G-sum and the counts (b[j], j < 32: W fits 32 bits on this path)
+__device__ __forceinline__ uint64_t ml_gs_S(uint64_t gsum, const int* b, int p, uint32_t k0) {
+    uint64_t s = gsum << (36 - p - (int)k0);
+    for (int j = 0; j < 32; ++j) s -= (uint64_t)(uint32_t)b[j] << (63 - j - p);
+    return s;
+}
+// marker in MlAccT::mmax: S holds the G-sum of a tile anchored at k0 = mmax & 0xff (a real merged register is a byte)
+constexpr uint32_t kMlGsMarker = 0x100u;
+
 // ---- K4 / K4c: tables in shared memory and the ML accumulator -------------------------------------------------------------
 struct SharedTables {
     const double* fgra_tab;    // [256] contribution of a merged register byte (sentinel outside [4p+4, 252))

@@ -100,9 +100,10 @@ struct DistParams {
     uint32_t* ml_scratch = nullptr;
     uint64_t ml_cells = 0;
     uint64_t ml_o_base = 0;
-    // optional (HLL): per-sketch smallest | largest << 8 register (launch_hll_minmax), indexed by sketch; nullptr: K4h runs
-    const uint32_t* hll_mm_ref = nullptr;
-    const uint32_t* hll_mm_qry = nullptr;
+    // optional (HLL, ULL ML): per-sketch smallest | largest << 8 register byte (launch_hll_minmax), indexed by sketch;
+    // nullptr: K4h runs instead of K4i / the ML tile kernel takes every S from its table
+    const uint32_t* reg_mm_ref = nullptr;
+    const uint32_t* reg_mm_qry = nullptr;
     // optional (HMH): expected-collision sums of pairs of SMALL sketches (cardinality <= 2^19), computed before the tile kernel:
     // hmh_slot_ref[i - hmh_row0] / hmh_slot_qry[j] = slot of the sketch's term vector (or -1), hmh_ec[slot_r * hmh_ec_ld + slot_q]
     // = the loop sum x of expectedCollision.  nullptr: every such pair runs the 41 x 1024 loop itself.
@@ -113,7 +114,7 @@ struct DistParams {
     uint32_t hmh_ec_ld = 0;
 };
 
-// mm[i] = min | max << 8 over the register bytes of HLL sketch i (cell_bytes a multiple of 16, 16-byte aligned array)
+// mm[i] = min | max << 8 over the register bytes of (HLL or ULL) sketch i (cell_bytes a multiple of 16, 16-byte aligned array)
 cudaError_t launch_hll_minmax(const void* regs, uint64_t n, uint32_t cell_bytes, uint32_t* mm, cudaStream_t st);
 
 // ---- HMH small-sketch path (dist_kernels.cu) ---------------------------------------------------------------------------------

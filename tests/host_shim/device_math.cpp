@@ -195,6 +195,36 @@ void dm_ml_counters_generic(const uint32_t* w, uint64_t n, int group, int nplane
     ml_counts_from_planes(acc, bb);
 }
 
+// the G-sum form of S (dist_tables.cuh): two sketches without empty / small-range registers through the staged formats of
+// dist_ml_tab_kernel's G-sum tiles -- reference side code << 9 and G, query side two registers per packed word -- one W lookup
+// and min(G_a, G_b) per register pair, eight terms per 32-bit batch; returns S rebuilt by ml_gs_S, the counts in bits[32]
+uint64_t dm_ml_gs_pair(const uint8_t* a, const uint8_t* b, uint32_t m, int p, uint32_t k0, uint64_t* gsum_out, int* bits) {
+    const uint32_t base = (uint32_t)(4 * p - 4);
+    uint64_t gsum = 0;
+    for (int j = 0; j < 32; ++j) bits[j] = 0;
+    for (uint32_t e = 0; e < m; e += 8) {
+        uint32_t batch = 0;
+        for (uint32_t i = 0; i < 8; i += 2) {
+            const uint32_t wb = ml_pack_b(fgra_code(b[e + i], base), ml_gs_n(b[e + i], p, k0), fgra_code(b[e + i + 1], base), ml_gs_n(b[e + i + 1], p, k0));
+            for (uint32_t h = 0; h < 2; ++h) {
+                const uint32_t ca = fgra_code(a[e + i + h], base);
+                const uint32_t ga = ml_gs_term(ml_gs_n(a[e + i + h], p, k0));
+                const uint32_t q = h ? ml_b_q1(wb) : ml_b_q0(wb);
+                const uint32_t gb = ml_gs_term(h ? ml_b_n1(wb) : ml_b_n0(wb));
+                batch += min(ga, gb);
+                const uint32_t w = (uint32_t)ml_w_of(ml_tab_merged(ca, q >> 2, base), p);
+                for (int j = 0; j < 32; ++j) bits[j] += (w >> j) & 1u;
+            }
+        }
+        gsum += batch;
+    }
+    *gsum_out = gsum;
+    return ml_gs_S(gsum, bits, p, k0);
+}
+uint32_t dm_ml_gs_max_reg(int p, uint32_t k0) { return ml_gs_max_reg(p, k0); }
+uint32_t dm_ml_gs_k(uint32_t r, int p) { return ml_gs_k(r, p); }
+uint64_t dm_ml_ret_of(uint32_t r, int p) { return ml_ret_of(r, p); }
+
 // ---- K4h: HLL registers as high words of 2^-r ---------------------------------------------------------------------------
 void dm_hll_recode(uint32_t w, uint32_t* out4, int* zero_byte) {
     const uint4 v = hll_recode(w);

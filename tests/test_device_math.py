@@ -414,6 +414,53 @@ def test_ml_pair_tables_sum_to_the_ml_statistics(dm, oracle, p):
         assert np.array_equal(bits, b_exp.astype(np.int64))
 
 
+@pytest.mark.parametrize("p", [4, 10, 14, 20, 26])
+def test_ml_g_sum_form_of_S_equals_the_contribution_sum(dm, oracle, p):
+    """K4c's G-sum tiles (dist_tables.cuh): for sketches without empty or small-range registers whose top levels lie within
+    27 of the smallest one (k0),  S = (sum of min(G_a, G_b)) << (36 - p - k0)  -  sum_j b[j] << (63 - j - p)  (mod 2^64) is
+    hash4j's sum of contribute() over the merged sketch -- through the staged formats the tile kernel uses (packed query
+    words, 32-bit batches of eight)."""
+    dm.dm_ml_gs_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
+    dm.dm_ml_gs_pair.restype = C.c_uint64
+    dm.dm_ml_gs_max_reg.argtypes, dm.dm_ml_gs_max_reg.restype = [C.c_int, C.c_uint32], C.c_uint32
+    dm.dm_ml_gs_k.argtypes, dm.dm_ml_gs_k.restype = [C.c_uint32, C.c_int], C.c_uint32
+    dm.dm_ml_ret_of.argtypes, dm.dm_ml_ret_of.restype = [C.c_uint32, C.c_int], C.c_uint64
+    dm.dm_ull_merge1.argtypes, dm.dm_ull_merge1.restype = [C.c_uint32, C.c_uint32], C.c_uint32
+    rng = np.random.default_rng(p)
+    m = min(1 << p, 1 << 14)                       # the identity is per register: 2^14 registers are plenty
+    base = 4 * p + 4
+    gsum, bits = C.c_uint64(0), np.zeros(32, dtype=np.int32)
+    for shape, kmin in (("genome", 0), ("genome", 2), ("flat", 0), ("flat", 2), ("all-low", 1), ("all-high", 0)):
+        if kmin + p > 36:
+            continue
+        kmax = min(kmin + 27, 28)                                   # the pair table ends inside k = 29 (codes <= 126)
+        if shape == "genome":
+            lvl = np.clip(np.floor(kmin + 6.0 - np.log2(-np.log(rng.random((2, m))))), kmin, kmax).astype(np.int64)
+        elif shape == "flat":
+            lvl = rng.integers(kmin, kmax + 1, size=(2, m))
+        elif shape == "all-low":
+            lvl = np.full((2, m), kmin)                             # eight copies of the largest term in every batch
+        else:
+            lvl = np.full((2, m), kmax)
+            lvl[0, 0] = kmin
+        regs = (base + 4 * lvl + rng.integers(0, 4, size=(2, m))).astype(np.uint8)
+        k0 = dm.dm_ml_gs_k(int(regs.min()), p)
+        assert k0 >= kmin and int(regs.max()) <= dm.dm_ml_gs_max_reg(p, k0) and k0 + p <= 36
+        S = dm.dm_ml_gs_pair(_p(regs[0]), _p(regs[1]), m, p, k0, C.byref(gsum), _p(bits))
+        if m == 1 << p:
+            S_exp, b_exp = oracle.ull_ml_stats(oracle.ull_merge(regs[0], regs[1], p), p)
+            assert np.array_equal(bits.astype(np.int64), b_exp.astype(np.int64)[:32]) and not b_exp[32:].any()
+            assert S == S_exp, (p, shape, hex(S), hex(S_exp))
+        else:
+            # larger precisions: the same identity register by register against the header's own contribute()
+            S_exp = 0
+            for ra, rb in zip(regs[0][:2048], regs[1][:2048]):
+                S_exp += dm.dm_ml_ret_of(dm.dm_ull_merge1(int(ra), int(rb)), p)
+            k0s = dm.dm_ml_gs_k(int(regs[:, :2048].min()), p)
+            S2 = dm.dm_ml_gs_pair(_p(regs[0]), _p(regs[1]), 2048, p, k0s, C.byref(gsum), _p(bits))
+            assert S2 == S_exp % (1 << 64), (p, shape)
+
+
 @pytest.mark.parametrize("k", [1, 2, 5, 12, 14, 15, 16, 17, 21, 24, 31, 32])
 def test_funnel_shift_kmer_windows_equal_string_level_canonical_kmers(dm, oracle, k):
     """kmer_windows.cuh (the sketch kernel's k-mer extraction: funnel-shift windows of the packed stream and of its per-word

@@ -486,6 +486,50 @@ def test_hmh_word_kernel_ragged_tiles_and_mixed_empties(oracle, gpu_ctx, n_ref, 
         np.testing.assert_array_equal(np.load(f"{tmp}/d.npy"), dense)
 
 
+@pytest.mark.parametrize("p", [5, 6, 10, 12])
+def test_ml_g_sum_tiles_equal_table_tiles_bit_for_bit(oracle, gpu_ctx, tmp_path, p):
+    """K4c on tiles whose sketches hold no empty / small-range register takes S from min(G_a, G_b) sums instead of the 64-bit
+    contribution table (dist_tables.cuh).  S and b[] are integers, so the distances must equal those of the
+    table form (LASH_ML_S=table, read once per process -> a child) bit for bit: plain G-sum tiles, a register at the last
+    level inside (k = 27), one just above (k = 28: the sketch is flagged, exact path), one outside the pair table, and
+    tiles that fall back to the table because one of their sketches has an empty or a small-range register."""
+    import subprocess
+    import sys
+    rng = np.random.default_rng(p)
+    m = 1 << p
+    n = 200                                                       # 13 row tiles x 4 column tiles
+    lvl = np.clip(np.floor(7.0 - np.log2(-np.log(rng.random((n, m))))), 0, 27).astype(np.int64)
+    regs = (4 * p + 4 + 4 * lvl + rng.integers(0, 4, size=(n, m))).astype(np.uint8)
+    regs[1::2] = np.where(rng.random((n // 2, m)) < 0.5, regs[0::2], regs[1::2])   # related neighbours
+    lo = 4 * p + 4
+    regs[5, 3] = lo + 4 * 27 + 2                                  # k = 27: last level of the G-sum window
+    regs[70, 9] = lo + 4 * 28 + 1                                 # k = 28: flagged
+    regs[71, 0] = 251                                             # outside the pair table
+    regs[130, 17] = 0                                             # an empty register: its tiles use the table
+    regs[131, 4] = lo - 2                                         # a small-range register
+    regs[199, :] = lo                                             # the largest G everywhere (32-bit batches at their maximum)
+    np.save(tmp_path / "regs.npy", regs)
+    child = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from lash_b200 import ALGO_ULL, EST_ML, ops\n"
+        "regs = np.load(%r)\n"
+        "with ops.Context(0) as ctx:\n"
+        "    d, _ = ops.dist(ctx, ALGO_ULL, %d, 16, EST_ML, 2, False, regs, regs)\n"
+        "    r, _ = ops.dist(ctx, ALGO_ULL, %d, 16, EST_ML, 2, False, regs[60:140], regs[100:])\n"
+        "np.save(%r, d); np.save(%r, r)\n" % (str(__import__('os').path.dirname(__import__('os').path.dirname(__file__))), str(tmp_path / "regs.npy"),
+                                               p, p, str(tmp_path / "table.npy"), str(tmp_path / "table_rect.npy")))
+    subprocess.run([sys.executable, "-c", child], check=True, env=dict(__import__('os').environ, LASH_ML_S="table"))
+    dense, w = ops.dist(gpu_ctx, ALGO_ULL, p, 16, EST_ML, 2, False, regs, regs)
+    assert w == 0
+    np.testing.assert_array_equal(dense, np.load(tmp_path / "table.npy"))
+    rect, _ = ops.dist(gpu_ctx, ALGO_ULL, p, 16, EST_ML, 2, False, regs[60:140], regs[100:])
+    np.testing.assert_array_equal(rect, np.load(tmp_path / "table_rect.npy"))
+    tri, _ = ops.dist(gpu_ctx, ALGO_ULL, p, 16, EST_ML, 2, False, regs, regs, triangular=True)
+    np.testing.assert_array_equal(tri, dense[np.tril_indices(n)])
+    exp = oracle.dist(ALGO_ULL, p, 16, EST_ML, 2, False, regs[:64], regs[:64], threads=8)
+    np.testing.assert_allclose(dense[:64, :64], exp, rtol=1e-11, atol=1e-15)
+
+
 def test_ml_two_kernel_form_matches_fused_in_every_output_layout(oracle, gpu_ctx, tmp_path):
     """ULL ML runs as a tile kernel that stores the pair statistics + ml_finish_kernel.  The scratch is
     addressed by output cell, so every output layout is its own case: dense, packed triangle, streamed dense blocks
