@@ -1332,70 +1332,126 @@ cudaError_t launch_hmh_slots(const double* card, uint64_t begin, uint64_t end, u
     return cudaGetLastError();
 }
 
+// Per sketch: 41 x 1024 terms, then kHmhEcTail doubles of which the first 41 are the rows' largest |term| (the tile product
+// uses them to stop early).  One CTA per (row, sketch).
 __global__ void __launch_bounds__(256) hmh_ec_fill_kernel(const double* __restrict__ card, const uint32_t* __restrict__ src,
                                                           const uint32_t* __restrict__ count, double* __restrict__ terms) {
+    __shared__ double s_max[8];
     const uint32_t s = blockIdx.y;
     if (s >= *count) return;
     const double n = card[src[s]];
-    double* out = terms + (size_t)s * kHmhEcLen;
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < (uint32_t)kHmhEcLen; e += gridDim.x * blockDim.x)
-        out[e] = hmh_ec_term(1 + (int)(e >> 10), 1 + (int)(e & 1023u), n);
+    double* out = terms + (size_t)s * kHmhEcTermsPerSketch;
+    const int i = 1 + (int)blockIdx.x;
+    double mx = 0.0;
+    for (uint32_t j = threadIdx.x; j < 1024u; j += blockDim.x) {
+        const double t = hmh_ec_term(i, 1 + (int)j, n);
+        out[(size_t)blockIdx.x * 1024u + j] = t;
+        mx = fmax(mx, fabs(t));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if ((threadIdx.x & 31u) == 0) s_max[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) mx = fmax(mx, s_max[w]);
+        out[kHmhEcLen + blockIdx.x] = mx;
+    }
 }
 cudaError_t launch_hmh_ec_fill(const double* card, const uint32_t* src, const uint32_t* count_dev, uint32_t cap, double* terms,
                                cudaStream_t st) {
     if (cap == 0) return cudaSuccess;
     if (cap > 65535) return cudaErrorInvalidValue;   // grid.y limit: the caller caps the slots below it
-    hmh_ec_fill_kernel<<<dim3(41, cap), 256, 0, st>>>(card, src, count_dev, terms);
+    hmh_ec_fill_kernel<<<dim3(kHmhEcRows, cap), 256, 0, st>>>(card, src, count_dev, terms);
     return cudaGetLastError();
 }
 
-constexpr int kEcTile = 64, kEcKC = 16, kEcThreads = 256;
-__global__ void __launch_bounds__(kEcThreads) hmh_ec_gemm_kernel(const double* __restrict__ tr, const uint32_t* __restrict__ src_r,
-                                                                  const uint32_t* __restrict__ count_r, const double* __restrict__ tq,
-                                                                  const uint32_t* __restrict__ src_q, const uint32_t* __restrict__ count_q,
-                                                                  int triangular, double* __restrict__ ec, uint32_t ld) {
+// 128 x 128 pairs per CTA, 8 x 8 per thread: 16 LDS.64 + 128 un-fused f64 operations per k (the 64 x 64 / 4 x 4 first version
+// ran at 45 % of the f64 pipe).  Every term is >= 0 (both factors are <= 0), so a pair's sum only grows; after each row of
+// 1024 terms the CTA checks whether, for every pair it owns, the largest product the remaining rows can hold is below half an
+// ulp of the sum so far (largest |term| of the rows still to come, per sketch, from the fill kernel; estimators.cuh:
+// hmh_ec_rest_is_absorbed): then every further addition of the reference's loop rounds back to the same double, and
+// the loop can stop -- typically after 23-25 of the 41 rows -- with the bit-identical result.
+constexpr int kEcTile = 128, kEcKC = 16, kEcThreads = 256, kEcM = 8;
+__global__ void __launch_bounds__(kEcThreads, 1) hmh_ec_gemm_kernel(const double* __restrict__ tr, const uint32_t* __restrict__ src_r,
+                                                                     const uint32_t* __restrict__ count_r, const double* __restrict__ tq,
+                                                                     const uint32_t* __restrict__ src_q, const uint32_t* __restrict__ count_q,
+                                                                     int triangular, double* __restrict__ ec, uint32_t ld) {
     // k-major tiles: sA[kk][row], sB[kk][col] (+1 pad against the transposing stores)
-    __shared__ double sA[kEcKC][kEcTile + 1];
-    __shared__ double sB[kEcKC][kEcTile + 1];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double (*sA)[kEcTile + 1] = reinterpret_cast<double (*)[kEcTile + 1]>(smem_raw);
+    double (*sB)[kEcTile + 1] = sA + kEcKC;
+    double (*sufA)[kEcTile] = reinterpret_cast<double (*)[kEcTile]>(sB + kEcKC);   // sufA[i][row] = largest |term| of rows i.. (from 0) of that sketch
+    double (*sufB)[kEcTile] = sufA + (kHmhEcRows + 1);
     const uint32_t nr = *count_r, nq = *count_q;
     const uint32_t r0 = blockIdx.y * kEcTile, q0 = blockIdx.x * kEcTile;
     if (r0 >= nr || q0 >= nq) return;
     if (triangular && src_r[min(r0 + kEcTile, nr) - 1] < src_q[q0]) return;   // every pair of the tile has j > i
     const uint32_t ty = threadIdx.x >> 4, tx = threadIdx.x & 15u;
-    double acc[4][4];
+    // suffix maxima of the row maxima (rows past the count: 0, they never hold the loop back)
+    {
+        const uint32_t e = threadIdx.x & (kEcTile - 1);
+        const bool side_b = threadIdx.x >= (uint32_t)kEcTile;
+        const uint32_t idx = (side_b ? q0 : r0) + e;
+        const bool valid = idx < (side_b ? nq : nr);
+        const double* rm = (side_b ? tq : tr) + (size_t)(valid ? idx : 0) * kHmhEcTermsPerSketch + kHmhEcLen;
+        double (*suf)[kEcTile] = side_b ? sufB : sufA;
+        double m = 0.0;
+        suf[kHmhEcRows][e] = 0.0;
+        for (int i = kHmhEcRows - 1; i >= 0; --i) {
+            m = valid ? fmax(m, rm[i]) : 0.0;
+            suf[i][e] = m;
+        }
+    }
+    double acc[kEcM][kEcM];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kEcM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    // loader: thread t brings 4 consecutive k of one row of each operand (rows past the count read row 0: never stored)
+        for (int j = 0; j < kEcM; ++j) acc[i][j] = 0.0;
+    // loader: thread t brings 4 consecutive k of two rows of each operand (rows past the count read row 0: never stored)
     const uint32_t lrow = threadIdx.x >> 2, lk = (threadIdx.x & 3u) * 4u;
-    const double* ga = tr + (size_t)(r0 + lrow < nr ? r0 + lrow : 0) * kHmhEcLen + lk;
-    const double* gb = tq + (size_t)(q0 + lrow < nq ? q0 + lrow : 0) * kHmhEcLen + lk;
+    const double* ga0 = tr + (size_t)(r0 + lrow < nr ? r0 + lrow : 0) * kHmhEcTermsPerSketch + lk;
+    const double* ga1 = tr + (size_t)(r0 + lrow + 64 < nr ? r0 + lrow + 64 : 0) * kHmhEcTermsPerSketch + lk;
+    const double* gb0 = tq + (size_t)(q0 + lrow < nq ? q0 + lrow : 0) * kHmhEcTermsPerSketch + lk;
+    const double* gb1 = tq + (size_t)(q0 + lrow + 64 < nq ? q0 + lrow + 64 : 0) * kHmhEcTermsPerSketch + lk;
     for (uint32_t k0 = 0; k0 < (uint32_t)kHmhEcLen; k0 += kEcKC) {
-        const double4 a4 = *reinterpret_cast<const double4*>(ga + k0);
-        const double4 b4 = *reinterpret_cast<const double4*>(gb + k0);
+        const double4 a40 = *reinterpret_cast<const double4*>(ga0 + k0), a41 = *reinterpret_cast<const double4*>(ga1 + k0);
+        const double4 b40 = *reinterpret_cast<const double4*>(gb0 + k0), b41 = *reinterpret_cast<const double4*>(gb1 + k0);
         __syncthreads();
-        sA[lk + 0][lrow] = a4.x; sA[lk + 1][lrow] = a4.y; sA[lk + 2][lrow] = a4.z; sA[lk + 3][lrow] = a4.w;
-        sB[lk + 0][lrow] = b4.x; sB[lk + 1][lrow] = b4.y; sB[lk + 2][lrow] = b4.z; sB[lk + 3][lrow] = b4.w;
+        if ((k0 & 1023u) == 0 && k0) {
+            // a row of the reference's loop is complete: can the rest still change any of this CTA's sums?
+            const uint32_t row = k0 >> 10;
+            bool done = true;
+#pragma unroll
+            for (int i = 0; i < kEcM; ++i)
+#pragma unroll
+                for (int j = 0; j < kEcM; ++j)
+                    done = done && (hmh_ec_rest_is_absorbed(sufA[row][ty * kEcM + i], sufB[row][j * 16 + tx], acc[i][j]) ||
+                                    r0 + ty * kEcM + i >= nr || q0 + j * 16 + tx >= nq);
+            if (__syncthreads_and(done)) break;
+        }
+        sA[lk + 0][lrow] = a40.x; sA[lk + 1][lrow] = a40.y; sA[lk + 2][lrow] = a40.z; sA[lk + 3][lrow] = a40.w;
+        sA[lk + 0][lrow + 64] = a41.x; sA[lk + 1][lrow + 64] = a41.y; sA[lk + 2][lrow + 64] = a41.z; sA[lk + 3][lrow + 64] = a41.w;
+        sB[lk + 0][lrow] = b40.x; sB[lk + 1][lrow] = b40.y; sB[lk + 2][lrow] = b40.z; sB[lk + 3][lrow] = b40.w;
+        sB[lk + 0][lrow + 64] = b41.x; sB[lk + 1][lrow + 64] = b41.y; sB[lk + 2][lrow + 64] = b41.z; sB[lk + 3][lrow + 64] = b41.w;
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < kEcKC; ++kk) {
-            double a[4], b[4];
+            double a[kEcM], b[kEcM];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+            for (int i = 0; i < kEcM; ++i) a[i] = sA[kk][ty * kEcM + i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = sB[kk][j * 16 + tx];    // lanes read consecutive doubles: no bank conflicts
+            for (int j = 0; j < kEcM; ++j) b[j] = sB[kk][j * 16 + tx];    // lanes read consecutive doubles: no bank conflicts
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < kEcM; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = acc[i][j] + a[i] * b[j];   // -fmad=false: multiply, then add, like the loop
+                for (int j = 0; j < kEcM; ++j) acc[i][j] = acc[i][j] + a[i] * b[j];   // -fmad=false: multiply, then add, like the loop
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kEcM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t r = r0 + ty * 4 + i, q = q0 + j * 16 + tx;
+        for (int j = 0; j < kEcM; ++j) {
+            const uint32_t r = r0 + ty * kEcM + i, q = q0 + j * 16 + tx;
             if (r < nr && q < nq) ec[(size_t)r * ld + q] = acc[i][j];
         }
 }
@@ -1405,7 +1461,10 @@ cudaError_t launch_hmh_ec_gemm(const double* terms_r, const uint32_t* src_r, con
     if (cap_r == 0 || cap_q == 0) return cudaSuccess;
     const dim3 grid((cap_q + kEcTile - 1) / kEcTile, (cap_r + kEcTile - 1) / kEcTile);
     if (grid.y > 65535) return cudaErrorInvalidValue;
-    hmh_ec_gemm_kernel<<<grid, kEcThreads, 0, st>>>(terms_r, src_r, count_r, terms_q, src_q, count_q, triangular, ec, ld);
+    constexpr size_t smem = 2 * sizeof(double) * ((size_t)kEcKC * (kEcTile + 1) + (size_t)(kHmhEcRows + 1) * kEcTile);
+    const cudaError_t e = cudaFuncSetAttribute(hmh_ec_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hmh_ec_gemm_kernel<<<grid, kEcThreads, smem, st>>>(terms_r, src_r, count_r, terms_q, src_q, count_q, triangular, ec, ld);
     return cudaGetLastError();
 }
 

@@ -278,6 +278,10 @@ __device__ __forceinline__ double hmh_ec_term(int i, int j, double n) {   // i i
     const double b2 = (1024.0 + j + 1.0) * inv_den;
     return pow_cr(1.0 - b2, n) - pow_cr(1.0 - b1, n);
 }
+// Early end of the loop, exact: every term is >= 0, so the sum x only grows, and an addition x + t with t < ulp(x) / 2 rounds
+// back to x.  bound_n / bound_m = the largest |term| of the rows still to come of the two sketches; their product bounds every
+// remaining product before rounding (after rounding at most one part in 2^53 more), and x * 2^-54 <= ulp(x) / 4.
+__device__ __forceinline__ bool hmh_ec_rest_is_absorbed(double bound_n, double bound_m, double x) { return bound_n * bound_m < x * 0x1p-54; }
 // which branch expectedCollision takes: true = the double loop
 __device__ __forceinline__ bool hmh_ec_is_small(double card) { return !(card > kHmhEcSmall); }
 

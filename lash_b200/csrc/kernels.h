@@ -124,7 +124,7 @@ cudaError_t launch_hmh_count_small(const double* card, uint64_t begin, uint64_t 
 // *count_dev = min(number of small sketches, cap)
 cudaError_t launch_hmh_slots(const double* card, uint64_t begin, uint64_t end, uint32_t cap, int32_t* slot, uint32_t* src,
                              uint32_t* count_dev, cudaStream_t st);
-// terms[slot][41 * 1024] of the first *count_dev slots
+// terms[slot][kHmhEcTermsPerSketch] of the first *count_dev slots: 41 x 1024 terms, then the largest |term| of each row
 cudaError_t launch_hmh_ec_fill(const double* card, const uint32_t* src, const uint32_t* count_dev, uint32_t cap, double* terms,
                                cudaStream_t st);
 // ec[r * ld + q] = sum over (i, j) in the reference's order of terms_r[r][ij] * terms_q[q][ij]; triangular: tiles whose largest
@@ -132,7 +132,7 @@ cudaError_t launch_hmh_ec_fill(const double* card, const uint32_t* src, const ui
 cudaError_t launch_hmh_ec_gemm(const double* terms_r, const uint32_t* src_r, const uint32_t* count_r, uint32_t cap_r,
                                const double* terms_q, const uint32_t* src_q, const uint32_t* count_q, uint32_t cap_q, int triangular,
                                double* ec, uint32_t ld, cudaStream_t st);
-constexpr uint32_t kHmhEcTermsPerSketch = 41u * 1024u;
+constexpr uint32_t kHmhEcTermsPerSketch = 41u * 1024u + 64u;   // the terms, then the 41 row maxima (padded)
 // 32-bit words of ML scratch per pair for sketches of precision p (S lo/hi, flag, bit planes)
 uint32_t ml_scratch_words(int p);
 // atomicMin of the smallest non-zero register byte into *out_dev (preset to 0xffffffff by the caller)

@@ -58,6 +58,40 @@ double dm_hmh_similarity(uint32_t C, uint32_t N, double card_q, double card_r) {
 double dm_hmh_ec_term(int i, int j, double n) { return hmh_ec_term(i, j, n); }
 double dm_hmh_ec(double n, double m) { return hmh_expected_collisions(n, m); }
 int dm_hmh_ec_rows(void) { return kHmhEcRows; }
+// the tile product's early end (hmh_ec_gemm_kernel): full 41-row sum in the reference's order, and the sum at the first row
+// boundary where hmh_ec_rest_is_absorbed holds; returns that row (41 = never), both sums through the pointers
+int dm_hmh_ec_early(double n, double m, double* full, double* early) {
+    static thread_local double tn[kHmhEcLen], tm[kHmhEcLen];
+    double sn[kHmhEcRows + 1], sm[kHmhEcRows + 1];
+    for (int i = 0; i < kHmhEcRows; ++i)
+        for (int j = 0; j < 1024; ++j) {
+            tn[i * 1024 + j] = hmh_ec_term(i + 1, j + 1, n);
+            tm[i * 1024 + j] = hmh_ec_term(i + 1, j + 1, m);
+        }
+    sn[kHmhEcRows] = sm[kHmhEcRows] = 0.0;
+    for (int i = kHmhEcRows - 1; i >= 0; --i) {
+        double a = 0.0, b = 0.0;
+        for (int j = 0; j < 1024; ++j) {
+            a = fmax(a, fabs(tn[i * 1024 + j]));
+            b = fmax(b, fabs(tm[i * 1024 + j]));
+        }
+        sn[i] = fmax(sn[i + 1], a);
+        sm[i] = fmax(sm[i + 1], b);
+    }
+    double x = 0.0;
+    int stop = kHmhEcRows;
+    *early = 0.0;
+    for (int i = 0; i < kHmhEcRows; ++i) {
+        if (i && stop == kHmhEcRows && hmh_ec_rest_is_absorbed(sn[i], sm[i], x)) {
+            stop = i;
+            *early = x;
+        }
+        for (int j = 0; j < 1024; ++j) x = x + tn[i * 1024 + j] * tm[i * 1024 + j];
+    }
+    if (stop == kHmhEcRows) *early = x;
+    *full = x;
+    return stop;
+}
 double dm_mash64(double frac, int k, int model) { return mash_distance_f64(frac, k, model); }
 float dm_mash32(float frac, int k, int model) { return mash_distance_f32(frac, k, model); }
 }

@@ -306,6 +306,7 @@ def test_hmh_and_mash_epilogues(est, oracle):
 
 
 def test_hmh_expected_collision_terms_and_sum(est, oracle):
+    d_ = C.c_double
     """K4m's small-sketch path (estimators.cuh: hmh_ec_term, kHmhEcRows): the term of rows beyond kHmhEcRows is exactly +0 for
     every cardinality that takes the loop (so cutting the 64 x 1024 loop at row 41 changes nothing), row 41 still holds a
     non-zero term, and the loop sum equals the oracle's expectedCollision (glibc pow there, correctly rounded pow here)."""
@@ -333,6 +334,18 @@ def test_hmh_expected_collision_terms_and_sum(est, oracle):
         assert abs(got - exp) <= 1e-13 * max(abs(exp), 1.0), (n, m, got, exp)
     # the closed form above 2^19 is untouched
     assert _close(est.dm_hmh_ec(3e6, 2e6), L.lo_hmh_expected_collisions(3e6, 2e6), ulps=4)
+    # the tile product's early end: wherever the rule fires, the partial sum IS the full 41-row sum
+    est.dm_hmh_ec_early.argtypes, est.dm_hmh_ec_early.restype = [d_, d_, C.c_void_p, C.c_void_p], C.c_int
+    full, early = C.c_double(0), C.c_double(0)
+    stops = []
+    rng = np.random.default_rng(3)
+    cases = [(1.0, 1.0), (2.0, 524288.0), (17.0, 3.0), (524288.0, 524288.0), (1000.0, 1000.0), (65536.0, 9.0), (300000.0, 120000.5)]
+    cases += [tuple(np.exp(rng.uniform(0, np.log(524288.0), size=2))) for _ in range(12)]
+    for n, m in cases:
+        stop = est.dm_hmh_ec_early(float(n), float(m), C.byref(full), C.byref(early))
+        assert early.value == full.value, (n, m, stop, early.value, full.value)
+        stops.append(stop)
+    assert min(stops) < 30, stops     # the rule does fire (typically after 23-27 rows)
 
 
 # ------------------------------------------------------------------------------------------------------------------

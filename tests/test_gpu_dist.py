@@ -250,6 +250,44 @@ def test_hmh_small_sketches_precomputed_expected_collisions(oracle, gpu_ctx):
         np.testing.assert_array_equal(rows[i], full_b[i, : i + 1])
 
 
+def test_hmh_small_sketch_tile_product_equals_the_per_pair_loop(gpu_ctx, tmp_path):
+    """hmh_ec_gemm_kernel (128 x 128 tiles, 8 x 8 pairs per thread, exact early end of the row loop) against the per-pair
+    41 x 1024 loop of the same library (LASH_HMH_EC=loop, read once per process -> a child): 300 simulated sketches of 150 to
+    4 x 10^5 k-mers -- several tiles, ragged edges, cardinalities orders of magnitude apart inside one tile -- plus a few large
+    ones; same arithmetic in the same order, so the distances must be equal bit for bit."""
+    import subprocess
+    import sys
+    rng = np.random.default_rng(9)
+    n, m = 300, 16384
+    per_reg = np.exp(rng.uniform(np.log(0.01), np.log(25.0), size=n))          # k-mers per register
+    per_reg[::37] = 400.0                                                       # large sketches in between (closed form)
+    regs = np.zeros((n, m), dtype=np.uint16)
+    for i in range(n):
+        hit = rng.random(m) < 1.0 - np.exp(-per_reg[i])
+        lvl = np.clip(np.floor(np.log2(max(per_reg[i], 1.0)) - np.log2(-np.log(rng.random(m)))), 0, 40).astype(np.int64)
+        regs[i] = np.where(hit, ((lvl + 1) << 10) | rng.integers(0, 1024, size=m), 0).astype(np.uint16)
+    regs[1::2] = np.where(rng.random((n // 2, m)) < 0.4, regs[0::2], regs[1::2])                # collisions between neighbours
+    np.save(tmp_path / "regs.npy", regs)
+    child = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from lash_b200 import ALGO_HMH, ops\n"
+        "regs = np.load(%r)\n"
+        "with ops.Context(0) as ctx:\n"
+        "    d, _ = ops.dist(ctx, ALGO_HMH, 14, 16, 0, 2, False, regs, regs, triangular=True)\n"
+        "    r, _ = ops.dist(ctx, ALGO_HMH, 14, 16, 0, 2, False, regs[100:290], regs[20:170])\n"
+        "np.save(%r, d); np.save(%r, r)\n" % (str(__import__('os').path.dirname(__import__('os').path.dirname(__file__))), str(tmp_path / "regs.npy"),
+                                               str(tmp_path / "loop.npy"), str(tmp_path / "loop_rect.npy")))
+    subprocess.run([sys.executable, "-c", child], check=True, env=dict(__import__('os').environ, LASH_HMH_EC="loop"))
+    cards = ops.cardinality(gpu_ctx, ALGO_HMH, 14, 0, regs)
+    assert (cards <= 524288).sum() > 250 and (cards > 524288).sum() >= 5
+    tri, _ = ops.dist(gpu_ctx, ALGO_HMH, 14, 16, 0, 2, False, regs, regs, triangular=True)
+    loop = np.load(tmp_path / "loop.npy")
+    assert ((loop > 0) & (loop < 1)).sum() > 100
+    np.testing.assert_array_equal(tri, loop)
+    rect, _ = ops.dist(gpu_ctx, ALGO_HMH, 14, 16, 0, 2, False, regs[100:290], regs[20:170])
+    np.testing.assert_array_equal(rect, np.load(tmp_path / "loop_rect.npy"))
+
+
 def test_hll_bias_regime_is_flagged_not_silently_different(oracle, gpu_ctx):
     """HLL++ estimates in (threshold, 5m] need Google's empirical bias tables (not reproducible
     offline): both sides must flag those cells instead of inventing a number."""
