@@ -22,6 +22,9 @@ struct HashConsts {
     //   new_lo = (kmer << 17) ^ (kmer >> 8) ^ nar_cl
     //   new_hi = kmer ^ ((kmer >> 15) | (nar_ch & 0xfffe0000)) ^ ((kmer << 24) + (nar_ch & 0x1ffff))
     uint32_t nar_cl, nar_ch;
+    // 2^29 as a RUN-TIME value: (h >> 35) + 8 of the wide-k hash runs as one IMAD.HI on the FMA pipe (the wide kernels are
+    // ALU-bound); with a literal ptxas strength-reduces it back to SHF + IADD
+    uint32_t two29;
 };
 
 constexpr uint64_t kSecretX_8_16 = 0xc73ab174c5ecd5a2ULL;   // readLE64(kSecret+8) ^ readLE64(kSecret+16)
@@ -37,6 +40,7 @@ inline HashConsts make_hash_consts(uint64_t seed) {
     uint64_t b64 = kSecretX_8_16 - sp;
     uint64_t b128 = kSecretX_16_24 + sp;
     HashConsts c;
+    c.two29 = 1u << 29;
     c.bf64_lo = (uint32_t)b64;
     c.bf64_hi = (uint32_t)(b64 >> 32);
     c.bf128_lo = (uint32_t)b128;
@@ -94,6 +98,26 @@ __device__ __forceinline__ uint32_t mad32_opaque(uint32_t a, uint32_t b, uint32_
     return r;
 #endif
 }
+// (h1 >> 3) + 8, the high-word part of  h ^= (h >> 35) + len.  FMA = true: one IMAD.HI (h1 * 2^29 >> 32, + 8) on the FMA-heavy
+// pipe instead of SHF + IADD on the ALU pipe.  LASH_WIDE_FMA=1 applies it -- together with the k-mer window's  >> wide_shr  as
+// IMAD.HI and HLL's cell address as IMAD -- to the wide-k kernels, whose ALU pipe is 84-88 % busy with the FMA pipe at 26 %.
+// Measured in round 2 (tools/variant_sweep, B200): 2.4 fewer ALU instructions per k-mer and 3 % SLOWER (HLL p14 k21 545 -> 530,
+// ULL p10 k31 545 -> 527 Gbp/s) -- as for k <= 16 (LASH_SHR8_IMAD, -1.7 %) IMAD.HI costs the FMA pipe more than the SHF it
+// replaces costs the ALU.  Default off.
+#ifndef LASH_WIDE_FMA
+#define LASH_WIDE_FMA 0
+#endif
+template <bool FMA>
+__device__ __forceinline__ uint32_t shr3_add8(uint32_t h1, const struct HashConsts& c) {
+    if (!FMA) return add32_opaque(h1 >> 3, 8u);
+#ifdef LASH_HOST_SHIM
+    return (uint32_t)(((uint64_t)h1 * c.two29) >> 32) + 8u;
+#else
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, %2, 8;" : "=r"(r) : "r"(h1), "r"(c.two29));
+    return r;
+#endif
+}
 // (lo, hi) * kPrimeMX2 mod 2^64 in three instructions
 __device__ __forceinline__ void mul_mx2(uint32_t& lo, uint32_t& hi) {
     constexpr uint32_t m_lo = (uint32_t)kPrimeMX2, m_hi = (uint32_t)(kPrimeMX2 >> 32);
@@ -102,18 +126,20 @@ __device__ __forceinline__ void mul_mx2(uint32_t& lo, uint32_t& hi) {
     lo = (uint32_t)w;
 }
 // tail of XXH3_rrmxmx after the rotate-xor stage, on halves
-__device__ __forceinline__ uint64_t xxh3_rrmxmx8_tail(uint32_t lo, uint32_t hi) {
+template <bool FMA = false>
+__device__ __forceinline__ uint64_t xxh3_rrmxmx8_tail(uint32_t lo, uint32_t hi, const HashConsts& c) {
     mul_mx2(lo, hi);
-    lo ^= add32_opaque(hi >> 3, 8u);  // h ^= (h >> 35) + len, no carry into the high word
+    lo ^= shr3_add8<FMA>(hi, c);      // h ^= (h >> 35) + len, no carry into the high word
     mul_mx2(lo, hi);
     return mk64(lo, hi);               // caller applies the final h ^= h >> 28 (or only the part it needs)
 }
-__device__ __forceinline__ uint32_t xxh3_rrmxmx8_tail_hi(uint32_t lo, uint32_t hi) {
+template <bool FMA = false>
+__device__ __forceinline__ uint32_t xxh3_rrmxmx8_tail_hi(uint32_t lo, uint32_t hi, const HashConsts& c) {
     constexpr uint32_t m_lo = (uint32_t)kPrimeMX2, m_hi = (uint32_t)(kPrimeMX2 >> 32);
     const uint64_t w = (uint64_t)lo * m_lo;                                   // IMAD.WIDE
     uint32_t h1 = mad32_opaque(lo, m_hi, (uint32_t)(w >> 32));                // + lo * M.hi
     h1 = mad32_opaque(hi, m_lo, h1);                                          // + hi * M.lo
-    const uint32_t l1 = (uint32_t)w ^ add32_opaque(h1 >> 3, 8u);              // h ^= (h >> 35) + 8
+    const uint32_t l1 = (uint32_t)w ^ shr3_add8<FMA>(h1, c);                  // h ^= (h >> 35) + 8
     return mad32_opaque(h1, m_lo, mad32_opaque(l1, m_hi, __umulhi(l1, m_lo)));  // high word of the second product
 }
 // pre-xorshift hash (h before `h ^= h >> 28`) of a k-mer that fits 32 bits; see HashConsts::nar_*
@@ -122,7 +148,7 @@ __device__ __forceinline__ uint64_t xxh3_64_narrow_pre(uint32_t kmer, const Hash
     const uint32_t t3 = kmer * (1u << 24) + (c.nar_ch & 0x1ffffu);      // disjoint bits: + is ^
     const uint32_t hi = kmer ^ t2 ^ t3;
     const uint32_t lo = (kmer * (1u << 17)) ^ (kmer >> 8) ^ c.nar_cl;
-    return xxh3_rrmxmx8_tail(lo, hi);
+    return xxh3_rrmxmx8_tail(lo, hi, c);
 }
 __device__ __forceinline__ uint32_t xxh3_64_narrow_pre_hi(uint32_t kmer, const HashConsts& c) {
     const uint32_t t2 = __funnelshift_r(kmer, c.nar_ch >> 17, 15);
@@ -133,7 +159,7 @@ __device__ __forceinline__ uint32_t xxh3_64_narrow_pre_hi(uint32_t kmer, const H
 #else
     const uint32_t lo = (kmer * (1u << 17)) ^ (kmer >> 8) ^ c.nar_cl;
 #endif
-    return xxh3_rrmxmx8_tail_hi(lo, hi);
+    return xxh3_rrmxmx8_tail_hi(lo, hi, c);
 }
 __device__ __forceinline__ uint32_t xxh3_64_wide_pre_hi(uint32_t v_lo, uint32_t v_hi, const HashConsts& c) {
     uint32_t lo = v_hi ^ c.bf64_lo, hi = v_lo ^ c.bf64_hi;
@@ -141,7 +167,7 @@ __device__ __forceinline__ uint32_t xxh3_64_wide_pre_hi(uint32_t v_lo, uint32_t 
     const uint32_t r24_lo = __funnelshift_l(hi, lo, 24), r24_hi = __funnelshift_l(lo, hi, 24);
     lo ^= r49_lo ^ r24_lo;
     hi ^= r49_hi ^ r24_hi;
-    return xxh3_rrmxmx8_tail_hi(lo, hi);
+    return xxh3_rrmxmx8_tail_hi<LASH_WIDE_FMA>(lo, hi, c);
 }
 // pre-xorshift hash of a general 64-bit k-mer value
 __device__ __forceinline__ uint64_t xxh3_64_wide_pre(uint32_t v_lo, uint32_t v_hi, const HashConsts& c) {
@@ -150,7 +176,7 @@ __device__ __forceinline__ uint64_t xxh3_64_wide_pre(uint32_t v_lo, uint32_t v_h
     const uint32_t r24_lo = __funnelshift_l(hi, lo, 24), r24_hi = __funnelshift_l(lo, hi, 24);
     lo ^= r49_lo ^ r24_lo;
     hi ^= r49_hi ^ r24_hi;
-    return xxh3_rrmxmx8_tail(lo, hi);
+    return xxh3_rrmxmx8_tail<LASH_WIDE_FMA>(lo, hi, c);
 }
 
 // xxh3_64_with_seed(le64(v), seed); v given as two 32-bit halves.

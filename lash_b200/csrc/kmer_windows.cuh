@@ -26,11 +26,13 @@ __device__ __forceinline__ uint32_t rc16(uint32_t f) {
     return ~y;
 }
 
-// narrow_shr = 32 - 2k, narrow_mask = 2^(2k) - 1 (k <= 16);  wide_shr = 64 - 2k, wide_mask_hi = 2^(2k-32) - 1 (k > 16)
+// narrow_shr = 32 - 2k, narrow_mask = 2^(2k) - 1 (k <= 16);  wide_shr = 64 - 2k, wide_mask_hi = 2^(2k-32) - 1 (k > 16);
+// wide_mul = 2^(32 - wide_shr) as a run-time value (0 for k = 32, where nothing is shifted): the high word's  >> wide_shr
+// runs as IMAD.HI on the FMA pipe (LASH_WIDE_FMA, hash.cuh)
 template <int KM>
 __device__ __forceinline__ void canonical_kmer(uint32_t A0, uint32_t B0, uint32_t C0, uint32_t Ar, uint32_t Br, uint32_t Cr, int sh,
                                                uint32_t narrow_shr, uint32_t narrow_mask, uint32_t wide_shr, uint32_t wide_mask_hi,
-                                               uint32_t& klo, uint32_t& khi) {
+                                               uint32_t wide_mul, uint32_t& klo, uint32_t& khi) {
     if (KM == K16) {
         klo = min(__funnelshift_l(B0, A0, sh), __funnelshift_r(Ar, Br, sh));
         khi = 0u;
@@ -42,7 +44,10 @@ __device__ __forceinline__ void canonical_kmer(uint32_t A0, uint32_t B0, uint32_
     } else {
         uint32_t fhi = __funnelshift_l(B0, A0, sh), flo = __funnelshift_l(C0, B0, sh);
         flo = __funnelshift_r(flo, fhi, wide_shr);
-        fhi >>= wide_shr;
+        if (LASH_WIDE_FMA)
+            fhi = wide_shr ? __umulhi(fhi, wide_mul) : fhi;   // uniform predicate
+        else
+            fhi >>= wide_shr;
         const uint32_t rlo = __funnelshift_r(Ar, Br, sh);
         const uint32_t rhi = __funnelshift_r(Br, Cr, sh) & wide_mask_hi;
         const uint64_t f64 = mk64(flo, fhi), r64 = mk64(rlo, rhi);

@@ -124,7 +124,9 @@ struct SmemAcc<HLL> {
         // h = g ^ (g >> 28): the index needs the low p bits of h.lo.  rho = clz(h.hi) + 1 = clz(g.hi) + 1: the xorshift
         // folds the top 4 bits of g.hi into its low 4 bits, which moves the highest set bit of neither a g.hi >= 2^28
         // nor (g.hi >> 28 == 0) a smaller one -- so h.hi is never materialised.
-        saddr = sbase + ((glo ^ __funnelshift_r(glo, ghi, 28)) & ((1u << p) - 1u)) * 4u;
+        const uint32_t idx = (glo ^ __funnelshift_r(glo, ghi, 28)) & ((1u << p) - 1u);
+        // wide k: the cell address as IMAD by a run-time 4 (FMA pipe) instead of LEA (ALU pipe, 88 % busy there)
+        saddr = (!NARROW && LASH_WIDE_FMA) ? mad32_opaque(idx, hc.two29 >> 27, sbase) : sbase + idx * 4u;
         v = 32u - bfind32(ghi);  // rho when g.hi != 0; g.hi == 0 (<=> h.hi == 0) -> 33 <= true rho (p <= 18)
         rare_word = ghi;
     }
@@ -267,6 +269,7 @@ __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
     const uint32_t narrow_mask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
     const uint32_t wide_shr = WIDE ? (uint32_t)(64 - 2 * k) : 0u;               // in [0,30]
     const uint32_t wide_mask_hi = (k >= 32) ? 0xffffffffu : ((1u << ((2 * k - 32) & 31)) - 1u);
+    const uint32_t wide_mul = (WIDE && k < 32) ? (hc.two29 >> 29) << ((32u - wide_shr) & 31u) : 0u;   // 2^(32 - wide_shr), run-time
 
     // Persistent CTAs: CTA c owns the contiguous tile range [c*T/G, (c+1)*T/G) of the (genome-ordered)
     // tile list, so equal-cost tiles are balanced statically with no tail, and the private accumulator
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
                 // canonical masked k-mer starting at base i of this word (sh = 2*i): funnel-shift windows
                 // of the forward stream and of the reverse-complemented stream, then min
                 auto kmer = [&](const int sh, uint32_t& klo, uint32_t& khi) {
-                    canonical_kmer<KM>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, klo, khi);
+                    canonical_kmer<KM>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, wide_mul, klo, khi);
                 };
                 // exact, checked, rolled path: partial validity, rare hashes, global accumulators
                 auto exact_block = [&](const uint32_t mask16) {

@@ -139,15 +139,16 @@ void dm_kmers(const uint8_t* packed, uint64_t n_bytes, uint64_t n_bases, int k, 
     const uint32_t narrow_mask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
     const uint32_t wide_shr = wide ? (uint32_t)(64 - 2 * k) : 0u;
     const uint32_t wide_mask_hi = (k >= 32) ? 0xffffffffu : ((1u << ((2 * k - 32) & 31)) - 1u);
+    const uint32_t wide_mul = (wide && k < 32) ? 1u << ((32u - wide_shr) & 31u) : 0u;
     for (uint64_t s0 = 0; s0 + (uint64_t)k <= n_bases; ++s0) {
         const uint64_t j = s0 >> 4;
         const int sh = 2 * (int)(s0 & 15);
         const uint32_t A0 = word(j), B0 = word(j + 1), C0 = word(j + 2);
         const uint32_t Ar = rc16(A0), Br = rc16(B0), Cr = rc16(C0);
         uint32_t klo, khi;
-        if (k == 16) canonical_kmer<K16>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, klo, khi);
-        else if (!wide) canonical_kmer<KNARROW>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, klo, khi);
-        else canonical_kmer<KWIDE>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, klo, khi);
+        if (k == 16) canonical_kmer<K16>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, wide_mul, klo, khi);
+        else if (!wide) canonical_kmer<KNARROW>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, wide_mul, klo, khi);
+        else canonical_kmer<KWIDE>(A0, B0, C0, Ar, Br, Cr, sh, narrow_shr, narrow_mask, wide_shr, wide_mask_hi, wide_mul, klo, khi);
         out[s0] = ((uint64_t)khi << 32) | klo;
     }
 }
