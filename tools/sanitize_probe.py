@@ -41,8 +41,25 @@ with ops.Context(0) as ctx:
     ull = (4 * (rng.integers(3, 12, size=(n, m)) + 9) + rng.integers(0, 4, size=(n, m))).astype(np.uint8)
     for est in (EST_FGRA, EST_ML):
         ops.dist(ctx, ALGO_ULL, 10, 16, est, 1, False, ull[: n // 2 + 3], ull)
+    ull[3, 7] = 0                                             # an empty register: the tiles of sketch 3 use the ML table form,
+    ull[5, 9] = 4 * 10 + 4 + 4 * 29                           # ... sketch 5 is flagged on G-sum tiles (28 levels above the rest)
+    ops.dist(ctx, ALGO_ULL, 10, 16, EST_ML, 1, False, ull[: n // 2 + 3], ull)
     hll = rng.integers(0, 30, size=(n, 1 << 12)).astype(np.uint8)
     ops.dist(ctx, ALGO_HLL, 12, 21, 0, 1, False, hll[: n // 2 - 3], hll)
+    hll_w = rng.integers(5, 20, size=(n, 1 << 12)).astype(np.uint8)   # K4i: windows above 0, a flagged sketch (hll_pair_exact)
+    hll_w[2, 11] = 50
+    ops.dist(ctx, ALGO_HLL, 12, 21, 0, 1, False, hll_w[: n // 2 - 3], hll_w)
+    if not small:                                             # K4i's 64 x 64 tile shape needs a grid of >= 8 tiles per SM
+        hll_7 = rng.integers(3, 25, size=(2300, 1 << 7)).astype(np.uint8)
+        hll_7[100, 5] = 58
+        ops.dist(ctx, ALGO_HLL, 7, 21, 0, 1, False, hll_7, hll_7)
+    # HMH sketches of few k-mers: slots, term vectors and the expected-collision tile product (two tiles when not --small)
+    ns = 20 if small else 140
+    dense3 = ((rng.integers(1, 12, size=(3, 16384)) << 10) | rng.integers(0, 1024, size=(3, 16384))).astype(np.uint16)
+    sparse = np.where(rng.random((ns, 16384)) < 0.05, ((rng.integers(1, 6, size=(ns, 16384)) << 10) | rng.integers(0, 1024, size=(ns, 16384))), 0).astype(np.uint16)
+    sparse[1::2] = np.where(rng.random((ns // 2, 16384)) < 0.5, sparse[0::2], sparse[1::2])
+    ops.dist(ctx, ALGO_HMH, 14, 16, 0, 1, False, np.concatenate([sparse, dense3]), sparse, triangular=False)
+    ops.dist(ctx, ALGO_HMH, 14, 16, 0, 1, False, sparse, sparse, triangular=True)
     hmh = ((rng.integers(0, 12, size=(n, 16384)) << 10) | rng.integers(0, 1024, size=(n, 16384))).astype(np.uint16)
     hmh[0, ::3] = 0
     ops.dist(ctx, ALGO_HMH, 14, 16, 0, 1, False, hmh[: n // 2 + 1], hmh)
