@@ -198,6 +198,9 @@ __device__ __forceinline__ void global_update(uint32_t* gacc, uint32_t idx, uint
 // split is by what fits one 32-bit word, with k == 16 (lash's default) special-cased because the
 // window IS the word (no shift, no mask).
 constexpr int kGroup = 16;  // k-mers whose atomics are deferred together (one 32-bit word of bases)
+#ifndef LASH_DEFER_QUARTERS
+#define LASH_DEFER_QUARTERS 1
+#endif
 
 // CTA size is a template parameter so that the register budget follows it.  Measured on B200 (tools/variant_sweep):
 // ~80 registers with 24 resident warps per SM beats 64 registers with 32 warps (+4 % at C2) and everything
@@ -355,7 +358,13 @@ __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
                 auto fast_block = [&](auto checked, const uint32_t mask16) {
                     constexpr bool CHECKED = decltype(checked)::value;
                     uint32_t addr[kGroup], need[kGroup];
-                    uint32_t any = 0u, rare = 0xffffffffu, rw_prev = 0xffffffffu;
+                    uint32_t rare = 0xffffffffu, rw_prev = 0xffffffffu;
+                    // The deferred atomics run in four quarters of four: late in a genome a warp's 512 k-mers hold one or two
+                    // updates, and walking all 16 predicated atomics for them costs more than four extra tests.  Measured
+                    // (tools/variant_sweep, B200): ULL k16 +1.0 %, HLL k21 +0.7 ... 1.8 %, 150 bp reads +1.4 %, HMH -0.7 % (its
+                    // block is entered more often: every new 10-bit signature is an update) -- so not for HMH.
+                    constexpr bool kQuarters = LASH_DEFER_QUARTERS && ALGO != HMH;
+                    uint32_t anyq[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int i = 0; i < kGroup; ++i) {
                         uint32_t klo, khi, v, rw;
@@ -363,14 +372,25 @@ __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
                         A::template prep<!WIDE, TB == kTbSmall>(klo, khi, hc, p, sbase, addr[i], v, rw);
                         need[i] = A::need(lds_u32(addr[i]), v);
                         if (CHECKED) need[i] = (mask16 & (1u << i)) ? need[i] : 0u;
-                        any |= need[i];
+                        anyq[kQuarters ? i >> 2 : 0] |= need[i];
                         if (i & 1) rare = __vimin3_u32(rare, rw_prev, rw);  // one VIMNMX3 per two k-mers
                         else rw_prev = rw;
                     }
-                    if (any) {
+                    if (anyq[0] | anyq[1] | anyq[2] | anyq[3]) {
+                        if constexpr (kQuarters) {
 #pragma unroll
-                        for (int i = 0; i < kGroup; ++i)
-                            if (need[i]) A::apply(addr[i], need[i]);
+                            for (int q = 0; q < 4; ++q) {
+                                if (anyq[q]) {
+#pragma unroll
+                                    for (int i = 4 * q; i < 4 * q + 4; ++i)
+                                        if (need[i]) A::apply(addr[i], need[i]);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < kGroup; ++i)
+                                if (need[i]) A::apply(addr[i], need[i]);
+                        }
                     }
                     if (rare == 0u) exact_block(mask16);  // some hash had 32 leading zeros where it matters
                 };
