@@ -201,6 +201,12 @@ constexpr int kGroup = 16;  // k-mers whose atomics are deferred together (one 3
 #ifndef LASH_DEFER_QUARTERS
 #define LASH_DEFER_QUARTERS 1
 #endif
+#ifndef LASH_W_UNROLL
+#define LASH_W_UNROLL 1
+#endif
+// the four word steps of a thread's 64 starts stay rolled: unrolled twice ULL k16 +0.3 %, HLL k21 -1.6 %, HMH +0.9 %; four
+// times -6 % everywhere (instruction cache: one straight-line block is ~6.5 KB) -- tools/variant_sweep, B200
+constexpr int kWordUnroll = LASH_W_UNROLL;
 
 // CTA size is a template parameter so that the register budget follows it.  Measured on B200 (tools/variant_sweep):
 // ~80 registers with 24 resident warps per SM beats 64 registers with 32 warps (+4 % at C2) and everything
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(TB, MinBlocks<TB>::value)
             // reverse complements of the words are carried across the four word steps (each word is the "B" of one
             // step and the "A" of the next; wide k-mers also look one word further)
             uint32_t rcA = rc16(f0), rcB = WIDE ? rc16(f1) : 0u;
-    #pragma unroll 1
+    #pragma unroll kWordUnroll
             for (int w = 0; w < 4; ++w) {
                 const uint32_t v16 = (uint32_t)(valid >> (16 * w)) & 0xffffu;
                 const uint32_t A0 = f0, B0 = f1, C0 = f2;
