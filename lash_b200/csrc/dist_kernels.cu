@@ -899,31 +899,60 @@ __global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParam
     if (dp.triangular && col0 > row_hi - 1) continue;  // tile entirely above the diagonal (CTA-uniform)
     double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 
+    // The registers of the NEXT chunk are fetched into registers before the current chunk is consumed, so the global-load
+    // latency hides behind ~17 us of table lookups instead of standing between two barriers (one CTA per SM: nothing else
+    // would cover it).  kPreA / kPreB words per thread at the largest chunk (256 registers = 64 words per row).
+    constexpr int kPreA = kTabTR * (kTabChunk / 4) / kTabThreads, kPreB = kTabTQ * (kTabChunk / 4) / kTabThreads;
+    uint32_t pre_a[kPreA], pre_b[kPreB];
+    auto fetch = [&](uint32_t c0) {
+#pragma unroll
+        for (int u = 0; u < kPreA; ++u) {
+            const uint32_t e = threadIdx.x + (uint32_t)u * kTabThreads;
+            const uint32_t r = e / chunk_words, w = e % chunk_words;
+            const uint64_t gi = row0 + r;
+            pre_a[u] = (e < (uint32_t)kTabTR * chunk_words && gi < dp.row_end) ? __ldg(reinterpret_cast<const uint32_t*>(gref + gi * cell_bytes + c0) + w) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kPreB; ++u) {
+            const uint32_t e = threadIdx.x + (uint32_t)u * kTabThreads;
+            const uint32_t r = e / chunk_words, w = e % chunk_words;
+            const uint64_t gj = col0 + r;
+            pre_b[u] = (e < (uint32_t)kTabTQ * chunk_words && gj < dp.n_qry) ? __ldg(reinterpret_cast<const uint32_t*>(gqry + gj * cell_bytes + c0) + w) : 0u;
+        }
+    };
+    fetch(0);
     for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk) {
         __syncthreads();  // previous chunk consumed (first pass: orders the table build)
         // stage + recode: reference side as byte offsets of the table ROW (code << 9: 128 words), query side as byte
         // offsets inside a row (code << 2)
-        for (uint32_t e = threadIdx.x; e < (uint32_t)kTabTR * chunk_words; e += kTabThreads) {
-            const uint32_t r = e / chunk_words, w = e % chunk_words;
-            const uint64_t gi = row0 + r;
-            const uint32_t v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint32_t*>(gref + gi * cell_bytes + c0) + w) : 0u;
-            uint4 o;
-            o.x = fgra_code(v & 0xffu, base) << 9;
-            o.y = fgra_code((v >> 8) & 0xffu, base) << 9;
-            o.z = fgra_code((v >> 16) & 0xffu, base) << 9;
-            o.w = fgra_code(v >> 24, base) << 9;
-            *reinterpret_cast<uint4*>(sa + r * a_stride + 4 * w) = o;
+#pragma unroll
+        for (int u = 0; u < kPreA; ++u) {
+            const uint32_t e = threadIdx.x + (uint32_t)u * kTabThreads;
+            if (e < (uint32_t)kTabTR * chunk_words) {
+                const uint32_t r = e / chunk_words, w = e % chunk_words;
+                const uint32_t v = pre_a[u];
+                uint4 o;
+                o.x = fgra_code(v & 0xffu, base) << 9;
+                o.y = fgra_code((v >> 8) & 0xffu, base) << 9;
+                o.z = fgra_code((v >> 16) & 0xffu, base) << 9;
+                o.w = fgra_code(v >> 24, base) << 9;
+                *reinterpret_cast<uint4*>(sa + r * a_stride + 4 * w) = o;
+            }
         }
-        for (uint32_t e = threadIdx.x; e < (uint32_t)kTabTQ * chunk_words; e += kTabThreads) {
-            const uint32_t r = e / chunk_words, w = e % chunk_words;
-            const uint64_t gj = col0 + r;
-            const uint32_t v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint32_t*>(gqry + gj * cell_bytes + c0) + w) : 0u;
-            uint2 o;
-            o.x = (fgra_code(v & 0xffu, base) << 2) | (fgra_code((v >> 8) & 0xffu, base) << 18);
-            o.y = (fgra_code((v >> 16) & 0xffu, base) << 2) | (fgra_code(v >> 24, base) << 18);
-            *reinterpret_cast<uint2*>(sb + r * b_stride + 4 * w) = o;
+#pragma unroll
+        for (int u = 0; u < kPreB; ++u) {
+            const uint32_t e = threadIdx.x + (uint32_t)u * kTabThreads;
+            if (e < (uint32_t)kTabTQ * chunk_words) {
+                const uint32_t r = e / chunk_words, w = e % chunk_words;
+                const uint32_t v = pre_b[u];
+                uint2 o;
+                o.x = (fgra_code(v & 0xffu, base) << 2) | (fgra_code((v >> 8) & 0xffu, base) << 18);
+                o.y = (fgra_code((v >> 16) & 0xffu, base) << 2) | (fgra_code(v >> 24, base) << 18);
+                *reinterpret_cast<uint2*>(sb + r * b_stride + 4 * w) = o;
+            }
         }
         __syncthreads();
+        if (c0 + chunk < cell_bytes) fetch(c0 + chunk);
         const uint32_t* pa0 = sa + ty * a_stride;
         const uint32_t* pa1 = sa + (ty + 16) * a_stride;
         const uint16_t* pb0 = sb + tx * b_stride;
@@ -1111,35 +1140,64 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
     acc[0].init();
     acc[1].init();
 
+    // the next chunk's registers are fetched before the current chunk is consumed (as in K4b: one CTA per SM, nothing else
+    // would cover the global-load latency between the two barriers)
+    constexpr int kPreA = kMlTabTR * (kMlTabChunk / 4) / kMlTabThreads, kPreB = kMlTabTQ * (kMlTabChunk / 4) / kMlTabThreads;
+    static_assert(kPreA >= 1 && kPreB >= 1, "prefetch registers per thread");
+    uint32_t pre_a[kPreA], pre_b[kPreB];
+    auto fetch = [&](uint32_t c0) {
+#pragma unroll
+        for (int u = 0; u < kPreA; ++u) {
+            const uint32_t e = threadIdx.x + (uint32_t)u * kMlTabThreads;
+            const uint32_t r = e / chunk_words, w = e % chunk_words;
+            const uint64_t gi = row0 + r;
+            pre_a[u] = (e < (uint32_t)kMlTabTR * chunk_words && gi < dp.row_end) ? __ldg(reinterpret_cast<const uint32_t*>(gref + gi * cell_bytes + c0) + w) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kPreB; ++u) {
+            const uint32_t e = threadIdx.x + (uint32_t)u * kMlTabThreads;
+            const uint32_t r = e / chunk_words, w = e % chunk_words;
+            const uint64_t gj = col0 + r;
+            pre_b[u] = (e < (uint32_t)kMlTabTQ * chunk_words && gj < dp.n_qry) ? __ldg(reinterpret_cast<const uint32_t*>(gqry + gj * cell_bytes + c0) + w) : 0u;
+        }
+    };
+    fetch(0);
     for (uint32_t c0 = 0; c0 < cell_bytes; c0 += chunk) {
         __syncthreads();
         // stage + recode: reference side code << 9 (byte offset of the 128-word table row), query side code << 2
-        for (uint32_t e = threadIdx.x; e < (uint32_t)kMlTabTR * chunk_words; e += kMlTabThreads) {
-            const uint32_t r = e / chunk_words, w = e % chunk_words;
-            const uint64_t gi = row0 + r;
-            const uint32_t v = gi < dp.row_end ? __ldg(reinterpret_cast<const uint32_t*>(gref + gi * cell_bytes + c0) + w) : 0u;
-            const uint32_t c0_ = fgra_code(v & 0xffu, base), c1_ = fgra_code((v >> 8) & 0xffu, base);
-            const uint32_t c2_ = fgra_code((v >> 16) & 0xffu, base), c3_ = fgra_code(v >> 24, base);
-            if (max(max(c0_, c1_), max(c2_, c3_)) == 127u) atomicOr(&sflag[r], 1u);
-            // G-sum tiles stage the absolute shared address of the W-plane row (one add per register saved in the loop)
-            const uint32_t a_off = gs ? rbase + 2u * kPlane : 0u;
-            *reinterpret_cast<uint4*>(sa + r * a_stride + 4 * w) = make_uint4((c0_ << 9) + a_off, (c1_ << 9) + a_off, (c2_ << 9) + a_off, (c3_ << 9) + a_off);
-            if (gs)
-                *reinterpret_cast<uint4*>(sga + r * a_stride + 4 * w) = make_uint4(ml_gs_term(ml_gs_n(v & 0xffu, p, k0)), ml_gs_term(ml_gs_n((v >> 8) & 0xffu, p, k0)),
-                                                                                   ml_gs_term(ml_gs_n((v >> 16) & 0xffu, p, k0)), ml_gs_term(ml_gs_n(v >> 24, p, k0)));
+#pragma unroll
+        for (int u = 0; u < kPreA; ++u) {
+            const uint32_t e = threadIdx.x + (uint32_t)u * kMlTabThreads;
+            if (e < (uint32_t)kMlTabTR * chunk_words) {
+                const uint32_t r = e / chunk_words, w = e % chunk_words;
+                const uint32_t v = pre_a[u];
+                const uint32_t c0_ = fgra_code(v & 0xffu, base), c1_ = fgra_code((v >> 8) & 0xffu, base);
+                const uint32_t c2_ = fgra_code((v >> 16) & 0xffu, base), c3_ = fgra_code(v >> 24, base);
+                if (max(max(c0_, c1_), max(c2_, c3_)) == 127u) atomicOr(&sflag[r], 1u);
+                // G-sum tiles stage the absolute shared address of the W-plane row (one add per register saved in the loop)
+                const uint32_t a_off = gs ? rbase + 2u * kPlane : 0u;
+                *reinterpret_cast<uint4*>(sa + r * a_stride + 4 * w) = make_uint4((c0_ << 9) + a_off, (c1_ << 9) + a_off, (c2_ << 9) + a_off, (c3_ << 9) + a_off);
+                if (gs)
+                    *reinterpret_cast<uint4*>(sga + r * a_stride + 4 * w) = make_uint4(ml_gs_term(ml_gs_n(v & 0xffu, p, k0)), ml_gs_term(ml_gs_n((v >> 8) & 0xffu, p, k0)),
+                                                                                       ml_gs_term(ml_gs_n((v >> 16) & 0xffu, p, k0)), ml_gs_term(ml_gs_n(v >> 24, p, k0)));
+            }
         }
-        for (uint32_t e = threadIdx.x; e < (uint32_t)kMlTabTQ * chunk_words; e += kMlTabThreads) {
-            const uint32_t r = e / chunk_words, w = e % chunk_words;
-            const uint64_t gj = col0 + r;
-            const uint32_t v = gj < dp.n_qry ? __ldg(reinterpret_cast<const uint32_t*>(gqry + gj * cell_bytes + c0) + w) : 0u;
-            const uint32_t c0_ = fgra_code(v & 0xffu, base), c1_ = fgra_code((v >> 8) & 0xffu, base);
-            const uint32_t c2_ = fgra_code((v >> 16) & 0xffu, base), c3_ = fgra_code(v >> 24, base);
-            if (max(max(c0_, c1_), max(c2_, c3_)) == 127u) atomicOr(&sflag[kMlTabTR + r], 1u);
-            *reinterpret_cast<uint2*>(sb + r * b_stride + 4 * w) =
-                make_uint2(ml_pack_b(c0_, ml_gs_n(v & 0xffu, p, k0), c1_, ml_gs_n((v >> 8) & 0xffu, p, k0)),
-                           ml_pack_b(c2_, ml_gs_n((v >> 16) & 0xffu, p, k0), c3_, ml_gs_n(v >> 24, p, k0)));
+#pragma unroll
+        for (int u = 0; u < kPreB; ++u) {
+            const uint32_t e = threadIdx.x + (uint32_t)u * kMlTabThreads;
+            if (e < (uint32_t)kMlTabTQ * chunk_words) {
+                const uint32_t r = e / chunk_words, w = e % chunk_words;
+                const uint32_t v = pre_b[u];
+                const uint32_t c0_ = fgra_code(v & 0xffu, base), c1_ = fgra_code((v >> 8) & 0xffu, base);
+                const uint32_t c2_ = fgra_code((v >> 16) & 0xffu, base), c3_ = fgra_code(v >> 24, base);
+                if (max(max(c0_, c1_), max(c2_, c3_)) == 127u) atomicOr(&sflag[kMlTabTR + r], 1u);
+                *reinterpret_cast<uint2*>(sb + r * b_stride + 4 * w) =
+                    make_uint2(ml_pack_b(c0_, ml_gs_n(v & 0xffu, p, k0), c1_, ml_gs_n((v >> 8) & 0xffu, p, k0)),
+                               ml_pack_b(c2_, ml_gs_n((v >> 16) & 0xffu, p, k0), c3_, ml_gs_n(v >> 24, p, k0)));
+            }
         }
         __syncthreads();
+        if (c0 + chunk < cell_bytes) fetch(c0 + chunk);
         const uint32_t* pa = sa + ty * a_stride;
         const uint16_t* pb0 = sb + tx * b_stride;
         const uint16_t* pb1 = sb + (tx + 32) * b_stride;
