@@ -199,9 +199,16 @@ int lash_dist(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, i
  * each rank takes a row range); out_dev is indexed like `out` above (full-matrix indexing).
  * card_ref_dev / card_qry_dev: per-sketch cardinalities from lash_cardinality_dev (ignored for HMH).
  * flags_dev: optional uint32 counter incremented for each pair in the HLL bias regime.
- * Register arrays should be 16-byte aligned (anything cudaMalloc returns is): the HLL tile kernel stages with 16-byte loads and
- * falls back to the slower generic kernel for unaligned pointers.  ULL ML allocates a per-context scratch (60 B per output cell
- * at p <= 11) for its two-kernel form and falls back to the fused kernel above LASH_ML_SCRATCH_MAX_MB (default 16 GiB). */
+ * Register arrays should be 16-byte aligned (anything cudaMalloc returns is): the HLL / HMH tile kernels stage with 16-byte loads
+ * and fall back to the slower generic kernel for unaligned pointers.  ULL ML allocates a per-context scratch (60 B per output cell
+ * at p <= 11) for its two-kernel form and falls back to the fused kernel above LASH_ML_SCRATCH_MAX_MB (default 16 GiB).
+ * HLL and ULL ML first make one pass over both register arrays for every sketch's smallest / largest register (4 B per sketch of
+ * context scratch; the tile kernels anchor their fixed-point windows on them).  HMH: when the row range and the query set both
+ * hold sketches of <= 2^19 k-mers, the call counts them (an 8-byte device-to-host copy and ONE stream synchronisation -- the
+ * only one in the device-resident API, so such a call cannot be captured in a CUDA graph) and precomputes hyperminhash's
+ * expected-collision loop for all pairs of them in context scratch (336 KB per small sketch + 8 B per small pair, capped by
+ * LASH_HMH_EC_MAX_MB, default 24 GiB; beyond the cap, or with LASH_HMH_EC=loop, the loop runs per pair as in the reference).
+ * One context's scratch serves one call at a time: concurrent lash_dist* calls need one context each. */
 int lash_dist_dev(lash_ctx* ctx, int algo, int p, int k, int estimator, int model, int fp32, const void* ref_dev,
                   uint64_t n_ref, const void* qry_dev, uint64_t n_qry, const double* card_ref_dev,
                   const double* card_qry_dev, int triangular, uint64_t row_begin, uint64_t row_end, void* out_dev,
