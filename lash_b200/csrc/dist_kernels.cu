@@ -1869,6 +1869,67 @@ cudaError_t launch_dist(const DistParams& dp, cudaStream_t st, uint32_t* n_launc
     return tiny ? launch_dist_t<MlAcc, 8>(dp, st) : launch_dist_t<MlAcc, 16>(dp, st);
 }
 
+// K3 for HLL, warp-parallel: the sum of 2^-r over a sketch whose registers lie within 29 levels of its smallest one is exact in
+// f64 in any order (dist_tables.cuh, K4i), so the 32 lanes sum their shares as integers and the total equals the reference's
+// sequential loop bit for bit; card_kernel<HllAcc> (one lane walking 2^p registers: 67 us per sketch at p = 14, 1.8 ms for C3's
+// 10 000 sketches on EVERY rank) remains for sketches outside the window (10^-3 of them), for unaligned arrays and p < 4.
+__global__ void __launch_bounds__(kCardWarps * 32) card_hll_int_kernel(const unsigned char* __restrict__ regs, uint64_t n, uint32_t cell_bytes, int p,
+                                                                       double* __restrict__ card, uint32_t* flags) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t i = (uint64_t)blockIdx.x * kCardWarps + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const unsigned char* g = regs + i * cell_bytes;
+    const uint4* src = reinterpret_cast<const uint4*>(g);
+    const uint32_t n16 = cell_bytes / 16;
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    for (uint32_t e = lane; e < n16; e += 32) {
+        const uint4 v = __ldg(src + e);
+        mn = __vminu4(__vminu4(mn, v.x), __vminu4(__vminu4(v.y, v.z), v.w));
+        mx = __vmaxu4(__vmaxu4(mx, v.x), __vmaxu4(__vmaxu4(v.y, v.z), v.w));
+    }
+    mn = __vminu4(mn, mn >> 16), mn = __vminu4(mn, mn >> 8) & 0xffu;
+    mx = __vmaxu4(mx, mx >> 16), mx = __vmaxu4(mx, mx >> 8) & 0xffu;
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, mn), hi = __reduce_max_sync(0xffffffffu, mx);
+    double sum;
+    uint32_t zero;
+    if (hi - lo <= (uint32_t)kHllIntW) {
+        uint64_t s64 = 0;
+        uint32_t z = 0;
+        for (uint32_t e = lane; e < n16; e += 32) {
+            const uint4 v = __ldg(src + e);
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 t = hll_int_recode(w4[k], lo);
+                s64 += (uint64_t)t.x + t.y + t.z + t.w;                                  // 4 * 2^28 per step: no overflow
+                z += (uint32_t)__popc(__vcmpeq4(w4[k], 0u)) >> 3;                           // empty registers (0xff per zero byte)
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            s64 += __shfl_xor_sync(0xffffffffu, s64, d);
+            z += __shfl_xor_sync(0xffffffffu, z, d);
+        }
+        sum = (double)s64 * __hiloint2double((int)((1023u - (uint32_t)kHllIntW - lo) << 20), 0);
+        zero = z;
+    } else {
+        sum = 0.0;
+        zero = 0;
+        if (lane == 0) {
+            for (uint32_t e = 0; e < cell_bytes; ++e) {   // the reference's loop
+                const uint32_t r = g[e];
+                zero += r == 0u;
+                sum += __hiloint2double((int)(kHllOne - (r << 20)), 0);
+            }
+        }
+    }
+    if (lane == 0) {
+        bool bias;
+        card[i] = hll_len(sum, zero, p, &bias);
+        if (bias && flags) atomicAdd(flags, 1u);
+    }
+}
+
 template <class ACC, int G>
 static cudaError_t launch_card_t(int algo, int p, const void* regs, uint64_t n, double* card, uint32_t* flags,
                                  cudaStream_t st) {
@@ -1886,7 +1947,16 @@ cudaError_t launch_cardinality(int algo, int p, int estimator, const void* regs,
         card_hmh_kernel<<<(unsigned)((n + kCardWarps - 1) / kCardWarps), kCardWarps * 32, 0, st>>>(reinterpret_cast<const uint32_t*>(regs), n, card);
         return cudaGetLastError();
     }
-    if (algo == HLL) return launch_card_t<HllAcc, 16>(algo, p, regs, n, card, flags, st);
+    if (algo == HLL) {
+        // LASH_HLL_KERNEL=float|table: the sequential kernel (A/B measurements)
+        static const bool seq = [] { const char* v = getenv("LASH_HLL_KERNEL"); return v && (std::string(v) == "float" || std::string(v) == "table"); }();
+        const uint32_t cb = cell_bytes_of(algo, p);
+        if (!seq && ((uintptr_t)regs & 15u) == 0 && cb % 16 == 0) {
+            card_hll_int_kernel<<<(unsigned)((n + kCardWarps - 1) / kCardWarps), kCardWarps * 32, 0, st>>>(reinterpret_cast<const unsigned char*>(regs), n, cb, p, card, flags);
+            return cudaGetLastError();
+        }
+        return launch_card_t<HllAcc, 16>(algo, p, regs, n, card, flags, st);
+    }
     const bool tiny = p == 3;
     if (estimator == 0)
         return tiny ? launch_card_t<FgraAcc, 8>(algo, p, regs, n, card, flags, st)

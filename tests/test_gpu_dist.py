@@ -101,6 +101,35 @@ def test_cardinalities(oracle, gpu_ctx, algo, p, k, est):
         assert np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize("p", [4, 7, 12, 14, 18])
+def test_hll_cardinalities_warp_parallel_equal_the_sequential_sum(oracle, gpu_ctx, p):
+    """card_hll_int_kernel: 32 lanes sum 2^-r as integers when the sketch's registers span at most 29 levels (exact, so equal
+    to the reference's sequential f64 loop bit for bit), one lane runs that loop otherwise.  Raw estimates have no libm call:
+    bit-exact; linear counting adds one log (<= 4 ulp); the bias regime is flagged as NaN on both sides."""
+    rng = np.random.default_rng(p)
+    m = 1 << p
+    rows = []
+    for lg in (-4.0, -1.0, 1.0, 5.0, 12.0, 25.0):                       # nearly empty ... huge
+        if lg < 0:
+            hit = rng.random(m) < 2.0 ** lg
+            rows.append((hit * np.clip(rng.geometric(0.5, size=m), 1, 64 - p + 1)).astype(np.uint8))
+        else:
+            rows.append(np.clip(np.floor(lg - np.log2(-np.log(rng.random(m)))) + 1, 1, 64 - p + 1).astype(np.uint8))
+    wide = rows[3].copy(); wide[1] = 64 - p + 1                          # spans more than 29 levels: sequential path
+    edge = np.full(m, 7, dtype=np.uint8); edge[2] = 7 + 28               # exactly the last level inside the window
+    over = np.full(m, 7, dtype=np.uint8); over[2] = 7 + 29               # first level outside
+    rows += [wide, edge, over, np.zeros(m, dtype=np.uint8), np.full(m, 64 - p + 1, dtype=np.uint8)]
+    regs = np.stack(rows)
+    got = ops.cardinality(gpu_ctx, ALGO_HLL, p, 0, regs)
+    exp = np.array([oracle.cardinality(ALGO_HLL, p, 0, r) for r in regs])
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+    ok = ~np.isnan(exp)
+    assert np.all(np.abs(got[ok] - exp[ok]) <= 4 * EPS * np.abs(exp[ok])), (got, exp)
+    raw = ok & (regs.min(axis=1) > 0)                                    # no empty register -> no linear counting, no log
+    assert raw.sum() >= 4
+    np.testing.assert_array_equal(got[raw], exp[raw])
+
+
 def test_triangular_packed_equals_dense_lower(oracle, gpu_ctx):
     """same_files rule (utils.rs:158-160,256-258,350-352): only j <= i, diagonal included."""
     regs = _sketches(oracle, ALGO_ULL, 10, 16, 45, 100_000)
