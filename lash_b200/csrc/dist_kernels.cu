@@ -1584,6 +1584,35 @@ __global__ void __launch_bounds__(kCardWarps * 32) card_hmh_kernel(const uint32_
     const uint64_t i = (uint64_t)blockIdx.x * kCardWarps + warp;
     if (i >= n) return;
     const uint32_t* g = regs + i * 8192u;
+    // Warp-parallel when exact: the terms 2^-lz of a sketch whose leading-zero counts span at most 29 levels sum to the same
+    // double in any order (no partial sum of the sequential loop rounds: 16384 * 2^28 < 2^53 units of 2^-(lo+28); K4i's
+    // argument), so the lanes add their shares as integers.  Otherwise lane 0 walks the registers as the reference does.
+    uint32_t mn = 63u, mx = 0u;
+    for (uint32_t w = lane; w < 8192u; w += 32) {
+        const uint32_t v = __ldg(g + w);
+        const uint32_t l0 = (v & 0xffffu) >> 10, l1 = v >> 26;
+        mn = min(mn, min(l0, l1));
+        mx = max(mx, max(l0, l1));
+    }
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, mn), hi = __reduce_max_sync(0xffffffffu, mx);
+    if (hi - lo <= (uint32_t)kHllIntW) {
+        uint64_t s64 = 0;
+        uint32_t z = 0;
+        for (uint32_t w = lane; w < 8192u; w += 32) {
+            const uint32_t v = __ldg(g + w);
+            const uint32_t l0 = (v & 0xffffu) >> 10, l1 = v >> 26;
+            s64 += (uint64_t)(1u << (kHllIntW - (l0 - lo))) + (1u << (kHllIntW - (l1 - lo)));
+            z += (l0 == 0u) + (l1 == 0u);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            s64 += __shfl_xor_sync(0xffffffffu, s64, d);
+            z += __shfl_xor_sync(0xffffffffu, z, d);
+        }
+        if (lane == 0)
+            card[i] = hmh_cardinality_from((double)s64 * __hiloint2double((int)((1023u - (uint32_t)kHllIntW - lo) << 20), 0), (double)z);
+        return;
+    }
     uint32_t* stage = s_stage[warp];
     double sum = 0.0, ez = 0.0;
     for (uint32_t w0 = 0; w0 < 8192u; w0 += kCardChunk / 4) {

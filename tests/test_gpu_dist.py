@@ -130,6 +130,29 @@ def test_hll_cardinalities_warp_parallel_equal_the_sequential_sum(oracle, gpu_ct
     np.testing.assert_array_equal(got[raw], exp[raw])
 
 
+def test_hmh_cardinalities_warp_parallel_and_sequential_paths(oracle, gpu_ctx):
+    """card_hmh_kernel sums 2^-lz warp-parallel as integers when a sketch's leading-zero counts span at most 29 levels (exact:
+    equal to the sequential loop), sequentially otherwise: dense, sparse (empty registers), wide-span, edge-of-window, empty
+    and saturated sketches against the oracle (the estimate adds beta(ez): a few ulp of libm)."""
+    rng = np.random.default_rng(21)
+    m = 16384
+    def sk(per_reg, sparse=1.0):
+        lvl = np.clip(np.floor(per_reg - np.log2(-np.log(rng.random(m)))), 0, 45).astype(np.int64)
+        hit = rng.random(m) < sparse
+        return np.where(hit, ((lvl + 1) << 10) | rng.integers(0, 1024, size=m), 0).astype(np.uint16)
+    rows = [sk(7.0), sk(2.0), sk(0.5, 0.3), sk(0.0, 0.01), sk(20.0)]
+    wide = sk(7.0); wide[5] = (51 << 10) | 3; wide[6] = (1 << 10) | 9          # spans 50 levels: sequential path
+    edge = np.full(m, (9 << 10) | 1, dtype=np.uint16); edge[3] = ((9 + 28) << 10) | 5   # last level inside the window
+    over = np.full(m, (9 << 10) | 1, dtype=np.uint16); over[3] = ((9 + 29) << 10) | 5   # first level outside
+    rows += [wide, edge, over, np.zeros(m, dtype=np.uint16), np.full(m, (50 << 10) | 1023, dtype=np.uint16)]
+    regs = np.stack(rows)
+    got = ops.cardinality(gpu_ctx, ALGO_HMH, 14, 0, regs)
+    exp = np.array([oracle.cardinality(ALGO_HMH, 14, 0, r) for r in regs])
+    fin = np.isfinite(exp)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert np.all(np.abs(got[fin] - exp[fin]) <= 8 * EPS * np.abs(exp[fin])), (got, exp)
+
+
 def test_triangular_packed_equals_dense_lower(oracle, gpu_ctx):
     """same_files rule (utils.rs:158-160,256-258,350-352): only j <= i, diagonal included."""
     regs = _sketches(oracle, ALGO_ULL, 10, 16, 45, 100_000)
