@@ -443,9 +443,12 @@ __global__ void __launch_bounds__(kHllThreads, 3) dist_hll_fast_kernel(DistParam
 // multiply-add by a run-time 1 (IMAD, FMA-heavy pipe; with a literal 1 ptxas turns it back into an ALU add), eight terms
 // per 32-bit batch, one IMAD.WIDE per batch into the 64-bit sum: 2.1 issue slots per register pair split evenly over the
 // two integer pipes.  Per tile: lo = min over the tile's sketches of their smallest register (zero registers included:
-// then lo = 0 and an empty register is the term 2^28), sketches whose largest register exceeds lo + 28 are flagged and
-// their pairs are redone by the sequential f64 loop (hll_pair_exact) -- 10^-3 of the sketches of 5 Mbp genomes at p = 14.
-// The zero count is only needed where both sketches hold an empty register, as in K4h.
+// then lo = 0 and an empty register is the term 2^28).  A tile that holds a sketch whose largest register exceeds lo + 28
+// (6 * 10^-4 of the sketches of 5 Mbp genomes at p = 14: 7 % of the tiles; every tile of a set that mixes tiny and huge
+// genomes) runs K4h's arithmetic instead -- registers recoded to the high word of 2^-r, VIMNMX + DADD in register order --
+// in the same staged layout: 1.5x slower than a fixed-point tile, never slower than K4h.  (The first version redid the
+// flagged pairs one by one from global memory: a flagged query column cost one lane per warp 8 x 2^p dependent adds, 0.5 ms
+// per tile, a cliff on mixed sets.)  The zero count is only needed where both sketches hold an empty register, as in K4h.
 // ------------------------------------------------------------------------------------------------
 __global__ void hll_minmax_kernel(const unsigned char* __restrict__ regs, uint64_t n, uint32_t cell_bytes, uint32_t* __restrict__ mm) {
     const uint64_t s = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -468,26 +471,6 @@ cudaError_t launch_hll_minmax(const void* regs, uint64_t n, uint32_t cell_bytes,
     if (n == 0) return cudaSuccess;
     hll_minmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(reinterpret_cast<const unsigned char*>(regs), n, cell_bytes, mm);
     return cudaGetLastError();
-}
-
-// the reference's loop on one pair, straight from global memory (flagged pairs only)
-__device__ __noinline__ void hll_pair_exact(const unsigned char* a, const unsigned char* b, uint32_t cell_bytes, double& sum, uint32_t& zero) {
-    double s = 0.0;
-    uint32_t z = 0;
-    for (uint32_t e = 0; e < cell_bytes; e += 16) {
-        const uint4 va = __ldg(reinterpret_cast<const uint4*>(a + e)), vb = __ldg(reinterpret_cast<const uint4*>(b + e));
-        const uint32_t m4[4] = {__vmaxu4(va.x, vb.x), __vmaxu4(va.y, vb.y), __vmaxu4(va.z, vb.z), __vmaxu4(va.w, vb.w)};
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t r = (m4[w] >> (8 * j)) & 0xffu;
-                z += (r == 0u);
-                s += __hiloint2double((int)(kHllOne - (r << 20)), 0);
-            }
-    }
-    sum = s;
-    zero = z;
 }
 
 __device__ __forceinline__ uint32_t mad_one(uint32_t a, uint32_t one, uint32_t c) {
@@ -560,13 +543,54 @@ __device__ __forceinline__ void hll_int_chunk(uint64_t (&sum)[kHiRM][kHiQM], uin
     }
 }
 
+// the same tile in K4h's arithmetic (staged words = high words of 2^-r): f64 adds in register order; the 64-bit accumulators
+// hold the doubles' bit patterns
+template <bool COUNT_ZERO, int kHiRM>
+__device__ __forceinline__ void hll_flt_chunk(uint64_t (&sum)[kHiRM][kHiQM], uint32_t (&zero)[kHiRM][kHiQM], const uint32_t* pa,
+                                              const uint32_t* pb, uint32_t a_row, uint32_t chunk) {
+    const uint32_t b_row32 = 32u * a_row, n_groups = chunk / 16;
+    double d[kHiRM][kHiQM];
+#pragma unroll
+    for (int r = 0; r < kHiRM; ++r)
+#pragma unroll
+        for (int c = 0; c < kHiQM; ++c) d[r][c] = __longlong_as_double((long long)sum[r][c]);
+#pragma unroll 1
+    for (uint32_t g = 0; g < n_groups; ++g) {
+#pragma unroll 1
+        for (uint32_t q = 0; q < 16; q += 4) {
+            uint4 a[kHiRM], b[kHiQM];
+#pragma unroll
+            for (int r = 0; r < kHiRM; ++r) a[r] = *reinterpret_cast<const uint4*>(pa + g * kHllIntGroup + r * a_row + q);
+#pragma unroll
+            for (int c = 0; c < kHiQM; ++c) b[c] = *reinterpret_cast<const uint4*>(pb + g * kHllIntGroup + c * b_row32 + q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int r = 0; r < kHiRM; ++r) {
+                    const uint32_t av = j == 0 ? a[r].x : j == 1 ? a[r].y : j == 2 ? a[r].z : a[r].w;
+#pragma unroll
+                    for (int c = 0; c < kHiQM; ++c) {
+                        const uint32_t bv = j == 0 ? b[c].x : j == 1 ? b[c].y : j == 2 ? b[c].z : b[c].w;
+                        const uint32_t m = min(av, bv);
+                        if (COUNT_ZERO) zero[r][c] += (m == kHllOne);
+                        d[r][c] += __hiloint2double((int)m, 0);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kHiRM; ++r)
+#pragma unroll
+        for (int c = 0; c < kHiQM; ++c) sum[r][c] = (uint64_t)__double_as_longlong(d[r][c]);
+}
+
 template <int kHiRM>
 __global__ void __launch_bounds__(kHllThreads, HiShape<kHiRM>::kMinBlocks) dist_hll_int_kernel(DistParams dp, uint32_t cell_bytes, uint32_t chunk, uint32_t one) {
     constexpr int kHiTR = HiShape<kHiRM>::kTR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_zero[2][2];                    // [chunk parity][ref, qry]: an empty register was staged
     __shared__ uint32_t s_lo;
-    __shared__ unsigned char s_flag[kHiTR + kHiTQ];    // sketch has a register above the tile's window
     const uint32_t stride = hll_int_stride(chunk);        // u32 per staged row (20-word groups + 16 B pad)
     uint32_t* sa = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* sb = sa + (size_t)kHiTR * stride;
@@ -599,7 +623,8 @@ __global__ void __launch_bounds__(kHllThreads, HiShape<kHiRM>::kMinBlocks) dist_
     }
     __syncthreads();
     const uint32_t lo = s_lo;
-    if (threadIdx.x < kHiTR + kHiTQ) s_flag[threadIdx.x] = ((my_mm >> 8) & 0xffu) > lo + (uint32_t)kHllIntW ? 1 : 0;
+    // a sketch above the window: the whole tile runs in f64 (CTA-uniform)
+    const bool flt = __syncthreads_or(threadIdx.x < kHiTR + kHiTQ && ((my_mm >> 8) & 0xffu) > lo + (uint32_t)kHllIntW) != 0;
 
     uint64_t sum[kHiRM][kHiQM];
     uint32_t zero[kHiRM][kHiQM];
@@ -620,10 +645,10 @@ __global__ void __launch_bounds__(kHllThreads, HiShape<kHiRM>::kMinBlocks) dist_
                                             : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
             za |= has_zero_byte(v.x) | has_zero_byte(v.y) | has_zero_byte(v.z) | has_zero_byte(v.w);
             uint4* dst = reinterpret_cast<uint4*>(sa + r * stride + kHllIntGroup * g);
-            dst[0] = hll_int_recode(v.x, lo);
-            dst[1] = hll_int_recode(v.y, lo);
-            dst[2] = hll_int_recode(v.z, lo);
-            dst[3] = hll_int_recode(v.w, lo);
+            dst[0] = flt ? hll_recode(v.x) : hll_int_recode(v.x, lo);
+            dst[1] = flt ? hll_recode(v.y) : hll_int_recode(v.y, lo);
+            dst[2] = flt ? hll_recode(v.z) : hll_int_recode(v.z, lo);
+            dst[3] = flt ? hll_recode(v.w) : hll_int_recode(v.w, lo);
         }
         for (uint32_t e = threadIdx.x; e < ((uint32_t)kHiTQ << g_shift); e += kHllThreads) {
             const uint32_t r = e >> g_shift, g = e & ((1u << g_shift) - 1u);
@@ -632,17 +657,22 @@ __global__ void __launch_bounds__(kHllThreads, HiShape<kHiRM>::kMinBlocks) dist_
                                           : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
             zb |= has_zero_byte(v.x) | has_zero_byte(v.y) | has_zero_byte(v.z) | has_zero_byte(v.w);
             uint4* dst = reinterpret_cast<uint4*>(sb + r * stride + kHllIntGroup * g);
-            dst[0] = hll_int_recode(v.x, lo);
-            dst[1] = hll_int_recode(v.y, lo);
-            dst[2] = hll_int_recode(v.z, lo);
-            dst[3] = hll_int_recode(v.w, lo);
+            dst[0] = flt ? hll_recode(v.x) : hll_int_recode(v.x, lo);
+            dst[1] = flt ? hll_recode(v.y) : hll_int_recode(v.y, lo);
+            dst[2] = flt ? hll_recode(v.z) : hll_int_recode(v.z, lo);
+            dst[3] = flt ? hll_recode(v.w) : hll_int_recode(v.w, lo);
         }
         if (za) s_zero[par][0] = 1u;
         if (zb) s_zero[par][1] = 1u;
         __syncthreads();
         const uint32_t* pa = sa + (wy * kHiRM) * stride;
         const uint32_t* pb = sb + tx * stride;
-        if (s_zero[par][0] & s_zero[par][1])  // CTA-uniform; an empty register anywhere means lo == 0
+        if (flt) {
+            if (s_zero[par][0] & s_zero[par][1])
+                hll_flt_chunk<true, kHiRM>(sum, zero, pa, pb, stride, chunk);
+            else
+                hll_flt_chunk<false, kHiRM>(sum, zero, pa, pb, stride, chunk);
+        } else if (s_zero[par][0] & s_zero[par][1])  // CTA-uniform; an empty register anywhere means lo == 0
             hll_int_chunk<true, 0, kHiRM>(sum, zero, pa, pb, stride, chunk, one);
         else if (chunk == (uint32_t)kHiChunk)
             hll_int_chunk<false, (int)hll_int_stride(kHiChunk), kHiRM>(sum, zero, pa, pb, stride, chunk, one);
@@ -659,12 +689,9 @@ __global__ void __launch_bounds__(kHllThreads, HiShape<kHiRM>::kMinBlocks) dist_
             const uint64_t i = row0 + wy * kHiRM + a, j = col0 + tx + 32 * b;
             if (i >= dp.row_end || j >= dp.n_qry) continue;
             if (dp.triangular && j > i) continue;
-            double sm = (double)sum[a][b] * scale;
-            uint32_t zr = zero[a][b];
-            if (s_flag[wy * kHiRM + a] | s_flag[kHiTR + tx + 32 * b])
-                hll_pair_exact(gref + (i << cell_shift), gqry + (j << cell_shift), cell_bytes, sm, zr);
+            const double sm = flt ? __longlong_as_double((long long)sum[a][b]) : (double)sum[a][b] * scale;
             bool bias;
-            const double U = hll_len(sm, zr, dp.p, &bias);
+            const double U = hll_len(sm, zero[a][b], dp.p, &bias);
             if (bias && dp.flags) atomicAdd(dp.flags, 1u);
             const double ca = dp.card_ref[i], cb = dp.card_qry[j];
             const double sim = (ca + cb - U) / U;
