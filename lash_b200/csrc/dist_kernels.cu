@@ -1041,11 +1041,13 @@ __global__ void __launch_bounds__(kTabThreads, 1) dist_fgra_tab_kernel(DistParam
 // per-pair path, so the inner loop carries no range check at all:
 //     2 address ops + LDS.64 + LDS.32 + 64-bit add + ~2.7 carry-save ops per register pair  (K4: ~21, of which the
 //     per-16-registers ripple through all counter planes was the largest part; here it runs once per 64 registers).
-// A warp owns ONE reference row (uniform -> broadcast loads) x 64 query columns, two per lane.
+// A warp owns TWO reference rows (uniform -> broadcast loads) x 32 query columns, one per lane: what is pulled out of a
+// query word (table column offset, G term) serves both rows.  (Round 1: one row x two columns per lane; on G-sum tiles that
+// kernel was ALU-bound at 86 % with three of its seven ALU instructions per register pair spent on the query side.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kMlTabThreads = 512;
-constexpr int kMlTabTR = 16, kMlTabTQ = 64;
-constexpr int kMlTabChunk = 128;
+constexpr int kMlTabTR = 32, kMlTabTQ = 32;
+constexpr int kMlTabChunk = 64;
 
 template <int NPL>
 __device__ __forceinline__ void ml_pair_epilogue(const DistParams& dp, MlAccT<NPL>& acc, uint64_t i, uint64_t j, uint64_t o, uint32_t cell_bytes) {
@@ -1124,7 +1126,7 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
         R[e + kTabN * kTabN] = (uint32_t)(ret >> 32);
         W[e] = (uint32_t)ml_w_of(m, p);
     }
-    const uint32_t ty = threadIdx.x >> 5, tx = threadIdx.x & 31u;  // ty: the warp's reference row
+    const uint32_t ty = threadIdx.x >> 5, tx = threadIdx.x & 31u;  // the warp's reference rows: ty and ty + 16; the lane's column: tx
     const unsigned char* gref = reinterpret_cast<const unsigned char*>(dp.ref);
     const unsigned char* gqry = reinterpret_cast<const unsigned char*>(dp.qry);
     const uint32_t chunk_words = chunk / 4;
@@ -1145,13 +1147,13 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
         __syncthreads();                      // the previous tile's epilogue has read sflag
         if (threadIdx.x == 0) s_lo = 0xffu;
         __syncthreads();
-        uint32_t mm = 0x00ffu;            // past the end (and threads beyond the tile's 80 sketches): min 255, max 0
+        uint32_t mm = 0x00ffu;            // past the end (and threads beyond the tile's sketches): min 255, max 0
         if (threadIdx.x < kMlTabTR) {
             if (row0 + threadIdx.x < dp.row_end) mm = dp.reg_mm_ref[row0 + threadIdx.x];
         } else if (threadIdx.x < kMlTabTR + kMlTabTQ) {
             if (col0 + (threadIdx.x - kMlTabTR) < dp.n_qry) mm = dp.reg_mm_qry[col0 + (threadIdx.x - kMlTabTR)];
         }
-        if (threadIdx.x < 96) {               // three whole warps cover the 80 sketches
+        if (threadIdx.x < (uint32_t)((kMlTabTR + kMlTabTQ + 31) / 32 * 32)) {   // whole warps cover the tile's sketches
             const uint32_t wmin = __reduce_min_sync(0xffffffffu, mm & 0xffu);
             if (tx == 0) atomicMin(&s_lo, wmin);
         }
@@ -1225,60 +1227,62 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
         }
         __syncthreads();
         if (c0 + chunk < cell_bytes) fetch(c0 + chunk);
-        const uint32_t* pa = sa + ty * a_stride;
-        const uint16_t* pb0 = sb + tx * b_stride;
-        const uint16_t* pb1 = sb + (tx + 32) * b_stride;
-        // 8 registers x 2 pairs: table lookups, S, and the Harley-Seal step; returns the two weight-8 carries
+        const uint32_t* pa0 = sa + ty * a_stride;
+        const uint32_t* pa1 = sa + (ty + 16) * a_stride;
+        const uint16_t* pb = sb + tx * b_stride;
+        // 8 registers x 2 pairs (two reference rows, one query column): table lookups, S, and the Harley-Seal step;
+        // returns the two weight-8 carries
         auto step8 = [&](uint32_t e, uint32_t& c0, uint32_t& c1) {
-            const uint4 al = *reinterpret_cast<const uint4*>(pa + e), ah = *reinterpret_cast<const uint4*>(pa + e + 4);
-            const uint4 b0 = *reinterpret_cast<const uint4*>(pb0 + e);
-            const uint4 b1 = *reinterpret_cast<const uint4*>(pb1 + e);
-            const uint32_t a[8] = {al.x, al.y, al.z, al.w, ah.x, ah.y, ah.z, ah.w};
-            const uint32_t b0w[4] = {b0.x, b0.y, b0.z, b0.w}, b1w[4] = {b1.x, b1.y, b1.z, b1.w};
+            const uint4 a0l = *reinterpret_cast<const uint4*>(pa0 + e), a0h = *reinterpret_cast<const uint4*>(pa0 + e + 4);
+            const uint4 a1l = *reinterpret_cast<const uint4*>(pa1 + e), a1h = *reinterpret_cast<const uint4*>(pa1 + e + 4);
+            const uint4 bq = *reinterpret_cast<const uint4*>(pb + e);
+            const uint32_t a0[8] = {a0l.x, a0l.y, a0l.z, a0l.w, a0h.x, a0h.y, a0h.z, a0h.w};
+            const uint32_t a1[8] = {a1l.x, a1l.y, a1l.z, a1l.w, a1h.x, a1h.y, a1h.z, a1h.w};
+            const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
             uint32_t w0[8], w1[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const uint32_t q0 = (i & 1) ? ml_b_q1(b0w[i >> 1]) : ml_b_q0(b0w[i >> 1]);
-                const uint32_t q1 = (i & 1) ? ml_b_q1(b1w[i >> 1]) : ml_b_q0(b1w[i >> 1]);
-                const uint32_t ar = rbase + a[i];
+                const uint32_t q = (i & 1) ? ml_b_q1(bw[i >> 1]) : ml_b_q0(bw[i >> 1]);
+                const uint32_t r0 = rbase + a0[i] + q, r1 = rbase + a1[i] + q;
                 uint32_t l0, h0, l1, h1;
-                asm("ld.shared.u32 %0, [%1];" : "=r"(l0) : "r"(ar + q0));
-                asm("ld.shared.u32 %0, [%1];" : "=r"(h0) : "r"(ar + q0 + kPlane));
-                asm("ld.shared.u32 %0, [%1];" : "=r"(w0[i]) : "r"(ar + q0 + 2u * kPlane));
-                asm("ld.shared.u32 %0, [%1];" : "=r"(l1) : "r"(ar + q1));
-                asm("ld.shared.u32 %0, [%1];" : "=r"(h1) : "r"(ar + q1 + kPlane));
-                asm("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"(ar + q1 + 2u * kPlane));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(l0) : "r"(r0));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(h0) : "r"(r0 + kPlane));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(w0[i]) : "r"(r0 + 2u * kPlane));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(l1) : "r"(r1));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(h1) : "r"(r1 + kPlane));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"(r1 + 2u * kPlane));
                 acc[0].S += ((uint64_t)h0 << 32) | l0;
                 acc[1].S += ((uint64_t)h1 << 32) | l1;
             }
             c0 = acc[0].csa8(w0);
             c1 = acc[1].csa8(w1);
         };
-        // the same 8 registers x 2 pairs on a G-sum tile: ONE table lookup (W); S as min of the two staged powers of two,
-        // eight per 32-bit batch
-        const uint32_t* pg = sga + ty * a_stride;
-        // ncu (n = 6000): ALU pipe 80 %, FMA-heavy 29 %, issue 64 % with the 16 resident warps the table leaves room for.
-        // Moving the three field shifts onto the FMA pipe (IMAD.HI by run-time powers of two: ALU 60 %, FMA-heavy 59 %) did
-        // not shorten the kernel (9.0 -> 9.5 ms, dispatch stalls x10): with four warps per scheduler it is the dependent
-        // LDS -> carry-save chains that set the pace, not a pipe.
+        // the same on a G-sum tile: ONE table lookup per pair (W); S as min of two staged powers of two, eight per 32-bit batch;
+        // the query side's column offset and G term are extracted once for the two rows.
+        // ncu, one-row version (n = 6000): ALU pipe 80-86 %, FMA-heavy 29 %.  Moving the field shifts onto the FMA pipe
+        // (IMAD.HI by run-time powers of two: ALU 60 %, FMA-heavy 59 %) did not shorten it (9.0 -> 9.5 ms, dispatch stalls x10).
+        const uint32_t* pg0 = sga + ty * a_stride;
+        const uint32_t* pg1 = sga + (ty + 16) * a_stride;
         auto step8g = [&](uint32_t e, uint32_t& c0, uint32_t& c1) {
-            const uint4 al = *reinterpret_cast<const uint4*>(pa + e), ah = *reinterpret_cast<const uint4*>(pa + e + 4);
-            const uint4 gl = *reinterpret_cast<const uint4*>(pg + e), gh = *reinterpret_cast<const uint4*>(pg + e + 4);
-            const uint4 b0 = *reinterpret_cast<const uint4*>(pb0 + e);
-            const uint4 b1 = *reinterpret_cast<const uint4*>(pb1 + e);
-            const uint32_t a[8] = {al.x, al.y, al.z, al.w, ah.x, ah.y, ah.z, ah.w};
-            const uint32_t ga[8] = {gl.x, gl.y, gl.z, gl.w, gh.x, gh.y, gh.z, gh.w};
-            const uint32_t b0w[4] = {b0.x, b0.y, b0.z, b0.w}, b1w[4] = {b1.x, b1.y, b1.z, b1.w};
+            const uint4 a0l = *reinterpret_cast<const uint4*>(pa0 + e), a0h = *reinterpret_cast<const uint4*>(pa0 + e + 4);
+            const uint4 a1l = *reinterpret_cast<const uint4*>(pa1 + e), a1h = *reinterpret_cast<const uint4*>(pa1 + e + 4);
+            const uint4 g0l = *reinterpret_cast<const uint4*>(pg0 + e), g0h = *reinterpret_cast<const uint4*>(pg0 + e + 4);
+            const uint4 g1l = *reinterpret_cast<const uint4*>(pg1 + e), g1h = *reinterpret_cast<const uint4*>(pg1 + e + 4);
+            const uint4 bq = *reinterpret_cast<const uint4*>(pb + e);
+            const uint32_t a0[8] = {a0l.x, a0l.y, a0l.z, a0l.w, a0h.x, a0h.y, a0h.z, a0h.w};
+            const uint32_t a1[8] = {a1l.x, a1l.y, a1l.z, a1l.w, a1h.x, a1h.y, a1h.z, a1h.w};
+            const uint32_t ga0[8] = {g0l.x, g0l.y, g0l.z, g0l.w, g0h.x, g0h.y, g0h.z, g0h.w};
+            const uint32_t ga1[8] = {g1l.x, g1l.y, g1l.z, g1l.w, g1h.x, g1h.y, g1h.z, g1h.w};
+            const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
             uint32_t w0[8], w1[8], s0 = 0u, s1 = 0u;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const uint32_t x0 = b0w[i >> 1], x1 = b1w[i >> 1];
-                const uint32_t q0 = (i & 1) ? ml_b_q1(x0) : ml_b_q0(x0), q1 = (i & 1) ? ml_b_q1(x1) : ml_b_q0(x1);
-                const uint32_t n0 = (i & 1) ? ml_b_n1(x0) : ml_b_n0(x0), n1 = (i & 1) ? ml_b_n1(x1) : ml_b_n0(x1);
-                const uint32_t g0 = min(ga[i], ml_gs_term(n0));
-                const uint32_t g1 = min(ga[i], ml_gs_term(n1));
-                asm("ld.shared.u32 %0, [%1];" : "=r"(w0[i]) : "r"(mad_one(q0, one, a[i])));
-                asm("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"(mad_one(q1, one, a[i])));
+                const uint32_t x = bw[i >> 1];
+                const uint32_t q = (i & 1) ? ml_b_q1(x) : ml_b_q0(x);
+                const uint32_t gb = ml_gs_term((i & 1) ? ml_b_n1(x) : ml_b_n0(x));
+                const uint32_t g0 = min(ga0[i], gb), g1 = min(ga1[i], gb);
+                asm("ld.shared.u32 %0, [%1];" : "=r"(w0[i]) : "r"(mad_one(q, one, a0[i])));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"(mad_one(q, one, a1[i])));
                 s0 = i == 0 ? g0 : mad_one(g0, one, s0);
                 s1 = i == 0 ? g1 : mad_one(g1, one, s1);
             }
@@ -1329,11 +1333,11 @@ __global__ void __launch_bounds__(kMlTabThreads, 1) dist_ml_tab_kernel(DistParam
 
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
-        const uint64_t i = row0 + ty, j = col0 + tx + 32 * b;
+        const uint64_t i = row0 + ty + 16 * b, j = col0 + tx;
         if (i >= dp.row_end || j >= dp.n_qry) continue;
         if (dp.triangular && j > i) continue;
         if (gs) acc[b].mmax = kMlGsMarker | k0;                             // S holds the G-sum: finish_union rebuilds S
-        if (sflag[ty] | sflag[kMlTabTR + tx + 32 * b]) acc[b].mmax = 255u;  // -> exact per-pair path in finish_union
+        if (sflag[ty + 16 * b] | sflag[kMlTabTR + tx]) acc[b].mmax = 255u;  // -> exact per-pair path in finish_union
         const uint64_t o = dp.packed_tri ? (i * (i + 1) / 2 + j) : ((i - dp.out_row0) * dp.n_qry + j);
         if (SPLIT) {
             uint32_t* sc = dp.ml_scratch + (o - dp.ml_o_base);  // consecutive lanes -> consecutive cells: coalesced per word
