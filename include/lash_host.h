@@ -49,7 +49,8 @@ int lash_fastx_close(lash_fastx* r);
  * Appends the bases of seq[0..n) that are one of "ACGT" to a packed stream that already holds
  * *n_bases bases (lash_gpu.h format: A0 C1 G2 T3, first base in the high bits of each byte);
  * `packed` must have room for (*n_bases + n + 3) / 4 + 16 bytes.  use_simd: 0 scalar table, 1 the default SIMD
- * path (AVX2+BMI2, 32 bytes per step; the 64-byte AVX-512 VBMI2 path with LASH_PACK_ISA=avx512), 2 AVX2, 3 AVX-512. */
+ * path (the 64-byte AVX-512 VBMI2 path where the CPU has it, else AVX2+BMI2 with 32 bytes per step; LASH_PACK_ISA=avx2 forces
+ * the latter), 2 AVX2, 3 AVX-512. */
 int lash_host_filter_pack(const uint8_t* seq, size_t n, uint8_t* packed, uint64_t* n_bases, int use_simd);
 /* 1 when the AVX2+BMI2 packer is usable on this CPU */
 int lash_host_pack_has_simd(void);

@@ -164,11 +164,12 @@ bool pack_has_simd() {
 
 uint64_t BaseStream::append_filtered(const uint8_t* s, size_t n, int use_simd) {
 #if defined(__x86_64__)
-    // The 64-byte AVX-512 path is opt-in (LASH_PACK_ISA=avx512, or use_simd == 3): on the build container's Xeon it
-    // measures the same as the 32-byte path within noise (3.0-4.1 GB/s per core, both), so the default stays the path
-    // that has been through the GPU box's end-to-end tests.
-    static const bool want512 = [] { const char* v = getenv("LASH_PACK_ISA"); return v && std::string(v) == "avx512"; }();
-    if ((use_simd == 3 || (use_simd == 1 && want512)) && pack_has_avx512()) return append_avx512(*this, s, n);
+    // Default: the 64-byte AVX-512 VBMI2 path where the CPU has it, else AVX2 + BMI2.  Round 1 measured the two the same
+    // (the reader's mmap traffic hid the packer); with the buffered reader of round 2 the 64-byte path is ahead, modestly, on the GPU
+    // boxes: pack-only 47.9 -> 52.5 Gbp/s on 16 workers and 15.6 -> 16.8 on 4 on one box, FASTA -> registers 49.2 -> 50.9 Gbp/s on
+    // another (tools/ingest_probe.py; in cache 5.8 vs 7.7 GB/s per core).  LASH_PACK_ISA=avx2 forces the 32-byte path (A/B), =avx512 is accepted for symmetry.
+    static const bool want_avx2 = [] { const char* v = getenv("LASH_PACK_ISA"); return v && std::string(v) == "avx2"; }();
+    if ((use_simd == 3 || (use_simd == 1 && !want_avx2)) && pack_has_avx512()) return append_avx512(*this, s, n);
     if (use_simd && pack_has_simd()) return append_avx2(*this, s, n);
 #endif
     (void)use_simd;

@@ -48,7 +48,7 @@ class BaseStream {
         if (bit) w_[n >> 5] &= (1ull << bit) - 1ull;
     }
     // filter + code + pack; the caller guarantees room() >= n.  Returns the number of bases kept.
-    // use_simd: 0 scalar table, 1 default (AVX2+BMI2 where present; AVX-512 VBMI2 with LASH_PACK_ISA=avx512), 2 AVX2+BMI2,
+    // use_simd: 0 scalar table, 1 default (AVX-512 VBMI2 where present, else AVX2+BMI2; LASH_PACK_ISA=avx2 forces the latter), 2 AVX2+BMI2,
     // 3 AVX-512 VBMI2 where present
     uint64_t append_filtered(const uint8_t* s, size_t n, int use_simd = 1);
     // LSB-first words -> ABI bytes, zero padding up to padded_bytes(); returns padded_bytes(size())
